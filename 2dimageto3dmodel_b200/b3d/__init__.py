@@ -1,0 +1,97 @@
+"""ctypes binding of libb3d.so (the C ABI in include/b3d.h) for the drop-in Python modules.
+
+No torch C++ extension, no CPU fallback: if the shared library is missing, or a tensor is not a
+contiguous CUDA fp32 tensor, the call fails loudly.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb3d.so")
+
+MODE_REFERENCE = 0
+MODE_PAPER = 1
+_MODES = {"R": MODE_REFERENCE, "reference": MODE_REFERENCE, "P": MODE_PAPER, "paper": MODE_PAPER,
+          0: MODE_REFERENCE, 1: MODE_PAPER}
+
+
+class B3DError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise B3DError(f"{LIB_PATH} is missing: build it with `make` (or __graft_entry__.build()). "
+                       "There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.b3d_last_error.restype = ctypes.c_char_p
+    lib.b3d_launch_count.restype = ctypes.c_uint64
+    lib.b3d_pc_silhouette_workspace_bytes.restype = ctypes.c_size_t
+    return lib
+
+
+lib = _load()
+
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_f = ctypes.c_float
+_sz = ctypes.c_size_t
+
+
+def _sig(name, *argtypes):
+    fn = getattr(lib, name)
+    fn.argtypes = list(argtypes)
+    fn.restype = ctypes.c_int
+    return fn
+
+
+_sig("b3d_pc_project", _vp, _vp, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp)
+_sig("b3d_pc_silhouette_fwd_hosttaps", _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp)
+_sig("b3d_pc_silhouette_bwd_hosttaps", _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp)
+_sig("b3d_pc_silhouette_fwd", _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp)
+_sig("b3d_pc_silhouette_bwd", _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp)
+_sig("b3d_pc_project_bwd", _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _vp, _vp, _vp)
+_sig("b3d_pc_splat_grid", _vp, _i, _i, _i, _i, _vp, _vp)
+
+
+def mode_id(mode):
+    try:
+        return _MODES[mode]
+    except KeyError:
+        raise B3DError(f"unknown semantics mode {mode!r} (use 'R' or 'P')") from None
+
+
+def check(rc):
+    if rc != 0:
+        raise B3DError(f"libb3d error {rc}: {lib.b3d_last_error().decode()}")
+
+
+def launch_count():
+    return int(lib.b3d_launch_count())
+
+
+def dev(t, name="tensor", dtype=torch.float32):
+    """Validate a tensor for the C ABI and return it (contiguous CUDA tensor of `dtype`)."""
+    if not isinstance(t, torch.Tensor):
+        raise B3DError(f"{name}: expected a torch.Tensor")
+    if not t.is_cuda:
+        raise B3DError(f"{name}: libb3d runs on CUDA tensors only (got device {t.device}); "
+                       "there is no CPU fallback")
+    if t.dtype != dtype:
+        raise B3DError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def ptr(t):
+    return _vp(t.data_ptr()) if t is not None else _vp(0)
+
+
+def stream_ptr(t=None):
+    return _vp(torch.cuda.current_stream(t.device if t is not None else None).cuda_stream)
+
+
+def host_floats(values):
+    arr = (ctypes.c_float * len(values))(*[float(v) for v in values])
+    return arr

@@ -1,0 +1,24 @@
+// libb3d core: thread-local error string, version, launch counter.
+#include <atomic>
+#include <stdarg.h>
+
+#include "b3d_common.cuh"
+
+namespace b3d {
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+}  // namespace b3d
+
+extern "C" {
+const char* b3d_last_error(void) { return b3d::g_err; }
+int b3d_version(void) { return 100; }
+uint64_t b3d_launch_count(void) { return b3d::g_launches.load(std::memory_order_relaxed); }
+}
