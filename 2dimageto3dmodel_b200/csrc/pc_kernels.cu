@@ -582,7 +582,7 @@ int check_sil_args(const char* who, const void* pg, const void* taps, int ktaps,
                 ktaps, MAX_TAPS);
     B3D_REQUIRE(mode == B3D_MODE_REFERENCE, B3D_EINVAL,
                 "%s: mode %d not available in this build (only B3D_MODE_REFERENCE)", who, mode);
-    B3D_REQUIRE(taps && (pg || N == 0), B3D_EINVAL, "%s: null pointer", who);
+    B3D_REQUIRE(taps && (pg || N == 0 || B == 0), B3D_EINVAL, "%s: null pointer", who);
     return B3D_OK;
 }
 
