@@ -54,6 +54,13 @@ _sig("b3d_pc_silhouette_fwd", _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _sz, 
 _sig("b3d_pc_silhouette_bwd", _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp)
 _sig("b3d_pc_project_bwd", _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _vp, _vp, _vp)
 _sig("b3d_pc_splat_grid", _vp, _i, _i, _i, _i, _vp, _vp)
+_sig("b3d_mesh_face_setup", _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp)
+_sig("b3d_mesh_render_fwd", _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp)
+_sig("b3d_flat_loss_fwd", _vp, _vp, _i, _i, _i, _vp, _vp)
+_sig("b3d_flat_loss_bwd", _vp, _vp, _i, _i, _i, _vp, _vp, _vp)
+_sig("b3d_rgba_mse_iou_fwd", _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp)
+_sig("b3d_rgba_mse_bwd", _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp)
+_sig("b3d_mesh_render_bwd", _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp)
 
 
 def mode_id(mode):

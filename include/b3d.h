@@ -108,6 +108,57 @@ B3D_API int b3d_pc_project_bwd(const float* points, const float* quat, const flo
  * Used by mode P and by the parity tests; grid is zeroed by the call. */
 B3D_API int b3d_pc_splat_grid(const float* pg, int B, int N, int V, int mode, float* grid, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Textured-mesh render path (replaces the kaolin dependency)
+ *   Renderer.forward                          rendering/renderer.py:39-77
+ * ------------------------------------------------------------------------------------------ */
+
+/* ortho_projection + per-face gathers          rendering/renderer.py:9-28,52-58
+ *   (kaolin dib_renderer.utils.datanormalize for normal1, renderer.py:52)
+ * verts [B,P,3]; faces [F,3] int32; uv [B,T,2] (uv_batched=1) or [T,2] (0); ft [F,3] int32.
+ * fgeo    [B,F,12] out: (ax,ay,bx,by,cx,cy)*multiplier, az,bz,cz, normal_z, 0,0
+ * fuv     [B,F,6]  out, nullable: per-face-corner uv
+ * normal1 [B,F,3]  out, nullable: unit face normals (the third value Renderer.forward returns)   */
+B3D_API int b3d_mesh_face_setup(const float* verts, const int32_t* faces, const float* uv,
+                                int uv_batched, const int32_t* ft, int B, int P, int F, int T,
+                                float* fgeo, float* fuv, float* normal1, void* stream);
+
+/* kaolin.graphics.dib_renderer.rasterizer.linear_rasterizer (renderer.py:60-67; defaults expand=0.02,
+ * knum=30, multiplier=1000, delta=7000, restated from SURVEY.md App. B — parity unpinned) fused with
+ * fragmentshader (rendering/fragment_shader.py:22-37, bilinear, align_corners=True).
+ * tex [B,3,Th,Tw] : imout = shaded image [B,H,W,3] (tex*hardmask, or lerp(bg,tex,hardmask) with bg [B,H,W,3])
+ * tex NULL        : imout = imfeat [B,H,W,3] = interpolated (u,v,1), what linear_rasterizer returns
+ * imidx [B,H,W] int32 face index + 1 (0 = background; bit-exact target), imwei [B,H,W,3] barycentrics,
+ * improb [B,H,W] soft silhouette (1 inside).                                                      */
+B3D_API int b3d_mesh_render_fwd(const float* fgeo, const float* fuv, const float* tex, const float* bg,
+                                int B, int F, int H, int W, int Th, int Tw, int32_t* imidx,
+                                float* imwei, float* imout, float* improb, void* stream);
+
+/* Adjoint: d_imout [B,H,W,3], d_improb [B,H,W] (nullable) -> dfp2d [B,F,6] (w.r.t. the UNSCALED 2-D
+ * face vertices), dfuv [B,F,6], dtex [B,3,Th,Tw] (all zeroed by the call).  No gradient to depth or
+ * normal_z (kaolin semantics).                                                                     */
+B3D_API int b3d_mesh_render_bwd(const float* fgeo, const float* fuv, const float* tex, int has_bg, int B,
+                                int F, int H, int W, int Th, int Tw, const int32_t* imidx,
+                                const float* imwei, const float* d_imout, const float* d_improb,
+                                float* dfp2d, float* dfuv, float* dtex, void* stream);
+
+/* loss_flat(mesh, norms)                        utils/losses.py:5-17
+ * norms [B,F,3]; ff [F,K] int32 face adjacency (negative ids index from the end, as torch does);
+ * loss [1] out (zeroed by the call).  bwd: gloss [1] upstream gradient -> dnorms [B,F,3].        */
+B3D_API int b3d_flat_loss_fwd(const float* norms, const int32_t* ff, int B, int F, int K, float* loss,
+                              void* stream);
+B3D_API int b3d_flat_loss_bwd(const float* norms, const int32_t* ff, int B, int F, int K,
+                              const float* gloss, float* dnorms, void* stream);
+
+/* nn.MSELoss()(cat(image, alpha).permute(0,3,1,2), X_real) + the counts mean_iou thresholds
+ *                                               run_reconstruction.py:225-231,429-431
+ * image [B,H,W,3], alpha [B,H,W], target [B,4,H,W]; loss [1] out; counts [B,2] int32 out, nullable:
+ * {|pred&real|, |pred|real|} at threshold 0.5.  bwd writes d_image, d_alpha (= 2 (x - t) gloss / n).  */
+B3D_API int b3d_rgba_mse_iou_fwd(const float* image, const float* alpha, const float* target, int B, int H,
+                                 int W, float* loss, int32_t* counts, void* stream);
+B3D_API int b3d_rgba_mse_bwd(const float* image, const float* alpha, const float* target, int B, int H,
+                             int W, const float* gloss, float* d_image, float* d_alpha, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
