@@ -102,3 +102,56 @@ def stream_ptr(t=None):
 def host_floats(values):
     arr = (ctypes.c_float * len(values))(*[float(v) for v in values])
     return arr
+
+
+# ---------------------------------------------------------------------------------------------
+# optional per-entry-point device timing (bench.py's kernel breakdown): CUDA events recorded on the
+# launching stream around every libb3d call.  Off by default; enabling swaps the ctypes attributes.
+# ---------------------------------------------------------------------------------------------
+_prof_records = None
+_prof_saved = {}
+
+
+def prof_enable():
+    global _prof_records
+    if _prof_records is not None:
+        return
+    _prof_records = []
+    for name in [n for n in dir(lib) if n.startswith("b3d_")] + list(_TIMED):
+        fn = getattr(lib, name)
+        if name in _prof_saved or not hasattr(fn, "argtypes") or name in ("b3d_last_error", "b3d_launch_count",
+                                                                          "b3d_version"):
+            continue
+        _prof_saved[name] = fn
+
+        def wrapper(*args, _fn=fn, _name=name):
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = _fn(*args)
+            e1.record()
+            _prof_records.append((_name, e0, e1))
+            return rc
+
+        setattr(lib, name, wrapper)
+
+
+def prof_disable():
+    """-> {entry point: [ms, ...]} and restores the plain ctypes functions."""
+    global _prof_records
+    if _prof_records is None:
+        return {}
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1 in _prof_records:
+        out.setdefault(name, []).append(e0.elapsed_time(e1))
+    for name, fn in _prof_saved.items():
+        setattr(lib, name, fn)
+    _prof_saved.clear()
+    _prof_records = None
+    return out
+
+
+_TIMED = ("b3d_pc_project", "b3d_pc_silhouette_fwd_hosttaps", "b3d_pc_silhouette_bwd_hosttaps", "b3d_pc_project_bwd",
+          "b3d_pc_splat_grid", "b3d_mesh_face_setup", "b3d_mesh_render_fwd", "b3d_mesh_render_bwd", "b3d_flat_loss_fwd",
+          "b3d_flat_loss_bwd", "b3d_rgba_mse_iou_fwd", "b3d_rgba_mse_bwd")

@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py — render+loss images/sec on B200 (BASELINE.json metric), one JSON line on stdout.
+
+Workload = BASELINE.json configs[1]: "CUB 256x256, 8000-pt cloud, full render+loss, batch=16 on 1xB200"
+(SURVEY.md §8d cfg2), per step and per GPU, forward + backward:
+  (i)  point path : EffectiveLossFunction(V=128)(points[16,8000,3], q, scale) -> sum-MSE vs mask[16,128,128]
+  (ii) mesh path  : mesh_map[16,3,32,32] -> template vertices (482 v / 960 f) -> pose -> DIB-R render 256x256
+                    with a 128x128 texture -> RGBA MSE vs X_real[16,4,256,256] + 5e-4 * loss_flat (+ mIoU)
+Synthetic, seeded inputs (no dataset exists offline).  No network / optimiser on this config.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+N>1 is launched by torchrun (one rank per GPU, NCCL); the batch is sharded per rank with no data-path
+collective (weak scaling: 16 images per GPU).  `--impl reference` times the oracle port (the reference's
+algorithm on the CPU, torch, all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "2dimageto3dmodel_b200")
+for p in (PKG, ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+B_PER_GPU, N_PTS, V, H, TEX, FLAT_COEF = 16, 8000, 128, 256, 128, 5e-4
+METRIC = "render+loss images/sec (cfg2: 8000-pt effective loss V=128 + CUB mesh render 256x256, fwd+bwd)"
+WORKLOAD = "cfg2: CUB 256x256, 8000-pt cloud, full render+loss, batch=16 per GPU"
+
+
+def host_inputs(B, seed, pin):
+    g = torch.Generator().manual_seed(seed)
+    pts = (torch.rand(B, N_PTS, 3, generator=g) * 2 - 1) * 0.45
+    shell = torch.nn.functional.normalize(torch.randn(B, N_PTS // 2, 3, generator=g), dim=-1)
+    pts[:, : N_PTS // 2] = shell * (0.33 + 0.01 * torch.randn(B, N_PTS // 2, 1, generator=g))
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, H), torch.linspace(-1, 1, H), indexing="ij")
+    disk = ((yy * yy + xx * xx) < 0.45).float()
+    x_real = torch.rand(B, 4, H, H, generator=g) * 2 - 1
+    x_real[:, 3] = disk
+    x_real[:, :3] *= disk
+    m = torch.nn.functional.interpolate(disk[None, None], size=(V, V), mode="bilinear", align_corners=True)[0, 0]
+    d = dict(points=pts, quat=torch.randn(B, 4, generator=g), scale=0.5 + 0.5 * torch.rand(B, 1, generator=g),
+             mask=m.expand(B, V, V).contiguous(), mesh_map=torch.randn(B, 3, 32, 32, generator=g) * 0.05,
+             tex=torch.rand(B, 3, TEX, TEX, generator=g) * 2 - 1,
+             rot=torch.nn.functional.normalize(torch.randn(B, 4, generator=g), dim=-1),
+             pscale=0.55 + 0.3 * torch.rand(B, 1, generator=g), ptrans=(torch.rand(B, 3, generator=g) - 0.5) * 0.3,
+             x_real=x_real)
+    return {k: (v.pin_memory() if pin else v) for k, v in d.items()}
+
+
+def template_path():
+    from oracle import mesh as M          # only the OBJ writer (the shipped templates cannot travel)
+    path = os.path.join(tempfile.mkdtemp(), "uvsphere_16rings.obj")
+    return M.write_uvsphere_obj(path, rings=16)
+
+
+# --------------------------------------------------------------------------------------------- CUDA arm
+class CudaWorkload:
+    def __init__(self, device):
+        from rendering.mesh_template import MeshTemplate
+        from rendering.renderer import Renderer
+        from utils.effective_loss_function import EffectiveLossFunction
+        self.dev = device
+        self.elf = EffectiveLossFunction(voxel_size=V).to(device)
+        self.tpl = MeshTemplate(template_path(), device=device)
+        self.renderer = Renderer(H, H)
+        self.flip = torch.tensor([1.0, -1.0, -1.0], device=device)
+
+    def step(self, d):
+        from b3d.mesh import rgba_mse_iou
+        from rendering.utils import qrot
+        from utils.losses import loss_flat
+        p, q, s = (d[k].requires_grad_(True) for k in ("points", "quat", "scale"))
+        sil = self.elf(p, q, s)
+        loss_pc = (sil - d["mask"]).square().sum() / sil.shape[0]        # unsupervised_part.py:111
+        mm, tex = d["mesh_map"].requires_grad_(True), d["tex"].requires_grad_(True)
+        raw = self.tpl.get_vertex_positions(mm)
+        vtx = (qrot(d["rot"], d["pscale"].unsqueeze(-1) * raw) + d["ptrans"].unsqueeze(1)) * self.flip
+        img, alpha = self.tpl.forward_renderer(self.renderer, vtx, tex)
+        recon, miou = rgba_mse_iou(img, alpha, d["x_real"])
+        flat = loss_flat(self.tpl.mesh, self.tpl.compute_normals(raw))
+        loss = loss_pc + recon + FLAT_COEF * flat
+        loss.backward()
+        return loss.detach(), (p.grad, q.grad, s.grad, mm.grad, tex.grad)
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def mark(self):
+        return len(self.rows)
+
+    def stop(self, lo=0, hi=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for r in self.rows[lo:hi] if len(r) >= 7] or [r for r in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        f = lambda x: float(x) if x.replace(".", "", 1).isdigit() else None
+        sm = [f(r[0]) for r in rows if f(r[0]) is not None]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": f(rows[0][1]),
+                "power_w_max": max((f(r[2]) or 0) for r in rows), "samples": len(rows), "reasons": reasons}
+
+
+def algorithmic_bytes(B):
+    """SURVEY.md §8(d) per-sample figures x the samples one launch processes (stated in DESIGN.md)."""
+    pc_fwd = 8 * V**3 + 4 * V**2 + 12 * N_PTS
+    pc_all = 20 * V**3 + 8 * V**2 + 36 * N_PTS
+    F_, Tw = 960, TEX + 2
+    mesh_fwd = 100 * F_ + 12 * TEX * Tw + H * H * 48
+    mesh_bwd = H * H * 32 + 12 * TEX * Tw + 60 * F_
+    return {"b3d_pc_silhouette_fwd_hosttaps": B * pc_fwd, "b3d_pc_silhouette_bwd_hosttaps": B * (pc_all - pc_fwd),
+            "b3d_mesh_render_fwd": B * mesh_fwd, "b3d_mesh_render_bwd": B * mesh_bwd}
+
+
+def run_cuda(args):
+    import b3d
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 with torch.distributed.run")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+
+    wl = CudaWorkload(dev)
+    B = B_PER_GPU
+    host = host_inputs(B, seed=1234 + rank, pin=True)       # each rank owns its shard of the global batch
+    h2d = sum(t.numel() * t.element_size() for t in host.values())
+    resident = {k: v.to(dev) for k, v in host.items()}
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)  # > 126 MB L2
+
+    def sync_all():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        sync_all()
+        evs = []
+        for _ in range(steps):
+            flush.zero_()                                    # evict L2 between timed iterations
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((e0, e1))
+        sync_all()
+        total = sum(a.elapsed_time(b) for a, b in evs)
+        if dist is not None:
+            t = torch.tensor([total], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total = float(t)
+        return total
+
+    def fresh(d):
+        return {k: v.detach() for k, v in d.items()}
+
+    def step_resident():
+        return wl.step(fresh(resident))[0]
+
+    host_loss = torch.empty(1).pin_memory()
+
+    def step_e2e():
+        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        loss, _ = wl.step(d)
+        host_loss.copy_(loss.reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()            # the user reads the loss every step
+        return loss
+
+    clocks = ClockSampler(local) if rank == 0 else None
+    time.sleep(0.3) if clocks else None
+    n0 = b3d.launch_count()
+    lo = clocks.mark() if clocks else 0
+    total_ms = timed(step_resident, args.steps, args.warmup)
+    hi = clocks.mark() if clocks else 0
+    launches = (b3d.launch_count() - n0) // (args.steps + args.warmup)
+    e2e_ms = timed(step_e2e, args.steps, args.warmup)
+    clk = clocks.stop(lo, max(hi, lo + 1)) if clocks else None
+
+    # per-entry-point device times (events on the launching stream), separate pass
+    b3d.prof_enable()
+    for _ in range(max(3, args.steps // 2)):
+        flush.zero_()
+        step_resident()
+    prof = {k: statistics.mean(v) for k, v in b3d.prof_disable().items()}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    ms = total_ms / args.steps
+    value = world * B / (ms / 1e3)
+    e2e_v = world * B / (e2e_ms / args.steps / 1e3)
+    alg = algorithmic_bytes(B)
+    cand = {k: prof[k] for k in alg if k in prof}
+    top = max(cand, key=cand.get)
+    ach = alg[top] / (cand[top] * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top)
+    except (OSError, ValueError):
+        pass
+    out = {
+        "metric": METRIC, "value": round(value, 2), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": world * B, "points": N_PTS, "voxels": V,
+                   "image": H, "faces": 960, "texture": TEX, "l2": "flushed between timed iterations (256 MB write)",
+                   "parallelism": f"dp{world} (batch shards, no data-path collective)", "semantics": "R"},
+        "e2e": {"value": round(e2e_v, 2), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": round(e2e_ms / args.steps, 4)},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "roofline": {"kernel": top, "bound": "hbm", "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s",
+                     "frac": round(ach / hbm_peak, 4), "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg[top], "ms_per_launch": round(cand[top], 4)},
+        "kernel_ms": {k: round(v, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1])},
+    }
+    if world == 1 and not os.environ.get("B3D_BENCH_NO_CPU"):
+        out["cpu_baseline"] = cpu_baseline(budget_s=25.0)
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+class OracleWorkload:
+    """The same step through oracle/ (the reference's algorithm on the CPU)."""
+
+    def __init__(self):
+        from oracle import mesh as M
+        self.M = M
+        path = template_path()
+        self.T = M.TemplateData(M.load_obj(path), path)
+
+    def step(self, d):
+        from oracle import pointcloud as O
+        M, T = self.M, self.T
+        p, q, s = (d[k].clone().requires_grad_(True) for k in ("points", "quat", "scale"))
+        sil = O.effective_loss_forward(p, q, s, V=V, kernel_size=21, sigma=3.0, mode="R")
+        loss_pc = O.silhouette_mse_sum(sil, d["mask"])
+        mm, tex = d["mesh_map"].clone().requires_grad_(True), d["tex"].clone().requires_grad_(True)
+        raw = M.get_vertex_positions(T, mm)
+        vtx = M.transform_vertices(raw, d["pscale"], d["ptrans"], d["rot"])
+        img, alpha, _ = M.forward_renderer(T, vtx, tex, H, H)
+        xf = torch.cat((img, alpha), dim=3).permute(0, 3, 1, 2)
+        recon = torch.nn.functional.mse_loss(xf, d["x_real"])
+        flat = M.loss_flat(T.ff, T.faces.shape[0], M.compute_normals(T, raw))
+        loss = loss_pc + recon + FLAT_COEF * flat
+        loss.backward()
+        return loss.detach()
+
+
+def cpu_baseline(budget_s, sample_b=2):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    wl = OracleWorkload()
+    d = host_inputs(sample_b, seed=1234, pin=False)
+    wl.step(d)                                             # warm-up
+    t0, n = time.perf_counter(), 0
+    while True:
+        wl.step(d)
+        n += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or n >= 8:
+            break
+    return {"value": round(sample_b * n / el, 4), "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": f"{n} steps of batch {sample_b} of the same workload through oracle/ (torch CPU, "
+                      f"{torch.get_num_threads()} threads); the reference's mesh rasteriser (kaolin) cannot run on CPU"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_b = 2
+    wl = OracleWorkload()
+    d = host_inputs(sample_b, seed=1234, pin=False)
+    for _ in range(min(args.warmup, 1)):
+        wl.step(d)
+    steps = min(args.steps, 6)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        wl.step(d)
+    el = time.perf_counter() - t0
+    v = sample_b * steps / el
+    sample = (f"{steps} steps of batch {sample_b} (bounded sample of the batch-16 workload) through oracle/ = the "
+              f"reference's algorithm in torch on the CPU, {cores} threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": "images/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": round(el / steps * 1e3, 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_step": sample_b, "points": N_PTS, "voxels": V, "image": H,
+                   "faces": 960, "texture": TEX, "semantics": "R"},
+        "cpu_baseline": {"value": round(v, 4), "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(v, 4), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b3d", choices=["b3d", "reference"])
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b3d":
+        args.warmup = 3
+    (run_reference if args.impl == "reference" else run_cuda)(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -263,12 +263,26 @@ def pixel_centres(H, W, dtype, device):
     return x0.view(1, 1, W), y0.view(1, H, 1)
 
 
+def _window(lo, hi, n, size, flip):
+    """Conservative pixel index range [i0, i1) whose centres can fall inside [lo, hi) (+-1 pixel)."""
+    # centre(i) = m/size * (2i + 1 - size)  (x)   or   m/size * (size - 2i - 1)  (y, flip)
+    a = (lo * size / MULTIPLIER + size - 1) / 2
+    b = (hi * size / MULTIPLIER + size - 1) / 2
+    if flip:
+        a, b = (size - 1) - b, (size - 1) - a
+    i0 = max(0, int(math.floor(a)) - 1)
+    i1 = min(n, int(math.ceil(b)) + 2)
+    return i0, max(i0, i1)
+
+
 def rasterize(p3d, p2d, normalz, attr, H, W, expand=EXPAND, knum=KNUM, multiplier=MULTIPLIER, delta=DELTA):
     """kaolin linear_rasterizer restated from SURVEY.md App. B (PARITY UNPINNED).
 
     p3d [B,F,9], p2d [B,F,6], normalz [B,F,1], attr [B,F,3d] ->
       imfeat [B,H,W,d], improb [B,H,W,1], imidx [B,H,W] int32 (face+1, 0 = background), imwei [B,H,W,3].
-    Differentiable w.r.t. p2d and attr (not p3d / normalz), like kaolin's backward."""
+    Differentiable w.r.t. p2d and attr (not p3d / normalz), like kaolin's backward.
+    The loops run face by face in face order, like kaolin's per-pixel loops; per face only the pixel
+    window that can pass its (expanded) bounding-box test is touched (an exact restriction)."""
     assert multiplier == MULTIPLIER
     B, Fn, _ = p2d.shape
     d = attr.shape[2] // 3
@@ -280,12 +294,14 @@ def rasterize(p3d, p2d, normalz, attr, H, W, expand=EXPAND, knum=KNUM, multiplie
     xmax = torch.maximum(torch.maximum(P[..., 0], P[..., 2]), P[..., 4])
     ymin = torch.minimum(torch.minimum(P[..., 1], P[..., 3]), P[..., 5])
     ymax = torch.maximum(torch.maximum(P[..., 1], P[..., 3]), P[..., 5])
+    bb = torch.stack([xmin, xmax, ymin, ymax], dim=-1).double().cpu().numpy()
+    front_np = (normalz[:, :, 0] >= 0).cpu().numpy()
 
-    def bary(Pf, sel=None):
+    def bary(Pf, xs, ys):
         ax, ay, bx, by, cx, cy = [Pf[..., i] for i in range(6)]
         m, p = bx - ax, by - ay
         n, q = cx - ax, cy - ay
-        s, t = x0 - ax, y0 - ay
+        s, t = xs - ax, ys - ay
         k3 = m * q - n * p
         w1 = (s * q - n * t) / (k3 + BARY_EPS)
         w2 = (m * t - s * p) / (k3 + BARY_EPS)
@@ -293,48 +309,81 @@ def rasterize(p3d, p2d, normalz, attr, H, W, expand=EXPAND, knum=KNUM, multiplie
 
     imidx = torch.zeros(B, H, W, dtype=torch.int32, device=dev)
     imdep = torch.full((B, H, W), DEPTH_INIT, dtype=dt, device=dev)
-    for f in range(Fn):
-        Pf = P[:, f].view(B, 1, 1, 6)
-        front = (normalz[:, f, 0] >= 0).view(B, 1, 1)
-        inbox = (x0 >= xmin[:, f].view(B, 1, 1)) & (x0 < xmax[:, f].view(B, 1, 1)) & \
-                (y0 >= ymin[:, f].view(B, 1, 1)) & (y0 < ymax[:, f].view(B, 1, 1))
-        w0, w1, w2 = bary(Pf)
-        inside = (w0 >= 0) & (w1 >= 0) & (w2 >= 0)
-        z = w0 * Z[:, f, 0].view(B, 1, 1) + w1 * Z[:, f, 1].view(B, 1, 1) + w2 * Z[:, f, 2].view(B, 1, 1)
-        upd = front & inbox & inside & (z > imdep)
-        imidx = torch.where(upd, torch.full_like(imidx, f + 1), imidx)
-        imdep = torch.where(upd, z, imdep)
+    for b in range(B):
+        for f in range(Fn):
+            if not front_np[b, f]:
+                continue
+            c0, c1 = _window(bb[b, f, 0], bb[b, f, 1], W, W, False)
+            r0, r1 = _window(bb[b, f, 2], bb[b, f, 3], H, H, True)
+            if c0 >= c1 or r0 >= r1:
+                continue
+            xs, ys = x0[0, :, c0:c1], y0[0, r0:r1, :]
+            inbox = (xs >= xmin[b, f]) & (xs < xmax[b, f]) & (ys >= ymin[b, f]) & (ys < ymax[b, f])
+            w0, w1, w2 = bary(P[b, f], xs, ys)
+            inside = (w0 >= 0) & (w1 >= 0) & (w2 >= 0)
+            z = w0 * Z[b, f, 0] + w1 * Z[b, f, 1] + w2 * Z[b, f, 2]
+            dep = imdep[b, r0:r1, c0:c1]
+            upd = inbox & inside & (z > dep)
+            imidx[b, r0:r1, c0:c1] = torch.where(upd, torch.full_like(imidx[b, r0:r1, c0:c1], f + 1),
+                                                 imidx[b, r0:r1, c0:c1])
+            imdep[b, r0:r1, c0:c1] = torch.where(upd, z, dep)
 
     covered = imidx > 0
     # differentiable barycentrics of the winning face
     sel = (imidx.long() - 1).clamp_min(0).view(B, H * W)
     Pd = (multiplier * p2d).gather(1, sel.unsqueeze(-1).expand(-1, -1, 6)).view(B, H, W, 6)
-    w0, w1, w2 = bary(Pd)
+    w0, w1, w2 = bary(Pd, x0, y0)
     cov = covered.to(dt)
     imwei = torch.stack([w0, w1, w2], dim=-1) * cov.unsqueeze(-1)
     A = attr.gather(1, sel.unsqueeze(-1).expand(-1, -1, 3 * d)).view(B, H, W, 3, d)
     imfeat = (imwei.unsqueeze(-1) * A).sum(dim=3)
 
-    # soft silhouette for uncovered pixels
+    # soft silhouette for uncovered pixels: first `knum` faces (face order) whose expanded box holds the pixel
     e = expand * multiplier
-    log_keep = torch.zeros(B, H, W, dtype=dt, device=dev)
     count = torch.zeros(B, H, W, dtype=torch.int32, device=dev)
     Pm = multiplier * p2d
-    for f in range(Fn):
-        near = (x0 >= (xmin[:, f] - e).view(B, 1, 1)) & (x0 < (xmax[:, f] + e).view(B, 1, 1)) & \
-               (y0 >= (ymin[:, f] - e).view(B, 1, 1)) & (y0 < (ymax[:, f] + e).view(B, 1, 1))
-        use = near & (~covered) & (count < knum)
-        if not bool(use.any()):
+    pieces = []        # (b, r0, r1, c0, c1, log(1 - p_k) masked)  — summed below, differentiably
+    for b in range(B):
+        if bool(covered[b].all()):
             continue
-        a = [Pm[:, f, i].view(B, 1, 1) for i in range(6)]
-        d2 = torch.minimum(torch.minimum(_seg_dist2(x0, y0, a[0], a[1], a[2], a[3]),
-                                         _seg_dist2(x0, y0, a[2], a[3], a[4], a[5])),
-                           _seg_dist2(x0, y0, a[4], a[5], a[0], a[1]))
-        pk = torch.exp(-delta * d2 / (multiplier * multiplier))
-        log_keep = log_keep + torch.where(use, torch.log1p(-pk.clamp(max=1 - 1e-7)), torch.zeros_like(pk))
-        count = count + use.to(torch.int32)
+        for f in range(Fn):
+            c0, c1 = _window(bb[b, f, 0] - e, bb[b, f, 1] + e, W, W, False)
+            r0, r1 = _window(bb[b, f, 2] - e, bb[b, f, 3] + e, H, H, True)
+            if c0 >= c1 or r0 >= r1:
+                continue
+            xs, ys = x0[0, :, c0:c1], y0[0, r0:r1, :]
+            near = (xs >= xmin[b, f] - e) & (xs < xmax[b, f] + e) & (ys >= ymin[b, f] - e) & (ys < ymax[b, f] + e)
+            cnt = count[b, r0:r1, c0:c1]
+            use = near & (~covered[b, r0:r1, c0:c1]) & (cnt < knum)
+            if not bool(use.any()):
+                continue
+            a = Pm[b, f]
+            d2 = torch.minimum(torch.minimum(_seg_dist2(xs, ys, a[0], a[1], a[2], a[3]),
+                                             _seg_dist2(xs, ys, a[2], a[3], a[4], a[5])),
+                               _seg_dist2(xs, ys, a[4], a[5], a[0], a[1]))
+            pk = torch.exp(-delta * d2 / (multiplier * multiplier))
+            lk = torch.where(use, torch.log1p(-pk.clamp(max=1 - 1e-7)), torch.zeros_like(pk))
+            pieces.append((b, r0, r1, c0, c1, lk))
+            count[b, r0:r1, c0:c1] = cnt + use.to(torch.int32)
+    log_keep = _SumWindows.apply((B, H, W), [p[:5] for p in pieces], x0, *[p[5] for p in pieces])
     improb = torch.where(covered, torch.ones_like(log_keep), 1 - torch.exp(log_keep))
     return imfeat, improb.unsqueeze(-1), imidx, imwei
+
+
+class _SumWindows(torch.autograd.Function):
+    """out = zeros(shape); out[b, r0:r1, c0:c1] += piece_i for every window (gradient: the slices)."""
+
+    @staticmethod
+    def forward(ctx, shape, wins, like, *pieces):
+        out = like.new_zeros(shape)
+        for (b, r0, r1, c0, c1), pc in zip(wins, pieces):
+            out[b, r0:r1, c0:c1] += pc
+        ctx.wins = wins
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return (None, None, None) + tuple(g[b, r0:r1, c0:c1] for (b, r0, r1, c0, c1) in ctx.wins)
 
 
 def texinterpolation(uv, texture):
