@@ -47,11 +47,12 @@ def _sig(name, *argtypes):
     return fn
 
 
-_sig("b3d_pc_project", _vp, _vp, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp)
-_sig("b3d_pc_silhouette_fwd_hosttaps", _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp)
-_sig("b3d_pc_silhouette_bwd_hosttaps", _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp)
-_sig("b3d_pc_silhouette_fwd", _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp)
-_sig("b3d_pc_silhouette_bwd", _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp)
+_sig("b3d_pc_bin_count", _i)
+_sig("b3d_pc_project", _vp, _vp, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp)
+_sig("b3d_pc_silhouette_fwd_hosttaps", _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp)
+_sig("b3d_pc_silhouette_bwd_hosttaps", _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp)
+_sig("b3d_pc_silhouette_fwd", _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp)
+_sig("b3d_pc_silhouette_bwd", _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp)
 _sig("b3d_pc_project_bwd", _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _vp, _vp, _vp)
 _sig("b3d_pc_splat_grid", _vp, _i, _i, _i, _i, _vp, _vp)
 _sig("b3d_mesh_face_setup", _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp)

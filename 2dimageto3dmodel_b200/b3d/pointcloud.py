@@ -27,8 +27,9 @@ def smoothing_taps(sigma, kernel_size=21, mode="R"):
     return [float(v) for v in k]
 
 
-def project(points, quat, V, fov=FIELD_OF_VIEW, cam_dist=CAMERA_VIEW_DISTANCE, want_aux=False):
-    """-> pg [B,N,4] (+ coords [B,N,3], base int32 [B,N,3], inb uint8 [B,N] when want_aux)."""
+def project(points, quat, V, fov=FIELD_OF_VIEW, cam_dist=CAMERA_VIEW_DISTANCE, want_aux=False, want_bins=False):
+    """-> pg [B,N,4] (+ coords [B,N,3], base int32 [B,N,3], inb uint8 [B,N] when want_aux)
+    (+ sorted [B,N,4], bin_start [B,nbins+1] when want_bins)."""
     points = dev(points, "point_cloud")
     quat = dev(quat, "rotation")
     B, N, three = points.shape
@@ -40,8 +41,14 @@ def project(points, quat, V, fov=FIELD_OF_VIEW, cam_dist=CAMERA_VIEW_DISTANCE, w
         coords = torch.empty(B, N, 3, device=points.device, dtype=torch.float32)
         base = torch.empty(B, N, 3, device=points.device, dtype=torch.int32)
         inb = torch.empty(B, N, device=points.device, dtype=torch.uint8)
+    srt = bins = None
+    if want_bins:
+        srt = torch.empty(B, N, 4, device=points.device, dtype=torch.float32)
+        bins = torch.empty(B, lib.b3d_pc_bin_count(V) + 1, device=points.device, dtype=torch.int32)
     check(lib.b3d_pc_project(ptr(points), ptr(quat), B, N, V, fov, cam_dist, ptr(pg), ptr(coords), ptr(base),
-                             ptr(inb), stream_ptr(points)))
+                             ptr(inb), ptr(srt), ptr(bins), stream_ptr(points)))
+    if want_bins:
+        return pg, srt, bins
     return (pg, coords, base, inb) if want_aux else pg
 
 
@@ -65,18 +72,18 @@ class _EffectiveLoss(torch.autograd.Function):
             sc = dev(scale.detach(), "scale").reshape(-1)
             if sc.numel() != B:
                 raise B3DError(f"scale must hold one value per sample, got shape {tuple(scale.shape)}")
-        pg = project(points, quat, V, fov, cam_dist)
+        pg, srt, bins = project(points, quat, V, fov, cam_dist, want_bins=True)
         sil = torch.empty(B, V, V, device=points.device, dtype=torch.float32)
         h = host_floats(taps)
-        check(lib.b3d_pc_silhouette_fwd_hosttaps(ptr(pg), ctypes.cast(h, ctypes.c_void_p), len(taps), ptr(sc), B, N,
-                                                 V, mode, ptr(sil), None, 0, stream_ptr(points)))
-        ctx.save_for_backward(points, quat, pg, sc if sc is not None else torch.empty(0))
+        check(lib.b3d_pc_silhouette_fwd_hosttaps(ptr(srt), ptr(bins), ctypes.cast(h, ctypes.c_void_p), len(taps),
+                                                 ptr(sc), B, N, V, mode, ptr(sil), None, 0, stream_ptr(points)))
+        ctx.save_for_backward(points, quat, pg, srt, bins, sc if sc is not None else torch.empty(0))
         ctx.cfg = (taps, V, mode, fov, cam_dist, scale.shape if scale is not None else None)
         return sil
 
     @staticmethod
     def backward(ctx, dsil):
-        points, quat, pg, sc = ctx.saved_tensors
+        points, quat, pg, srt, bins, sc = ctx.saved_tensors
         taps, V, mode, fov, cam_dist, scale_shape = ctx.cfg
         has_scale = scale_shape is not None
         B, N, _ = points.shape
@@ -85,7 +92,7 @@ class _EffectiveLoss(torch.autograd.Function):
         dscale = torch.empty(B, device=points.device, dtype=torch.float32) if has_scale else None
         h = host_floats(taps)
         st = stream_ptr(points)
-        check(lib.b3d_pc_silhouette_bwd_hosttaps(ptr(pg), ctypes.cast(h, ctypes.c_void_p), len(taps),
+        check(lib.b3d_pc_silhouette_bwd_hosttaps(ptr(srt), ptr(bins), ctypes.cast(h, ctypes.c_void_p), len(taps),
                                                  ptr(sc) if has_scale else None, ptr(dsil), B, N, V, mode, ptr(dpg),
                                                  ptr(dscale), None, 0, st))
         dpoints = torch.empty_like(points)

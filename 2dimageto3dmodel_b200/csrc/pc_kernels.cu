@@ -123,21 +123,88 @@ __device__ __forceinline__ void axis_weights(float g, float f, int mode, float& 
 }
 
 // ----------------------------------------------------------------------------------------------
-// register-blocked 1-D blur along z of one shared-memory column (stride cs between depths).
-// out[j] = sum_k taps[k] * in[zb + j + k - KT/2], zero padding (smooth_voxels.py:69-73).
+// binning: counting sort of the in-bounds points of one sample by the (BY x BX) cell bin of their base
+// voxel (y,x).  One CTA per sample; histogram, scan and scatter stay in shared memory.
+//   sorted[b, pos] = (gz, gy, gx, bits(original index));   bin_start[b, 0..nbins]
 // ----------------------------------------------------------------------------------------------
-template <int KT, bool CLAMP_IN, bool REVERSED>
+constexpr int BIN_Y = 8, BIN_X = 16;
+constexpr int BIN_THREADS = 512;
+constexpr int MAX_BINS = 4096;
+
+__device__ __forceinline__ int bin_of(float gy, float gx, int nbx) {
+    return ((int)floorf(gy) / BIN_Y) * nbx + (int)floorf(gx) / BIN_X;
+}
+
+__global__ void __launch_bounds__(BIN_THREADS)
+pc_bin_kernel(const float4* __restrict__ pg, int N, int nbx, int nbins, float4* __restrict__ sorted,
+              int32_t* __restrict__ bin_start) {
+    __shared__ int hist[MAX_BINS + 1];
+    __shared__ int wsum[BIN_THREADS / 32];
+    __shared__ int carry;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float4* p = pg + (size_t)b * N;
+    for (int i = tid; i <= nbins; i += BIN_THREADS) hist[i] = 0;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int n = tid; n < N; n += BIN_THREADS) {
+        const float4 g = p[n];
+        if (g.w != 0.f) atomicAdd(&hist[bin_of(g.y, g.z, nbx)], 1);
+    }
+    __syncthreads();
+    // exclusive scan of hist[0..nbins) in chunks of BIN_THREADS
+    for (int base = 0; base < nbins; base += BIN_THREADS) {
+        const int i = base + tid;
+        const int v = i < nbins ? hist[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((tid & 31) >= o) x += y;
+        }
+        if ((tid & 31) == 31) wsum[tid >> 5] = x;
+        __syncthreads();
+        int off = carry;
+        for (int w = 0; w < (tid >> 5); ++w) off += wsum[w];
+        if (i < nbins) hist[i] = off + x - v;
+        __syncthreads();
+        if (tid == BIN_THREADS - 1) carry = off + x;
+        __syncthreads();
+    }
+    if (tid == 0) hist[nbins] = carry;
+    __syncthreads();
+    int32_t* bs = bin_start + (size_t)b * (nbins + 1);
+    for (int i = tid; i <= nbins; i += BIN_THREADS) bs[i] = hist[i];
+    __syncthreads();
+    float4* out = sorted + (size_t)b * N;
+    for (int n = tid; n < N; n += BIN_THREADS) {
+        const float4 g = p[n];
+        if (g.w == 0.f) continue;
+        const int pos = atomicAdd(&hist[bin_of(g.y, g.z, nbx)], 1);     // hist doubles as the cursor
+        out[pos] = make_float4(g.x, g.y, g.z, __int_as_float(n));
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// register-blocked 1-D blur along z of one shared-memory column (stride cs between depths).
+// out[j] = sum_k taps[k] * |in[zb + j + k - KT/2]|, zero padding (smooth_voxels.py:69-73).  The stored
+// occupancy is already clamped to [0,1]; its sign bit carries the clamp mask (backward), hence fabsf.
+// ----------------------------------------------------------------------------------------------
+template <int KT, bool REVERSED, bool ABS>
 __device__ __forceinline__ void blur_window(const float* colp, int cs, int V, int zb, const Taps& taps,
                                             float (&out)[ZB]) {
     if constexpr (KT > 0) {
         constexpr int H = KT / 2, W = ZB + KT - 1;
         float in[W];
+        if (zb >= H && zb + ZB + H <= V) {
 #pragma unroll
-        for (int i = 0; i < W; ++i) {
-            const int z = zb - H + i;
-            float v = (z >= 0 && z < V) ? colp[z * cs] : 0.f;
-            if (CLAMP_IN) v = clamp_nan(v, 0.f, 1.f);        // trilinear_interpolation.py:74
-            in[i] = v;
+            for (int i = 0; i < W; ++i) in[i] = ABS ? fabsf(colp[(zb - H + i) * cs]) : colp[(zb - H + i) * cs];
+        } else {
+#pragma unroll
+            for (int i = 0; i < W; ++i) {
+                const int z = zb - H + i;
+                const float v = (z >= 0 && z < V) ? colp[z * cs] : 0.f;
+                in[i] = ABS ? fabsf(v) : v;
+            }
         }
 #pragma unroll
         for (int j = 0; j < ZB; ++j) {
@@ -155,9 +222,8 @@ __device__ __forceinline__ void blur_window(const float* colp, int cs, int V, in
 #pragma unroll
             for (int j = 0; j < ZB; ++j) {
                 const int z = zb + j + k - H;
-                float v = (z >= 0 && z < V) ? colp[z * cs] : 0.f;
-                if (CLAMP_IN) v = clamp_nan(v, 0.f, 1.f);
-                out[j] = fmaf(t, v, out[j]);
+                const float v = (z >= 0 && z < V) ? colp[z * cs] : 0.f;
+                out[j] = fmaf(t, ABS ? fabsf(v) : v, out[j]);
             }
         }
     }
@@ -168,192 +234,213 @@ __device__ __forceinline__ float scaled(float S, bool has_scale, float sc) {
     return has_scale ? clamp_nan(S * sc, 0.f, 1.f) : S;
 }
 
-// ----------------------------------------------------------------------------------------------
-// forward: splat into a shared-memory patch, then the column walk
-// ----------------------------------------------------------------------------------------------
-template <int KT>
-__global__ void __launch_bounds__(NTHREADS)
-pc_sil_fwd_kernel(const float4* __restrict__ pg, const Taps taps, const float* __restrict__ scale, int N,
-                  int V, int TY, int mode, float* __restrict__ sil) {
-    extern __shared__ float sm[];
-    const int b = blockIdx.z, ty0 = blockIdx.y * TY, tx0 = blockIdx.x * TX;
-    const int ncol = TY * TX;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < V * ncol; i += NTHREADS) sm[i] = 0.f;
-    __syncthreads();
+constexpr int TILE_THREADS = 512;
 
-    const float4* p = pg + (size_t)b * N;
-    for (int n0 = 0; n0 < N; n0 += 4 * NTHREADS) {
-        float4 g[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int n = n0 + u * NTHREADS + tid;
-            g[u] = n < N ? __ldg(p + n) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (g[u].w == 0.f) continue;
-            const float fzf = floorf(g[u].x), fyf = floorf(g[u].y), fxf = floorf(g[u].z);
-            const int ly = (int)fyf - ty0, lx = (int)fxf - tx0;
-            if (ly < -1 || ly >= TY || lx < -1 || lx >= TX) continue;
+// Splat the points of the bins overlapping base cells [cy0-1, cy1] x [cx0-1, cx1] into a shared patch
+// covering cells [cy0, cy1] x [cx0, cx1] (row pitch `pitch`), depth-major.
+__device__ __forceinline__ void splat_bins(const float4* __restrict__ sorted, const int32_t* __restrict__ bs,
+                                           int nbx, int nby, int cy0, int cy1, int cx0, int cx1, int pitch,
+                                           int ncol, int mode, float* A) {
+    const int by_lo = max(cy0 - 1, 0) / BIN_Y, by_hi = min(cy1 / BIN_Y, nby - 1);
+    const int bx_lo = max(cx0 - 1, 0) / BIN_X, bx_hi = min(cx1 / BIN_X, nbx - 1);
+    for (int by = by_lo; by <= by_hi; ++by) {
+        const int lo = bs[by * nbx + bx_lo], hi = bs[by * nbx + bx_hi + 1];
+        for (int n = lo + threadIdx.x; n < hi; n += TILE_THREADS) {
+            const float4 g = __ldg(sorted + n);
+            const float fzf = floorf(g.x), fyf = floorf(g.y), fxf = floorf(g.z);
+            const int ly = (int)fyf - cy0, lx = (int)fxf - cx0;
+            if (ly < -1 || ly > cy1 - cy0 || lx < -1 || lx > cx1 - cx0) continue;
             const int fz = (int)fzf;
             float wz[2], wy[2], wx[2];
-            axis_weights(g[u].x, fzf, mode, wz[0], wz[1]);
-            axis_weights(g[u].y, fyf, mode, wy[0], wy[1]);
-            axis_weights(g[u].z, fxf, mode, wx[0], wx[1]);
+            axis_weights(g.x, fzf, mode, wz[0], wz[1]);
+            axis_weights(g.y, fyf, mode, wy[0], wy[1]);
+            axis_weights(g.z, fxf, mode, wx[0], wx[1]);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int cy = ly + j;
-                if (cy < 0 || cy >= TY) continue;
+                if (cy < 0 || cy > cy1 - cy0) continue;
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                     const int cx = lx + k;
-                    if (cx < 0 || cx >= TX) continue;
+                    if (cx < 0 || cx > cx1 - cx0) continue;
 #pragma unroll
                     for (int i = 0; i < 2; ++i)     // trilinear_interpolation.py:40-41: (gz_i*gy_j)*gx_k
-                        atomicAdd(&sm[(fz + i) * ncol + cy * TX + cx], mul(mul(wz[i], wy[j]), wx[k]));
+                        atomicAdd(&A[(fz + i) * ncol + cy * pitch + cx], mul(mul(wz[i], wy[j]), wx[k]));
                 }
             }
         }
     }
+}
+
+// in place: G -> clamp(G, 0, 1) with the sign bit set where the clamp was active (G outside [0,1])
+__device__ __forceinline__ void clamp_patch(float* A, int n) {
+    for (int i = threadIdx.x; i < n; i += TILE_THREADS) {
+        const float g = A[i];
+        const float c = clamp_nan(g, 0.f, 1.f);
+        A[i] = (g >= 0.f && g <= 1.f) ? c : -c;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// forward.  Work items are (column, block of ZB depths): every item blurs its block, turns it into
+// occupancies and reduces it to (transmittance of the block, silhouette gathered inside the block);
+// a second, short pass chains the blocks of each column.
+// ----------------------------------------------------------------------------------------------
+template <int KT>
+__global__ void __launch_bounds__(TILE_THREADS)
+pc_sil_fwd_kernel(const float4* __restrict__ sorted, const int32_t* __restrict__ bin_start, const Taps taps,
+                  const float* __restrict__ scale, int N, int V, int TY, int mode, int nbx, int nby,
+                  float* __restrict__ sil) {
+    extern __shared__ float sm[];
+    const int b = blockIdx.z, ty0 = blockIdx.y * TY, tx0 = blockIdx.x * TX;
+    const int ncol = TY * TX, nzb = (V + ZB - 1) / ZB;
+    float* A = sm;                       // [V][ncol]
+    float* blkP = sm + V * ncol;         // [nzb][ncol] transmittance of the block
+    float* blkS = blkP + nzb * ncol;     // [nzb][ncol] silhouette collected inside the block
+    const int tid = threadIdx.x;
+    for (int i = tid; i < V * ncol; i += TILE_THREADS) A[i] = 0.f;
+    __syncthreads();
+    splat_bins(sorted + (size_t)b * N, bin_start + (size_t)b * (nbx * nby + 1), nbx, nby, ty0,
+               min(ty0 + TY, V) - 1, tx0, min(tx0 + TX, V) - 1, TX, ncol, mode, A);
+    __syncthreads();
+    clamp_patch(A, V * ncol);
     __syncthreads();
 
     const bool has_scale = scale != nullptr;
     const float sc = has_scale ? scale[b] : 1.f;
     const float c0 = (mode == B3D_MODE_REFERENCE) ? expf(TERM_EPS) : 1.f;   // D10 pad row
-    for (int col = tid; col < ncol; col += NTHREADS) {
-        const int y = ty0 + col / TX, x = tx0 + col % TX;
-        if (y >= V || x >= V) continue;
-        const float* colp = sm + col;
+    for (int it = tid; it < nzb * ncol; it += TILE_THREADS) {
+        const int col = it % ncol, zb = (it / ncol) * ZB;
+        float S[ZB];
+        blur_window<KT, false, true>(A + col, ncol, V, zb, taps, S);
         float T = 1.f, acc = 0.f;
-        for (int zb = 0; zb < V; zb += ZB) {
-            float S[ZB];
-            blur_window<KT, true, false>(colp, ncol, V, zb, taps, S);
 #pragma unroll
-            for (int j = 0; j < ZB; ++j) {
-                const int z = zb + j;
-                if (z >= V) break;
+        for (int j = 0; j < ZB; ++j) {
+            if (zb + j < V) {
                 const float o = clamp_nan(scaled(S[j], has_scale, sc), TERM_EPS, 1.f - TERM_EPS);
                 float term = o * T;                       // o_k * prod_{j<k}(1-o_j)
-                if (z == 0) term *= c0;
+                if (zb + j == 0) term *= c0;
                 acc += term;
                 T *= (1.f - o);
             }
+        }
+        blkP[it] = T;
+        blkS[it] = acc;
+    }
+    __syncthreads();
+    for (int col = tid; col < ncol; col += TILE_THREADS) {
+        const int y = ty0 + col / TX, x = tx0 + col % TX;
+        if (y >= V || x >= V) continue;
+        float T = 1.f, acc = 0.f;
+        for (int k = 0; k < nzb; ++k) {
+            acc = fmaf(T, blkS[k * ncol + col], acc);
+            T *= blkP[k * ncol + col];
         }
         sil[((size_t)b * V + (V - 1 - y)) * V + x] = acc;   // flip(1): effective_loss_function.py:81
     }
 }
 
 // ----------------------------------------------------------------------------------------------
-// backward
+// backward (patch with a +1 halo so that every point is owned by exactly one CTA)
 // ----------------------------------------------------------------------------------------------
 template <int KT>
-__global__ void __launch_bounds__(NTHREADS)
-pc_sil_bwd_kernel(const float4* __restrict__ pg, const Taps taps, const float* __restrict__ scale,
-                  const float* __restrict__ dsil, int N, int V, int TY, int mode,
-                  float4* __restrict__ dpg, float* __restrict__ dscale) {
+__global__ void __launch_bounds__(TILE_THREADS)
+pc_sil_bwd_kernel(const float4* __restrict__ sorted, const int32_t* __restrict__ bin_start, const Taps taps,
+                  const float* __restrict__ scale, const float* __restrict__ dsil, int N, int V, int TY, int mode,
+                  int nbx, int nby, float4* __restrict__ dpg, float* __restrict__ dscale) {
     extern __shared__ float sm[];
     __shared__ float red[32];
     const int b = blockIdx.z, ty0 = blockIdx.y * TY, tx0 = blockIdx.x * TX;
-    const int EY = TY + 1, EX = TX + 1, ncol = EY * EX;
-    float* A1 = sm;                 // raw sums G -> (+-)T_z -> dG
-    float* A2 = sm + V * ncol;      // blurred S -> dS
+    const int cy1 = min(ty0 + TY, V - 1), cx1 = min(tx0 + TX, V - 1);     // extended patch, clipped to the grid
+    const int EX = TX + 1, ncol = (TY + 1) * EX, nzb = (V + ZB - 1) / ZB;
+    float* A1 = sm;                      // clamped occupancy (sign = clamp mask) -> dG
+    float* A2 = A1 + V * ncol;           // blurred S -> dS
+    float* blkA = A2 + V * ncol;         // [nzb][ncol] transmittance of the block
+    float* blkB = blkA + nzb * ncol;     // [nzb][ncol] offset of the block's Q recurrence -> Q just after the block
+    float* blkT = blkB + nzb * ncol;     // [nzb][ncol] transmittance at the start of the block
     const int tid = threadIdx.x;
-    for (int i = tid; i < V * ncol; i += NTHREADS) A1[i] = 0.f;
+    for (int i = tid; i < V * ncol; i += TILE_THREADS) A1[i] = 0.f;
     __syncthreads();
-
-    // splat every point touching the extended patch [ty0, ty0+TY] x [tx0, tx0+TX]
-    const float4* p = pg + (size_t)b * N;
-    for (int n0 = 0; n0 < N; n0 += 4 * NTHREADS) {
-        float4 g[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int n = n0 + u * NTHREADS + tid;
-            g[u] = n < N ? __ldg(p + n) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (g[u].w == 0.f) continue;
-            const float fzf = floorf(g[u].x), fyf = floorf(g[u].y), fxf = floorf(g[u].z);
-            const int ly = (int)fyf - ty0, lx = (int)fxf - tx0;
-            if (ly < -1 || ly > TY || lx < -1 || lx > TX) continue;
-            const int fz = (int)fzf;
-            float wz[2], wy[2], wx[2];
-            axis_weights(g[u].x, fzf, mode, wz[0], wz[1]);
-            axis_weights(g[u].y, fyf, mode, wy[0], wy[1]);
-            axis_weights(g[u].z, fxf, mode, wx[0], wx[1]);
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int cy = ly + j;
-                if (cy < 0 || cy > TY) continue;
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const int cx = lx + k;
-                    if (cx < 0 || cx > TX) continue;
-#pragma unroll
-                    for (int i = 0; i < 2; ++i)
-                        atomicAdd(&A1[(fz + i) * ncol + cy * EX + cx], mul(mul(wz[i], wy[j]), wx[k]));
-                }
-            }
-        }
-    }
+    const float4* sp = sorted + (size_t)b * N;
+    const int32_t* bs = bin_start + (size_t)b * (nbx * nby + 1);
+    splat_bins(sp, bs, nbx, nby, ty0, cy1, tx0, cx1, EX, ncol, mode, A1);
+    __syncthreads();
+    clamp_patch(A1, V * ncol);
     __syncthreads();
 
     const bool has_scale = scale != nullptr;
     const float sc = has_scale ? scale[b] : 1.f;
     const float c0 = (mode == B3D_MODE_REFERENCE) ? expf(TERM_EPS) : 1.f;
+    const int nitems = nzb * ncol;
+
+    // pass 1: S = blur_z(O); per block: a = prod(1-o), b = Q at block start for Q = 0 after the block
+    for (int it = tid; it < nitems; it += TILE_THREADS) {
+        const int col = it % ncol, zb = (it / ncol) * ZB;
+        float S[ZB];
+        blur_window<KT, false, true>(A1 + col, ncol, V, zb, taps, S);
+        float a = 1.f, q = 0.f;
+#pragma unroll
+        for (int j = ZB - 1; j >= 0; --j) {
+            if (zb + j < V) {
+                A2[(zb + j) * ncol + col] = S[j];
+                const float o = clamp_nan(scaled(S[j], has_scale, sc), TERM_EPS, 1.f - TERM_EPS);
+                q = fmaf(1.f - o, q, o);            // Q_z = o_z + (1 - o_z) Q_{z+1}
+                a *= (1.f - o);
+            }
+        }
+        blkA[it] = a;
+        blkB[it] = q;
+    }
+    __syncthreads();
+    // pass 2: chain the blocks of a column: T at the start of each block, Q just after each block
+    for (int col = tid; col < ncol; col += TILE_THREADS) {
+        float T = 1.f;
+        for (int k = 0; k < nzb; ++k) {
+            blkT[k * ncol + col] = T;
+            T *= blkA[k * ncol + col];
+        }
+        float Q = 0.f;
+        for (int k = nzb - 1; k >= 0; --k) {
+            const float bq = blkB[k * ncol + col];
+            blkB[k * ncol + col] = Q;               // Q just after block k
+            Q = fmaf(blkA[k * ncol + col], Q, bq);
+        }
+    }
+    __syncthreads();
+    // pass 3: d sil / d S inside each block
     float dsc = 0.f;
-    for (int col = tid; col < ncol; col += NTHREADS) {
+    for (int it = tid; it < nitems; it += TILE_THREADS) {
+        const int col = it % ncol, zb = (it / ncol) * ZB;
         const int cy = col / EX, cx = col % EX;
         const int y = ty0 + cy, x = tx0 + cx;
         if (y >= V || x >= V) continue;
         const bool owned = cy < TY && cx < TX;      // halo columns are owned by the neighbour patch
-        float* c1 = A1 + col;
-        float* c2 = A2 + col;
-        // (a) S = blur_z(clamp(G, 0, 1))
-        for (int zb = 0; zb < V; zb += ZB) {
-            float S[ZB];
-            blur_window<KT, true, false>(c1, ncol, V, zb, taps, S);
-#pragma unroll
-            for (int j = 0; j < ZB; ++j)
-                if (zb + j < V) c2[(zb + j) * ncol] = S[j];
-        }
-        // (b) prefix transmittance T_z; its sign bit keeps the clamp mask 0 <= G <= 1
-        float T = 1.f;
-        for (int z = 0; z < V; ++z) {
-            const float G = c1[z * ncol];
-            const float o = clamp_nan(scaled(c2[z * ncol], has_scale, sc), TERM_EPS, 1.f - TERM_EPS);
-            c1[z * ncol] = (G >= 0.f && G <= 1.f) ? T : -T;
-            T *= (1.f - o);
-        }
-        // (c) suffix silhouette Q_{z+1}; d sil / d o_z = T_z (1 - Q_{z+1})   (z = 0: c0 - Q_1)
         const float go = dsil[((size_t)b * V + (V - 1 - y)) * V + x];
-        float Q = 0.f;
-        for (int z = V - 1; z >= 0; --z) {
-            const float S = c2[z * ncol];
-            const float t = has_scale ? S * sc : S;
-            const float s2 = has_scale ? clamp_nan(t, 0.f, 1.f) : S;
-            const float o = clamp_nan(s2, TERM_EPS, 1.f - TERM_EPS);
-            const float Tz = fabsf(c1[z * ncol]);
-            const float coef = (z == 0) ? (c0 - Q) : Tz * (1.f - Q);
-            float d = go * coef;
-            d = (s2 >= TERM_EPS && s2 <= 1.f - TERM_EPS) ? d : 0.f;      // clamp(eps, 1-eps) adjoint
-            if (has_scale) {
-                d = (t >= 0.f && t <= 1.f) ? d : 0.f;                    // clamp(0, 1) adjoint
-                if (owned) dsc = fmaf(d, S, dsc);
-                d *= sc;
-            }
-            c2[z * ncol] = d;
-            Q = fmaf(1.f - o, Q, o);
-        }
-        // (d) dG = mask * blur_z^T(dS)
-        for (int zb = 0; zb < V; zb += ZB) {
-            float D[ZB];
-            blur_window<KT, false, true>(c2, ncol, V, zb, taps, D);
+        float S[ZB], o[ZB], Tz[ZB];
+        float T = blkT[it];
 #pragma unroll
-            for (int j = 0; j < ZB; ++j) {
-                const int z = zb + j;
-                if (z < V) c1[z * ncol] = signbit(c1[z * ncol]) ? 0.f : D[j];
+        for (int j = 0; j < ZB; ++j) {
+            S[j] = (zb + j < V) ? A2[(zb + j) * ncol + col] : 0.f;
+            o[j] = clamp_nan(scaled(S[j], has_scale, sc), TERM_EPS, 1.f - TERM_EPS);
+            Tz[j] = T;
+            T *= (1.f - o[j]);
+        }
+        float Q = blkB[it];
+#pragma unroll
+        for (int j = ZB - 1; j >= 0; --j) {
+            if (zb + j < V) {
+                const float t = has_scale ? S[j] * sc : S[j];
+                const float s2 = has_scale ? clamp_nan(t, 0.f, 1.f) : S[j];
+                const float coef = (zb + j == 0) ? (c0 - Q) : Tz[j] * (1.f - Q);   // d sil / d o_z
+                float d = go * coef;
+                d = (s2 >= TERM_EPS && s2 <= 1.f - TERM_EPS) ? d : 0.f;           // clamp(eps, 1-eps) adjoint
+                if (has_scale) {
+                    d = (t >= 0.f && t <= 1.f) ? d : 0.f;                         // clamp(0, 1) adjoint
+                    if (owned) dsc = fmaf(d, S[j], dsc);
+                    d *= sc;
+                }
+                A2[(zb + j) * ncol + col] = d;
+                Q = fmaf(1.f - o[j], Q, o[j]);
             }
         }
     }
@@ -362,34 +449,51 @@ pc_sil_bwd_kernel(const float4* __restrict__ pg, const Taps taps, const float* _
         if (tid == 0 && tot != 0.f) atomicAdd(dscale + b, tot);
     }
     __syncthreads();
+    // pass 4: dG = mask * blur_z^T(dS)
+    for (int it = tid; it < nitems; it += TILE_THREADS) {
+        const int col = it % ncol, zb = (it / ncol) * ZB;
+        float D[ZB];
+        blur_window<KT, true, false>(A2 + col, ncol, V, zb, taps, D);
+#pragma unroll
+        for (int j = 0; j < ZB; ++j) {
+            const int z = zb + j;
+            if (z < V) A1[z * ncol + col] = signbit(A1[z * ncol + col]) ? 0.f : D[j];
+        }
+    }
+    __syncthreads();
 
     // gather: every in-bounds point is owned by the patch holding its base cell
     float4* dp = dpg + (size_t)b * N;
-    for (int n = tid; n < N; n += NTHREADS) {
-        const float4 g = __ldg(p + n);
-        if (g.w == 0.f) continue;
-        const float fzf = floorf(g.x), fyf = floorf(g.y), fxf = floorf(g.z);
-        const int ly = (int)fyf - ty0, lx = (int)fxf - tx0;
-        if (ly < 0 || ly >= TY || lx < 0 || lx >= TX) continue;
-        const int fz = (int)fzf;
-        float wz[2], wy[2], wx[2];
-        axis_weights(g.x, fzf, mode, wz[0], wz[1]);
-        axis_weights(g.y, fyf, mode, wy[0], wy[1]);
-        axis_weights(g.z, fxf, mode, wx[0], wx[1]);
-        float dz = 0.f, dy = 0.f, dx = 0.f;
+    const int oy1 = min(ty0 + TY, V) - 1, ox1 = min(tx0 + TX, V) - 1;   // owned base cells
+    const int by_lo = ty0 / BIN_Y, by_hi = min(oy1 / BIN_Y, nby - 1);
+    const int bx_lo = tx0 / BIN_X, bx_hi = min(ox1 / BIN_X, nbx - 1);
+    for (int by = by_lo; by <= by_hi; ++by) {
+        const int lo = bs[by * nbx + bx_lo], hi = bs[by * nbx + bx_hi + 1];
+        for (int n = lo + tid; n < hi; n += TILE_THREADS) {
+            const float4 g = __ldg(sp + n);
+            const float fzf = floorf(g.x), fyf = floorf(g.y), fxf = floorf(g.z);
+            const int ly = (int)fyf - ty0, lx = (int)fxf - tx0;
+            if (ly < 0 || ly >= TY || lx < 0 || lx >= TX) continue;
+            const int fz = (int)fzf;
+            float wz[2], wy[2], wx[2];
+            axis_weights(g.x, fzf, mode, wz[0], wz[1]);
+            axis_weights(g.y, fyf, mode, wy[0], wy[1]);
+            axis_weights(g.z, fxf, mode, wx[0], wx[1]);
+            float dz = 0.f, dy = 0.f, dx = 0.f;
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
+            for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
+                for (int j = 0; j < 2; ++j)
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const float d = A1[(fz + i) * ncol + (ly + j) * EX + lx + k];
-                    // d w0/dg = -1, d w1/dg = +1 in both modes (floor has zero gradient)
-                    dz += d * (i ? 1.f : -1.f) * wy[j] * wx[k];
-                    dy += d * wz[i] * (j ? 1.f : -1.f) * wx[k];
-                    dx += d * wz[i] * wy[j] * (k ? 1.f : -1.f);
-                }
-        dp[n] = make_float4(dz, dy, dx, 0.f);
+                    for (int k = 0; k < 2; ++k) {
+                        const float d = A1[(fz + i) * ncol + (ly + j) * EX + lx + k];
+                        // d w0/dg = -1, d w1/dg = +1 in both modes (floor has zero gradient)
+                        dz += d * (i ? 1.f : -1.f) * wy[j] * wx[k];
+                        dy += d * wz[i] * (j ? 1.f : -1.f) * wx[k];
+                        dx += d * wz[i] * wy[j] * (k ? 1.f : -1.f);
+                    }
+            dp[__float_as_int(g.w)] = make_float4(dz, dy, dx, 0.f);
+        }
     }
 }
 
@@ -480,47 +584,130 @@ __global__ void __launch_bounds__(NTHREADS) clamp01_kernel(float* __restrict__ x
 // ----------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------
-constexpr size_t SMEM_BUDGET = 200 * 1024;
+constexpr size_t SMEM_BUDGET = 220 * 1024;
+
+size_t patch_bytes(int V, int ty, bool bwd) {
+    const size_t nzb = (V + ZB - 1) / ZB;
+    if (bwd) {
+        const size_t ncol = (size_t)(ty + 1) * (TX + 1);
+        return 4 * (2 * V * ncol + 3 * nzb * ncol);
+    }
+    const size_t ncol = (size_t)ty * TX;
+    return 4 * (V * ncol + 2 * nzb * ncol);
+}
 
 int pick_ty(int V, bool bwd) {
     if (const char* e = getenv(bwd ? "B3D_PC_TY_BWD" : "B3D_PC_TY_FWD")) {
         const int v = atoi(e);
-        if (v >= 1 && v <= 64) return v;
+        if (v >= 1 && v <= 64 && patch_bytes(V, v, bwd) <= SMEM_BUDGET) return v;
     }
-    for (int ty = 16; ty >= 1; ty >>= 1) {
-        const size_t bytes = bwd ? 2ull * V * (ty + 1) * (TX + 1) * 4 : 1ull * V * ty * TX * 4;
-        if (bytes <= SMEM_BUDGET) return ty;
-    }
+    for (int ty = 16; ty >= 1; ty >>= 1)
+        if (patch_bytes(V, ty, bwd) <= SMEM_BUDGET) return ty;
     return 0;
 }
 
-size_t patch_bytes(int V, int ty, bool bwd) {
-    return bwd ? 2ull * V * (ty + 1) * (TX + 1) * 4 : 1ull * V * ty * TX * 4;
-}
-
 int load_taps(const float* taps_dev, int ktaps, Taps& t, cudaStream_t st) {
-    // taps live in device memory (the caller's buffer may be produced on the stream): stage through
-    // a small pinned-free copy.  21 floats; the sync here is on the caller's stream only.
+    // taps in device memory: 21 floats read back on the caller's stream (the hosttaps entry avoids this)
     B3D_CUDA_OK(cudaMemcpyAsync(t.w, taps_dev, sizeof(float) * ktaps, cudaMemcpyDeviceToHost, st));
     B3D_CUDA_OK(cudaStreamSynchronize(st));
     t.n = ktaps;
     return B3D_OK;
 }
 
+inline int bins_x(int V) { return (V + BIN_X - 1) / BIN_X; }
+inline int bins_y(int V) { return (V + BIN_Y - 1) / BIN_Y; }
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+    B3D_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return B3D_OK;
+}
+
+int sil_fwd_impl(const float* sorted, const int32_t* bin_start, const Taps& t, const float* scale, int B, int N,
+                 int V, int mode, float* sil, cudaStream_t st) {
+    const int TY = pick_ty(V, false);
+    B3D_REQUIRE(TY > 0, B3D_EINVAL, "b3d_pc_silhouette_fwd: V=%d does not fit the shared-memory patch", V);
+    const size_t smem = patch_bytes(V, TY, false);
+    dim3 grid(b3d::ceil_div(V, TX), b3d::ceil_div(V, TY), B);
+    if (t.n == 21) {
+        if (int rc = set_smem(pc_sil_fwd_kernel<21>, smem)) return rc;
+        pc_sil_fwd_kernel<21><<<grid, TILE_THREADS, smem, st>>>((const float4*)sorted, bin_start, t, scale, N, V, TY,
+                                                               mode, bins_x(V), bins_y(V), sil);
+    } else {
+        if (int rc = set_smem(pc_sil_fwd_kernel<0>, smem)) return rc;
+        pc_sil_fwd_kernel<0><<<grid, TILE_THREADS, smem, st>>>((const float4*)sorted, bin_start, t, scale, N, V, TY,
+                                                              mode, bins_x(V), bins_y(V), sil);
+    }
+    B3D_LAUNCH_OK();
+    return B3D_OK;
+}
+
+int sil_bwd_impl(const float* sorted, const int32_t* bin_start, const Taps& t, const float* scale,
+                 const float* dsil, int B, int N, int V, int mode, float* dpg, float* dscale, cudaStream_t st) {
+    const int TY = pick_ty(V, true);
+    B3D_REQUIRE(TY > 0, B3D_EINVAL, "b3d_pc_silhouette_bwd: V=%d does not fit the shared-memory patch", V);
+    const size_t smem = patch_bytes(V, TY, true);
+    if (dscale) B3D_CUDA_OK(cudaMemsetAsync(dscale, 0, sizeof(float) * B, st));
+    dim3 grid(b3d::ceil_div(V, TX), b3d::ceil_div(V, TY), B);
+    if (t.n == 21) {
+        if (int rc = set_smem(pc_sil_bwd_kernel<21>, smem)) return rc;
+        pc_sil_bwd_kernel<21><<<grid, TILE_THREADS, smem, st>>>((const float4*)sorted, bin_start, t, scale, dsil, N, V,
+                                                               TY, mode, bins_x(V), bins_y(V), (float4*)dpg, dscale);
+    } else {
+        if (int rc = set_smem(pc_sil_bwd_kernel<0>, smem)) return rc;
+        pc_sil_bwd_kernel<0><<<grid, TILE_THREADS, smem, st>>>((const float4*)sorted, bin_start, t, scale, dsil, N, V,
+                                                              TY, mode, bins_x(V), bins_y(V), (float4*)dpg, dscale);
+    }
+    B3D_LAUNCH_OK();
+    return B3D_OK;
+}
+
+int check_sil_args(const char* who, const void* sorted, const void* bin_start, const void* taps, int ktaps, int B,
+                   int N, int V, int mode) {
+    B3D_REQUIRE(B >= 0 && N >= 0 && V >= 2, B3D_EINVAL, "%s: bad sizes B=%d N=%d V=%d", who, B, N, V);
+    B3D_REQUIRE(ktaps >= 1 && ktaps <= MAX_TAPS && (ktaps & 1), B3D_EINVAL, "%s: ktaps=%d must be odd, <= %d", who,
+                ktaps, MAX_TAPS);
+    B3D_REQUIRE(mode == B3D_MODE_REFERENCE, B3D_EINVAL,
+                "%s: mode %d not available in this build (only B3D_MODE_REFERENCE)", who, mode);
+    B3D_REQUIRE(taps && (B == 0 || (bin_start && (sorted || N == 0))), B3D_EINVAL, "%s: null pointer", who);
+    return B3D_OK;
+}
+
+void fill_taps(Taps& t, const float* host, int n) {
+    for (int i = 0; i < n; ++i) t.w[i] = host[i];
+    t.n = n;
+}
+
 }  // namespace
 
 extern "C" {
 
+int b3d_pc_bin_count(int V) { return V >= 2 ? bins_x(V) * bins_y(V) : 0; }
+
 int b3d_pc_project(const float* points, const float* quat, int B, int N, int V, float fov, float cam_dist,
-                   float* pg, float* coords, int32_t* base, uint8_t* inb, void* stream) {
+                   float* pg, float* coords, int32_t* base, uint8_t* inb, float* sorted, int32_t* bin_start,
+                   void* stream) {
     B3D_REQUIRE(B >= 0 && N >= 0 && V >= 2, B3D_EINVAL, "b3d_pc_project: bad sizes B=%d N=%d V=%d", B, N, V);
-    if (B == 0 || N == 0) return B3D_OK;
+    if (B == 0) return B3D_OK;
+    B3D_REQUIRE((sorted == nullptr) == (bin_start == nullptr), B3D_EINVAL,
+                "b3d_pc_project: sorted and bin_start go together");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nbins = b3d_pc_bin_count(V);
+    B3D_REQUIRE(nbins <= MAX_BINS, B3D_EINVAL, "b3d_pc_project: V=%d needs more than %d bins", V, MAX_BINS);
+    if (N == 0) {
+        if (bin_start) B3D_CUDA_OK(cudaMemsetAsync(bin_start, 0, sizeof(int32_t) * (size_t)B * (nbins + 1), st));
+        return B3D_OK;
+    }
     B3D_REQUIRE(points && quat && pg, B3D_EINVAL, "b3d_pc_project: null pointer");
     B3D_CHECK_ALIGNED(pg);
     dim3 grid(b3d::ceil_div(N, NTHREADS), B);
-    pc_project_kernel<<<grid, NTHREADS, 0, (cudaStream_t)stream>>>(points, quat, N, V, fov, cam_dist, (float4*)pg,
-                                                                  coords, base, inb);
+    pc_project_kernel<<<grid, NTHREADS, 0, st>>>(points, quat, N, V, fov, cam_dist, (float4*)pg, coords, base, inb);
     B3D_LAUNCH_OK();
+    if (sorted) {
+        B3D_CHECK_ALIGNED(sorted);
+        pc_bin_kernel<<<B, BIN_THREADS, 0, st>>>((const float4*)pg, N, bins_x(V), nbins, (float4*)sorted, bin_start);
+        B3D_LAUNCH_OK();
+    }
     return B3D_OK;
 }
 
@@ -529,124 +716,62 @@ size_t b3d_pc_silhouette_workspace_bytes(int B, int V, int mode) {
     return 2ull * (size_t)B * V * V * V * sizeof(float);
 }
 
-}  // extern "C"
-
-namespace {
-
-template <typename K>
-int set_smem(K kernel, size_t bytes) {
-    B3D_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    return B3D_OK;
-}
-
-int sil_fwd_impl(const float* pg, const Taps& t, const float* scale, int B, int N, int V, int mode, float* sil,
-                 cudaStream_t st) {
-    const int TY = pick_ty(V, false);
-    B3D_REQUIRE(TY > 0, B3D_EINVAL, "b3d_pc_silhouette_fwd: V=%d does not fit the shared-memory patch", V);
-    const size_t smem = patch_bytes(V, TY, false);
-    dim3 grid(b3d::ceil_div(V, TX), b3d::ceil_div(V, TY), B);
-    if (t.n == 21) {
-        if (int rc = set_smem(pc_sil_fwd_kernel<21>, smem)) return rc;
-        pc_sil_fwd_kernel<21><<<grid, NTHREADS, smem, st>>>((const float4*)pg, t, scale, N, V, TY, mode, sil);
-    } else {
-        if (int rc = set_smem(pc_sil_fwd_kernel<0>, smem)) return rc;
-        pc_sil_fwd_kernel<0><<<grid, NTHREADS, smem, st>>>((const float4*)pg, t, scale, N, V, TY, mode, sil);
-    }
-    B3D_LAUNCH_OK();
-    return B3D_OK;
-}
-
-int sil_bwd_impl(const float* pg, const Taps& t, const float* scale, const float* dsil, int B, int N, int V,
-                 int mode, float* dpg, float* dscale, cudaStream_t st) {
-    const int TY = pick_ty(V, true);
-    B3D_REQUIRE(TY > 0, B3D_EINVAL, "b3d_pc_silhouette_bwd: V=%d does not fit the shared-memory patch", V);
-    const size_t smem = patch_bytes(V, TY, true);
-    if (dscale) B3D_CUDA_OK(cudaMemsetAsync(dscale, 0, sizeof(float) * B, st));
-    dim3 grid(b3d::ceil_div(V, TX), b3d::ceil_div(V, TY), B);
-    if (t.n == 21) {
-        if (int rc = set_smem(pc_sil_bwd_kernel<21>, smem)) return rc;
-        pc_sil_bwd_kernel<21><<<grid, NTHREADS, smem, st>>>((const float4*)pg, t, scale, dsil, N, V, TY, mode,
-                                                           (float4*)dpg, dscale);
-    } else {
-        if (int rc = set_smem(pc_sil_bwd_kernel<0>, smem)) return rc;
-        pc_sil_bwd_kernel<0><<<grid, NTHREADS, smem, st>>>((const float4*)pg, t, scale, dsil, N, V, TY, mode,
-                                                          (float4*)dpg, dscale);
-    }
-    B3D_LAUNCH_OK();
-    return B3D_OK;
-}
-
-int check_sil_args(const char* who, const void* pg, const void* taps, int ktaps, int B, int N, int V, int mode) {
-    B3D_REQUIRE(B >= 0 && N >= 0 && V >= 2, B3D_EINVAL, "%s: bad sizes B=%d N=%d V=%d", who, B, N, V);
-    B3D_REQUIRE(ktaps >= 1 && ktaps <= MAX_TAPS && (ktaps & 1), B3D_EINVAL, "%s: ktaps=%d must be odd, <= %d", who,
-                ktaps, MAX_TAPS);
-    B3D_REQUIRE(mode == B3D_MODE_REFERENCE, B3D_EINVAL,
-                "%s: mode %d not available in this build (only B3D_MODE_REFERENCE)", who, mode);
-    B3D_REQUIRE(taps && (pg || N == 0 || B == 0), B3D_EINVAL, "%s: null pointer", who);
-    return B3D_OK;
-}
-
-}  // namespace
-
-extern "C" {
-
 // taps given in HOST memory (the Python wrapper computes them with the reference's torch expression on
 // the CPU, 21 floats): avoids the device->host sync of the device-taps entry points.
-int b3d_pc_silhouette_fwd_hosttaps(const float* pg, const float* taps_host, int ktaps, const float* scale, int B,
-                                   int N, int V, int mode, float* sil, void* workspace, size_t workspace_bytes,
-                                   void* stream) {
+int b3d_pc_silhouette_fwd_hosttaps(const float* sorted, const int32_t* bin_start, const float* taps_host, int ktaps,
+                                   const float* scale, int B, int N, int V, int mode, float* sil, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
     (void)workspace;
     (void)workspace_bytes;
-    if (int rc = check_sil_args("b3d_pc_silhouette_fwd", pg, taps_host, ktaps, B, N, V, mode)) return rc;
+    if (int rc = check_sil_args("b3d_pc_silhouette_fwd", sorted, bin_start, taps_host, ktaps, B, N, V, mode)) return rc;
     if (B == 0) return B3D_OK;
     B3D_REQUIRE(sil, B3D_EINVAL, "b3d_pc_silhouette_fwd: null output");
     Taps t;
-    for (int i = 0; i < ktaps; ++i) t.w[i] = taps_host[i];
-    t.n = ktaps;
-    return sil_fwd_impl(pg, t, scale, B, N, V, mode, sil, (cudaStream_t)stream);
+    fill_taps(t, taps_host, ktaps);
+    return sil_fwd_impl(sorted, bin_start, t, scale, B, N, V, mode, sil, (cudaStream_t)stream);
 }
 
-int b3d_pc_silhouette_fwd(const float* pg, const float* taps, int ktaps, const float* scale, int B, int N, int V,
-                          int mode, float* sil, void* workspace, size_t workspace_bytes, void* stream) {
-    (void)workspace;
-    (void)workspace_bytes;
-    if (int rc = check_sil_args("b3d_pc_silhouette_fwd", pg, taps, ktaps, B, N, V, mode)) return rc;
-    if (B == 0) return B3D_OK;
-    B3D_REQUIRE(sil, B3D_EINVAL, "b3d_pc_silhouette_fwd: null output");
-    Taps t;
-    if (int rc = load_taps(taps, ktaps, t, (cudaStream_t)stream)) return rc;
-    return sil_fwd_impl(pg, t, scale, B, N, V, mode, sil, (cudaStream_t)stream);
-}
-
-int b3d_pc_silhouette_bwd_hosttaps(const float* pg, const float* taps_host, int ktaps, const float* scale,
-                                   const float* dsil, int B, int N, int V, int mode, float* dpg, float* dscale,
-                                   void* workspace, size_t workspace_bytes, void* stream) {
-    (void)workspace;
-    (void)workspace_bytes;
-    if (int rc = check_sil_args("b3d_pc_silhouette_bwd", pg, taps_host, ktaps, B, N, V, mode)) return rc;
-    if (B == 0) return B3D_OK;
-    B3D_REQUIRE(dsil && (dpg || N == 0), B3D_EINVAL, "b3d_pc_silhouette_bwd: null pointer");
-    B3D_REQUIRE((scale == nullptr) == (dscale == nullptr), B3D_EINVAL,
-                "b3d_pc_silhouette_bwd: scale and dscale must both be given or both be NULL");
-    Taps t;
-    for (int i = 0; i < ktaps; ++i) t.w[i] = taps_host[i];
-    t.n = ktaps;
-    return sil_bwd_impl(pg, t, scale, dsil, B, N, V, mode, dpg, dscale, (cudaStream_t)stream);
-}
-
-int b3d_pc_silhouette_bwd(const float* pg, const float* taps, int ktaps, const float* scale, const float* dsil,
-                          int B, int N, int V, int mode, float* dpg, float* dscale, void* workspace,
+int b3d_pc_silhouette_fwd(const float* sorted, const int32_t* bin_start, const float* taps, int ktaps,
+                          const float* scale, int B, int N, int V, int mode, float* sil, void* workspace,
                           size_t workspace_bytes, void* stream) {
     (void)workspace;
     (void)workspace_bytes;
-    if (int rc = check_sil_args("b3d_pc_silhouette_bwd", pg, taps, ktaps, B, N, V, mode)) return rc;
+    if (int rc = check_sil_args("b3d_pc_silhouette_fwd", sorted, bin_start, taps, ktaps, B, N, V, mode)) return rc;
+    if (B == 0) return B3D_OK;
+    B3D_REQUIRE(sil, B3D_EINVAL, "b3d_pc_silhouette_fwd: null output");
+    Taps t;
+    if (int rc = load_taps(taps, ktaps, t, (cudaStream_t)stream)) return rc;
+    return sil_fwd_impl(sorted, bin_start, t, scale, B, N, V, mode, sil, (cudaStream_t)stream);
+}
+
+int b3d_pc_silhouette_bwd_hosttaps(const float* sorted, const int32_t* bin_start, const float* taps_host, int ktaps,
+                                   const float* scale, const float* dsil, int B, int N, int V, int mode, float* dpg,
+                                   float* dscale, void* workspace, size_t workspace_bytes, void* stream) {
+    (void)workspace;
+    (void)workspace_bytes;
+    if (int rc = check_sil_args("b3d_pc_silhouette_bwd", sorted, bin_start, taps_host, ktaps, B, N, V, mode)) return rc;
+    if (B == 0) return B3D_OK;
+    B3D_REQUIRE(dsil && (dpg || N == 0), B3D_EINVAL, "b3d_pc_silhouette_bwd: null pointer");
+    B3D_REQUIRE((scale == nullptr) == (dscale == nullptr), B3D_EINVAL,
+                "b3d_pc_silhouette_bwd: scale and dscale must both be given or both be NULL");
+    Taps t;
+    fill_taps(t, taps_host, ktaps);
+    return sil_bwd_impl(sorted, bin_start, t, scale, dsil, B, N, V, mode, dpg, dscale, (cudaStream_t)stream);
+}
+
+int b3d_pc_silhouette_bwd(const float* sorted, const int32_t* bin_start, const float* taps, int ktaps,
+                          const float* scale, const float* dsil, int B, int N, int V, int mode, float* dpg,
+                          float* dscale, void* workspace, size_t workspace_bytes, void* stream) {
+    (void)workspace;
+    (void)workspace_bytes;
+    if (int rc = check_sil_args("b3d_pc_silhouette_bwd", sorted, bin_start, taps, ktaps, B, N, V, mode)) return rc;
     if (B == 0) return B3D_OK;
     B3D_REQUIRE(dsil && (dpg || N == 0), B3D_EINVAL, "b3d_pc_silhouette_bwd: null pointer");
     B3D_REQUIRE((scale == nullptr) == (dscale == nullptr), B3D_EINVAL,
                 "b3d_pc_silhouette_bwd: scale and dscale must both be given or both be NULL");
     Taps t;
     if (int rc = load_taps(taps, ktaps, t, (cudaStream_t)stream)) return rc;
-    return sil_bwd_impl(pg, t, scale, dsil, B, N, V, mode, dpg, dscale, (cudaStream_t)stream);
+    return sil_bwd_impl(sorted, bin_start, t, scale, dsil, B, N, V, mode, dpg, dscale, (cudaStream_t)stream);
 }
 
 int b3d_pc_project_bwd(const float* points, const float* quat, const float* pg, const float* dpg, int B, int N,

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
 def test_error_reporting_without_gpu():
     import b3d
     # argument validation happens before any CUDA call
-    rc = b3d.lib.b3d_pc_project(None, None, 1, 1, 1, 1.875, 2.0, None, None, None, None, None)
+    rc = b3d.lib.b3d_pc_project(None, None, 1, 1, 1, 1.875, 2.0, None, None, None, None, None, None, None)
     assert rc == -1
     assert b"bad sizes" in b3d.lib.b3d_last_error()
     assert b3d.lib.b3d_version() >= 100
