@@ -689,7 +689,7 @@ int b3d_pc_project(const float* points, const float* quat, int B, int N, int V, 
                    void* stream) {
     B3D_REQUIRE(B >= 0 && N >= 0 && V >= 2, B3D_EINVAL, "b3d_pc_project: bad sizes B=%d N=%d V=%d", B, N, V);
     if (B == 0) return B3D_OK;
-    B3D_REQUIRE((sorted == nullptr) == (bin_start == nullptr), B3D_EINVAL,
+    B3D_REQUIRE(N == 0 || (sorted == nullptr) == (bin_start == nullptr), B3D_EINVAL,
                 "b3d_pc_project: sorted and bin_start go together");
     cudaStream_t st = (cudaStream_t)stream;
     const int nbins = b3d_pc_bin_count(V);
