@@ -8,10 +8,21 @@ import torch
 from . import B3DError, check, dev, lib, ptr, stream_ptr
 
 
+_i32_cache = {}
+
+
 def _i32(t, name):
-    if t.dtype != torch.int32:
-        t = t.to(torch.int32)
-    return dev(t, name, torch.int32)
+    """Index tensors arrive as int64 (the reference's LongTensors); the kernels take int32.  The converted
+    copy is cached per source tensor (template topology never changes) so no cast kernel runs per step."""
+    if t.dtype == torch.int32:
+        return dev(t, name, torch.int32)
+    key = (t.data_ptr(), tuple(t.shape), t._version, str(t.device))
+    hit = _i32_cache.get(key)
+    if hit is None:
+        if len(_i32_cache) > 64:
+            _i32_cache.clear()
+        hit = _i32_cache[key] = dev(t.to(torch.int32), name, torch.int32)
+    return hit
 
 
 def face_setup(verts, faces, uv=None, ft=None, want_normals=True):

@@ -135,6 +135,7 @@ class MeshTemplate:
         self.tangent_map = frames.to(device)
         self.nonneg_tangent_map = frames[nonneg].to(device)
         self.is_symmetric = is_symmetric
+        self._mirror_x = torch.tensor([-1.0, 1.0, 1.0], device=device)
 
     # ---- deformation ---------------------------------------------------------------------------------
     def deform(self, deltas):
@@ -167,7 +168,7 @@ class MeshTemplate:
         if self.is_symmetric:
             full = moved.new_zeros(B, self.topo_map.shape[0], 3)
             full[:, self.nonneg_indices] = moved
-            full[:, self.neg_indices] = full[:, self.pos_indices] * moved.new_tensor([-1.0, 1.0, 1.0])
+            full[:, self.neg_indices] = full[:, self.pos_indices] * self._mirror_x.to(moved.dtype)
             moved = full * self.symmetry_mask
         return self.mesh.vertices.unsqueeze(0) + moved
 
