@@ -164,6 +164,17 @@ B3D_API int b3d_rgba_mse_iou_fwd(const float* image, const float* alpha, const f
 B3D_API int b3d_rgba_mse_bwd(const float* image, const float* alpha, const float* target, int B, int H,
                              int W, const float* gloss, float* d_image, float* d_alpha, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Chamfer / pairwise nearest neighbour (north-star kernel; no reference implementation exists —
+ * the reference's only pairwise-NN site is rendering/mesh_template.py:33-39).
+ * query [B,N,3], cand [B,M,3] -> dist [B,N] = min_j |q_i - c_j|^2, idx [B,N] int32 = argmin (lowest index on
+ * ties; bit-exact target).  bwd ACCUMULATES into dquery [B,N,3] and dcand [B,M,3] (caller zeroes them).
+ * ------------------------------------------------------------------------------------------ */
+B3D_API int b3d_chamfer_nn(const float* query, const float* cand, int B, int N, int M, float* dist,
+                           int32_t* idx, void* stream);
+B3D_API int b3d_chamfer_bwd(const float* query, const float* cand, const int32_t* idx, const float* gdist,
+                            int B, int N, int M, float* dquery, float* dcand, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
