@@ -1,0 +1,72 @@
+"""Dense conv2d over libb3d's tcgen05 implicit-GEMM kernel (NHWC fp32 activations, tf32 tensor cores).
+
+Reference call sites: nn.Conv2d layers of /root/reference/code/models/gan.py (:57-65, :163-177, :294-302,
+:359, :364) — 3x3 / 1x1 / 5x5 stride 1 and 4x4 stride 2, zero padding along y only (x padding is explicit:
+replicate / circular pads are materialised by the caller exactly as the reference does)."""
+import ctypes
+
+import torch
+
+from . import B3DError, check, dev, lib, ptr, stream_ptr
+
+
+def _ints(v):
+    return (ctypes.c_int * len(v))(*v)
+
+
+def taps_layout(weight):
+    """[Cout,Cin,kh,kw] -> tap-major K-major rows [kh*kw, Cout, Cin]."""
+    co, ci, kh, kw = weight.shape
+    return weight.permute(2, 3, 0, 1).reshape(kh * kw, co, ci).contiguous()
+
+
+def conv2d_nhwc(x, weight, bias=None, pad_y=0, stride=1, leaky=1.0, wt=None):
+    """x [N,H,W,Cin] (Cin % 32 == 0), weight [Cout,Cin,kh,kw] -> [N,Hout,Wout,Cout]; zero pad along y only."""
+    x = dev(x, "x")
+    N, H, W, Cin = x.shape
+    Cout, Cin_w, kh, kw = weight.shape
+    if Cin_w != Cin:
+        raise B3DError(f"conv2d: input has {Cin} channels, weight expects {Cin_w}")
+    wt = dev(taps_layout(weight) if wt is None else wt, "weight")
+    Hout = (H + 2 * pad_y - kh) // stride + 1
+    Wout = (W - kw) // stride + 1
+    out = torch.empty(N, Hout, Wout, Cout, device=x.device, dtype=torch.float32)
+    dy = [r - pad_y for r in range(kh) for _ in range(kw)]
+    dx = [s for _ in range(kh) for s in range(kw)]
+    b = dev(bias, "bias") if bias is not None else None
+    check(lib.b3d_conv2d_tf32(ptr(x), ptr(wt), ptr(b), ptr(out), N, H, W, Cin, Hout, Wout, Cout, kh * kw, _ints(dy),
+                              _ints(dx), stride, stride, Hout, Wout, Cout, 1, 1, 0, 0, float(leaky), stream_ptr(x)))
+    return out
+
+
+def conv2d_dgrad_nhwc(dy_, weight, in_hw, pad_y=0, stride=1):
+    """Gradient w.r.t. the (x-padded) input [N,H,W,Cin] of conv2d_nhwc, from dy_ [N,Hout,Wout,Cout] (Cout % 32 == 0)."""
+    g = dev(dy_, "grad_output")
+    N, Hout, Wout, Cout = g.shape
+    Cout_w, Cin, kh, kw = weight.shape
+    H, W = in_hw
+    dxo = torch.empty(N, H, W, Cin, device=g.device, dtype=torch.float32)
+    st = stream_ptr(g)
+    if stride == 1:
+        wt = weight.permute(2, 3, 1, 0).reshape(kh * kw, Cin, Cout).contiguous()        # [tap][Cin][Cout]
+        dy = [pad_y - r for r in range(kh) for _ in range(kw)]
+        dx = [-s for _ in range(kh) for s in range(kw)]
+        check(lib.b3d_conv2d_tf32(ptr(g), ptr(wt), None, ptr(dxo), N, Hout, Wout, Cout, H, W, Cin, kh * kw, _ints(dy),
+                                  _ints(dx), 1, 1, H, W, Cin, 1, 1, 0, 0, 1.0, st))
+        return dxo
+    if stride != 2:
+        raise B3DError("conv2d_dgrad: stride must be 1 or 2")
+    # input row y' = 2*yo + r - pad_y  =>  for the class y' = 2*a + cy only taps with (cy + pad_y - r) even take part
+    for cy in range(2):
+        for cx in range(2):
+            rs = [(r, s) for r in range(kh) for s in range(kw) if (cy + pad_y - r) % 2 == 0 and (cx - s) % 2 == 0]
+            Ha, Wa = (H - cy + 1) // 2, (W - cx + 1) // 2
+            if not rs:
+                dxo[:, cy::2, cx::2] = 0
+                continue
+            wt = torch.stack([weight[:, :, r, s].t() for r, s in rs]).contiguous()      # [taps][Cin][Cout]
+            dy = [(cy + pad_y - r) // 2 for r, s in rs]
+            dx = [(cx - s) // 2 for r, s in rs]
+            check(lib.b3d_conv2d_tf32(ptr(g), ptr(wt), None, ptr(dxo), N, Hout, Wout, Cout, Ha, Wa, Cin, len(rs),
+                                      _ints(dy), _ints(dx), 1, 1, H, W, Cin, 2, 2, cy, cx, 1.0, st))
+    return dxo

@@ -1,0 +1,225 @@
+// Implicit-GEMM 2-D convolution on the 5th-generation tensor cores (sm_100a): the dense convs of the
+// conv-GAN generator / discriminators (models/gan.py:57-65,163-177,294-302,359,364).
+//
+//   Y[n, y, x, co] = sum_t sum_ci  X[n, sy*y + dy[t], sx*x + dx[t], ci] * Wt[t, co, ci]      (NHWC, fp32)
+//
+// "Tap-shifted TMA" formulation: no im2col buffer.  A CTA owns 128 output pixels (a BW x BH x BI box of
+// the output) x BN output channels.  For every filter tap t and every 32-channel slice of Cin the TMA
+// producer issues ONE 4-D tiled load of the input box shifted by (dy[t], dx[t]) — out-of-bounds rows and
+// columns are zero-filled by the TMA unit, which IS the convolution's zero padding — and one 3-D load of
+// the weight slice; both land in 128-byte-swizzled K-major tiles that `tcgen05.mma.kind::tf32` consumes
+// directly (fp32 words, tf32 precision, fp32 accumulation in TMEM).  The same kernel computes
+//   * fprop   (dy = r - pad_y, dx = s, Wt[t] = W[:, :, r, s]),
+//   * dgrad   (dy = pad_y - r, dx = -s, Wt[t] = W[:, :, r, s]^T)  — the "full" correlation falls out of the
+//     TMA zero fill, and strided (4x4 / stride 2) dgrad runs as 4 parity classes with a strided epilogue,
+//   * strided fprop (element strides in the tensor map).
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2-5 =
+// epilogue (TMEM -> registers -> bias / LeakyReLU -> global).  STAGES-deep mbarrier ring between producer
+// and MMA; tcgen05.commit frees a stage and finally signals the epilogue.
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int BM = 128;         // output pixels per CTA  (UMMA M)
+constexpr int BK = 32;          // fp32 channels per K slice = 128 B = one swizzle row
+constexpr int UMMA_K = 8;       // tf32
+constexpr int MAX_TAPS = 25;
+constexpr int NTHREADS = 192;
+
+struct ConvParams {
+    int N, Hout, Wout, Cout;          // logical output extent covered by tiles (before the epilogue transform)
+    int BW, BH, BI;                   // output box per CTA, BW*BH*BI == 128
+    int tiles_x, tiles_y;             // tiles along W and H (tiles along N = gridDim.x / (tiles_x*tiles_y))
+    int ntaps, kslices;               // filter taps, Cin / 32
+    int sy, sx;                       // input coordinate = s * out + d[t]
+    int dy[MAX_TAPS], dx[MAX_TAPS];
+    // epilogue: out pixel (n, oy*y + ooy, ox*x + oox) of a tensor [N, OH, OW, OC], channel offset 0
+    int OH, OW, OC, osy, osx, ooy, oox;
+    float leaky;                      // 1.0 = identity
+    int accumulate;                   // 1: out += result (used by the parity classes of strided dgrad? no: disjoint)
+};
+
+template <int BN, int STAGES>
+struct Smem {
+    static constexpr int A_BYTES = BM * BK * 4;
+    static constexpr int B_BYTES = BN * BK * 4;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                 const ConvParams p, const float* __restrict__ bias, float* __restrict__ out) {
+    using S = Smem<BN, STAGES>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + STAGES * S::STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* acc_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // tile coordinates
+    int t = blockIdx.x;
+    const int tx = t % p.tiles_x;
+    t /= p.tiles_x;
+    const int ty = t % p.tiles_y;
+    const int tn = t / p.tiles_y;
+    const int x0 = tx * p.BW, y0 = ty * p.BH, n0 = tn * p.BI;
+    const int c0 = blockIdx.y * BN;
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tmap_x);
+        tc::tma_prefetch_desc(&tmap_w);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            tc::mbar_init(full + s, 1);
+            tc::mbar_init(empty + s, 1);
+        }
+        tc::mbar_init(acc_full, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) tc::tmem_alloc<(BN < 32 ? 32 : BN)>(tmem_slot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot;
+    const int KI = p.ntaps * p.kslices;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < KI; ++it) {
+                const int s = it % STAGES, ph = (it / STAGES) & 1;
+                tc::mbar_wait(empty + s, ph ^ 1);
+                const int tap = it / p.kslices, ks = it % p.kslices;
+                unsigned char* a = base + s * S::STAGE_BYTES;
+                unsigned char* b = a + S::A_BYTES;
+                tc::mbar_arrive_expect_tx(full + s, S::STAGE_BYTES);
+                tc::tma_load_4d(a, &tmap_x, full + s, ks * BK, p.sx * x0 + p.dx[tap], p.sy * y0 + p.dy[tap], n0);
+                tc::tma_load_3d(b, &tmap_w, full + s, ks * BK, c0, tap);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc::umma_idesc_tf32(BM, BN);
+            for (int it = 0; it < KI; ++it) {
+                const int s = it % STAGES, ph = (it / STAGES) & 1;
+                tc::mbar_wait(full + s, ph);
+                tc::tc_fence_after();
+                const uint32_t a = tc::smem_u32(base + s * S::STAGE_BYTES);
+                const uint32_t b = a + S::A_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint64_t da = tc::umma_desc_k128(a + k * UMMA_K * 4);
+                    const uint64_t db = tc::umma_desc_k128(b + k * UMMA_K * 4);
+                    tc::umma_tf32(tmem_acc, da, db, idesc, (it | k) ? 1u : 0u);
+                }
+                tc::umma_commit(empty + s);          // frees the stage when these MMAs have read it
+            }
+            tc::umma_commit(acc_full);               // accumulator complete
+        }
+    } else {
+        // epilogue warps 2..5: TMEM lane quarter = warp % 4
+        const int q = warp & 3;
+        const int r = q * 32 + lane;                 // row of the tile = output pixel
+        const int bx = r % p.BW, by = (r / p.BW) % p.BH, bi = r / (p.BW * p.BH);
+        const int n = n0 + bi, y = y0 + by, x = x0 + bx;
+        const bool valid = n < p.N && y < p.Hout && x < p.Wout;
+        float* dst = out + (((size_t)n * p.OH + (size_t)(p.osy * y + p.ooy)) * p.OW + (size_t)(p.osx * x + p.oox)) * p.OC;
+        tc::mbar_wait(acc_full, 0);
+        tc::tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            float v[32];
+            tc::tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int co = c0 + c + j;
+                    if (co < p.Cout) {
+                        float o = v[j] + (bias ? __ldg(bias + co) : 0.f);
+                        o = o >= 0.f ? o : o * p.leaky;
+                        dst[co] = o;
+                    }
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tc::tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_acc);
+}
+
+template <int BN, int STAGES>
+int launch(const CUtensorMap& mx, const CUtensorMap& mw, const ConvParams& p, const float* bias, float* out,
+           int tiles, cudaStream_t st) {
+    using S = Smem<BN, STAGES>;
+    B3D_CUDA_OK(cudaFuncSetAttribute(conv_tf32_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     S::TOTAL));
+    dim3 grid(tiles, b3d::ceil_div(p.Cout, BN));
+    conv_tf32_kernel<BN, STAGES><<<grid, NTHREADS, S::TOTAL, st>>>(mx, mw, p, bias, out);
+    B3D_LAUNCH_OK();
+    return B3D_OK;
+}
+
+int pow2_floor(int v) {
+    int p = 1;
+    while (p * 2 <= v) p *= 2;
+    return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+// x   [N, H, W, Cin]  NHWC fp32, Cin % 32 == 0
+// wt  [ntaps, Cout, Cin] fp32 (tap-major, K-major rows)
+// out [N, OH, OW, OC]; the tile grid covers (Hout, Wout) logical outputs, written to (osy*y+ooy, osx*x+oox)
+int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* out, int N, int H, int W, int Cin,
+                    int Hout, int Wout, int Cout, int ntaps, const int* dy, const int* dx, int sy, int sx, int OH,
+                    int OW, int OC, int osy, int osx, int ooy, int oox, float leaky, void* stream) {
+    B3D_REQUIRE(N > 0 && H > 0 && W > 0 && Hout > 0 && Wout > 0 && Cout > 0, B3D_EINVAL, "b3d_conv2d_tf32: bad sizes");
+    B3D_REQUIRE(Cin > 0 && Cin % BK == 0, B3D_EINVAL, "b3d_conv2d_tf32: Cin=%d must be a multiple of %d", Cin, BK);
+    B3D_REQUIRE(ntaps >= 1 && ntaps <= MAX_TAPS && dy && dx, B3D_EINVAL, "b3d_conv2d_tf32: bad taps");
+    B3D_REQUIRE(x && wt && out, B3D_EINVAL, "b3d_conv2d_tf32: null pointer");
+    B3D_REQUIRE(sy >= 1 && sy <= 2 && sx >= 1 && sx <= 2, B3D_EINVAL, "b3d_conv2d_tf32: stride must be 1 or 2");
+    B3D_CHECK_ALIGNED(x);
+    B3D_CHECK_ALIGNED(wt);
+
+    ConvParams p{};
+    p.N = N; p.Hout = Hout; p.Wout = Wout; p.Cout = Cout;
+    p.BW = pow2_floor(Wout < BM ? Wout : BM);
+    p.BH = pow2_floor(Hout < BM / p.BW ? Hout : BM / p.BW);
+    p.BI = BM / (p.BW * p.BH);
+    p.tiles_x = b3d::ceil_div(Wout, p.BW);
+    p.tiles_y = b3d::ceil_div(Hout, p.BH);
+    const int tiles = p.tiles_x * p.tiles_y * b3d::ceil_div(N, p.BI);
+    p.ntaps = ntaps; p.kslices = Cin / BK; p.sy = sy; p.sx = sx;
+    for (int t = 0; t < ntaps; ++t) { p.dy[t] = dy[t]; p.dx[t] = dx[t]; }
+    p.OH = OH; p.OW = OW; p.OC = OC; p.osy = osy; p.osx = osx; p.ooy = ooy; p.oox = oox;
+    p.leaky = leaky;
+
+    CUtensorMap mx, mw;
+    {
+        const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        const uint64_t strides[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
+        const uint32_t box[4] = {(uint32_t)BK, (uint32_t)(sx * (p.BW - 1) + 1), (uint32_t)(sy * (p.BH - 1) + 1),
+                                 (uint32_t)p.BI};
+        const uint32_t es[4] = {1, (uint32_t)sx, (uint32_t)sy, 1};
+        if (int rc = tc::make_tmap_f32(&mx, x, 4, dims, strides, box, es)) return rc;
+    }
+    const int BN = Cout > 64 ? 128 : 64;
+    {
+        const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)ntaps};
+        const uint64_t strides[2] = {(uint64_t)Cin * 4, (uint64_t)Cout * Cin * 4};
+        const uint32_t box[3] = {(uint32_t)BK, (uint32_t)BN, 1};
+        if (int rc = tc::make_tmap_f32(&mw, wt, 3, dims, strides, box)) return rc;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (BN == 128) return launch<128, 6>(mx, mw, p, bias, out, tiles, st);
+    return launch<64, 8>(mx, mw, p, bias, out, tiles, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,61 @@
+"""tcgen05 implicit-GEMM conv (tf32) against torch's fp32 conv2d (TF32 disabled) on the same inputs.
+Tolerance: tf32 keeps 10 mantissa bits (the tensor core truncates fp32 operands), so each product carries
+<= 2^-9 relative error; we require max |err| <= 4e-3 * max|ref| (cuDNN's TF32 path, the reference's default
+on Ampere+, is in the same class)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+TOL = 4e-3
+
+
+def ref_conv(x_nchw, w, b, pad_y, stride):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return torch.nn.functional.conv2d(x_nchw, w, b, stride=stride, padding=(pad_y, 0))
+
+
+CASES = [  # N, Cin, H, W(x-padded), Cout, k, pad_y, stride, bias, leaky
+    (2, 64, 8, 16, 64, 1, 0, 1, False, 1.0),        # pure GEMM, one tile per image
+    (2, 128, 16, 18, 128, 3, 1, 1, False, 1.0),     # ResBlockUp conv (gan.py:294)
+    (3, 512, 8, 6, 512, 3, 1, 1, False, 1.0),       # blk1: 8x4 images, 4 images per tile, 2 N tiles x 4 Cout tiles
+    (2, 64, 32, 36, 3, 5, 2, 1, True, 1.0),         # conv_final 5x5 -> 3 channels (gan.py:359)
+    (2, 32, 32, 34, 64, 4, 1, 2, True, 0.2),        # discriminator 4x4 / stride 2 + bias + LeakyReLU (gan.py:163)
+    (1, 256, 64, 66, 128, 3, 1, 1, False, 1.0),     # multiple tiles along y
+    (5, 96, 10, 20, 40, 3, 1, 1, True, 1.0),        # ragged: N, H, Cout not multiples of the tile
+]
+
+
+@pytest.mark.parametrize("N,Cin,H,W,Cout,k,pad_y,stride,bias,leaky", CASES)
+def test_fprop(N, Cin, H, W, Cout, k, pad_y, stride, bias, leaky):
+    from b3d.conv import conv2d_nhwc
+    g = torch.Generator().manual_seed(Cin + Cout + k)
+    x = torch.randn(N, Cin, H, W, generator=g).cuda()
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).cuda()
+    b = torch.randn(Cout, generator=g).cuda() if bias else None
+    ref = torch.nn.functional.leaky_relu(ref_conv(x, w, b, pad_y, stride), leaky) if leaky != 1.0 else ref_conv(x, w, b, pad_y, stride)
+    out = conv2d_nhwc(x.permute(0, 2, 3, 1).contiguous(), w, b, pad_y=pad_y, stride=stride, leaky=leaky)
+    torch.cuda.synchronize()
+    out = out.permute(0, 3, 1, 2)
+    assert out.shape == ref.shape
+    err = float((out - ref).abs().max())
+    assert err <= TOL * float(ref.abs().max()), (err, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("N,Cin,H,W,Cout,k,pad_y,stride", [
+    (2, 64, 16, 18, 128, 3, 1, 1), (2, 32, 32, 36, 64, 5, 2, 1), (2, 64, 16, 18, 64, 4, 1, 2), (3, 128, 8, 6, 256, 3, 1, 1),
+    (2, 96, 9, 12, 64, 1, 0, 1),
+])
+def test_dgrad(N, Cin, H, W, Cout, k, pad_y, stride):
+    from b3d.conv import conv2d_dgrad_nhwc
+    g = torch.Generator().manual_seed(Cin * 3 + Cout + k)
+    x = torch.randn(N, Cin, H, W, generator=g).cuda().requires_grad_(True)
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).cuda()
+    y = ref_conv(x, w, None, pad_y, stride)
+    gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(1)).cuda()
+    ref, = torch.autograd.grad(y, x, gy)
+    out = conv2d_dgrad_nhwc(gy.permute(0, 2, 3, 1).contiguous(), w, (H, W), pad_y=pad_y, stride=stride)
+    torch.cuda.synchronize()
+    out = out.permute(0, 3, 1, 2)
+    err = float((out - ref).abs().max())
+    assert err <= TOL * float(ref.abs().max()), (err, float(ref.abs().max()))
