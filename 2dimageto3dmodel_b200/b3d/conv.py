@@ -70,3 +70,19 @@ def conv2d_dgrad_nhwc(dy_, weight, in_hw, pad_y=0, stride=1):
             check(lib.b3d_conv2d_tf32(ptr(g), ptr(wt), None, ptr(dxo), N, Hout, Wout, Cout, Ha, Wa, Cin, len(rs),
                                       _ints(dy), _ints(dx), 1, 1, H, W, Cin, 2, 2, cy, cx, 1.0, st))
     return dxo
+
+
+def conv2d_wgrad(dy_nchw, x_nchw, kh, kw, pad_y=0, stride=1):
+    """dW [Cout,Cin,kh,kw] from dy [N,Cout,Hout,Wout] and the (x-padded) input x [N,Cin,H,W], both NCHW-contiguous."""
+    g, x = dev(dy_nchw, "grad_output"), dev(x_nchw, "input")
+    N, Cout, Hout, Wout = g.shape
+    _, Cin, H, W = x.shape
+    if W % 4 or Wout % 4:       # 16-byte TMA rows: pad the pixel rows with zeros (only the tiny 4xN layers hit this)
+        pw, pwo = (-W) % 4, (-Wout) % 4
+        x = torch.nn.functional.pad(x, (0, pw))
+        g = torch.nn.functional.pad(g, (0, pwo))
+        W, Wout = W + pw, Wout + pwo
+    dw = torch.zeros(Cout, Cin, kh, kw, device=g.device, dtype=torch.float32)
+    check(lib.b3d_conv2d_wgrad_tf32(ptr(g), ptr(x), ptr(dw), N, Cin, H, W, Cout, Hout, Wout, kh, kw, pad_y, stride,
+                                    stream_ptr(g)))
+    return dw

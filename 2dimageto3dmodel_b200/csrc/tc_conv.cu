@@ -152,6 +152,115 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     if (warp == 2) tc::tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_acc);
 }
 
+// ----------------------------------------------------------------------------------------------
+// wgrad:  dW[co, ci, r, s] += sum_{n,y,x} dY[n, co, y, x] * X[n, ci, sy*y + r - pad_y, sx*x + s]     (NCHW operands)
+// GEMM with M = Cout (128 rows), N = Cin (BN), K = output pixels.  Pixel-contiguous (NCHW) tensors make both
+// operands K-major: a K slice is a BWk x BHk box of 32 output pixels of one image; the X box is the same box
+// shifted by the tap (zero fill = padding) and strided for stride-2 convs.  One CTA per (co tile, ci tile, tap,
+// K split); partial sums are reduced into dW with red.global.add.f32 (dW zeroed by the caller).
+// ----------------------------------------------------------------------------------------------
+struct WgradParams {
+    int N, Hout, Wout, Cout, Cin;
+    int BWk, BHk;                  // pixel box of one K slice, BWk * BHk == 32
+    int kx, ky;                    // K slices along x and y per image
+    int kh, kw, pad_y, sy, sx;
+    int splits;                    // K splits (gridDim.z / taps)
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NTHREADS, 1)
+wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
+                  const WgradParams p, float* __restrict__ dw) {
+    using S = Smem<BN, STAGES>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + STAGES * S::STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* acc_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int co0 = blockIdx.x * BM, ci0 = blockIdx.y * BN;
+    const int tap = blockIdx.z % (p.kh * p.kw), split = blockIdx.z / (p.kh * p.kw);
+    const int r = tap / p.kw, s = tap % p.kw;
+    const int per_img = p.kx * p.ky;
+    const long long ktotal = (long long)p.N * per_img;
+    const long long k_lo = ktotal * split / p.splits, k_hi = ktotal * (split + 1) / p.splits;
+    const int KI = (int)(k_hi - k_lo);
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tmap_dy);
+        tc::tma_prefetch_desc(&tmap_x);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            tc::mbar_init(full + i, 1);
+            tc::mbar_init(empty + i, 1);
+        }
+        tc::mbar_init(acc_full, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) tc::tmem_alloc<(BN < 32 ? 32 : BN)>(tmem_slot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < KI; ++it) {
+                const int st = it % STAGES, ph = (it / STAGES) & 1;
+                tc::mbar_wait(empty + st, ph ^ 1);
+                const long long k = k_lo + it;
+                const int n = (int)(k / per_img), rem = (int)(k % per_img);
+                const int x0 = (rem % p.kx) * p.BWk, y0 = (rem / p.kx) * p.BHk;
+                unsigned char* a = base + st * S::STAGE_BYTES;
+                unsigned char* b = a + S::A_BYTES;
+                tc::mbar_arrive_expect_tx(full + st, S::STAGE_BYTES);
+                tc::tma_load_4d(a, &tmap_dy, full + st, x0, y0, co0, n);
+                tc::tma_load_4d(b, &tmap_x, full + st, p.sx * x0 + s, p.sy * y0 + r - p.pad_y, ci0, n);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc::umma_idesc_tf32(BM, BN);
+            for (int it = 0; it < KI; ++it) {
+                const int st = it % STAGES, ph = (it / STAGES) & 1;
+                tc::mbar_wait(full + st, ph);
+                tc::tc_fence_after();
+                const uint32_t a = tc::smem_u32(base + st * S::STAGE_BYTES);
+                const uint32_t b = a + S::A_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                    tc::umma_tf32(tmem_acc, tc::umma_desc_k128(a + k * UMMA_K * 4), tc::umma_desc_k128(b + k * UMMA_K * 4),
+                                  idesc, (it | k) ? 1u : 0u);
+                tc::umma_commit(empty + st);
+            }
+            tc::umma_commit(acc_full);
+        }
+    } else if (KI > 0) {
+        const int q = warp & 3;
+        const int co = co0 + q * 32 + lane;
+        tc::mbar_wait(acc_full, 0);
+        tc::tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            float v[32];
+            tc::tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            if (co < p.Cout) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int ci = ci0 + c + j;
+                    if (ci < p.Cin) atomicAdd(dw + (((size_t)co * p.Cin + ci) * p.kh + r) * p.kw + s, v[j]);
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tc::tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_acc);
+}
+
 template <int BN, int STAGES>
 int launch(const CUtensorMap& mx, const CUtensorMap& mw, const ConvParams& p, const float* bias, float* out,
            int tiles, cudaStream_t st) {
@@ -220,6 +329,59 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
     cudaStream_t st = (cudaStream_t)stream;
     if (BN == 128) return launch<128, 6>(mx, mw, p, bias, out, tiles, st);
     return launch<64, 8>(mx, mw, p, bias, out, tiles, st);
+}
+
+// dy_nchw [N,Cout,Hout,Wout], x_nchw [N,Cin,H,W] (x already padded along x), dw [Cout,Cin,kh,kw] (accumulated into)
+int b3d_conv2d_wgrad_tf32(const float* dy_nchw, const float* x_nchw, float* dw, int N, int Cin, int H, int W, int Cout,
+                          int Hout, int Wout, int kh, int kw, int pad_y, int stride, void* stream) {
+    B3D_REQUIRE(N > 0 && Cin > 0 && Cout > 0 && H > 0 && W > 0 && Hout > 0 && Wout > 0, B3D_EINVAL,
+                "b3d_conv2d_wgrad_tf32: bad sizes");
+    B3D_REQUIRE(kh * kw <= MAX_TAPS && (stride == 1 || stride == 2), B3D_EINVAL, "b3d_conv2d_wgrad_tf32: bad kernel/stride");
+    B3D_REQUIRE(dy_nchw && x_nchw && dw, B3D_EINVAL, "b3d_conv2d_wgrad_tf32: null pointer");
+    B3D_REQUIRE(W % 4 == 0 && Wout % 4 == 0, B3D_EINVAL,
+                "b3d_conv2d_wgrad_tf32: W=%d and Wout=%d must be multiples of 4 (16-byte TMA rows)", W, Wout);
+    WgradParams p{};
+    p.N = N; p.Hout = Hout; p.Wout = Wout; p.Cout = Cout; p.Cin = Cin;
+    p.BWk = pow2_floor(Wout < BK ? Wout : BK);
+    p.BHk = BK / p.BWk;
+    p.kx = b3d::ceil_div(Wout, p.BWk);
+    p.ky = b3d::ceil_div(Hout, p.BHk);
+    p.kh = kh; p.kw = kw; p.pad_y = pad_y; p.sy = stride; p.sx = stride;
+    const int BN = Cin > 64 ? 128 : 64;
+    const int base_ctas = b3d::ceil_div(Cout, BM) * b3d::ceil_div(Cin, BN) * kh * kw;
+    const long long ktotal = (long long)N * p.kx * p.ky;
+    int splits = (2 * 148 + base_ctas - 1) / base_ctas;          // aim at ~2 waves of CTAs
+    if (splits > ktotal / 8) splits = (int)(ktotal / 8);         // at least 8 K slices per CTA
+    if (splits < 1) splits = 1;
+    p.splits = splits;
+
+    CUtensorMap mdy, mx;
+    {
+        const uint64_t dims[4] = {(uint64_t)Wout, (uint64_t)Hout, (uint64_t)Cout, (uint64_t)N};
+        const uint64_t strides[3] = {(uint64_t)Wout * 4, (uint64_t)Hout * Wout * 4, (uint64_t)Cout * Hout * Wout * 4};
+        const uint32_t box[4] = {(uint32_t)p.BWk, (uint32_t)p.BHk, (uint32_t)BM, 1};
+        if (int rc = tc::make_tmap_f32(&mdy, dy_nchw, 4, dims, strides, box)) return rc;
+    }
+    {
+        const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)Cin, (uint64_t)N};
+        const uint64_t strides[3] = {(uint64_t)W * 4, (uint64_t)H * W * 4, (uint64_t)Cin * H * W * 4};
+        const uint32_t box[4] = {(uint32_t)(stride * (p.BWk - 1) + 1), (uint32_t)(stride * (p.BHk - 1) + 1), (uint32_t)BN, 1};
+        const uint32_t es[4] = {(uint32_t)stride, (uint32_t)stride, 1, 1};
+        if (int rc = tc::make_tmap_f32(&mx, x_nchw, 4, dims, strides, box, es)) return rc;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(b3d::ceil_div(Cout, BM), b3d::ceil_div(Cin, BN), kh * kw * splits);
+    if (BN == 128) {
+        using S = Smem<128, 6>;
+        B3D_CUDA_OK(cudaFuncSetAttribute(wgrad_tf32_kernel<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        wgrad_tf32_kernel<128, 6><<<grid, NTHREADS, S::TOTAL, st>>>(mdy, mx, p, dw);
+    } else {
+        using S = Smem<64, 8>;
+        B3D_CUDA_OK(cudaFuncSetAttribute(wgrad_tf32_kernel<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        wgrad_tf32_kernel<64, 8><<<grid, NTHREADS, S::TOTAL, st>>>(mdy, mx, p, dw);
+    }
+    B3D_LAUNCH_OK();
+    return B3D_OK;
 }
 
 }  // extern "C"

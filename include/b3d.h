@@ -189,6 +189,14 @@ B3D_API int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, 
                             int sy, int sx, int OH, int OW, int OC, int osy, int osx, int ooy, int oox,
                             float leaky, void* stream);
 
+/* Weight gradient of the same convolution (split-K tcgen05 GEMM over the output pixels):
+ *   dw[co, ci, r, s] += sum_{n,y,x} dy[n, co, y, x] * x[n, ci, stride*y + r - pad_y, stride*x + s]
+ * dy_nchw [N,Cout,Hout,Wout], x_nchw [N,Cin,H,W] (NCHW: pixel-contiguous rows make both operands K-major;
+ * W and Wout multiples of 4), dw [Cout,Cin,kh,kw] ACCUMULATED into (caller zeroes it).            */
+B3D_API int b3d_conv2d_wgrad_tf32(const float* dy_nchw, const float* x_nchw, float* dw, int N, int Cin, int H,
+                                  int W, int Cout, int Hout, int Wout, int kh, int kw, int pad_y, int stride,
+                                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif
