@@ -73,16 +73,20 @@ def conv2d_dgrad_nhwc(dy_, weight, in_hw, pad_y=0, stride=1):
 
 
 def conv2d_wgrad(dy_nchw, x_nchw, kh, kw, pad_y=0, stride=1):
-    """dW [Cout,Cin,kh,kw] from dy [N,Cout,Hout,Wout] and the (x-padded) input x [N,Cin,H,W], both NCHW-contiguous."""
-    g, x = dev(dy_nchw, "grad_output"), dev(x_nchw, "input")
+    """dW [Cout,Cin,kh,kw] from dy [N,Cout,Hout,Wout] and the (x-padded) input x [N,Cin,H,W] (NCHW)."""
+    g, x = dy_nchw, x_nchw
     N, Cout, Hout, Wout = g.shape
     _, Cin, H, W = x.shape
-    if W % 4 or Wout % 4:       # 16-byte TMA rows: pad the pixel rows with zeros (only the tiny 4xN layers hit this)
-        pw, pwo = (-W) % 4, (-Wout) % 4
-        x = torch.nn.functional.pad(x, (0, pw))
-        g = torch.nn.functional.pad(g, (0, pwo))
-        W, Wout = W + pw, Wout + pwo
+    if W % stride:                                   # keep the input row pitch a multiple of the stride
+        x = torch.nn.functional.pad(x, (0, stride - W % stride))
+        W = x.shape[3]
+    if (H * W) % 4 or (Hout * (W // stride)) % 4:    # 16-byte TMA strides: widen the rows (zeros)
+        x = torch.nn.functional.pad(x, (0, 4 * stride - W % (4 * stride)))
+        W = x.shape[3]
+    Wp = W // stride
+    g = torch.nn.functional.pad(g, (0, Wp - Wout))   # dY with the input's row pitch; pad columns are zero
+    g, x = dev(g, "grad_output"), dev(x, "input")
     dw = torch.zeros(Cout, Cin, kh, kw, device=g.device, dtype=torch.float32)
-    check(lib.b3d_conv2d_wgrad_tf32(ptr(g), ptr(x), ptr(dw), N, Cin, H, W, Cout, Hout, Wout, kh, kw, pad_y, stride,
+    check(lib.b3d_conv2d_wgrad_tf32(ptr(g), ptr(x), ptr(dw), N, Cin, H, W, Cout, Hout, Wp, kh, kw, pad_y, stride,
                                     stream_ptr(g)))
     return dw

@@ -153,17 +153,20 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 }
 
 // ----------------------------------------------------------------------------------------------
-// wgrad:  dW[co, ci, r, s] += sum_{n,y,x} dY[n, co, y, x] * X[n, ci, sy*y + r - pad_y, sx*x + s]     (NCHW operands)
+// wgrad:  dW[co, ci, r, s] += sum_{n,y,x} dY[n, co, y, x] * X[n, ci, st*y + r - pad_y, st*x + s]     (NCHW operands)
 // GEMM with M = Cout (128 rows), N = Cin (BN), K = output pixels.  Pixel-contiguous (NCHW) tensors make both
-// operands K-major: a K slice is a BWk x BHk box of 32 output pixels of one image; the X box is the same box
-// shifted by the tap (zero fill = padding) and strided for stride-2 convs.  One CTA per (co tile, ci tile, tap,
-// K split); partial sums are reduced into dW with red.global.add.f32 (dW zeroed by the caller).
+// operands K-major.  dY is stored with the row pitch Wp = W / st of the input, so that in the FLATTENED pixel index
+// q = y*Wp + x the input element of tap (r,s) sits at st*q + (r - pad_y)*W + s: a K slice is 32 consecutive q of one
+// image for dY and the same window, shifted by a constant (and strided for st = 2), for X — full 128-byte rows for
+// every layer size; rows above/below the image fall outside [0, H*W) and are zero-filled by the TMA (= y padding);
+// the pad columns of dY are zero, so the wrapped products vanish.  One CTA per (co tile, ci tile, tap, K split);
+// partial sums are reduced into dW with red.global.add.f32 (dW zeroed by the caller).
 // ----------------------------------------------------------------------------------------------
 struct WgradParams {
-    int N, Hout, Wout, Cout, Cin;
-    int BWk, BHk;                  // pixel box of one K slice, BWk * BHk == 32
-    int kx, ky;                    // K slices along x and y per image
-    int kh, kw, pad_y, sy, sx;
+    int N, Cout, Cin;
+    int W;                         // input row pitch
+    int kslices;                   // K slices per image = ceil(Hout * Wp / 32)
+    int kh, kw, pad_y, st;
     int splits;                    // K splits (gridDim.z / taps)
 };
 
@@ -183,10 +186,10 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
     const int co0 = blockIdx.x * BM, ci0 = blockIdx.y * BN;
     const int tap = blockIdx.z % (p.kh * p.kw), split = blockIdx.z / (p.kh * p.kw);
     const int r = tap / p.kw, s = tap % p.kw;
-    const int per_img = p.kx * p.ky;
-    const long long ktotal = (long long)p.N * per_img;
+    const long long ktotal = (long long)p.N * p.kslices;
     const long long k_lo = ktotal * split / p.splits, k_hi = ktotal * (split + 1) / p.splits;
     const int KI = (int)(k_hi - k_lo);
+    const int shift = (r - p.pad_y) * p.W + s;
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&tmap_dy);
@@ -212,13 +215,12 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
                 const int st = it % STAGES, ph = (it / STAGES) & 1;
                 tc::mbar_wait(empty + st, ph ^ 1);
                 const long long k = k_lo + it;
-                const int n = (int)(k / per_img), rem = (int)(k % per_img);
-                const int x0 = (rem % p.kx) * p.BWk, y0 = (rem / p.kx) * p.BHk;
+                const int n = (int)(k / p.kslices), q0 = (int)(k % p.kslices) * BK;
                 unsigned char* a = base + st * S::STAGE_BYTES;
                 unsigned char* b = a + S::A_BYTES;
                 tc::mbar_arrive_expect_tx(full + st, S::STAGE_BYTES);
-                tc::tma_load_4d(a, &tmap_dy, full + st, x0, y0, co0, n);
-                tc::tma_load_4d(b, &tmap_x, full + st, p.sx * x0 + s, p.sy * y0 + r - p.pad_y, ci0, n);
+                tc::tma_load_3d(a, &tmap_dy, full + st, q0, co0, n);
+                tc::tma_load_3d(b, &tmap_x, full + st, p.st * q0 + shift, ci0, n);
             }
         }
     } else if (warp == 1) {
@@ -331,25 +333,27 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
     return launch<64, 8>(mx, mw, p, bias, out, tiles, st);
 }
 
-// dy_nchw [N,Cout,Hout,Wout], x_nchw [N,Cin,H,W] (x already padded along x), dw [Cout,Cin,kh,kw] (accumulated into)
-int b3d_conv2d_wgrad_tf32(const float* dy_nchw, const float* x_nchw, float* dw, int N, int Cin, int H, int W, int Cout,
-                          int Hout, int Wout, int kh, int kw, int pad_y, int stride, void* stream) {
-    B3D_REQUIRE(N > 0 && Cin > 0 && Cout > 0 && H > 0 && W > 0 && Hout > 0 && Wout > 0, B3D_EINVAL,
+// dyp [N,Cout,Hout,Wp] with Wp = W / stride (columns >= Wout are zero), x_nchw [N,Cin,H,W] (already padded along x),
+// dw [Cout,Cin,kh,kw] (accumulated into)
+int b3d_conv2d_wgrad_tf32(const float* dyp, const float* x_nchw, float* dw, int N, int Cin, int H, int W, int Cout,
+                          int Hout, int Wp, int kh, int kw, int pad_y, int stride, void* stream) {
+    B3D_REQUIRE(N > 0 && Cin > 0 && Cout > 0 && H > 0 && W > 0 && Hout > 0 && Wp > 0, B3D_EINVAL,
                 "b3d_conv2d_wgrad_tf32: bad sizes");
     B3D_REQUIRE(kh * kw <= MAX_TAPS && (stride == 1 || stride == 2), B3D_EINVAL, "b3d_conv2d_wgrad_tf32: bad kernel/stride");
-    B3D_REQUIRE(dy_nchw && x_nchw && dw, B3D_EINVAL, "b3d_conv2d_wgrad_tf32: null pointer");
-    B3D_REQUIRE(W % 4 == 0 && Wout % 4 == 0, B3D_EINVAL,
-                "b3d_conv2d_wgrad_tf32: W=%d and Wout=%d must be multiples of 4 (16-byte TMA rows)", W, Wout);
+    B3D_REQUIRE(dyp && x_nchw && dw, B3D_EINVAL, "b3d_conv2d_wgrad_tf32: null pointer");
+    B3D_REQUIRE(Wp * stride == W, B3D_EINVAL, "b3d_conv2d_wgrad_tf32: dY row pitch %d must equal W / stride = %d / %d", Wp, W,
+                stride);
+    B3D_REQUIRE((H * W) % 4 == 0 && (Hout * Wp) % 4 == 0, B3D_EINVAL,
+                "b3d_conv2d_wgrad_tf32: image planes must be multiples of 4 floats (16-byte TMA strides)");
+    B3D_CHECK_ALIGNED(dyp);
+    B3D_CHECK_ALIGNED(x_nchw);
     WgradParams p{};
-    p.N = N; p.Hout = Hout; p.Wout = Wout; p.Cout = Cout; p.Cin = Cin;
-    p.BWk = pow2_floor(Wout < BK ? Wout : BK);
-    p.BHk = BK / p.BWk;
-    p.kx = b3d::ceil_div(Wout, p.BWk);
-    p.ky = b3d::ceil_div(Hout, p.BHk);
-    p.kh = kh; p.kw = kw; p.pad_y = pad_y; p.sy = stride; p.sx = stride;
+    p.N = N; p.Cout = Cout; p.Cin = Cin; p.W = W;
+    p.kslices = b3d::ceil_div(Hout * Wp, BK);
+    p.kh = kh; p.kw = kw; p.pad_y = pad_y; p.st = stride;
     const int BN = Cin > 64 ? 128 : 64;
     const int base_ctas = b3d::ceil_div(Cout, BM) * b3d::ceil_div(Cin, BN) * kh * kw;
-    const long long ktotal = (long long)N * p.kx * p.ky;
+    const long long ktotal = (long long)N * p.kslices;
     int splits = (2 * 148 + base_ctas - 1) / base_ctas;          // aim at ~2 waves of CTAs
     if (splits > ktotal / 8) splits = (int)(ktotal / 8);         // at least 8 K slices per CTA
     if (splits < 1) splits = 1;
@@ -357,17 +361,17 @@ int b3d_conv2d_wgrad_tf32(const float* dy_nchw, const float* x_nchw, float* dw, 
 
     CUtensorMap mdy, mx;
     {
-        const uint64_t dims[4] = {(uint64_t)Wout, (uint64_t)Hout, (uint64_t)Cout, (uint64_t)N};
-        const uint64_t strides[3] = {(uint64_t)Wout * 4, (uint64_t)Hout * Wout * 4, (uint64_t)Cout * Hout * Wout * 4};
-        const uint32_t box[4] = {(uint32_t)p.BWk, (uint32_t)p.BHk, (uint32_t)BM, 1};
-        if (int rc = tc::make_tmap_f32(&mdy, dy_nchw, 4, dims, strides, box)) return rc;
+        const uint64_t dims[3] = {(uint64_t)Hout * Wp, (uint64_t)Cout, (uint64_t)N};
+        const uint64_t strides[2] = {(uint64_t)Hout * Wp * 4, (uint64_t)Cout * Hout * Wp * 4};
+        const uint32_t box[3] = {(uint32_t)BK, (uint32_t)BM, 1};
+        if (int rc = tc::make_tmap_f32(&mdy, dyp, 3, dims, strides, box)) return rc;
     }
     {
-        const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)Cin, (uint64_t)N};
-        const uint64_t strides[3] = {(uint64_t)W * 4, (uint64_t)H * W * 4, (uint64_t)Cin * H * W * 4};
-        const uint32_t box[4] = {(uint32_t)(stride * (p.BWk - 1) + 1), (uint32_t)(stride * (p.BHk - 1) + 1), (uint32_t)BN, 1};
-        const uint32_t es[4] = {(uint32_t)stride, (uint32_t)stride, 1, 1};
-        if (int rc = tc::make_tmap_f32(&mx, x_nchw, 4, dims, strides, box, es)) return rc;
+        const uint64_t dims[3] = {(uint64_t)H * W, (uint64_t)Cin, (uint64_t)N};
+        const uint64_t strides[2] = {(uint64_t)H * W * 4, (uint64_t)Cin * H * W * 4};
+        const uint32_t box[3] = {(uint32_t)(stride * (BK - 1) + 1), (uint32_t)BN, 1};
+        const uint32_t es[3] = {(uint32_t)stride, 1, 1};
+        if (int rc = tc::make_tmap_f32(&mx, x_nchw, 3, dims, strides, box, es)) return rc;
     }
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(b3d::ceil_div(Cout, BM), b3d::ceil_div(Cin, BN), kh * kw * splits);
