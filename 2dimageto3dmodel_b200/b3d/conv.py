@@ -72,21 +72,13 @@ def conv2d_dgrad_nhwc(dy_, weight, in_hw, pad_y=0, stride=1):
     return dxo
 
 
-def conv2d_wgrad(dy_nchw, x_nchw, kh, kw, pad_y=0, stride=1):
-    """dW [Cout,Cin,kh,kw] from dy [N,Cout,Hout,Wout] and the (x-padded) input x [N,Cin,H,W] (NCHW)."""
-    g, x = dy_nchw, x_nchw
-    N, Cout, Hout, Wout = g.shape
-    _, Cin, H, W = x.shape
-    if W % stride:                                   # keep the input row pitch a multiple of the stride
-        x = torch.nn.functional.pad(x, (0, stride - W % stride))
-        W = x.shape[3]
-    if (H * W) % 4 or (Hout * (W // stride)) % 4:    # 16-byte TMA strides: widen the rows (zeros)
-        x = torch.nn.functional.pad(x, (0, 4 * stride - W % (4 * stride)))
-        W = x.shape[3]
-    Wp = W // stride
-    g = torch.nn.functional.pad(g, (0, Wp - Wout))   # dY with the input's row pitch; pad columns are zero
-    g, x = dev(g, "grad_output"), dev(x, "input")
+def conv2d_wgrad_nhwc(dy_, x, kh, kw, pad_y=0, stride=1):
+    """dW [Cout,Cin,kh,kw] from dy_ [N,Hout,Wout,Cout] and the (x-padded) input x [N,H,W,Cin], both NHWC
+    (channel counts multiples of 4)."""
+    g, x = dev(dy_, "grad_output"), dev(x, "input")
+    N, Hout, Wout, Cout = g.shape
+    _, H, W, Cin = x.shape
     dw = torch.zeros(Cout, Cin, kh, kw, device=g.device, dtype=torch.float32)
-    check(lib.b3d_conv2d_wgrad_tf32(ptr(g), ptr(x), ptr(dw), N, Cin, H, W, Cout, Hout, Wp, kh, kw, pad_y, stride,
+    check(lib.b3d_conv2d_wgrad_tf32(ptr(g), ptr(x), ptr(dw), N, H, W, Cin, Hout, Wout, Cout, kh, kw, pad_y, stride,
                                     stream_ptr(g)))
     return dw

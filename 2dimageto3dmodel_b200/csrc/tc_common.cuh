@@ -128,12 +128,25 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
     return d;
 }
 
-// instruction descriptor for kind::tf32: D = fp32, A/B = tf32, both K-major, M x N tile
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+// MN-major operand, 128-byte swizzle: the tile is stored as [mn block of 32][k rows][32 fp32 along M/N]; one
+// swizzle atom = 8 k-rows x 128 B.  Leading byte offset = distance between consecutive 32-wide M/N blocks,
+// stride byte offset = distance between consecutive groups of 8 k-rows.
+__device__ __forceinline__ uint64_t umma_desc_mn128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// instruction descriptor for kind::tf32: D = fp32, A/B = tf32, M x N tile; *_mn = operand is M/N-major (transposed)
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, bool a_mn = false, bool b_mn = false) {
     return (1u << 4)                       // c_format = F32
            | (2u << 7)                     // a_format = TF32
            | (2u << 10)                    // b_format = TF32
-           | (0u << 15) | (0u << 16)       // a, b K-major
+           | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16)
            | ((uint32_t)(N >> 3) << 17)    // n_dim
            | ((uint32_t)(M >> 4) << 24);   // m_dim
 }

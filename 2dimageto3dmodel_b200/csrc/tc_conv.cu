@@ -153,19 +153,18 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 }
 
 // ----------------------------------------------------------------------------------------------
-// wgrad:  dW[co, ci, r, s] += sum_{n,y,x} dY[n, co, y, x] * X[n, ci, st*y + r - pad_y, st*x + s]     (NCHW operands)
-// GEMM with M = Cout (128 rows), N = Cin (BN), K = output pixels.  Pixel-contiguous (NCHW) tensors make both
-// operands K-major.  dY is stored with the row pitch Wp = W / st of the input, so that in the FLATTENED pixel index
-// q = y*Wp + x the input element of tap (r,s) sits at st*q + (r - pad_y)*W + s: a K slice is 32 consecutive q of one
-// image for dY and the same window, shifted by a constant (and strided for st = 2), for X — full 128-byte rows for
-// every layer size; rows above/below the image fall outside [0, H*W) and are zero-filled by the TMA (= y padding);
-// the pad columns of dY are zero, so the wrapped products vanish.  One CTA per (co tile, ci tile, tap, K split);
-// partial sums are reduced into dW with red.global.add.f32 (dW zeroed by the caller).
+// wgrad:  dW[co, ci, r, s] += sum_{n,y,x} dY[n, y, x, co] * X[n, st*y + r - pad_y, st*x + s, ci]      (NHWC operands)
+// GEMM with M = Cout (128), N = Cin (BN), K = output pixels.  In NHWC the reduction index (pixel) is the SLOW index
+// of both operands, i.e. they are M/N-major: a K slice is a BWk x BHk box of 32 output pixels, loaded as 32-channel
+// wide TMA boxes ([32 pixels][32 channels], 128-byte swizzled rows) — four for dY, BN/32 for X, the X boxes shifted
+// by the tap on the OUTER dims (zero fill = padding, element strides for stride 2).  tcgen05.mma reads them through
+// MN-major shared-memory descriptors (transposed operands), so no NCHW copy of any activation is ever made.
+// One CTA per (co tile, ci tile, tap, K split); partial sums are reduced into dW with red.global.add.f32.
 // ----------------------------------------------------------------------------------------------
 struct WgradParams {
-    int N, Cout, Cin;
-    int W;                         // input row pitch
-    int kslices;                   // K slices per image = ceil(Hout * Wp / 32)
+    int N, Hout, Wout, Cout, Cin;
+    int BWk, BHk;                  // pixel box of one K slice, BWk * BHk == 32
+    int kx, ky;                    // K slices along x and y per image
     int kh, kw, pad_y, st;
     int splits;                    // K splits (gridDim.z / taps)
 };
@@ -175,6 +174,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
                   const WgradParams p, float* __restrict__ dw) {
     using S = Smem<BN, STAGES>;
+    constexpr int BLK = BK * 32 * 4;          // one [32 pixels][32 channels] box = 4 KB
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(base + STAGES * S::STAGE_BYTES);
@@ -186,10 +186,10 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
     const int co0 = blockIdx.x * BM, ci0 = blockIdx.y * BN;
     const int tap = blockIdx.z % (p.kh * p.kw), split = blockIdx.z / (p.kh * p.kw);
     const int r = tap / p.kw, s = tap % p.kw;
-    const long long ktotal = (long long)p.N * p.kslices;
+    const int per_img = p.kx * p.ky;
+    const long long ktotal = (long long)p.N * per_img;
     const long long k_lo = ktotal * split / p.splits, k_hi = ktotal * (split + 1) / p.splits;
     const int KI = (int)(k_hi - k_lo);
-    const int shift = (r - p.pad_y) * p.W + s;
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&tmap_dy);
@@ -215,17 +215,21 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
                 const int st = it % STAGES, ph = (it / STAGES) & 1;
                 tc::mbar_wait(empty + st, ph ^ 1);
                 const long long k = k_lo + it;
-                const int n = (int)(k / p.kslices), q0 = (int)(k % p.kslices) * BK;
+                const int n = (int)(k / per_img), rem = (int)(k % per_img);
+                const int x0 = (rem % p.kx) * p.BWk, y0 = (rem / p.kx) * p.BHk;
                 unsigned char* a = base + st * S::STAGE_BYTES;
                 unsigned char* b = a + S::A_BYTES;
                 tc::mbar_arrive_expect_tx(full + st, S::STAGE_BYTES);
-                tc::tma_load_3d(a, &tmap_dy, full + st, q0, co0, n);
-                tc::tma_load_3d(b, &tmap_x, full + st, p.st * q0 + shift, ci0, n);
+#pragma unroll
+                for (int mb = 0; mb < BM / 32; ++mb) tc::tma_load_4d(a + mb * BLK, &tmap_dy, full + st, co0 + mb * 32, x0, y0, n);
+#pragma unroll
+                for (int nb = 0; nb < BN / 32; ++nb)
+                    tc::tma_load_4d(b + nb * BLK, &tmap_x, full + st, ci0 + nb * 32, p.st * x0 + s, p.st * y0 + r - p.pad_y, n);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = tc::umma_idesc_tf32(BM, BN);
+            constexpr uint32_t idesc = tc::umma_idesc_tf32(BM, BN, true, true);
             for (int it = 0; it < KI; ++it) {
                 const int st = it % STAGES, ph = (it / STAGES) & 1;
                 tc::mbar_wait(full + st, ph);
@@ -233,9 +237,9 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
                 const uint32_t a = tc::smem_u32(base + st * S::STAGE_BYTES);
                 const uint32_t b = a + S::A_BYTES;
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k)
-                    tc::umma_tf32(tmem_acc, tc::umma_desc_k128(a + k * UMMA_K * 4), tc::umma_desc_k128(b + k * UMMA_K * 4),
-                                  idesc, (it | k) ? 1u : 0u);
+                for (int k = 0; k < BK / UMMA_K; ++k)      // 8 pixel rows = one swizzle atom (1024 B) per MMA
+                    tc::umma_tf32(tmem_acc, tc::umma_desc_mn128(a + k * 1024, BLK, 1024),
+                                  tc::umma_desc_mn128(b + k * 1024, BLK, 1024), idesc, (it | k) ? 1u : 0u);
                 tc::umma_commit(empty + st);
             }
             tc::umma_commit(acc_full);
@@ -333,27 +337,28 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
     return launch<64, 8>(mx, mw, p, bias, out, tiles, st);
 }
 
-// dyp [N,Cout,Hout,Wp] with Wp = W / stride (columns >= Wout are zero), x_nchw [N,Cin,H,W] (already padded along x),
+// dy [N,Hout,Wout,Cout], x [N,H,W,Cin] NHWC (x already padded along x; Cin, Cout multiples of 4),
 // dw [Cout,Cin,kh,kw] (accumulated into)
-int b3d_conv2d_wgrad_tf32(const float* dyp, const float* x_nchw, float* dw, int N, int Cin, int H, int W, int Cout,
-                          int Hout, int Wp, int kh, int kw, int pad_y, int stride, void* stream) {
-    B3D_REQUIRE(N > 0 && Cin > 0 && Cout > 0 && H > 0 && W > 0 && Hout > 0 && Wp > 0, B3D_EINVAL,
+int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, int N, int H, int W, int Cin, int Hout, int Wout,
+                          int Cout, int kh, int kw, int pad_y, int stride, void* stream) {
+    B3D_REQUIRE(N > 0 && Cin > 0 && Cout > 0 && H > 0 && W > 0 && Hout > 0 && Wout > 0, B3D_EINVAL,
                 "b3d_conv2d_wgrad_tf32: bad sizes");
     B3D_REQUIRE(kh * kw <= MAX_TAPS && (stride == 1 || stride == 2), B3D_EINVAL, "b3d_conv2d_wgrad_tf32: bad kernel/stride");
-    B3D_REQUIRE(dyp && x_nchw && dw, B3D_EINVAL, "b3d_conv2d_wgrad_tf32: null pointer");
-    B3D_REQUIRE(Wp * stride == W, B3D_EINVAL, "b3d_conv2d_wgrad_tf32: dY row pitch %d must equal W / stride = %d / %d", Wp, W,
-                stride);
-    B3D_REQUIRE((H * W) % 4 == 0 && (Hout * Wp) % 4 == 0, B3D_EINVAL,
-                "b3d_conv2d_wgrad_tf32: image planes must be multiples of 4 floats (16-byte TMA strides)");
-    B3D_CHECK_ALIGNED(dyp);
-    B3D_CHECK_ALIGNED(x_nchw);
+    B3D_REQUIRE(dy && x && dw, B3D_EINVAL, "b3d_conv2d_wgrad_tf32: null pointer");
+    B3D_REQUIRE(Cin % 4 == 0 && Cout % 4 == 0, B3D_EINVAL,
+                "b3d_conv2d_wgrad_tf32: Cin=%d and Cout=%d must be multiples of 4 (16-byte TMA strides)", Cin, Cout);
+    B3D_CHECK_ALIGNED(dy);
+    B3D_CHECK_ALIGNED(x);
     WgradParams p{};
-    p.N = N; p.Cout = Cout; p.Cin = Cin; p.W = W;
-    p.kslices = b3d::ceil_div(Hout * Wp, BK);
+    p.N = N; p.Hout = Hout; p.Wout = Wout; p.Cout = Cout; p.Cin = Cin;
+    p.BWk = pow2_floor(Wout < BK ? Wout : BK);
+    p.BHk = BK / p.BWk;
+    p.kx = b3d::ceil_div(Wout, p.BWk);
+    p.ky = b3d::ceil_div(Hout, p.BHk);
     p.kh = kh; p.kw = kw; p.pad_y = pad_y; p.st = stride;
     const int BN = Cin > 64 ? 128 : 64;
     const int base_ctas = b3d::ceil_div(Cout, BM) * b3d::ceil_div(Cin, BN) * kh * kw;
-    const long long ktotal = (long long)N * p.kslices;
+    const long long ktotal = (long long)N * p.kx * p.ky;
     int splits = (2 * 148 + base_ctas - 1) / base_ctas;          // aim at ~2 waves of CTAs
     if (splits > ktotal / 8) splits = (int)(ktotal / 8);         // at least 8 K slices per CTA
     if (splits < 1) splits = 1;
@@ -361,17 +366,17 @@ int b3d_conv2d_wgrad_tf32(const float* dyp, const float* x_nchw, float* dw, int 
 
     CUtensorMap mdy, mx;
     {
-        const uint64_t dims[3] = {(uint64_t)Hout * Wp, (uint64_t)Cout, (uint64_t)N};
-        const uint64_t strides[2] = {(uint64_t)Hout * Wp * 4, (uint64_t)Cout * Hout * Wp * 4};
-        const uint32_t box[3] = {(uint32_t)BK, (uint32_t)BM, 1};
-        if (int rc = tc::make_tmap_f32(&mdy, dyp, 3, dims, strides, box)) return rc;
+        const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)Wout, (uint64_t)Hout, (uint64_t)N};
+        const uint64_t strides[3] = {(uint64_t)Cout * 4, (uint64_t)Wout * Cout * 4, (uint64_t)Hout * Wout * Cout * 4};
+        const uint32_t box[4] = {32, (uint32_t)p.BWk, (uint32_t)p.BHk, 1};
+        if (int rc = tc::make_tmap_f32(&mdy, dy, 4, dims, strides, box)) return rc;
     }
     {
-        const uint64_t dims[3] = {(uint64_t)H * W, (uint64_t)Cin, (uint64_t)N};
-        const uint64_t strides[2] = {(uint64_t)H * W * 4, (uint64_t)Cin * H * W * 4};
-        const uint32_t box[3] = {(uint32_t)(stride * (BK - 1) + 1), (uint32_t)BN, 1};
-        const uint32_t es[3] = {(uint32_t)stride, 1, 1};
-        if (int rc = tc::make_tmap_f32(&mx, x_nchw, 3, dims, strides, box, es)) return rc;
+        const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        const uint64_t strides[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
+        const uint32_t box[4] = {32, (uint32_t)(stride * (p.BWk - 1) + 1), (uint32_t)(stride * (p.BHk - 1) + 1), 1};
+        const uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+        if (int rc = tc::make_tmap_f32(&mx, x, 4, dims, strides, box, es)) return rc;
     }
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(b3d::ceil_div(Cout, BM), b3d::ceil_div(Cin, BN), kh * kw * splits);

@@ -189,14 +189,13 @@ B3D_API int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, 
                             int sy, int sx, int OH, int OW, int OC, int osy, int osx, int ooy, int oox,
                             float leaky, void* stream);
 
-/* Weight gradient of the same convolution (split-K tcgen05 GEMM over the output pixels):
- *   dw[co, ci, r, s] += sum_{n,y,x} dy[n, co, y, x] * x[n, ci, stride*y + r - pad_y, stride*x + s]
- * NCHW operands (pixel-contiguous rows make both K-major).  dyp [N,Cout,Hout,Wp] is dy stored with the row pitch
- * Wp = W / stride of the input (columns >= Wout zero) so that a tap is a constant shift of the flattened pixel
- * index; x_nchw [N,Cin,H,W] (x already padded); H*W and Hout*Wp multiples of 4.
+/* Weight gradient of the same convolution (split-K tcgen05 GEMM over the output pixels, M/N-major operands
+ * straight from the NHWC tensors):
+ *   dw[co, ci, r, s] += sum_{n,y,x} dy[n, y, x, co] * x[n, stride*y + r - pad_y, stride*x + s, ci]
+ * dy [N,Hout,Wout,Cout], x [N,H,W,Cin] (x already padded along x; Cin, Cout multiples of 4),
  * dw [Cout,Cin,kh,kw] is ACCUMULATED into (caller zeroes it).                                          */
-B3D_API int b3d_conv2d_wgrad_tf32(const float* dyp, const float* x_nchw, float* dw, int N, int Cin, int H, int W,
-                                  int Cout, int Hout, int Wp, int kh, int kw, int pad_y, int stride,
+B3D_API int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, int N, int H, int W, int Cin,
+                                  int Hout, int Wout, int Cout, int kh, int kw, int pad_y, int stride,
                                   void* stream);
 
 #ifdef __cplusplus
