@@ -20,14 +20,16 @@ def taps_layout(weight):
     return weight.permute(2, 3, 0, 1).reshape(kh * kw, co, ci).contiguous()
 
 
-def conv2d_nhwc(x, weight, bias=None, pad_y=0, stride=1, leaky=1.0, wt=None):
+def conv2d_nhwc(x, weight, bias=None, pad_y=0, stride=1, leaky=1.0, wt=None, cin_major=False):
     """x [N,H,W,Cin] (Cin % 32 == 0), weight [Cout,Cin,kh,kw] -> [N,Hout,Wout,Cout]; zero pad along y only."""
     x = dev(x, "x")
     N, H, W, Cin = x.shape
     Cout, Cin_w, kh, kw = weight.shape
     if Cin_w != Cin:
         raise B3DError(f"conv2d: input has {Cin} channels, weight expects {Cin_w}")
-    wt = dev(taps_layout(weight) if wt is None else wt, "weight")
+    if wt is None:
+        wt = weight.permute(2, 3, 1, 0).reshape(kh * kw, Cin, Cout).contiguous() if cin_major else taps_layout(weight)
+    wt = dev(wt, "weight")
     Hout = (H + 2 * pad_y - kh) // stride + 1
     Wout = (W - kw) // stride + 1
     out = torch.empty(N, Hout, Wout, Cout, device=x.device, dtype=torch.float32)
@@ -35,7 +37,8 @@ def conv2d_nhwc(x, weight, bias=None, pad_y=0, stride=1, leaky=1.0, wt=None):
     dx = [s for _ in range(kh) for s in range(kw)]
     b = dev(bias, "bias") if bias is not None else None
     check(lib.b3d_conv2d_tf32(ptr(x), ptr(wt), ptr(b), ptr(out), N, H, W, Cin, Hout, Wout, Cout, kh * kw, _ints(dy),
-                              _ints(dx), stride, stride, Hout, Wout, Cout, 1, 1, 0, 0, float(leaky), stream_ptr(x)))
+                              _ints(dx), stride, stride, Hout, Wout, Cout, 1, 1, 0, 0, float(leaky), int(cin_major),
+                              stream_ptr(x)))
     return out
 
 
@@ -52,7 +55,7 @@ def conv2d_dgrad_nhwc(dy_, weight, in_hw, pad_y=0, stride=1):
         dy = [pad_y - r for r in range(kh) for _ in range(kw)]
         dx = [-s for _ in range(kh) for s in range(kw)]
         check(lib.b3d_conv2d_tf32(ptr(g), ptr(wt), None, ptr(dxo), N, Hout, Wout, Cout, H, W, Cin, kh * kw, _ints(dy),
-                                  _ints(dx), 1, 1, H, W, Cin, 1, 1, 0, 0, 1.0, st))
+                                  _ints(dx), 1, 1, H, W, Cin, 1, 1, 0, 0, 1.0, 0, st))
         return dxo
     if stride != 2:
         raise B3DError("conv2d_dgrad: stride must be 1 or 2")
@@ -68,7 +71,7 @@ def conv2d_dgrad_nhwc(dy_, weight, in_hw, pad_y=0, stride=1):
             dy = [(cy + pad_y - r) // 2 for r, s in rs]
             dx = [(cx - s) // 2 for r, s in rs]
             check(lib.b3d_conv2d_tf32(ptr(g), ptr(wt), None, ptr(dxo), N, Hout, Wout, Cout, Ha, Wa, Cin, len(rs),
-                                      _ints(dy), _ints(dx), 1, 1, H, W, Cin, 2, 2, cy, cx, 1.0, st))
+                                      _ints(dy), _ints(dx), 1, 1, H, W, Cin, 2, 2, cy, cx, 1.0, 0, st))
     return dxo
 
 

@@ -36,7 +36,7 @@ struct ConvParams {
     // epilogue: out pixel (n, oy*y + ooy, ox*x + oox) of a tensor [N, OH, OW, OC], channel offset 0
     int OH, OW, OC, osy, osx, ooy, oox;
     float leaky;                      // 1.0 = identity
-    int accumulate;                   // 1: out += result (used by the parity classes of strided dgrad? no: disjoint)
+    int dbg_lbo, dbg_sbo;             // MN-major descriptor offsets (bytes)
 };
 
 template <int BN, int STAGES>
@@ -47,7 +47,7 @@ struct Smem {
     static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool WMN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const ConvParams p, const float* __restrict__ bias, float* __restrict__ out) {
@@ -98,12 +98,17 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 unsigned char* b = a + S::A_BYTES;
                 tc::mbar_arrive_expect_tx(full + s, S::STAGE_BYTES);
                 tc::tma_load_4d(a, &tmap_x, full + s, ks * BK, p.sx * x0 + p.dx[tap], p.sy * y0 + p.dy[tap], n0);
-                tc::tma_load_3d(b, &tmap_w, full + s, ks * BK, c0, tap);
+                if constexpr (WMN) {      // weights [tap][Cin][Cout]: 32 cin rows x 32 cout per box (N-major B operand)
+#pragma unroll
+                    for (int nb = 0; nb < BN / 32; ++nb) tc::tma_load_3d(b + nb * 4096, &tmap_w, full + s, c0 + nb * 32, ks * BK, tap);
+                } else {
+                    tc::tma_load_3d(b, &tmap_w, full + s, ks * BK, c0, tap);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = tc::umma_idesc_tf32(BM, BN);
+            constexpr uint32_t idesc = tc::umma_idesc_tf32(BM, BN, false, WMN);
             for (int it = 0; it < KI; ++it) {
                 const int s = it % STAGES, ph = (it / STAGES) & 1;
                 tc::mbar_wait(full + s, ph);
@@ -113,7 +118,7 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k) {
                     const uint64_t da = tc::umma_desc_k128(a + k * UMMA_K * 4);
-                    const uint64_t db = tc::umma_desc_k128(b + k * UMMA_K * 4);
+                    const uint64_t db = WMN ? tc::umma_desc_mn128(b + k * 1024, p.dbg_lbo, p.dbg_sbo) : tc::umma_desc_k128(b + k * UMMA_K * 4);
                     tc::umma_tf32(tmem_acc, da, db, idesc, (it | k) ? 1u : 0u);
                 }
                 tc::umma_commit(empty + s);          // frees the stage when these MMAs have read it
@@ -267,14 +272,14 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
     if (warp == 2) tc::tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_acc);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool WMN>
 int launch(const CUtensorMap& mx, const CUtensorMap& mw, const ConvParams& p, const float* bias, float* out,
            int tiles, cudaStream_t st) {
     using S = Smem<BN, STAGES>;
-    B3D_CUDA_OK(cudaFuncSetAttribute(conv_tf32_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B3D_CUDA_OK(cudaFuncSetAttribute(conv_tf32_kernel<BN, STAGES, WMN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      S::TOTAL));
     dim3 grid(tiles, b3d::ceil_div(p.Cout, BN));
-    conv_tf32_kernel<BN, STAGES><<<grid, NTHREADS, S::TOTAL, st>>>(mx, mw, p, bias, out);
+    conv_tf32_kernel<BN, STAGES, WMN><<<grid, NTHREADS, S::TOTAL, st>>>(mx, mw, p, bias, out);
     B3D_LAUNCH_OK();
     return B3D_OK;
 }
@@ -294,7 +299,7 @@ extern "C" {
 // out [N, OH, OW, OC]; the tile grid covers (Hout, Wout) logical outputs, written to (osy*y+ooy, osx*x+oox)
 int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* out, int N, int H, int W, int Cin,
                     int Hout, int Wout, int Cout, int ntaps, const int* dy, const int* dx, int sy, int sx, int OH,
-                    int OW, int OC, int osy, int osx, int ooy, int oox, float leaky, void* stream) {
+                    int OW, int OC, int osy, int osx, int ooy, int oox, float leaky, int w_cin_major, void* stream) {
     B3D_REQUIRE(N > 0 && H > 0 && W > 0 && Hout > 0 && Wout > 0 && Cout > 0, B3D_EINVAL, "b3d_conv2d_tf32: bad sizes");
     B3D_REQUIRE(Cin > 0 && Cin % BK == 0, B3D_EINVAL, "b3d_conv2d_tf32: Cin=%d must be a multiple of %d", Cin, BK);
     B3D_REQUIRE(ntaps >= 1 && ntaps <= MAX_TAPS && dy && dx, B3D_EINVAL, "b3d_conv2d_tf32: bad taps");
@@ -315,6 +320,9 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
     for (int t = 0; t < ntaps; ++t) { p.dy[t] = dy[t]; p.dx[t] = dx[t]; }
     p.OH = OH; p.OW = OW; p.OC = OC; p.osy = osy; p.osx = osx; p.ooy = ooy; p.oox = oox;
     p.leaky = leaky;
+    p.dbg_lbo = 4096; p.dbg_sbo = 1024;
+    if (const char* e = getenv("B3D_DBG_LBO")) p.dbg_lbo = atoi(e);
+    if (const char* e = getenv("B3D_DBG_SBO")) p.dbg_sbo = atoi(e);
 
     CUtensorMap mx, mw;
     {
@@ -326,15 +334,24 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
         if (int rc = tc::make_tmap_f32(&mx, x, 4, dims, strides, box, es)) return rc;
     }
     const int BN = Cout > 64 ? 128 : 64;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (w_cin_major) {        // wt [ntaps, Cin, Cout]: the B operand is N-major (no weight transpose for dgrad)
+        B3D_REQUIRE(Cout % 4 == 0, B3D_EINVAL, "b3d_conv2d_tf32: Cout=%d must be a multiple of 4 for cin-major weights", Cout);
+        const uint64_t dims[3] = {(uint64_t)Cout, (uint64_t)Cin, (uint64_t)ntaps};
+        const uint64_t strides[2] = {(uint64_t)Cout * 4, (uint64_t)Cout * Cin * 4};
+        const uint32_t box[3] = {32, (uint32_t)BK, 1};
+        if (int rc = tc::make_tmap_f32(&mw, wt, 3, dims, strides, box)) return rc;
+        if (BN == 128) return launch<128, 6, true>(mx, mw, p, bias, out, tiles, st);
+        return launch<64, 8, true>(mx, mw, p, bias, out, tiles, st);
+    }
     {
         const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)ntaps};
         const uint64_t strides[2] = {(uint64_t)Cin * 4, (uint64_t)Cout * Cin * 4};
         const uint32_t box[3] = {(uint32_t)BK, (uint32_t)BN, 1};
         if (int rc = tc::make_tmap_f32(&mw, wt, 3, dims, strides, box)) return rc;
     }
-    cudaStream_t st = (cudaStream_t)stream;
-    if (BN == 128) return launch<128, 6>(mx, mw, p, bias, out, tiles, st);
-    return launch<64, 8>(mx, mw, p, bias, out, tiles, st);
+    if (BN == 128) return launch<128, 6, false>(mx, mw, p, bias, out, tiles, st);
+    return launch<64, 8, false>(mx, mw, p, bias, out, tiles, st);
 }
 
 // dy [N,Hout,Wout,Cout], x [N,H,W,Cin] NHWC (x already padded along x; Cin, Cout multiples of 4),

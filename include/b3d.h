@@ -180,14 +180,15 @@ B3D_API int b3d_chamfer_bwd(const float* query, const float* cand, const int32_t
  * as a tcgen05 / TMA implicit GEMM (tf32 inputs, fp32 accumulate — cuDNN's default TF32 class).
  *   out[n, osy*y+ooy, osx*x+oox, co] = leaky( bias[co] + sum_t sum_ci x[n, sy*y+dy[t], sx*x+dx[t], ci] * wt[t, co, ci] )
  * x [N,H,W,Cin] NHWC fp32 (Cin % 32 == 0; reads outside [0,H)x[0,W) are zero = the conv's zero padding),
- * wt [ntaps,Cout,Cin], bias [Cout] nullable, out [N,OH,OW,OC]; (y,x) run over [0,Hout)x[0,Wout).
+ * wt [ntaps,Cout,Cin] (w_cin_major = 0) or [ntaps,Cin,Cout] (w_cin_major = 1: N-major B operand, Cout % 4 == 0),
+ * bias [Cout] nullable, out [N,OH,OW,OC]; (y,x) run over [0,Hout)x[0,Wout).
  * fprop: dy = r - pad_y, dx = s.  dgrad: dy = pad_y - r, dx = -s with wt[t] = W[:,:,r,s]^T (strided dgrad = one
  * call per output parity class with osy = osx = 2).  leaky = negative slope of the fused LeakyReLU (1 = none).
  * ------------------------------------------------------------------------------------------ */
 B3D_API int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* out, int N, int H, int W,
                             int Cin, int Hout, int Wout, int Cout, int ntaps, const int* dy, const int* dx,
                             int sy, int sx, int OH, int OW, int OC, int osy, int osx, int ooy, int oox,
-                            float leaky, void* stream);
+                            float leaky, int w_cin_major, void* stream);
 
 /* Weight gradient of the same convolution (split-K tcgen05 GEMM over the output pixels, M/N-major operands
  * straight from the NHWC tensors):
