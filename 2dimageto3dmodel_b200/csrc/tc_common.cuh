@@ -131,13 +131,14 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
 // MN-major operand, 128-byte swizzle: the tile is stored as [mn block of 32][k rows][32 fp32 along M/N]; one
 // swizzle atom = 8 k-rows x 128 B.  Leading byte offset = distance between consecutive 32-wide M/N blocks,
 // stride byte offset = distance between consecutive groups of 8 k-rows.
-__device__ __forceinline__ uint64_t umma_desc_mn128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t umma_desc_mn128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                     uint32_t layout_type = 1) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)layout_type << 61;                   // 1 = SWIZZLE_128B with 32-byte atoms (32-bit MN-major)
     return d;
 }
 
@@ -170,7 +171,8 @@ inline EncodeTiledFn encode_fn() {
 
 // fp32 tensor, `rank` dims listed innermost first; strides in BYTES for dims 1..rank-1; 128-byte swizzle
 inline int make_tmap_f32(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
-                         const uint32_t* box, const uint32_t* elem_strides = nullptr) {
+                         const uint32_t* box, const uint32_t* elem_strides = nullptr,
+                         CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) {
         b3d::set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -185,7 +187,7 @@ inline int make_tmap_f32(CUtensorMap* m, const void* base, int rank, const uint6
         if (i > 0) gs[i - 1] = strides_b[i - 1];
     }
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         b3d::set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, inner box %u)", (int)r, rank, box[0]);

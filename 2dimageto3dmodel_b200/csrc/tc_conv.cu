@@ -36,7 +36,7 @@ struct ConvParams {
     // epilogue: out pixel (n, oy*y + ooy, ox*x + oox) of a tensor [N, OH, OW, OC], channel offset 0
     int OH, OW, OC, osy, osx, ooy, oox;
     float leaky;                      // 1.0 = identity
-    int dbg_lbo, dbg_sbo;             // MN-major descriptor offsets (bytes)
+    int dbg_lbo, dbg_sbo, dbg_lt;     // MN-major descriptor offsets (bytes), layout type
 };
 
 template <int BN, int STAGES>
@@ -118,7 +118,7 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k) {
                     const uint64_t da = tc::umma_desc_k128(a + k * UMMA_K * 4);
-                    const uint64_t db = WMN ? tc::umma_desc_mn128(b + k * 1024, p.dbg_lbo, p.dbg_sbo) : tc::umma_desc_k128(b + k * UMMA_K * 4);
+                    const uint64_t db = WMN ? tc::umma_desc_mn128(b + k * 1024, p.dbg_lbo, p.dbg_sbo, p.dbg_lt) : tc::umma_desc_k128(b + k * UMMA_K * 4);
                     tc::umma_tf32(tmem_acc, da, db, idesc, (it | k) ? 1u : 0u);
                 }
                 tc::umma_commit(empty + s);          // frees the stage when these MMAs have read it
@@ -320,9 +320,12 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
     for (int t = 0; t < ntaps; ++t) { p.dy[t] = dy[t]; p.dx[t] = dx[t]; }
     p.OH = OH; p.OW = OW; p.OC = OC; p.osy = osy; p.osx = osx; p.ooy = ooy; p.oox = oox;
     p.leaky = leaky;
-    p.dbg_lbo = 4096; p.dbg_sbo = 1024;
+    p.dbg_lbo = 4096; p.dbg_sbo = 512; p.dbg_lt = 1;
+    int dbg_swz = 4;
     if (const char* e = getenv("B3D_DBG_LBO")) p.dbg_lbo = atoi(e);
     if (const char* e = getenv("B3D_DBG_SBO")) p.dbg_sbo = atoi(e);
+    if (const char* e = getenv("B3D_DBG_LT")) p.dbg_lt = atoi(e);
+    if (const char* e = getenv("B3D_DBG_SWZ")) dbg_swz = atoi(e);
 
     CUtensorMap mx, mw;
     {
@@ -340,7 +343,7 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
         const uint64_t dims[3] = {(uint64_t)Cout, (uint64_t)Cin, (uint64_t)ntaps};
         const uint64_t strides[2] = {(uint64_t)Cout * 4, (uint64_t)Cout * Cin * 4};
         const uint32_t box[3] = {32, (uint32_t)BK, 1};
-        if (int rc = tc::make_tmap_f32(&mw, wt, 3, dims, strides, box)) return rc;
+        if (int rc = tc::make_tmap_f32(&mw, wt, 3, dims, strides, box, nullptr, (CUtensorMapSwizzle)dbg_swz)) return rc;
         if (BN == 128) return launch<128, 6, true>(mx, mw, p, bias, out, tiles, st);
         return launch<64, 8, true>(mx, mw, p, bias, out, tiles, st);
     }
