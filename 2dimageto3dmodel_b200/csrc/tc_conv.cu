@@ -161,9 +161,10 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 // wgrad:  dW[co, ci, r, s] += sum_{n,y,x} dY[n, y, x, co] * X[n, st*y + r - pad_y, st*x + s, ci]      (NHWC operands)
 // GEMM with M = Cout (128), N = Cin (BN), K = output pixels.  In NHWC the reduction index (pixel) is the SLOW index
 // of both operands, i.e. they are M/N-major: a K slice is a BWk x BHk box of 32 output pixels, loaded as 32-channel
-// wide TMA boxes ([32 pixels][32 channels], 128-byte swizzled rows) — four for dY, BN/32 for X, the X boxes shifted
-// by the tap on the OUTER dims (zero fill = padding, element strides for stride 2).  tcgen05.mma reads them through
-// MN-major shared-memory descriptors (transposed operands), so no NCHW copy of any activation is ever made.
+// wide TMA boxes ([32 pixels][32 channels], CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) — four for dY, BN/32 for X, the X
+// boxes shifted by the tap on the OUTER dims (zero fill = padding, element strides for stride 2).  tcgen05.mma reads
+// them through MN-major shared-memory descriptors (layout SWIZZLE_128B_BASE32B — the 32-bit transpose layout: 4-row
+// atoms, SBO 512 B, LBO 4096 B; plain SWIZZLE_128B yields zeros for tf32, measured), so no NCHW copy is ever made.
 // One CTA per (co tile, ci tile, tap, K split); partial sums are reduced into dW with red.global.add.f32.
 // ----------------------------------------------------------------------------------------------
 struct WgradParams {
@@ -242,9 +243,9 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
                 const uint32_t a = tc::smem_u32(base + st * S::STAGE_BYTES);
                 const uint32_t b = a + S::A_BYTES;
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k)      // 8 pixel rows = one swizzle atom (1024 B) per MMA
-                    tc::umma_tf32(tmem_acc, tc::umma_desc_mn128(a + k * 1024, BLK, 1024),
-                                  tc::umma_desc_mn128(b + k * 1024, BLK, 1024), idesc, (it | k) ? 1u : 0u);
+                for (int k = 0; k < BK / UMMA_K; ++k)      // 8 pixel rows (two 4-row swizzle atoms, 1024 B) per MMA
+                    tc::umma_tf32(tmem_acc, tc::umma_desc_mn128(a + k * 1024, BLK, 512),
+                                  tc::umma_desc_mn128(b + k * 1024, BLK, 512), idesc, (it | k) ? 1u : 0u);
                 tc::umma_commit(empty + st);
             }
             tc::umma_commit(acc_full);
@@ -320,12 +321,7 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
     for (int t = 0; t < ntaps; ++t) { p.dy[t] = dy[t]; p.dx[t] = dx[t]; }
     p.OH = OH; p.OW = OW; p.OC = OC; p.osy = osy; p.osx = osx; p.ooy = ooy; p.oox = oox;
     p.leaky = leaky;
-    p.dbg_lbo = 4096; p.dbg_sbo = 512; p.dbg_lt = 1;
-    int dbg_swz = 4;
-    if (const char* e = getenv("B3D_DBG_LBO")) p.dbg_lbo = atoi(e);
-    if (const char* e = getenv("B3D_DBG_SBO")) p.dbg_sbo = atoi(e);
-    if (const char* e = getenv("B3D_DBG_LT")) p.dbg_lt = atoi(e);
-    if (const char* e = getenv("B3D_DBG_SWZ")) dbg_swz = atoi(e);
+    p.dbg_lbo = 4096; p.dbg_sbo = 512; p.dbg_lt = 1;     // 32-bit MN-major: SWIZZLE_128B_BASE32B, 4-row atoms
 
     CUtensorMap mx, mw;
     {
@@ -343,7 +339,7 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
         const uint64_t dims[3] = {(uint64_t)Cout, (uint64_t)Cin, (uint64_t)ntaps};
         const uint64_t strides[2] = {(uint64_t)Cout * 4, (uint64_t)Cout * Cin * 4};
         const uint32_t box[3] = {32, (uint32_t)BK, 1};
-        if (int rc = tc::make_tmap_f32(&mw, wt, 3, dims, strides, box, nullptr, (CUtensorMapSwizzle)dbg_swz)) return rc;
+        if (int rc = tc::make_tmap_f32(&mw, wt, 3, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
         if (BN == 128) return launch<128, 6, true>(mx, mw, p, bias, out, tiles, st);
         return launch<64, 8, true>(mx, mw, p, bias, out, tiles, st);
     }
@@ -389,14 +385,14 @@ int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, int N, int
         const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)Wout, (uint64_t)Hout, (uint64_t)N};
         const uint64_t strides[3] = {(uint64_t)Cout * 4, (uint64_t)Wout * Cout * 4, (uint64_t)Hout * Wout * Cout * 4};
         const uint32_t box[4] = {32, (uint32_t)p.BWk, (uint32_t)p.BHk, 1};
-        if (int rc = tc::make_tmap_f32(&mdy, dy, 4, dims, strides, box)) return rc;
+        if (int rc = tc::make_tmap_f32(&mdy, dy, 4, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
     }
     {
         const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
         const uint64_t strides[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
         const uint32_t box[4] = {32, (uint32_t)(stride * (p.BWk - 1) + 1), (uint32_t)(stride * (p.BHk - 1) + 1), 1};
         const uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
-        if (int rc = tc::make_tmap_f32(&mx, x, 4, dims, strides, box, es)) return rc;
+        if (int rc = tc::make_tmap_f32(&mx, x, 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
     }
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(b3d::ceil_div(Cout, BM), b3d::ceil_div(Cin, BN), kh * kw * splits);
