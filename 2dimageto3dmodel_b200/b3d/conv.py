@@ -85,3 +85,53 @@ def conv2d_wgrad_nhwc(dy_, x, kh, kw, pad_y=0, stride=1):
     check(lib.b3d_conv2d_wgrad_tf32(ptr(g), ptr(x), ptr(dw), N, H, W, Cin, Hout, Wout, Cout, kh, kw, pad_y, stride,
                                     stream_ptr(g)))
     return dw
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# autograd: y = conv(x, w) + b on NHWC tensors; fprop / dgrad / wgrad all on the tcgen05 kernels
+# ------------------------------------------------------------------------------------------------------------------
+def _pad_last(t, mult):
+    c = t.shape[-1]
+    return t if c % mult == 0 else torch.nn.functional.pad(t, (0, mult - c % mult))
+
+
+class _Conv2dNHWC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, pad_y, stride):
+        x = dev(x.detach(), "x")
+        w = weight.detach()
+        Cin = x.shape[3]
+        if Cin % 32:                                    # thin inputs (discriminator stems: 8 / 11 channels): zero-pad K
+            x = _pad_last(x, 32)
+            w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, x.shape[3] - Cin))
+        y = conv2d_nhwc(x, w, bias.detach() if bias is not None else None, pad_y=pad_y, stride=stride)
+        ctx.save_for_backward(x, w)
+        ctx.cfg = (pad_y, stride, Cin, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        pad_y, stride, Cin, has_bias = ctx.cfg
+        Cout, _, kh, kw = w.shape
+        gy = dev(gy, "grad_output")
+        gb = gy.sum(dim=(0, 1, 2)) if has_bias and ctx.needs_input_grad[2] else None
+        gyp, wp = gy, w
+        if Cout % 32:                                   # heads with 1 / 3 output channels: zero-pad the reduction dim
+            gyp = _pad_last(gy, 32)
+            wp = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, 0, 0, gyp.shape[3] - Cout))
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = conv2d_dgrad_nhwc(gyp, wp, (x.shape[1], x.shape[2]), pad_y=pad_y, stride=stride)[..., :Cin]
+        if ctx.needs_input_grad[1]:
+            gw = conv2d_wgrad_nhwc(gyp, x, kh, kw, pad_y=pad_y, stride=stride)[:Cout, :Cin]
+        return gx, gw, gb, None, None
+
+
+def conv2d(x_nchw, weight, bias=None, pad_y=0, stride=1):
+    """Drop-in for F.conv2d(x, w, b, stride, padding=(pad_y, 0)) on logically-NCHW tensors: runs on the tcgen05
+    kernels over the channels-last storage (a no-copy view when x is already channels_last) and returns a
+    logically-NCHW, channels-last tensor."""
+    x = x_nchw.permute(0, 2, 3, 1)
+    y = _Conv2dNHWC.apply(x, weight, bias, int(pad_y), int(stride))
+    return y.permute(0, 3, 1, 2)

@@ -1,0 +1,351 @@
+"""Drop-in for /root/reference/code/models/gan.py: the conv-GAN texture/mesh generator and the multi-scale
+discriminators, with every nn.Conv2d running on libb3d's tcgen05 / TMA implicit-GEMM kernels
+(csrc/tc_conv.cu: fprop, dgrad, wgrad; tf32 inputs, fp32 accumulate).
+
+Module tree, parameter and buffer names equal the reference's, so its checkpoints load with strict=True
+(`blk1.conv1.weight_orig / weight_u / weight_v`, `blk1.norm1.norm.running_mean`, `blk1.norm1.fc_gamma.weight`,
+`emb_class.weight`, `fc.weight`, ... — SURVEY.md §8b).  Spectral normalisation is torch's own
+nn.utils.spectral_norm hook (parameter plumbing, one mat-vec per layer), as in the reference.
+Activations stay logically NCHW (the reference's interface) and physically channels-last, which is what the
+kernels read; x-padding (replicate for the symmetric generator, circular for the discriminators) is explicit
+as in the reference, y-padding is the convolution's zero padding (TMA out-of-bounds fill).
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from b3d import B3DError
+from b3d.conv import conv2d as _tc_conv2d
+from rendering.utils import adjust_poles, circpad, symmetrize_texture
+
+
+class TCConv2d(nn.Conv2d):
+    """nn.Conv2d (same parameters / state dict) whose forward runs on the tensor-core kernels."""
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise B3DError("models.gan convolutions run on CUDA only (libb3d tcgen05 kernels); there is no CPU fallback")
+        if self.padding[1] != 0 or self.stride[0] != self.stride[1] or self.dilation != (1, 1) or self.groups != 1:
+            raise B3DError("TCConv2d supports zero padding along y only, square strides, no dilation / groups")
+        return _tc_conv2d(x, self.weight, self.bias, pad_y=self.padding[0], stride=self.stride[0])
+
+
+def positional_encoding(Ny, Nx):
+    """[4, Ny, Nx] = cos/sin of the latitude (rows, 0..pi) and of the longitude (columns, -pi..pi, wrapping
+    smoothly); for a half-width (symmetric) map only the central half of the longitudes is kept (reference :9-20)."""
+    half = (Nx == Ny // 2)
+    lat = torch.arange(Ny, dtype=torch.float64) * (math.pi / Ny)
+    lon = -math.pi + torch.arange(Ny, dtype=torch.float64) * (2 * math.pi / Ny)
+    rows, cols = lat.view(Ny, 1).expand(Ny, Ny), lon.view(1, Ny).expand(Ny, Ny)
+    enc = torch.stack((rows.cos(), rows.sin(), cols.cos(), cols.sin()))
+    if half:
+        enc = enc[:, :, Ny // 4: Ny - Ny // 4]
+    return enc.numpy()
+
+
+def _norm_and_bias(args):
+    if args.norm_d == 'instance':
+        return (lambda ch: nn.InstanceNorm2d(ch, affine=True)), False
+    if args.norm_d == 'none':
+        return (lambda ch: (lambda x: x)), True
+    raise ValueError(f"norm_d={args.norm_d!r}")
+
+
+class _DiscriminatorBase(nn.Module):
+    """Shared pieces of the two discriminators: wrap-around padding, positional channels, projection head."""
+
+    def _setup(self, args, circular, positional_embeddings):
+        self.args = args
+        self.circular = circular
+        self.positional_embeddings = positional_embeddings
+        if circular:
+            self.pad = lambda x: circpad(x, 2)       # in front of the 5x5 convolutions
+            self.pad2 = lambda x: circpad(x, 1)      # in front of the 4x4 / stride-2 convolutions
+        else:
+            self.pad = lambda x: x
+        if positional_embeddings:
+            self.pos_emb = None
+
+    def _with_positions(self, x, extra=()):
+        parts = [x, *extra]
+        if self.positional_embeddings:
+            if self.pos_emb is None:
+                self.pos_emb = torch.FloatTensor(positional_encoding(x.shape[2], x.shape[3])).unsqueeze(0)
+            parts.append(self.pos_emb.to(x.device).expand(x.shape[0], -1, -1, -1))
+        return torch.cat(parts, dim=1) if len(parts) > 1 else x
+
+    def _project(self, y, feat, c, caption):
+        a = self.args
+        if a.conditional_class:        # projection discriminator
+            emb = self.projector(c[:, 0])
+            if a.conditional_color:
+                emb = emb + self.projector_col1(c[:, 1])
+            y = y + (feat * emb[:, :, None, None]).sum(dim=1, keepdim=True)
+        elif a.conditional_text:
+            att, _ = self.att(feat, *caption)
+            y = y + (feat * att).sum(dim=1, keepdim=True)
+        return y
+
+
+class MeshDiscriminator(_DiscriminatorBase):
+    def __init__(self, args, nc, circular=True, positional_embeddings=True):
+        super().__init__()
+        norm_layer, bias = _norm_and_bias(args)
+        self._setup(args, circular, positional_embeddings)
+        if args.conditional_text:
+            self.att = SpatialAttention(256, args.text_embedding_dim)
+        k5pad = (2, 0) if circular else 2
+        if positional_embeddings:
+            nc += 4
+        sn = nn.utils.spectral_norm
+        self.conv1 = sn(TCConv2d(nc, 64, 5, padding=k5pad, stride=1))
+        self.conv2 = sn(TCConv2d(64, 128, 4, padding=(1, 0), stride=2, bias=bias))
+        self.bn2 = norm_layer(128)
+        self.conv3 = sn(TCConv2d(128, 256, 4, padding=(1, 0), stride=2, bias=bias))
+        self.bn3 = norm_layer(256)
+        self.conv4 = sn(TCConv2d(256, 1, 5, padding=k5pad, stride=1))
+        self.relu = nn.LeakyReLU(0.2, inplace=True)
+        if args.conditional_class:
+            self.projector = nn.Embedding(args.n_classes[0], 256)
+            if args.conditional_color:
+                self.projector_col1 = nn.Embedding(args.n_classes[1], 256)
+
+    def forward(self, texture, mesh_map, c=None, caption=None):
+        x = F.avg_pool2d(texture, texture.shape[2] // mesh_map.shape[2])      # texture at mesh resolution (32x32)
+        x = self._with_positions(x, (mesh_map,))
+        mask = None
+        if self.args.mask_output:
+            with torch.no_grad():
+                mask = F.avg_pool2d(x[:, 3:4], 4)
+        x = self.relu(self.conv1(self.pad(x)))
+        x = self.relu(self.bn2(self.conv2(self.pad2(x))))
+        x = self.relu(self.bn3(self.conv3(self.pad2(x))))
+        y = self._project(self.conv4(self.pad(x)), x, c, caption)
+        return y, mask
+
+
+class TextureDiscriminator(_DiscriminatorBase):
+    def __init__(self, args, nc, downsample=1, circular=True, positional_embeddings=True):
+        super().__init__()
+        norm_layer, bias = _norm_and_bias(args)
+        self._setup(args, circular, positional_embeddings)
+        if args.conditional_text:
+            self.att = SpatialAttention(512, args.text_embedding_dim)
+        k5pad = (2, 0) if circular else 2
+        if positional_embeddings:
+            nc += 4
+        sn = nn.utils.spectral_norm
+        # full-resolution 512^2 textures (and all 1024^2 ones) are halved by the very first layer
+        self.stride_first = (downsample == 1 and args.texture_resolution >= 512) or args.texture_resolution >= 1024 \
+            or args.conditional_text
+        if self.stride_first:
+            self.padconv1 = self.pad2
+            self.conv1 = sn(TCConv2d(nc, 64, 4, padding=(1, 0), stride=2))
+        else:
+            self.padconv1 = self.pad
+            self.conv1 = sn(TCConv2d(nc, 64, 5, padding=k5pad, stride=1))
+        self.conv2 = sn(TCConv2d(64, 128, 4, padding=(1, 0), stride=2, bias=bias))
+        self.bn2 = norm_layer(128)
+        self.conv3 = sn(TCConv2d(128, 256, 4, padding=(1, 0), stride=2, bias=bias))
+        self.bn3 = norm_layer(256)
+        self.conv4 = sn(TCConv2d(256, 512, 4, padding=(1, 0), stride=2, bias=bias))
+        self.bn4 = norm_layer(512)
+        self.conv5 = sn(TCConv2d(512, 1, 5, padding=k5pad, stride=1))
+        self.relu = nn.LeakyReLU(0.2, inplace=True)
+        self.downsample = downsample
+        if args.conditional_class:
+            self.projector = nn.Embedding(args.n_classes[0], 512)
+            if args.conditional_color:
+                self.projector_col1 = nn.Embedding(args.n_classes[1], 512)
+
+    def forward(self, x, c=None, caption=None):
+        if self.downsample > 1:
+            x = F.avg_pool2d(x, self.downsample)
+        mask = None
+        if self.args.mask_output:
+            with torch.no_grad():
+                mask = F.avg_pool2d(x[:, 3:4], 16 if self.stride_first else 8)
+        x = self._with_positions(x)
+        x = self.relu(self.conv1(self.padconv1(x)))
+        x = self.relu(self.bn2(self.conv2(self.pad2(x))))
+        x = self.relu(self.bn3(self.conv3(self.pad2(x))))
+        x = self.relu(self.bn4(self.conv4(self.pad2(x))))
+        y = self._project(self.conv5(self.pad(x)), x, c, caption)
+        return y, mask
+
+
+class MultiScaleDiscriminator(nn.Module):
+    def __init__(self, args, nc):
+        super().__init__()
+        self.args = args
+        if args.num_discriminators not in (2, 3):
+            raise ValueError("num_discriminators must be 2 or 3")
+        self.d1 = TextureDiscriminator(args, nc, 1)
+        self.d2 = TextureDiscriminator(args, nc, 2) if args.texture_only else MeshDiscriminator(args, nc + 3)
+        if args.num_discriminators == 3:
+            self.d3 = TextureDiscriminator(args, nc, 4)
+
+    def forward(self, x, mesh_map=None, c=None, caption=None):
+        d1, m1 = self.d1(x, c, caption)
+        d2, m2 = self.d2(x, c, caption) if self.args.texture_only else self.d2(x, mesh_map, c, caption)
+        if self.args.num_discriminators == 3:
+            d3, m3 = self.d3(x, c, caption)
+            return [d1, d2, d3], [m1, m2, m3]
+        return [d1, d2], [m1, m2]
+
+
+class ConditionalBatchNorm2d(nn.Module):
+    def __init__(self, args, ch, emb_dim):
+        super().__init__()
+        kind = args.norm_g
+        if kind == 'syncbatch':
+            from sync_batchnorm import SynchronizedBatchNorm2d
+            self.norm = SynchronizedBatchNorm2d(ch, affine=False)
+        elif kind == 'batch':
+            self.norm = nn.BatchNorm2d(ch, affine=False)
+        elif kind == 'instance':
+            self.norm = nn.InstanceNorm2d(ch, affine=False)
+        elif kind == 'none':
+            self.norm = lambda x: x
+        else:
+            raise ValueError(f"norm_g={kind!r}")
+        self.fc_gamma = nn.Linear(emb_dim, ch)
+        self.fc_beta = nn.Linear(emb_dim, ch)
+
+    def forward(self, x, z):
+        g = self.fc_gamma(z)[:, :, None, None]
+        b = self.fc_beta(z)[:, :, None, None]
+        return self.norm(x) * (1 + g) + b
+
+
+class ResBlockUp(nn.Module):
+    def __init__(self, args, ch_in, ch_out, emb_dim, pad_fn):
+        super().__init__()
+        mid = min(ch_in, ch_out)
+        self.ch_out = ch_out
+        sn = nn.utils.spectral_norm
+        self.conv1 = sn(TCConv2d(ch_in, mid, 3, padding=(1, 0), bias=False))
+        self.conv2 = sn(TCConv2d(mid, ch_out, 3, padding=(1, 0), bias=False))
+        self.norm1 = ConditionalBatchNorm2d(args, mid, emb_dim)
+        self.norm2 = ConditionalBatchNorm2d(args, ch_out, emb_dim)
+        self.relu = nn.LeakyReLU(0.2, inplace=True)
+        self.pad = pad_fn
+        self.shortcut = sn(TCConv2d(ch_in, ch_out, 1, bias=False)) if ch_in != ch_out else (lambda x: x)
+
+    def forward(self, x, z):
+        skip = self.shortcut(x)
+        h = self.relu(self.norm1(self.conv1(self.pad(x, 1)), z))
+        h = self.relu(self.norm2(self.conv2(self.pad(h, 1)), z))
+        return h + skip
+
+
+class Generator(nn.Module):
+    def __init__(self, args, emb_dim, symmetric=True, mesh_head=True):
+        super().__init__()
+        self.relu = nn.LeakyReLU(0.2, inplace=True)
+        self.up = lambda x: F.interpolate(x, scale_factor=2, mode='nearest')
+        self.args, self.symmetric, self.mesh_head = args, symmetric, mesh_head
+        self.height, self.width = 8, (4 if symmetric else 8)
+        if symmetric:    # half-width map: an even-mirror border equals edge replication for 3x3 / 5x5 kernels
+            self.pad = lambda x, amount: F.pad(x, (amount, amount, 0, 0), mode='replicate')
+        else:
+            self.pad = lambda x, amount: circpad(x, amount)
+
+        if args.conditional_class and args.conditional_color:
+            self.emb_class = nn.Embedding(args.n_classes[0], emb_dim // 2)
+            self.emb_color = nn.Embedding(args.n_classes[1], emb_dim // 2)
+            emb_dim += emb_dim
+        elif args.conditional_class:
+            self.emb_class = nn.Embedding(args.n_classes[0], emb_dim)
+            emb_dim += emb_dim
+
+        self.fc = nn.Linear(emb_dim, self.height * self.width * 512)
+        block = lambda cin, cout: ResBlockUp(args, cin, cout, emb_dim, self.pad)
+        self.blk1 = block(512, 512)
+        self.blk2 = block(512, 256)
+        res = args.texture_resolution
+        if res >= 256:
+            self.blk3a = block(256, 256)
+        if res >= 512:
+            self.blk3b = block(256, 256)
+        if res >= 1024:
+            self.blk3c = block(256, 256)
+        if args.conditional_text:
+            self.att = SpatialAttention(256, args.text_embedding_dim)
+        self.blk4 = block(256, 128)
+        self.blk5 = block(128, 128)
+        self.blk6 = block(128, 64)
+        self.conv_final = TCConv2d(64, 3, 5, padding=(2, 0))
+        if mesh_head:
+            self.blk3_mesh = block(256, 64)
+            self.conv_mesh = TCConv2d(64, 3, 5, padding=(2, 0))
+            with torch.no_grad():      # start from the undeformed template
+                self.conv_mesh.weight.zero_()
+                self.conv_mesh.bias.zero_()
+
+    def forward(self, z, c=None, caption=None, return_attention=False):
+        a = self.args
+        if a.conditional_class:
+            if c is None:
+                raise AssertionError("class-conditional generator needs c")
+            cond = [z, self.emb_class(c[:, 0])]
+            if a.conditional_color:
+                cond.append(self.emb_color(c[:, 1]))
+            z = torch.cat(cond, dim=1)
+
+        x = self.fc(z).view(z.shape[0], -1, self.height, self.width)
+        x = x.contiguous(memory_format=torch.channels_last)
+        x = self.up(self.blk1(x, z))
+        x = self.blk2(x, z)
+        attention_map = None
+        if a.conditional_text:
+            att, attention_map = self.att(x, *caption)
+            x = x + att
+        x = self.up(x)
+
+        t = x
+        for name in ('blk3a', 'blk3b', 'blk3c'):
+            if hasattr(self, name):
+                t = self.up(getattr(self, name)(t, z))
+        t = self.up(self.blk4(t, z))
+        t = self.up(self.blk5(t, z))
+        t = self.relu(self.blk6(t, z))
+        x_tex = torch.tanh(self.conv_final(self.pad(t, 2)))
+
+        x_mesh = None
+        if self.mesh_head:
+            m = self.relu(self.blk3_mesh(x, z))
+            x_mesh = adjust_poles(self.conv_mesh(self.pad(m, 2)))
+
+        if self.symmetric:
+            x_tex = symmetrize_texture(x_tex)
+            if x_mesh is not None:
+                x_mesh = symmetrize_texture(x_mesh)
+            if attention_map is not None:
+                attention_map = symmetrize_texture(attention_map)
+        return (x_tex, x_mesh, attention_map) if return_attention else (x_tex, x_mesh)
+
+
+class SpatialAttention(nn.Module):
+    """Word-level attention of the text-conditional variant (reference :433-481, AttnGAN-style).  Kept for
+    state-dict / constructor compatibility; the text branch is dead in the reference (its RNN_Encoder is never
+    defined), so it runs on stock torch ops."""
+
+    def __init__(self, input_dim, context_dim):
+        super().__init__()
+        self.conv_context = nn.Conv2d(context_dim, input_dim, 1, stride=1, padding=0, bias=False)
+        self.sm = nn.Softmax(dim=1)
+
+    def forward(self, input, context, mask):
+        B, _, ih, iw = input.shape
+        L = context.size(2)
+        q = input.reshape(B, -1, ih * iw).transpose(1, 2)                    # B x HW x C
+        src = self.conv_context(context.unsqueeze(3)).squeeze(3)              # B x C x L
+        att = torch.bmm(q, src).view(B * ih * iw, L)
+        if mask is not None:
+            att = att + mask.unsqueeze(1).expand(-1, ih * iw, -1).reshape(B * ih * iw, L).float() * -10000
+        att = self.sm(att).view(B, ih * iw, L).transpose(1, 2)                # B x L x HW
+        out = torch.bmm(src, att).view(B, -1, ih, iw)
+        return out, att.reshape(B, -1, ih, iw)

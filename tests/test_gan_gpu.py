@@ -1,0 +1,83 @@
+"""The CUDA GAN (tcgen05 convs) against golden vectors produced by the reference's modules on the CPU
+(tests/golden/make_golden_gan.py): same seeds -> same weights, same inputs; one generator step and one
+discriminator step in training mode (spectral-norm power iteration, batch statistics, hinge losses, backward).
+
+Tolerance: the reference golden is exact fp32; the tensor cores compute in tf32 (10-bit mantissa, the class
+cuDNN uses by default).  Through ~25 stacked convolutions we allow 2e-2 of the largest magnitude for
+activations, 2e-2 relative for losses, and 6e-2 relative for per-parameter gradient norms."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+sys.path.insert(0, GOLDEN)
+import gan_common as GC          # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def close(a, ref, tol):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a
+    err = float(np.abs(a - ref).max())
+    lim = tol * max(float(np.abs(ref).max()), 1e-6)
+    assert err <= lim, (err, lim)
+
+
+def test_gan_steps_match_reference_golden():
+    from models import gan
+    from utils.losses import GANLoss
+    d = np.load(os.path.join(GOLDEN, "gan_reference.npz"))
+    args = GC.make_args(256, 2)
+    G, D = GC.build(gan, args)
+    G.cuda().train(); D.cuda().train()
+    crit = GANLoss('hinge', tensor=torch.cuda.FloatTensor)
+    z, c, alpha, tex, mesh = [t.cuda() for t in GC.inputs(args)]
+    loss, pred_tex, pred_mesh, dout, mask = GC.g_step(G, D, crit, z, c, alpha)
+    loss.mean().backward()
+    close(pred_tex[:, :, ::16, ::16], d["tex_probe"], 2e-2)
+    assert abs(float(pred_tex.double().sum()) - float(d["tex_sum"])) < 2e-2 * pred_tex.numel() ** 0.5 * 5
+    close(pred_mesh, d["mesh"], 2e-2)
+    close(dout[0], d["d_out0"], 2e-2)
+    close(dout[1], d["d_out1"], 2e-2)
+    close(mask[0], d["mask0"], 1e-6)
+    close(mask[1], d["mask1"], 1e-6)
+    assert abs(float(loss) - float(d["g_loss"])) < 2e-2 * abs(float(d["g_loss"]))
+    params = dict(G.named_parameters())
+    for name, ref in zip(d["g_grad_names"], d["g_grad_norms"]):
+        got = float(params[str(name)].grad.norm())
+        assert abs(got - ref) <= 6e-2 * ref + 1e-7, (str(name), got, ref)
+    close(G.blk5.conv1.weight_orig.grad[:4, :4], d["g_grad_probe"], 6e-2)
+    close(G.blk1.conv1.weight_u, d["sn_u_blk1"], 1e-4)
+    close(G.blk6.norm2.norm.running_mean, d["bn_mean_blk6"], 2e-2)
+    G.zero_grad(); D.zero_grad()
+    lf, lr, dout = GC.d_step(G, D, crit, z, c, alpha, tex, mesh)
+    (lf.mean() + lr.mean()).backward()
+    assert abs(float(lf) - float(d["d_loss_fake"])) < 2e-2 * abs(float(d["d_loss_fake"]))
+    assert abs(float(lr) - float(d["d_loss_real"])) < 2e-2 * abs(float(d["d_loss_real"]))
+    close(dout[0], d["dd_out0"], 2e-2)
+    params = dict(D.named_parameters())
+    for name, ref in zip(d["d_grad_names"], d["d_grad_norms"]):
+        got = float(params[str(name)].grad.norm())
+        assert abs(got - ref) <= 6e-2 * ref + 1e-7, (str(name), got, ref)
+
+
+def test_shipped_size_generator_runs_and_is_symmetric():
+    """512^2 generator (the shipped checkpoints' architecture), 3 discriminators: shapes, symmetry, finiteness."""
+    from models import gan
+    args = GC.make_args(512, 3)
+    G, D = GC.build(gan, args)
+    G.cuda().eval(); D.cuda().eval()
+    z, c, alpha, tex, mesh = [t.cuda() for t in GC.inputs(args, B=2)]
+    with torch.no_grad():
+        t, m = G(z, c)
+        out, masks = D(torch.cat((t * alpha, alpha), 1), m, c)
+    assert t.shape == (2, 3, 512, 512) and m.shape == (2, 3, 32, 32)
+    assert torch.equal(t, t.flip(3)) is False          # not trivially symmetric about the image centre ...
+    w = t.shape[3]
+    assert torch.allclose(t[..., : w // 4], t[..., w // 4: w // 2].flip(3))     # ... but mirrored about the seam
+    assert [o.shape for o in out] == [(2, 1, 32, 32), (2, 1, 8, 8), (2, 1, 16, 16)]
+    assert all(torch.isfinite(o).all() for o in out) and float(t.abs().max()) <= 1.0
