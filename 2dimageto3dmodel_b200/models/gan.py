@@ -73,7 +73,10 @@ class _DiscriminatorBase(nn.Module):
         if self.positional_embeddings:
             if self.pos_emb is None:
                 self.pos_emb = torch.FloatTensor(positional_encoding(x.shape[2], x.shape[3])).unsqueeze(0)
-            parts.append(self.pos_emb.to(x.device).expand(x.shape[0], -1, -1, -1))
+            dev_copy = getattr(self, '_pos_emb_dev', None)
+            if dev_copy is None or dev_copy.device != x.device:      # uploaded once, not per forward
+                dev_copy = self._pos_emb_dev = self.pos_emb.to(x.device)
+            parts.append(dev_copy.expand(x.shape[0], -1, -1, -1))
         return torch.cat(parts, dim=1) if len(parts) > 1 else x
 
     def _project(self, y, feat, c, caption):

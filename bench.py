@@ -31,9 +31,35 @@ for p in (PKG, ROOT):
 
 import torch  # noqa: E402
 
-B_PER_GPU, N_PTS, V, H, TEX, FLAT_COEF = 16, 8000, 128, 256, 128, 5e-4
-METRIC = "render+loss images/sec (cfg2: 8000-pt effective loss V=128 + CUB mesh render 256x256, fwd+bwd)"
-WORKLOAD = "cfg2: CUB 256x256, 8000-pt cloud, full render+loss, batch=16 per GPU"
+N_PTS, V, H, TEX, FLAT_COEF = 8000, 128, 256, 128, 5e-4
+WORKLOADS = {
+    # BASELINE.json configs[1]
+    "cfg2": dict(batch=16, gan=False, metric="render+loss images/sec (cfg2: 8000-pt effective loss V=128 + CUB mesh render 256x256, fwd+bwd)",
+                 name="cfg2: CUB 256x256, 8000-pt cloud, full render+loss, batch=16 per GPU"),
+    # BASELINE.json configs[2] = the configuration the metric "render+loss+GAN images/sec" is quoted on
+    "cfg3": dict(batch=32, gan=True, metric="render+loss+GAN images/sec (cfg3: cfg2 render+loss at batch 32 + conv-GAN 256x256 G/D iteration, 1 G : 2 D, Adam)",
+                 name="cfg3: CUB 256x256 render+loss + conv-GAN G/D step, batch=32 per GPU"),
+}
+GAN_RES = 256
+
+
+def gan_args():
+    import types
+    return types.SimpleNamespace(texture_resolution=GAN_RES, conditional_class=True, conditional_color=False,
+                                 conditional_text=False, norm_g='syncbatch', norm_d='none', n_classes=(200,),
+                                 mask_output=True, texture_only=False, num_discriminators=2, text_embedding_dim=256,
+                                 latent_dim=64, loss='hinge', lr_g=1e-4, lr_d=4e-4, d_steps_per_g=2,
+                                 mesh_regularization=1e-4, g_running_average_alpha=0.999, symmetric_g=True)
+
+
+def gan_host_inputs(B, seed, pin):
+    g = torch.Generator().manual_seed(seed + 77)
+    R = GAN_RES
+    alpha = (torch.rand(B, 1, R // 8, R // 8, generator=g) > 0.4).float()
+    d = dict(X_tex=torch.rand(B, 3, R, R, generator=g) * 2 - 1,
+             X_alpha=torch.nn.functional.interpolate(alpha, size=(R, R), mode="bilinear", align_corners=False),
+             X_mesh=torch.randn(B, 3, 32, 32, generator=g) * 0.05, C=torch.randint(0, 200, (B, 1), generator=g))
+    return {k: (v.pin_memory() if pin else v) for k, v in d.items()}
 
 
 def host_inputs(B, seed, pin):
@@ -64,7 +90,7 @@ def template_path():
 
 # --------------------------------------------------------------------------------------------- CUDA arm
 class CudaWorkload:
-    def __init__(self, device):
+    def __init__(self, device, gan=False):
         from rendering.mesh_template import MeshTemplate
         from rendering.renderer import Renderer
         from utils.effective_loss_function import EffectiveLossFunction
@@ -73,15 +99,35 @@ class CudaWorkload:
         self.tpl = MeshTemplate(template_path(), device=device)
         self.renderer = Renderer(H, H)
         self.flip = torch.tensor([1.0, -1.0, -1.0], device=device)
+        self.gan = None
+        if gan:
+            from gan_training import GANTrainer
+            torch.manual_seed(4321)                      # identical replicas on every rank
+            self.gan = GANTrainer(gan_args(), mesh_template=self.tpl, device=device, capturable=True)
 
     def step(self, d):
+        """One training iteration.  cfg2: render+loss fwd+bwd.  cfg3: three iterations (G, D, D — the reference's
+        1 : d_steps_per_g alternation, main.py:691), each = render+loss fwd+bwd + one GAN step with its optimiser."""
+        if self.gan is None:
+            return self.render_step(d)
+        loss = None
+        for it in range(3):
+            rl, _ = self.render_step(d)
+            if it == 0:
+                gl = self.gan.g_step(d["X_alpha"], d["C"])
+            else:
+                gl = self.gan.d_step(d["X_tex"], d["X_alpha"], d["X_mesh"], d["C"])
+            loss = rl + gl if loss is None else loss + rl + gl
+        return loss, None
+
+    def render_step(self, d):
         from b3d.mesh import rgba_mse_iou
         from rendering.utils import qrot
         from utils.losses import loss_flat
-        p, q, s = (d[k].requires_grad_(True) for k in ("points", "quat", "scale"))
+        p, q, s = (d[k].detach().requires_grad_(True) for k in ("points", "quat", "scale"))
         sil = self.elf(p, q, s)
         loss_pc = (sil - d["mask"]).square().sum() / sil.shape[0]        # unsupervised_part.py:111
-        mm, tex = d["mesh_map"].requires_grad_(True), d["tex"].requires_grad_(True)
+        mm, tex = d["mesh_map"].detach().requires_grad_(True), d["tex"].detach().requires_grad_(True)
         raw = self.tpl.get_vertex_positions(mm)
         vtx = (qrot(d["rot"], d["pscale"].unsqueeze(-1) * raw) + d["ptrans"].unsqueeze(1)) * self.flip
         img, alpha = self.tpl.forward_renderer(self.renderer, vtx, tex)
@@ -162,9 +208,14 @@ def run_cuda(args):
         pass
     hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
 
-    wl = CudaWorkload(dev)
-    B = B_PER_GPU
+    cfg = WORKLOADS[args.workload]
+    METRIC, WORKLOAD = cfg["metric"], cfg["name"]
+    wl = CudaWorkload(dev, gan=cfg["gan"])
+    B = cfg["batch"]
+    iters_per_step = 3 if cfg["gan"] else 1
     host = host_inputs(B, seed=1234 + rank, pin=True)       # each rank owns its shard of the global batch
+    if cfg["gan"]:
+        host.update(gan_host_inputs(B, seed=1234 + rank, pin=True))
     h2d = sum(t.numel() * t.element_size() for t in host.values())
     resident = {k: v.to(dev) for k, v in host.items()}
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)  # > 126 MB L2
@@ -248,19 +299,35 @@ def run_cuda(args):
     for _ in range(max(3, args.steps // 2)):
         flush.zero_()
         wl.step(fresh(resident))
-    prof = {k: statistics.mean(v) for k, v in b3d.prof_disable().items()}
+    torch.cuda.synchronize()
+    nprof = max(3, args.steps // 2)
+    raw_prof = b3d.prof_disable()
+    prof = {k: statistics.mean(v) for k, v in raw_prof.items()}
+    prof_tot = {k: sum(v) / nprof for k, v in raw_prof.items()}     # ms per step per entry point
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
     ms = total_ms / args.steps
-    value = world * B / (ms / 1e3)
-    e2e_v = world * B / (e2e_ms / args.steps / 1e3)
+    value = world * B * iters_per_step / (ms / 1e3)
+    e2e_v = world * B * iters_per_step / (e2e_ms / args.steps / 1e3)
     alg = algorithmic_bytes(B)
     cand = {k: prof[k] for k in alg if k in prof}
     top = max(cand, key=cand.get)
     ach = alg[top] / (cand[top] * 1e-3) / 1e9
+    tensor = None
+    if cfg["gan"]:
+        # dense-conv FLOPs of one G + two D iterations (SURVEY §8d / App. D at 256^2, nd=2: G 17.09, D 14.76 GF/img fwd;
+        # G-step 3(G+D), D-step G+6D) over the time spent inside the tcgen05 conv entry points
+        gf_img = (3 * (17.09 + 14.76) + 2 * (17.09 + 6 * 14.76))
+        conv_ms = sum(v for k, v in prof_tot.items() if k.startswith("b3d_conv2d"))
+        tpeak = peaks.get("bf16_tflops_sustained", 1415.7) / 2.0      # tf32 = half the bf16 rate
+        tensor = {"kernel": "conv_tf32 + wgrad_tf32 (tcgen05 kind::tf32)", "bound": "tensor",
+                  "achieved": round(gf_img * B / (conv_ms * 1e-3) / 1e3, 1), "peak": round(tpeak, 1), "unit": "TFLOP/s",
+                  "frac": round(gf_img * B / (conv_ms * 1e-3) / 1e3 / tpeak, 4), "traffic": None,
+                  "peak_source": "measured bf16 sustained / 2 (tf32 dense = half the bf16 rate)",
+                  "conv_ms_per_step": round(conv_ms, 3), "gflop_per_step": round(gf_img * B, 1)}
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top)
@@ -270,7 +337,8 @@ def run_cuda(args):
         "metric": METRIC, "value": round(value, 2), "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": world * B, "points": N_PTS, "voxels": V,
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": world * B,
+                   "iterations_per_step": iters_per_step, "points": N_PTS, "voxels": V,
                    "image": H, "faces": 960, "texture": TEX, "l2": "flushed between timed iterations (256 MB write)",
                    "parallelism": f"dp{world} (batch shards, no data-path collective)", "semantics": "R",
                    "cuda_graph": graph is not None},
@@ -281,26 +349,53 @@ def run_cuda(args):
         "roofline": {"kernel": top, "bound": "hbm", "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s",
                      "frac": round(ach / hbm_peak, 4), "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg[top], "ms_per_launch": round(cand[top], 4)},
-        "kernel_ms": {k: round(v, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1])},
+        "kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(prof_tot.items(), key=lambda kv: -kv[1])},
     }
+    if tensor is not None:
+        out["roofline_tensor"] = tensor
+        out["dtype"] = "tf32 (convs) / f32"
     if world == 1 and not os.environ.get("B3D_BENCH_NO_CPU"):
-        out["cpu_baseline"] = cpu_baseline(budget_s=25.0)
+        out["cpu_baseline"] = cpu_baseline(cfg, budget_s=25.0)
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
 
 
 # --------------------------------------------------------------------------------------------- CPU arm
-class OracleWorkload:
-    """The same step through oracle/ (the reference's algorithm on the CPU)."""
+def cpu_threads():
+    """torch's CPU kernels stop scaling (and regress) far below the 100+ hardware threads of the GPU hosts on these
+    small per-op tensors: use at most 32 and report that number as `cores`."""
+    n = min(os.cpu_count() or 1, 32)
+    torch.set_num_threads(n)
+    return n
 
-    def __init__(self):
+
+class OracleWorkload:
+    """The same step through oracle/ (the reference's algorithm restated in torch, on the CPU)."""
+
+    def __init__(self, gan=False):
         from oracle import mesh as M
         self.M = M
         path = template_path()
         self.T = M.TemplateData(M.load_obj(path), path)
+        self.gan = None
+        if gan:
+            from models import gan as gan_modules           # only to CONSTRUCT the initial state dicts on the CPU
+            from oracle import gan as OG
+            self.OG, self.args = OG, gan_args()
+            torch.manual_seed(4321)
+            G = gan_modules.Generator(self.args, 64, symmetric=True, mesh_head=True)
+            D = gan_modules.MultiScaleDiscriminator(self.args, 4)
+            self.sg = {k: v.clone() for k, v in G.state_dict().items()}
+            self.sd = {k: v.clone() for k, v in D.state_dict().items()}
+            for sdict in (self.sg, self.sd):
+                for k in OG.trainable(sdict):
+                    sdict[k].requires_grad_(True)
+            self.opt_g = torch.optim.Adam([self.sg[k] for k in OG.trainable(self.sg)], lr=1e-4, betas=(0.0, 0.9))
+            self.opt_d = torch.optim.Adam([self.sd[k] for k in OG.trainable(self.sd)], lr=4e-4, betas=(0.0, 0.9))
+            self.gan = True
 
-    def step(self, d):
+    def render_step(self, d):
         from oracle import pointcloud as O
         M, T = self.M, self.T
         p, q, s = (d[k].clone().requires_grad_(True) for k in ("points", "quat", "scale"))
@@ -317,50 +412,83 @@ class OracleWorkload:
         loss.backward()
         return loss.detach()
 
+    def step(self, d):
+        if self.gan is None:
+            return self.render_step(d)
+        OG, M, T = self.OG, self.M, self.T
+        total = 0.0
+        for it in range(3):
+            total = total + self.render_step(d)
+            B = d["C"].shape[0]
+            z = torch.randn(B, 64)
+            if it == 0:
+                self.opt_g.zero_grad(set_to_none=True)
+                loss, tex, mesh, _, _ = OG.g_loss(self.sg, self.sd, self.args, z, d["C"], d["X_alpha"])
+                flat = M.loss_flat(T.ff, T.faces.shape[0], M.compute_normals(T, M.get_vertex_positions(T, mesh)))
+                (loss + 1e-4 * flat).backward()
+                self.opt_g.step()
+            else:
+                self.opt_d.zero_grad(set_to_none=True)
+                lf, lr, _ = OG.d_loss(self.sg, self.sd, self.args, z, d["C"], d["X_alpha"], d["X_tex"], d["X_mesh"])
+                (lf + lr).backward()
+                self.opt_d.step()
+                loss = lf + lr
+            total = total + loss.detach()
+        return total
 
-def cpu_baseline(budget_s, sample_b=2):
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    wl = OracleWorkload()
+
+def cpu_inputs(cfg, sample_b):
     d = host_inputs(sample_b, seed=1234, pin=False)
-    wl.step(d)                                             # warm-up
+    if cfg["gan"]:
+        d.update(gan_host_inputs(sample_b, seed=1234, pin=False))
+    return d
+
+
+def cpu_baseline(cfg, budget_s, sample_b=2):
+    cores = cpu_threads()
+    wl = OracleWorkload(gan=cfg["gan"])
+    d = cpu_inputs(cfg, sample_b)
+    iters = 3 if cfg["gan"] else 1
+    t0 = time.perf_counter()
+    wl.step(d)                                             # warm-up (also sizes the timed part)
+    warm = time.perf_counter() - t0
+    nmax = max(1, min(8, int(budget_s / max(warm, 1e-3))))
     t0, n = time.perf_counter(), 0
-    while True:
+    while n < nmax:
         wl.step(d)
         n += 1
-        el = time.perf_counter() - t0
-        if el > budget_s or n >= 8:
-            break
-    return {"value": round(sample_b * n / el, 4), "unit": "images/s", "cores": cores, "kind": "port",
-            "sample": f"{n} steps of batch {sample_b} of the same workload through oracle/ (torch CPU, "
-                      f"{torch.get_num_threads()} threads); the reference's mesh rasteriser (kaolin) cannot run on CPU"}
+    el = time.perf_counter() - t0
+    return {"value": round(sample_b * iters * n / el, 4), "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": f"{n} steps ({iters} iteration(s) each) of batch {sample_b} of the same workload through oracle/ "
+                      f"(the reference's algorithm in torch on the CPU, {cores} threads)"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    sample_b = 2
-    wl = OracleWorkload()
-    d = host_inputs(sample_b, seed=1234, pin=False)
-    for _ in range(min(args.warmup, 1)):
+    cfg = WORKLOADS[args.workload]
+    cores = cpu_threads()
+    sample_b, iters = 2, (3 if cfg["gan"] else 1)
+    wl = OracleWorkload(gan=cfg["gan"])
+    d = cpu_inputs(cfg, sample_b)
+    warm = min(args.warmup, 1)
+    for _ in range(warm):
         wl.step(d)
-    steps = min(args.steps, 6)
+    steps = max(1, min(args.steps, 3 if cfg["gan"] else 6))
     t0 = time.perf_counter()
     for _ in range(steps):
         wl.step(d)
     el = time.perf_counter() - t0
-    v = sample_b * steps / el
-    sample = (f"{steps} steps of batch {sample_b} (bounded sample of the batch-16 workload) through oracle/ = the "
-              f"reference's algorithm in torch on the CPU, {cores} threads")
+    v = sample_b * iters * steps / el
+    sample = (f"{steps} steps ({iters} iteration(s) each) of batch {sample_b} (bounded sample of the batch-{cfg['batch']} "
+              f"workload) through oracle/ = the reference's algorithm in torch on the CPU, {cores} threads")
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": "images/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": round(el / steps * 1e3, 2),
+        "impl": "reference", "metric": cfg["metric"], "value": round(v, 4), "unit": "images/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": round(el / steps * 1e3, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_step": sample_b, "points": N_PTS, "voxels": V, "image": H,
-                   "faces": 960, "texture": TEX, "semantics": "R"},
+        "config": {"workload": cfg["name"], "batch_per_step": sample_b, "iterations_per_step": iters, "points": N_PTS,
+                   "voxels": V, "image": H, "faces": 960, "texture": TEX, "semantics": "R"},
         "cpu_baseline": {"value": round(v, 4), "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(v, 4), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -372,6 +500,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b3d", choices=["b3d", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b3d":
