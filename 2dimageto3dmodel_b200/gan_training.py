@@ -117,9 +117,20 @@ class GANTrainer:
             torch._foreach_mul_(fl_dst, alpha)
             torch._foreach_add_(fl_dst, fl_src, alpha=1 - alpha)
 
+    def _freeze_discriminator(self, frozen):
+        for p in self.trainer.discriminator.parameters():
+            p.requires_grad_(not frozen)
+
     def g_step(self, X_alpha, C, noise=None, epoch=1000):
         self.optimizer_g.zero_grad(set_to_none=True)
-        loss, pred_tex, pred_mesh = self.trainer('g', None, X_alpha, None, C, None, noise)
+        # The reference back-propagates the generator loss into the discriminator's weights as well and throws those
+        # gradients away (optimizer_d.zero_grad() precedes every D step, main.py:717).  Freezing D here skips that
+        # wasted weight-gradient work; the gradient that reaches the generator is unchanged.
+        self._freeze_discriminator(True)
+        try:
+            loss, pred_tex, pred_mesh = self.trainer('g', None, X_alpha, None, C, None, noise)
+        finally:
+            self._freeze_discriminator(False)
         loss_gan = loss.mean()
         total = loss_gan
         if pred_mesh is not None and self.mesh_template is not None:
