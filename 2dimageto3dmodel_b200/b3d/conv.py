@@ -4,6 +4,7 @@ Reference call sites: nn.Conv2d layers of /root/reference/code/models/gan.py (:5
 :359, :364) — 3x3 / 1x1 / 5x5 stride 1 and 4x4 stride 2, zero padding along y only (x padding is explicit:
 replicate / circular pads are materialised by the caller exactly as the reference does)."""
 import ctypes
+import os
 
 import torch
 
@@ -36,6 +37,14 @@ def conv2d_nhwc(x, weight, bias=None, pad_y=0, stride=1, leaky=1.0, wt=None, cin
     dy = [r - pad_y for r in range(kh) for _ in range(kw)]
     dx = [s for _ in range(kh) for s in range(kw)]
     b = dev(bias, "bias") if bias is not None else None
+    if stride == 1 and not cin_major and not os.environ.get("B3D_CONV_V1"):
+        # halo-staged kernel (tc_conv2.cu); falls through to the per-tap kernel when the halo does not fit in smem
+        rc = lib.b3d_conv2d_flat_tf32(ptr(x), ptr(wt), ptr(b), ptr(out), N, H, W, Cin, Hout, Wout, Cout, kh * kw,
+                                      _ints(dy), _ints(dx), Hout, Wout, Cout, float(leaky), stream_ptr(x))
+        if rc == 0:
+            return out
+        if b"does not fit" not in lib.b3d_last_error():
+            check(rc)
     check(lib.b3d_conv2d_tf32(ptr(x), ptr(wt), ptr(b), ptr(out), N, H, W, Cin, Hout, Wout, Cout, kh * kw, _ints(dy),
                               _ints(dx), stride, stride, Hout, Wout, Cout, 1, 1, 0, 0, float(leaky), int(cin_major),
                               stream_ptr(x)))

@@ -190,6 +190,14 @@ B3D_API int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, 
                             int sy, int sx, int OH, int OW, int OC, int osy, int osx, int ooy, int oox,
                             float leaky, int w_cin_major, void* stream);
 
+/* Stride-1 variant with a halo-staged input and R stacked accumulators (csrc/tc_conv2.cu): x [N,H,P,Cin] with P the
+ * padded width (row pitch), taps (dy, dx >= 0); same weights / bias / LeakyReLU semantics as b3d_conv2d_tf32, output
+ * out[n,y,x,co] for y < Hout, x < Wout of a tensor [N,OH,OW,OC].  Returns B3D_EINVAL ("does not fit") when the halo
+ * (max tap offset - min tap offset rows of 128 B) exceeds shared memory; callers then use b3d_conv2d_tf32.          */
+B3D_API int b3d_conv2d_flat_tf32(const float* x, const float* wt, const float* bias, float* out, int N, int H, int P,
+                                 int Cin, int Hout, int Wout, int Cout, int ntaps, const int* dy, const int* dx,
+                                 int OH, int OW, int OC, float leaky, void* stream);
+
 /* Weight gradient of the same convolution (split-K tcgen05 GEMM over the output pixels, M/N-major operands
  * straight from the NHWC tensors):
  *   dw[co, ci, r, s] += sum_{n,y,x} dy[n, y, x, co] * x[n, stride*y + r - pad_y, stride*x + s, ci]
