@@ -229,8 +229,7 @@ int b3d_conv2d_flat_tf32(const float* x, const float* wt, const float* bias, flo
     p.main_boxes = p.staged_rows / 256;
     p.tail_rows = p.staged_rows % 256;
     p.OH = OH; p.OW = OW; p.OC = OC; p.leaky = leaky;
-    p.use_base_offset = 1;
-    if (const char* e = getenv("B3D_CONV_BASE_OFFSET")) p.use_base_offset = atoi(e);
+    p.use_base_offset = 0;      // measured: the swizzle is keyed on absolute smem address bits; a non-zero base_offset breaks it
 
     CUtensorMap m_main, m_tail, m_w;
     const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)H * P, (uint64_t)N};
