@@ -86,14 +86,15 @@ def conv2d_dgrad_nhwc(dy_, weight, in_hw, pad_y=0, stride=1):
 
 def conv2d_wgrad_nhwc(dy_, x, kh, kw, pad_y=0, stride=1):
     """dW [Cout,Cin,kh,kw] from dy_ [N,Hout,Wout,Cout] and the (x-padded) input x [N,H,W,Cin], both NHWC
-    (channel counts multiples of 4)."""
-    g, x = dev(dy_, "grad_output"), dev(x, "input")
+    (channel counts that are not multiples of 32 are zero-padded here)."""
+    co_real, ci_real = dy_.shape[3], x.shape[3]
+    g, x = dev(_pad_last(dy_, 32), "grad_output"), dev(_pad_last(x, 32), "input")
     N, Hout, Wout, Cout = g.shape
     _, H, W, Cin = x.shape
     dw = torch.zeros(Cout, Cin, kh, kw, device=g.device, dtype=torch.float32)
     check(lib.b3d_conv2d_wgrad_tf32(ptr(g), ptr(x), ptr(dw), N, H, W, Cin, Hout, Wout, Cout, kh, kw, pad_y, stride,
                                     stream_ptr(g)))
-    return dw
+    return dw if (co_real, ci_real) == (Cout, Cin) else dw[:co_real, :ci_real]
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -48,7 +48,7 @@ struct Smem {
 };
 
 template <int BN, int STAGES, bool WMN>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS, 2)
 conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const ConvParams p, const float* __restrict__ bias, float* __restrict__ out) {
     using S = Smem<BN, STAGES>;
@@ -140,13 +140,29 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             float v[32];
             tc::tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
             if (valid) {
+                const int cb = c0 + c;
+                if (cb + 32 <= p.Cout && (p.OC & 3) == 0) {       // full 32-channel run: 8 x 16-byte stores
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int co = c0 + c + j;
-                    if (co < p.Cout) {
-                        float o = v[j] + (bias ? __ldg(bias + co) : 0.f);
-                        o = o >= 0.f ? o : o * p.leaky;
-                        dst[co] = o;
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 o;
+                        o.x = v[j] + (bias ? __ldg(bias + cb + j) : 0.f);
+                        o.y = v[j + 1] + (bias ? __ldg(bias + cb + j + 1) : 0.f);
+                        o.z = v[j + 2] + (bias ? __ldg(bias + cb + j + 2) : 0.f);
+                        o.w = v[j + 3] + (bias ? __ldg(bias + cb + j + 3) : 0.f);
+                        o.x = o.x >= 0.f ? o.x : o.x * p.leaky;
+                        o.y = o.y >= 0.f ? o.y : o.y * p.leaky;
+                        o.z = o.z >= 0.f ? o.z : o.z * p.leaky;
+                        o.w = o.w >= 0.f ? o.w : o.w * p.leaky;
+                        *reinterpret_cast<float4*>(dst + cb + j) = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int co = cb + j;
+                        if (co < p.Cout) {
+                            float o = v[j] + (bias ? __ldg(bias + co) : 0.f);
+                            dst[co] = o >= 0.f ? o : o * p.leaky;
+                        }
                     }
                 }
             }
@@ -226,11 +242,9 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
                 unsigned char* a = base + st * S::STAGE_BYTES;
                 unsigned char* b = a + S::A_BYTES;
                 tc::mbar_arrive_expect_tx(full + st, S::STAGE_BYTES);
-#pragma unroll
-                for (int mb = 0; mb < BM / 32; ++mb) tc::tma_load_4d(a + mb * BLK, &tmap_dy, full + st, co0 + mb * 32, x0, y0, n);
-#pragma unroll
-                for (int nb = 0; nb < BN / 32; ++nb)
-                    tc::tma_load_4d(b + nb * BLK, &tmap_x, full + st, ci0 + nb * 32, p.st * x0 + s, p.st * y0 + r - p.pad_y, n);
+                // channels are split as (32, C/32) in the tensor maps: ONE 5-D box lands all 32-channel blocks back to back
+                tc::tma_load_5d(a, &tmap_dy, full + st, 0, x0, y0, n, co0 / 32);
+                tc::tma_load_5d(b, &tmap_x, full + st, 0, p.st * x0 + s, p.st * y0 + r - p.pad_y, n, ci0 / 32);
             }
         }
     } else if (warp == 1) {
@@ -340,8 +354,8 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
         const uint64_t strides[2] = {(uint64_t)Cout * 4, (uint64_t)Cout * Cin * 4};
         const uint32_t box[3] = {32, (uint32_t)BK, 1};
         if (int rc = tc::make_tmap_f32(&mw, wt, 3, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
-        if (BN == 128) return launch<128, 6, true>(mx, mw, p, bias, out, tiles, st);
-        return launch<64, 8, true>(mx, mw, p, bias, out, tiles, st);
+        if (BN == 128) return launch<128, 3, true>(mx, mw, p, bias, out, tiles, st);
+        return launch<64, 4, true>(mx, mw, p, bias, out, tiles, st);
     }
     {
         const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)ntaps};
@@ -349,8 +363,8 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
         const uint32_t box[3] = {(uint32_t)BK, (uint32_t)BN, 1};
         if (int rc = tc::make_tmap_f32(&mw, wt, 3, dims, strides, box)) return rc;
     }
-    if (BN == 128) return launch<128, 6, false>(mx, mw, p, bias, out, tiles, st);
-    return launch<64, 8, false>(mx, mw, p, bias, out, tiles, st);
+    if (BN == 128) return launch<128, 3, false>(mx, mw, p, bias, out, tiles, st);
+    return launch<64, 4, false>(mx, mw, p, bias, out, tiles, st);
 }
 
 // dy [N,Hout,Wout,Cout], x [N,H,W,Cin] NHWC (x already padded along x; Cin, Cout multiples of 4),
@@ -361,8 +375,8 @@ int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, int N, int
                 "b3d_conv2d_wgrad_tf32: bad sizes");
     B3D_REQUIRE(kh * kw <= MAX_TAPS && (stride == 1 || stride == 2), B3D_EINVAL, "b3d_conv2d_wgrad_tf32: bad kernel/stride");
     B3D_REQUIRE(dy && x && dw, B3D_EINVAL, "b3d_conv2d_wgrad_tf32: null pointer");
-    B3D_REQUIRE(Cin % 4 == 0 && Cout % 4 == 0, B3D_EINVAL,
-                "b3d_conv2d_wgrad_tf32: Cin=%d and Cout=%d must be multiples of 4 (16-byte TMA strides)", Cin, Cout);
+    B3D_REQUIRE(Cin % 32 == 0 && Cout % 32 == 0, B3D_EINVAL,
+                "b3d_conv2d_wgrad_tf32: Cin=%d and Cout=%d must be multiples of 32 (pad the channels with zeros)", Cin, Cout);
     B3D_CHECK_ALIGNED(dy);
     B3D_CHECK_ALIGNED(x);
     WgradParams p{};
@@ -381,18 +395,19 @@ int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, int N, int
     p.splits = splits;
 
     CUtensorMap mdy, mx;
-    {
-        const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)Wout, (uint64_t)Hout, (uint64_t)N};
-        const uint64_t strides[3] = {(uint64_t)Cout * 4, (uint64_t)Wout * Cout * 4, (uint64_t)Hout * Wout * Cout * 4};
-        const uint32_t box[4] = {32, (uint32_t)p.BWk, (uint32_t)p.BHk, 1};
-        if (int rc = tc::make_tmap_f32(&mdy, dy, 4, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+    {   // dims: (32 channels, W, H, N, channel block) — the block dim is outermost so that a box of BM/32 blocks is contiguous
+        const uint64_t dims[5] = {32, (uint64_t)Wout, (uint64_t)Hout, (uint64_t)N, (uint64_t)Cout / 32};
+        const uint64_t strides[4] = {(uint64_t)Cout * 4, (uint64_t)Wout * Cout * 4, (uint64_t)Hout * Wout * Cout * 4, 128};
+        const uint32_t box[5] = {32, (uint32_t)p.BWk, (uint32_t)p.BHk, 1, (uint32_t)(BM / 32)};
+        if (int rc = tc::make_tmap_f32(&mdy, dy, 5, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
     }
     {
-        const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-        const uint64_t strides[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
-        const uint32_t box[4] = {32, (uint32_t)(stride * (p.BWk - 1) + 1), (uint32_t)(stride * (p.BHk - 1) + 1), 1};
-        const uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
-        if (int rc = tc::make_tmap_f32(&mx, x, 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+        const uint64_t dims[5] = {32, (uint64_t)W, (uint64_t)H, (uint64_t)N, (uint64_t)Cin / 32};
+        const uint64_t strides[4] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4, 128};
+        const uint32_t box[5] = {32, (uint32_t)(stride * (p.BWk - 1) + 1), (uint32_t)(stride * (p.BHk - 1) + 1), 1,
+                                 (uint32_t)(BN / 32)};
+        const uint32_t es[5] = {1, (uint32_t)stride, (uint32_t)stride, 1, 1};
+        if (int rc = tc::make_tmap_f32(&mx, x, 5, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
     }
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(b3d::ceil_div(Cout, BM), b3d::ceil_div(Cin, BN), kh * kw * splits);

@@ -155,12 +155,29 @@ conv_flat_tf32_kernel(const __grid_constant__ CUtensorMap tmap_main, const __gri
                 float v[32];
                 tc::tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * BN + c), v);
                 if (valid) {
+                    const int cb = c0 + c;
+                    if (cb + 32 <= p.Cout && (p.OC & 3) == 0) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int co = c0 + c + i;
-                        if (co < p.Cout) {
-                            float o = v[i] + (bias ? __ldg(bias + co) : 0.f);
-                            dst[co] = o >= 0.f ? o : o * p.leaky;
+                        for (int i = 0; i < 32; i += 4) {
+                            float4 o;
+                            o.x = v[i] + (bias ? __ldg(bias + cb + i) : 0.f);
+                            o.y = v[i + 1] + (bias ? __ldg(bias + cb + i + 1) : 0.f);
+                            o.z = v[i + 2] + (bias ? __ldg(bias + cb + i + 2) : 0.f);
+                            o.w = v[i + 3] + (bias ? __ldg(bias + cb + i + 3) : 0.f);
+                            o.x = o.x >= 0.f ? o.x : o.x * p.leaky;
+                            o.y = o.y >= 0.f ? o.y : o.y * p.leaky;
+                            o.z = o.z >= 0.f ? o.z : o.z * p.leaky;
+                            o.w = o.w >= 0.f ? o.w : o.w * p.leaky;
+                            *reinterpret_cast<float4*>(dst + cb + i) = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int co = cb + i;
+                            if (co < p.Cout) {
+                                float o = v[i] + (bias ? __ldg(bias + co) : 0.f);
+                                dst[co] = o >= 0.f ? o : o * p.leaky;
+                            }
                         }
                     }
                 }
