@@ -37,7 +37,12 @@ def conv2d_nhwc(x, weight, bias=None, pad_y=0, stride=1, leaky=1.0, wt=None, cin
     dy = [r - pad_y for r in range(kh) for _ in range(kw)]
     dx = [s for _ in range(kh) for s in range(kw)]
     b = dev(bias, "bias") if bias is not None else None
-    if stride == 1 and not cin_major and not os.environ.get("B3D_CONV_V1"):
+    # the halo-staged kernel wins on wide-N layers with enough tiles to fill the GPU twice; elsewhere the per-tap kernel
+    # (2 CTAs / SM) is as fast or faster (profiles/r1_conv_layers.md)
+    use_flat = stride == 1 and not cin_major and Cout > 64 and N * Hout * W >= 2 * 148 * 384
+    if os.environ.get("B3D_CONV_FLAT"):
+        use_flat = stride == 1 and not cin_major and os.environ["B3D_CONV_FLAT"] == "1"
+    if use_flat:
         # halo-staged kernel (tc_conv2.cu); falls through to the per-tap kernel when the halo does not fit in smem
         rc = lib.b3d_conv2d_flat_tf32(ptr(x), ptr(wt), ptr(b), ptr(out), N, H, W, Cin, Hout, Wout, Cout, kh * kw,
                                       _ints(dy), _ints(dx), Hout, Wout, Cout, float(leaky), stream_ptr(x))
@@ -143,5 +148,13 @@ def conv2d(x_nchw, weight, bias=None, pad_y=0, stride=1):
     kernels over the channels-last storage (a no-copy view when x is already channels_last) and returns a
     logically-NCHW, channels-last tensor."""
     x = x_nchw.permute(0, 2, 3, 1)
+    Cout, Cin, kh, kw = weight.shape
+    if stride == 1 and kw > 1 and Cin * kw <= 64:
+        # thin stems (discriminator conv1: 8 or 11 input channels, 5x5): fold the kw horizontal taps into the channel
+        # dimension — X'[n,y,x, s*Cin + c] = X[n,y,x+s,c] — so the tensor cores see kh taps of kw*Cin real channels
+        # instead of kh*kw taps of Cin channels zero-padded to 32.
+        Wout = x.shape[2] - kw + 1
+        x = torch.cat([x[:, :, s:s + Wout, :] for s in range(kw)], dim=3)
+        weight = weight.permute(0, 3, 1, 2).reshape(Cout, kw * Cin, kh, 1)          # [co, s*Cin + c, r, 0]
     y = _Conv2dNHWC.apply(x, weight, bias, int(pad_y), int(stride))
     return y.permute(0, 3, 1, 2)

@@ -78,3 +78,30 @@ def test_wgrad(N, Cin, H, W, Cout, k, pad_y, stride):
     torch.cuda.synchronize()
     err = float((out - ref).abs().max())
     assert err <= TOL * float(ref.abs().max()), (err, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("N,Cin,H,W,Cout,k,pad_y,stride,bias", [
+    (2, 8, 32, 36, 64, 5, 2, 1, True),       # discriminator stem, 8 channels: kw folded into K
+    (2, 11, 32, 36, 64, 5, 2, 1, True),      # mesh discriminator stem, 11 channels
+    (2, 8, 32, 34, 64, 4, 1, 2, True),       # 512^2 stem: 4x4 / stride 2 (channels zero-padded to 32)
+    (2, 64, 16, 20, 3, 5, 2, 1, True),       # 3-channel head
+    (2, 256, 16, 18, 128, 3, 1, 1, False),
+])
+def test_conv2d_autograd_matches_torch(N, Cin, H, W, Cout, k, pad_y, stride, bias):
+    """b3d.conv.conv2d (the function models/gan.py calls) forward + all three gradients vs torch fp32."""
+    from b3d.conv import conv2d
+    g = torch.Generator().manual_seed(Cin * 7 + Cout)
+    x0 = torch.randn(N, Cin, H, W, generator=g).cuda()
+    w0 = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).cuda()
+    b0 = torch.randn(Cout, generator=g).cuda() if bias else None
+    outs = []
+    for impl in ("torch", "b3d"):
+        x, w = x0.clone().requires_grad_(True), w0.clone().requires_grad_(True)
+        b = b0.clone().requires_grad_(True) if bias else None
+        y = ref_conv(x, w, b, pad_y, stride) if impl == "torch" else conv2d(x.contiguous(memory_format=torch.channels_last), w, b, pad_y, stride)
+        gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(3)).cuda()
+        grads = torch.autograd.grad(y, [x, w] + ([b] if bias else []), gy)
+        outs.append([y.detach()] + list(grads))
+    for a, r in zip(outs[1], outs[0]):
+        assert a.shape == r.shape
+        assert float((a - r).abs().max()) <= TOL * float(r.abs().max()), (a.shape, float((a - r).abs().max()), float(r.abs().max()))
