@@ -26,8 +26,9 @@ def adjust_poles(tex):
 
 
 def circpad(x, amount=1):
-    """Wrap-around padding along x only (reference :29-33)."""
-    return F.pad(x, (amount, amount, 0, 0), mode='circular')
+    """Wrap-around padding along x only (reference :29-33).  Written as a concatenation: unlike
+    F.pad(mode='circular') it keeps a channels-last tensor channels-last, which the conv kernels read directly."""
+    return torch.cat((x[..., -amount:], x, x[..., :amount]), dim=3)
 
 
 def qrot(q, v):
