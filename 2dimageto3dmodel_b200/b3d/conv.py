@@ -112,22 +112,32 @@ def _pad_last(t, mult):
 
 class _Conv2dNHWC(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, pad_y, stride):
+    def forward(ctx, x, weight, bias, pad_y, stride, leaky=1.0):
         x = dev(x.detach(), "x")
         w = weight.detach()
         Cin = x.shape[3]
         if Cin % 32:                                    # thin inputs (discriminator stems: 8 / 11 channels): zero-pad K
             x = _pad_last(x, 32)
             w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, x.shape[3] - Cin))
-        y = conv2d_nhwc(x, w, bias.detach() if bias is not None else None, pad_y=pad_y, stride=stride)
-        ctx.save_for_backward(x, w)
-        ctx.cfg = (pad_y, stride, Cin, bias is not None)
+        y = conv2d_nhwc(x, w, bias.detach() if bias is not None else None, pad_y=pad_y, stride=stride, leaky=leaky)
+        if leaky != 1.0:
+            ctx.save_for_backward(x, w, y)
+        else:
+            ctx.save_for_backward(x, w)
+        ctx.cfg = (pad_y, stride, Cin, bias is not None, leaky)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x, w = ctx.saved_tensors
-        pad_y, stride, Cin, has_bias = ctx.cfg
+        pad_y, stride, Cin, has_bias, leaky = ctx.cfg
+        if leaky != 1.0:                  # LeakyReLU was fused into the epilogue: mask the incoming gradient by sign(y)
+            x, w, y = ctx.saved_tensors
+            gy = dev(gy, "grad_output")
+            masked = torch.empty_like(gy)
+            check(lib.b3d_leaky_bwd(ptr(gy), ptr(y), ptr(masked), gy.numel(), float(leaky), stream_ptr(gy)))
+            gy = masked
+        else:
+            x, w = ctx.saved_tensors
         Cout, _, kh, kw = w.shape
         gy = dev(gy, "grad_output")
         gb = gy.sum(dim=(0, 1, 2)) if has_bias and ctx.needs_input_grad[2] else None
@@ -140,10 +150,10 @@ class _Conv2dNHWC(torch.autograd.Function):
             gx = conv2d_dgrad_nhwc(gyp, wp, (x.shape[1], x.shape[2]), pad_y=pad_y, stride=stride)[..., :Cin]
         if ctx.needs_input_grad[1]:
             gw = conv2d_wgrad_nhwc(gyp, x, kh, kw, pad_y=pad_y, stride=stride)[:Cout, :Cin]
-        return gx, gw, gb, None, None
+        return gx, gw, gb, None, None, None
 
 
-def conv2d(x_nchw, weight, bias=None, pad_y=0, stride=1):
+def conv2d(x_nchw, weight, bias=None, pad_y=0, stride=1, leaky=1.0):
     """Drop-in for F.conv2d(x, w, b, stride, padding=(pad_y, 0)) on logically-NCHW tensors: runs on the tcgen05
     kernels over the channels-last storage (a no-copy view when x is already channels_last) and returns a
     logically-NCHW, channels-last tensor."""
@@ -156,5 +166,5 @@ def conv2d(x_nchw, weight, bias=None, pad_y=0, stride=1):
         Wout = x.shape[2] - kw + 1
         x = torch.cat([x[:, :, s:s + Wout, :] for s in range(kw)], dim=3)
         weight = weight.permute(0, 3, 1, 2).reshape(Cout, kw * Cin, kh, 1)          # [co, s*Cin + c, r, 0]
-    y = _Conv2dNHWC.apply(x, weight, bias, int(pad_y), int(stride))
+    y = _Conv2dNHWC.apply(x, weight, bias, int(pad_y), int(stride), float(leaky))
     return y.permute(0, 3, 1, 2)

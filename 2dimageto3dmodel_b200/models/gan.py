@@ -18,18 +18,20 @@ import torch.nn.functional as F
 
 from b3d import B3DError
 from b3d.conv import conv2d as _tc_conv2d
+from b3d.ew import CIRCULAR, REPLICATE, pad_x
 from rendering.utils import adjust_poles, circpad, symmetrize_texture
 
 
 class TCConv2d(nn.Conv2d):
     """nn.Conv2d (same parameters / state dict) whose forward runs on the tensor-core kernels."""
 
-    def forward(self, x):
+    def forward(self, x, leaky=1.0):
+        """`leaky` != 1 fuses LeakyReLU(leaky) into the convolution's epilogue (conv -> bias -> activation in one pass)."""
         if not x.is_cuda:
             raise B3DError("models.gan convolutions run on CUDA only (libb3d tcgen05 kernels); there is no CPU fallback")
         if self.padding[1] != 0 or self.stride[0] != self.stride[1] or self.dilation != (1, 1) or self.groups != 1:
             raise B3DError("TCConv2d supports zero padding along y only, square strides, no dilation / groups")
-        return _tc_conv2d(x, self.weight, self.bias, pad_y=self.padding[0], stride=self.stride[0])
+        return _tc_conv2d(x, self.weight, self.bias, pad_y=self.padding[0], stride=self.stride[0], leaky=leaky)
 
 
 def positional_encoding(Ny, Nx):
@@ -49,8 +51,15 @@ def _norm_and_bias(args):
     if args.norm_d == 'instance':
         return (lambda ch: nn.InstanceNorm2d(ch, affine=True)), False
     if args.norm_d == 'none':
-        return (lambda ch: (lambda x: x)), True
+        return (lambda ch: None), True          # no norm layer: conv -> bias -> LeakyReLU runs in the conv epilogue
     raise ValueError(f"norm_d={args.norm_d!r}")
+
+
+def _conv_norm_act(conv, norm, x):
+    """LeakyReLU(0.2)(norm(conv(x))): one fused kernel when there is no norm layer."""
+    if norm is None:
+        return conv(x, leaky=0.2)
+    return F.leaky_relu(norm(conv(x)), 0.2)
 
 
 class _DiscriminatorBase(nn.Module):
@@ -61,8 +70,8 @@ class _DiscriminatorBase(nn.Module):
         self.circular = circular
         self.positional_embeddings = positional_embeddings
         if circular:
-            self.pad = lambda x: circpad(x, 2)       # in front of the 5x5 convolutions
-            self.pad2 = lambda x: circpad(x, 1)      # in front of the 4x4 / stride-2 convolutions
+            self.pad = lambda x: pad_x(x, 2, CIRCULAR)       # in front of the 5x5 convolutions
+            self.pad2 = lambda x: pad_x(x, 1, CIRCULAR)      # in front of the 4x4 / stride-2 convolutions
         else:
             self.pad = lambda x: x
         if positional_embeddings:
@@ -122,9 +131,9 @@ class MeshDiscriminator(_DiscriminatorBase):
         if self.args.mask_output:
             with torch.no_grad():
                 mask = F.avg_pool2d(x[:, 3:4], 4)
-        x = self.relu(self.conv1(self.pad(x)))
-        x = self.relu(self.bn2(self.conv2(self.pad2(x))))
-        x = self.relu(self.bn3(self.conv3(self.pad2(x))))
+        x = self.conv1(self.pad(x), leaky=0.2)
+        x = _conv_norm_act(self.conv2, self.bn2, self.pad2(x))
+        x = _conv_norm_act(self.conv3, self.bn3, self.pad2(x))
         y = self._project(self.conv4(self.pad(x)), x, c, caption)
         return y, mask
 
@@ -171,10 +180,10 @@ class TextureDiscriminator(_DiscriminatorBase):
             with torch.no_grad():
                 mask = F.avg_pool2d(x[:, 3:4], 16 if self.stride_first else 8)
         x = self._with_positions(x)
-        x = self.relu(self.conv1(self.padconv1(x)))
-        x = self.relu(self.bn2(self.conv2(self.pad2(x))))
-        x = self.relu(self.bn3(self.conv3(self.pad2(x))))
-        x = self.relu(self.bn4(self.conv4(self.pad2(x))))
+        x = self.conv1(self.padconv1(x), leaky=0.2)
+        x = _conv_norm_act(self.conv2, self.bn2, self.pad2(x))
+        x = _conv_norm_act(self.conv3, self.bn3, self.pad2(x))
+        x = _conv_norm_act(self.conv4, self.bn4, self.pad2(x))
         y = self._project(self.conv5(self.pad(x)), x, c, caption)
         return y, mask
 
@@ -252,9 +261,9 @@ class Generator(nn.Module):
         self.args, self.symmetric, self.mesh_head = args, symmetric, mesh_head
         self.height, self.width = 8, (4 if symmetric else 8)
         if symmetric:    # half-width map: an even-mirror border equals edge replication for 3x3 / 5x5 kernels
-            self.pad = lambda x, amount: F.pad(x, (amount, amount, 0, 0), mode='replicate')
+            self.pad = lambda x, amount: pad_x(x, amount, REPLICATE)
         else:
-            self.pad = lambda x, amount: circpad(x, amount)
+            self.pad = lambda x, amount: pad_x(x, amount, CIRCULAR)
 
         if args.conditional_class and args.conditional_color:
             self.emb_class = nn.Embedding(args.n_classes[0], emb_dim // 2)

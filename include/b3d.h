@@ -207,6 +207,16 @@ B3D_API int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, in
                                   int Hout, int Wout, int Cout, int kh, int kw, int pad_y, int stride,
                                   void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * One-pass NHWC helpers between the GAN's convolutions.
+ * b3d_pad_x_*: padding along x of x [rows = N*H, W, C] -> out [rows, W + 2*amount, C]; mode 0 = replicate
+ *   (F.pad(..., mode='replicate'), models/gan.py:329), 1 = circular (circpad, rendering/utils.py:29-33); C % 4 == 0.
+ * b3d_leaky_bwd: out = gy * (y >= 0 ? 1 : slope) — gradient of the LeakyReLU fused into the conv epilogue.
+ * ------------------------------------------------------------------------------------------ */
+B3D_API int b3d_pad_x_fwd(const float* x, float* out, long long rows, int W, int C, int amount, int mode, void* stream);
+B3D_API int b3d_pad_x_bwd(const float* gout, float* gx, long long rows, int W, int C, int amount, int mode, void* stream);
+B3D_API int b3d_leaky_bwd(const float* gy, const float* y, float* out, long long n, float slope, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

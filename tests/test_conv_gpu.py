@@ -105,3 +105,42 @@ def test_conv2d_autograd_matches_torch(N, Cin, H, W, Cout, k, pad_y, stride, bia
     for a, r in zip(outs[1], outs[0]):
         assert a.shape == r.shape
         assert float((a - r).abs().max()) <= TOL * float(r.abs().max()), (a.shape, float((a - r).abs().max()), float(r.abs().max()))
+
+
+@pytest.mark.parametrize("mode", ["replicate", "circular"])
+@pytest.mark.parametrize("N,C,H,W,a", [(2, 8, 5, 7, 2), (3, 64, 16, 4, 1), (1, 12, 3, 9, 2)])
+def test_pad_x_matches_torch(mode, N, C, H, W, a):
+    from b3d.ew import CIRCULAR, REPLICATE, pad_x
+    g = torch.Generator().manual_seed(N * C + W)
+    x0 = torch.randn(N, C, H, W, generator=g).cuda()
+    outs = []
+    for impl in (0, 1):
+        x = x0.clone().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        if impl == 0:
+            y = torch.nn.functional.pad(x, (a, a, 0, 0), mode=mode)
+        else:
+            y = pad_x(x, a, REPLICATE if mode == "replicate" else CIRCULAR)
+        gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(4)).cuda()
+        gx, = torch.autograd.grad(y, x, gy)
+        outs.append((y.detach(), gx))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.allclose(outs[0][1], outs[1][1], atol=1e-6)
+
+
+def test_fused_leaky_epilogue_autograd():
+    from b3d.conv import conv2d
+    g = torch.Generator().manual_seed(9)
+    x0 = torch.randn(2, 64, 16, 18, generator=g).cuda()
+    w0 = (torch.randn(128, 64, 4, 4, generator=g) / 32).cuda()
+    b0 = torch.randn(128, generator=g).cuda()
+    res = []
+    for impl in (0, 1):
+        x, w, b = x0.clone().requires_grad_(True), w0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+        if impl == 0:
+            y = torch.nn.functional.leaky_relu(ref_conv(x, w, b, 1, 2), 0.2)
+        else:
+            y = conv2d(x.contiguous(memory_format=torch.channels_last), w, b, 1, 2, leaky=0.2)
+        gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(5)).cuda()
+        res.append([y.detach()] + list(torch.autograd.grad(y, [x, w, b], gy)))
+    for a, r in zip(res[1], res[0]):
+        assert float((a - r).abs().max()) <= 2 * TOL * float(r.abs().max())
