@@ -318,9 +318,11 @@ def run_cuda(args):
     ach = alg[top] / (cand[top] * 1e-3) / 1e9
     tensor = None
     if cfg["gan"]:
-        # dense-conv FLOPs of one G + two D iterations (SURVEY §8d / App. D at 256^2, nd=2: G 17.09, D 14.76 GF/img fwd;
-        # G-step 3(G+D), D-step G+6D) over the time spent inside the tcgen05 conv entry points
-        gf_img = (3 * (17.09 + 14.76) + 2 * (17.09 + 6 * 14.76))
+        # dense-conv FLOPs of one G + two D iterations (SURVEY §8d / App. D at 256^2, nd=2: G 17.09, D 14.76 GF/img fwd),
+        # counting only what is executed: G-step = fwd G+D, dgrad+wgrad G, dgrad D (the reference's discarded D wgrad is
+        # skipped) = 3G + 2D; D-step = G fwd + D fwd/dgrad/wgrad on 2B images = G + 6D — over the time spent inside the
+        # tcgen05 conv entry points
+        gf_img = (3 * 17.09 + 2 * 14.76) + 2 * (17.09 + 6 * 14.76)
         conv_ms = sum(v for k, v in prof_tot.items() if k.startswith("b3d_conv2d"))
         tpeak = peaks.get("bf16_tflops_sustained", 1415.7) / 2.0      # tf32 = half the bf16 rate
         tensor = {"kernel": "conv_tf32 + wgrad_tf32 (tcgen05 kind::tf32)", "bound": "tensor",
