@@ -195,12 +195,15 @@ def run_cuda(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 with torch.distributed.run")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference)")
+    if os.environ.get("B3D_SINGLE_GPU"):      # development aid: all ranks share cuda:0 (use with B3D_DIST_BACKEND=gloo)
+        local = 0
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        backend = os.environ.get("B3D_DIST_BACKEND", "nccl")
+        dist.init_process_group(backend, **({"device_id": dev} if backend == "nccl" else {}))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -250,7 +253,9 @@ def run_cuda(args):
 
     host_loss = torch.empty(1).pin_memory()
     graph = None
-    if not args.no_graph:
+    # N > 1: the step contains collectives (gradient all-reduce, SyncBN statistics); they are launched eagerly, not
+    # captured (capturing NCCL needs process-wide capture-safe error handling) — the cfg3 step is GPU-bound either way.
+    if not args.no_graph and (world == 1 or not cfg["gan"]):
         # the step has no host synchronisation: capture it once (forward + backward) and replay it
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
