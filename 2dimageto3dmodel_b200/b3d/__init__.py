@@ -38,6 +38,7 @@ _vp = ctypes.c_void_p
 _i = ctypes.c_int
 _f = ctypes.c_float
 _sz = ctypes.c_size_t
+_ll = ctypes.c_longlong
 
 
 def _sig(name, *argtypes):
@@ -61,10 +62,17 @@ _sig("b3d_conv2d_tf32", _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp,
      _f, _i, _vp)
 _sig("b3d_conv2d_flat_tf32", _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _f, _vp)
 _sig("b3d_conv2d_wgrad_tf32", _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp)
-_ll = ctypes.c_longlong
 _sig("b3d_pad_x_fwd", _vp, _vp, _ll, _i, _i, _i, _i, _vp)
 _sig("b3d_pad_x_bwd", _vp, _vp, _ll, _i, _i, _i, _i, _vp)
 _sig("b3d_leaky_bwd", _vp, _vp, _vp, _ll, _f, _vp)
+_sig("b3d_vox_blur_axis", _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp)
+_sig("b3d_vox_scale_clamp", _vp, _vp, _vp, _i, _i, _vp)
+_sig("b3d_vox_scale_clamp_bwd", _vp, _vp, _vp, _vp, _vp, _i, _i, _vp)
+_sig("b3d_vox_termination", _vp, _i, _i, _i, _vp, _vp, _vp)
+_sig("b3d_vox_termination_bwd", _vp, _vp, _i, _i, _i, _vp, _vp)
+_sig("b3d_vox_splat_sorted", _vp, _vp, _i, _i, _i, _i, _vp, _vp)
+_sig("b3d_vox_clamp01", _vp, ctypes.c_longlong, _vp)
+_sig("b3d_vox_gather", _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp)
 _sig("b3d_chamfer_nn", _vp, _vp, _i, _i, _i, _vp, _vp, _vp)
 _sig("b3d_chamfer_bwd", _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp)
 _sig("b3d_flat_loss_fwd", _vp, _vp, _i, _i, _i, _vp, _vp)

@@ -114,6 +114,31 @@ B3D_API int b3d_pc_project_bwd(const float* points, const float* quat, const flo
 B3D_API int b3d_pc_splat_grid(const float* pg, int B, int N, int V, int mode, float* grid, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Dense voxel-grid kernels: the stand-alone VoxelsSmooth / termination_probs surface and mode P.
+ *   b3d_vox_blur_axis        one separable kernel of VoxelsSmooth.smooth (utils/smooth_voxels.py:62-73): zero-padded
+ *                            cross-correlation of in [B,V,V,V] along axis 1 (z), 2 (y) or 3 (x); taps in HOST memory;
+ *                            reversed = 1 applies the adjoint.
+ *   b3d_vox_scale_clamp(+_bwd)  clamp(in * scale[b], 0, 1) (smooth_voxels.py:80-82) and its adjoint (dscale zeroed by the call)
+ *   b3d_vox_termination(+_bwd)  termination_probs [B,V+1,V,V] (nullable) and/or the silhouette [B,V,V] = sum of the first V
+ *                            terms flipped along y (effective_loss_function.py:18-56,79-81); mode selects the epsilon pads
+ *   b3d_vox_splat_sorted     raw (unclamped) trilinear scatter of the bin-sorted points (grid zeroed by the call)
+ *   b3d_vox_clamp01          in-place clamp to [0,1] (trilinear_interpolation.py:74)
+ *   b3d_vox_gather           adjoint of clamp + splat: dgrid masked by 0 <= raw <= 1, gathered at the 8 corners -> dpg
+ * ------------------------------------------------------------------------------------------ */
+B3D_API int b3d_vox_blur_axis(const float* in, float* out, const float* taps_host, int ktaps, int axis, int reversed,
+                              int B, int V, void* stream);
+B3D_API int b3d_vox_scale_clamp(const float* in, const float* scale, float* out, int B, int V, void* stream);
+B3D_API int b3d_vox_scale_clamp_bwd(const float* in, const float* scale, const float* gout, float* gin, float* dscale,
+                                    int B, int V, void* stream);
+B3D_API int b3d_vox_termination(const float* vox, int B, int V, int mode, float* probs, float* sil, void* stream);
+B3D_API int b3d_vox_termination_bwd(const float* vox, const float* dsil, int B, int V, int mode, float* dvox, void* stream);
+B3D_API int b3d_vox_splat_sorted(const float* sorted, const int32_t* bin_start, int B, int N, int V, int mode, float* grid,
+                                 void* stream);
+B3D_API int b3d_vox_clamp01(float* x, long long n, void* stream);
+B3D_API int b3d_vox_gather(const float* sorted, const int32_t* bin_start, const float* raw, float* dgrid, int B, int N, int V,
+                           int mode, float* dpg, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Textured-mesh render path (replaces the kaolin dependency)
  *   Renderer.forward                          rendering/renderer.py:39-77
  * ------------------------------------------------------------------------------------------ */
