@@ -30,7 +30,9 @@ def _worker(rank, world, port, q):
     p1, p2 = torch.nn.Parameter(torch.zeros(3)), torch.nn.Parameter(torch.zeros(2, 2))
     p1.grad, p2.grad = torch.full((3,), float(rank + 1)), torch.full((2, 2), float(10 * (rank + 1)))
     _allreduce_grads([p1, p2], world)
-    q.put((rank, y.detach(), xs.grad, bn.running_mean.clone(), bn.running_var.clone(), p1.grad.clone(), p2.grad.clone()))
+    # plain numpy payloads: tensors in an mp.Queue travel through shared-memory handles that die with the worker
+    q.put((rank, y.detach().numpy(), xs.grad.numpy(), bn.running_mean.numpy().copy(), bn.running_var.numpy().copy(),
+           p1.grad.numpy().copy(), p2.grad.numpy().copy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -43,6 +45,7 @@ def test_syncbn_and_grad_allreduce_world2():
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    res = [(r[0],) + tuple(torch.from_numpy(a) for a in r[1:]) for r in res]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
