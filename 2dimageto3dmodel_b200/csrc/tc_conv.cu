@@ -191,12 +191,24 @@ struct WgradParams {
     int splits;                    // K splits (gridDim.z / taps)
 };
 
-template <int BN, int STAGES>
+template <int BN, int T>
+struct WgradSmem {
+    static constexpr int A_BYTES = BM * BK * 4;
+    static constexpr int B_BYTES = (BN / 32) * (T == 1 ? 32 : 36) * 128;
+    static constexpr int STAGE_BYTES = ((A_BYTES + B_BYTES + 1023) / 1024) * 1024;
+};
+
+// T > 1: the CTA computes T horizontally adjacent taps (r, s0 .. s0+T-1) at once.  They share the dY tile, and their X
+// operands are views of ONE staged window of 32 + T - 1 (rounded to 36) pixels shifted by s rows — T accumulators of BN
+// columns in TMEM, ~T x fewer bytes per MAC through the L2 -> SM path that bounds this kernel (profiles/r1_conv_layers.md).
+template <int BN, int STAGES, int T>
 __global__ void __launch_bounds__(NTHREADS, 1)
 wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
                   const WgradParams p, float* __restrict__ dw) {
-    using S = Smem<BN, STAGES>;
-    constexpr int BLK = BK * 32 * 4;          // one [32 pixels][32 channels] box = 4 KB
+    constexpr int BLK = BK * 32 * 4;                      // dY: one [32 pixels][32 channels] box = 4 KB
+    constexpr int WROWS = T == 1 ? 32 : 36;               // X window rows (pixels) per 32-channel block
+    constexpr int XBLK = WROWS * 128;
+    using S = WgradSmem<BN, T>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(base + STAGES * S::STAGE_BYTES);
@@ -206,8 +218,9 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int co0 = blockIdx.x * BM, ci0 = blockIdx.y * BN;
-    const int tap = blockIdx.z % (p.kh * p.kw), split = blockIdx.z / (p.kh * p.kw);
-    const int r = tap / p.kw, s = tap % p.kw;
+    const int groups = p.kh * (p.kw / T);                 // tap groups: T == 1 -> every tap, else one per kernel row
+    const int grp = blockIdx.z % groups, split = blockIdx.z / groups;
+    const int r = T == 1 ? grp / p.kw : grp, s = T == 1 ? grp % p.kw : 0;
     const int per_img = p.kx * p.ky;
     const long long ktotal = (long long)p.N * per_img;
     const long long k_lo = ktotal * split / p.splits, k_hi = ktotal * (split + 1) / p.splits;
@@ -225,7 +238,8 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
         tc::mbar_init(acc_full, 1);
         tc::fence_barrier_init();
     }
-    if (warp == 2) tc::tmem_alloc<(BN < 32 ? 32 : BN)>(tmem_slot);
+    constexpr uint32_t TCOLS = T * BN <= 64 ? 64 : T * BN <= 128 ? 128 : T * BN <= 256 ? 256 : 512;
+    if (warp == 2) tc::tmem_alloc<TCOLS>(tmem_slot);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -257,9 +271,11 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
                 const uint32_t a = tc::smem_u32(base + st * S::STAGE_BYTES);
                 const uint32_t b = a + S::A_BYTES;
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k)      // 8 pixel rows (two 4-row swizzle atoms, 1024 B) per MMA
-                    tc::umma_tf32(tmem_acc, tc::umma_desc_mn128(a + k * 1024, BLK, 512),
-                                  tc::umma_desc_mn128(b + k * 1024, BLK, 512), idesc, (it | k) ? 1u : 0u);
+                for (int t = 0; t < T; ++t)
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)      // 8 pixel rows (two 4-row swizzle atoms, 1024 B) per MMA
+                        tc::umma_tf32(tmem_acc + t * BN, tc::umma_desc_mn128(a + k * 1024, BLK, 512),
+                                      tc::umma_desc_mn128(b + (t + 8 * k) * 128, XBLK, 512), idesc, (it | k) ? 1u : 0u);
                 tc::umma_commit(empty + st);
             }
             tc::umma_commit(acc_full);
@@ -270,21 +286,35 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
         tc::mbar_wait(acc_full, 0);
         tc::tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-            float v[32];
-            tc::tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-            if (co < p.Cout) {
+        for (int t = 0; t < T; ++t)
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                float v[32];
+                tc::tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * BN + c), v);
+                if (co < p.Cout) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int ci = ci0 + c + j;
-                    if (ci < p.Cin) atomicAdd(dw + (((size_t)co * p.Cin + ci) * p.kh + r) * p.kw + s, v[j]);
+                    for (int j = 0; j < 32; ++j) {
+                        const int ci = ci0 + c + j;
+                        if (ci < p.Cin) atomicAdd(dw + (((size_t)co * p.Cin + ci) * p.kh + r) * p.kw + s + t, v[j]);
+                    }
                 }
             }
-        }
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 2) tc::tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_acc);
+    if (warp == 2) tc::tmem_dealloc<TCOLS>(tmem_acc);
+}
+
+template <int BN, int STAGES, int T>
+int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, const WgradParams& p, float* dw, dim3 grid, cudaStream_t st) {
+    constexpr int WROWS = T == 1 ? 32 : 36;
+    constexpr int STAGE = ((BM * BK * 4 + (BN / 32) * WROWS * 128 + 1023) / 1024) * 1024;
+    constexpr int TOTAL = STAGES * STAGE + 1024 + 256;
+    static_assert(TOTAL <= 227 * 1024, "wgrad pipeline does not fit shared memory");
+    B3D_CUDA_OK(cudaFuncSetAttribute(wgrad_tf32_kernel<BN, STAGES, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOTAL));
+    wgrad_tf32_kernel<BN, STAGES, T><<<grid, NTHREADS, TOTAL, st>>>(mdy, mx, p, dw);
+    B3D_LAUNCH_OK();
+    return B3D_OK;
 }
 
 template <int BN, int STAGES, bool WMN>
@@ -386,8 +416,11 @@ int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, int N, int
     p.kx = b3d::ceil_div(Wout, p.BWk);
     p.ky = b3d::ceil_div(Hout, p.BHk);
     p.kh = kh; p.kw = kw; p.pad_y = pad_y; p.st = stride;
-    const int BN = Cin > 64 ? 128 : 64;
-    const int base_ctas = b3d::ceil_div(Cout, BM) * b3d::ceil_div(Cin, BN) * kh * kw;
+    // a row of kw taps per CTA when the K slice is a 32-pixel row segment (Wout >= 32) of a stride-1 conv
+    int T = 1;
+    if (stride == 1 && Wout >= BK && (kw == 3 || kw == 5) && !getenv("B3D_WGRAD_T1")) T = kw;
+    const int BN = (Cin > 64 && T != 5) ? 128 : 64;          // T * BN <= 512 TMEM columns
+    const int base_ctas = b3d::ceil_div(Cout, BM) * b3d::ceil_div(Cin, BN) * kh * (kw / T);
     const long long ktotal = (long long)N * p.kx * p.ky;
     int splits = (2 * 148 + base_ctas - 1) / base_ctas;          // aim at ~2 waves of CTAs
     if (splits > ktotal / 8) splits = (int)(ktotal / 8);         // at least 8 K slices per CTA
@@ -404,24 +437,18 @@ int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, int N, int
     {
         const uint64_t dims[5] = {32, (uint64_t)W, (uint64_t)H, (uint64_t)N, (uint64_t)Cin / 32};
         const uint64_t strides[4] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4, 128};
-        const uint32_t box[5] = {32, (uint32_t)(stride * (p.BWk - 1) + 1), (uint32_t)(stride * (p.BHk - 1) + 1), 1,
+        const uint32_t box[5] = {32, (uint32_t)(T == 1 ? stride * (p.BWk - 1) + 1 : 36), (uint32_t)(stride * (p.BHk - 1) + 1), 1,
                                  (uint32_t)(BN / 32)};
         const uint32_t es[5] = {1, (uint32_t)stride, (uint32_t)stride, 1, 1};
         if (int rc = tc::make_tmap_f32(&mx, x, 5, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid(b3d::ceil_div(Cout, BM), b3d::ceil_div(Cin, BN), kh * kw * splits);
-    if (BN == 128) {
-        using S = Smem<128, 6>;
-        B3D_CUDA_OK(cudaFuncSetAttribute(wgrad_tf32_kernel<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-        wgrad_tf32_kernel<128, 6><<<grid, NTHREADS, S::TOTAL, st>>>(mdy, mx, p, dw);
-    } else {
-        using S = Smem<64, 8>;
-        B3D_CUDA_OK(cudaFuncSetAttribute(wgrad_tf32_kernel<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-        wgrad_tf32_kernel<64, 8><<<grid, NTHREADS, S::TOTAL, st>>>(mdy, mx, p, dw);
-    }
-    B3D_LAUNCH_OK();
-    return B3D_OK;
+    dim3 grid(b3d::ceil_div(Cout, BM), b3d::ceil_div(Cin, BN), kh * (kw / T) * splits);
+    if (T == 3 && BN == 128) return launch_wgrad<128, 6, 3>(mdy, mx, p, dw, grid, st);
+    if (T == 3) return launch_wgrad<64, 8, 3>(mdy, mx, p, dw, grid, st);
+    if (T == 5) return launch_wgrad<64, 8, 5>(mdy, mx, p, dw, grid, st);
+    if (BN == 128) return launch_wgrad<128, 6, 1>(mdy, mx, p, dw, grid, st);
+    return launch_wgrad<64, 8, 1>(mdy, mx, p, dw, grid, st);
 }
 
 }  // extern "C"
