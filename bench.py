@@ -201,6 +201,8 @@ def run_cuda(args):
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
+        # NCCL collectives are captured into the step's CUDA graph: the watchdog must not poll CUDA during capture
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
         import torch.distributed as dist
         backend = os.environ.get("B3D_DIST_BACKEND", "nccl")
         dist.init_process_group(backend, **({"device_id": dev} if backend == "nccl" else {}))
@@ -253,9 +255,11 @@ def run_cuda(args):
 
     host_loss = torch.empty(1).pin_memory()
     graph = None
-    # N > 1: the step contains collectives (gradient all-reduce, SyncBN statistics); they are launched eagerly, not
-    # captured (capturing NCCL needs process-wide capture-safe error handling) — the cfg3 step is GPU-bound either way.
-    if not args.no_graph and (world == 1 or not cfg["gan"]):
+    # N > 1: the step contains NCCL collectives (gradient all-reduce, SyncBN statistics); they are captured into the
+    # graph too (thread-local capture mode, NCCL async error handling off).  B3D_DDP_EAGER=1 launches eagerly instead.
+    capture_ok = world == 1 or not cfg["gan"] or (os.environ.get("B3D_DIST_BACKEND", "nccl") == "nccl"
+                                                  and not os.environ.get("B3D_DDP_EAGER"))
+    if not args.no_graph and capture_ok:
         # the step has no host synchronisation: capture it once (forward + backward) and replay it
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -264,7 +268,7 @@ def run_cuda(args):
                 wl.step(fresh(resident))
         torch.cuda.current_stream().wait_stream(side)
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        with torch.cuda.graph(graph, capture_error_mode="thread_local" if world > 1 else "global"):
             g_loss, g_grads = wl.step(fresh(resident))
 
     def step_resident():
