@@ -314,9 +314,17 @@ def run_cuda(args):
     prof = {k: statistics.mean(v) for k, v in raw_prof.items()}
     prof_tot = {k: sum(v) / nprof for k, v in raw_prof.items()}     # ms per step per entry point
 
-    if rank != 0:
+    def finish():
+        """All ranks leave together; with NCCL captured in a CUDA graph the communicator teardown can block, so multi-rank
+        runs end with a barrier and a hard exit (the JSON line is flushed first)."""
         if dist is not None:
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            dist.barrier()
+            sys.stdout.flush()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
     ms = total_ms / args.steps
     value = world * B * iters_per_step / (ms / 1e3)
@@ -367,9 +375,8 @@ def run_cuda(args):
         out["dtype"] = "tf32 (convs) / f32"
     if world == 1 and not os.environ.get("B3D_BENCH_NO_CPU"):
         out["cpu_baseline"] = cpu_baseline(cfg, budget_s=25.0)
-    print(json.dumps(out))
-    if dist is not None:
-        dist.destroy_process_group()
+    print(json.dumps(out), flush=True)
+    finish()
 
 
 # --------------------------------------------------------------------------------------------- CPU arm
