@@ -35,3 +35,104 @@ def pad_x(x_nchw, amount, mode):
             return torch.nn.functional.pad(x_nchw, (amount, amount, 0, 0), mode='replicate')
         return torch.cat((x_nchw[..., -amount:], x_nchw, x_nchw[..., :amount]), dim=3)
     return _PadX.apply(x_nchw.permute(0, 2, 3, 1), int(amount), int(mode)).permute(0, 3, 1, 2)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fused conditional-batch-norm -> LeakyReLU -> (+ residual) -> (LeakyReLU) -> x2 nearest upsample -> replicate pad
+# ------------------------------------------------------------------------------------------------------------------
+def _dist_world():
+    import torch.distributed as dist
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+class _CBNActPad(torch.autograd.Function):
+    """y [N,H,W,C] (conv output, NHWC), gamma_t = 1 + gamma [N,C], beta [N,C], mean / invstd [C] (already computed)
+    -> out [N, up*H, up*W + 2*pad, C].  `skip` (optional) [N,H,Ws,C] read at pixel offset skip_off.
+    `batch_stats`: the statistics were computed from y (training mode), so dy carries the batch-norm coupling terms."""
+
+    @staticmethod
+    def forward(ctx, y, gamma_t, beta, mean, invstd, skip, skip_off, up, pad, post_leaky, batch_stats, sync):
+        y = dev(y.detach(), "y")
+        N, H, W, C = y.shape
+        gt, bt = gamma_t.detach().contiguous(), beta.detach().contiguous()
+        scale = (invstd[None, :] * gt).contiguous()
+        shift = (bt - mean[None, :] * scale).contiguous()
+        sk = dev(skip.detach(), "skip") if skip is not None else None
+        pitch = sk.shape[2] if sk is not None else 0
+        out = torch.empty(N, up * H, up * W + 2 * pad, C, device=y.device, dtype=torch.float32)
+        check(lib.b3d_cbn_act_fwd(ptr(y), ptr(scale), ptr(shift), ptr(sk), pitch, skip_off, ptr(out), N, H, W, C, up, pad, 0.2,
+                                  int(post_leaky), stream_ptr(y)))
+        ctx.save_for_backward(y, gt, scale, shift, mean, invstd, sk if sk is not None else torch.empty(0))
+        ctx.cfg = (skip_off, up, pad, post_leaky, batch_stats, sync, sk is not None, skip.shape if skip is not None else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        y, gt, scale, shift, mean, invstd, sk = ctx.saved_tensors
+        skip_off, up, pad, post_leaky, batch_stats, sync, has_skip, skip_shape = ctx.cfg
+        N, H, W, C = y.shape
+        gout = dev(gout, "grad")
+        st = stream_ptr(y)
+        ga = torch.empty_like(y)
+        gskip, gpitch = None, 0
+        if has_skip and ctx.needs_input_grad[5]:
+            gpitch = skip_shape[2]
+            gskip = torch.zeros(skip_shape, device=y.device) if gpitch != W else torch.empty(skip_shape, device=y.device)
+        S1 = torch.empty(N, C, device=y.device)
+        S2 = torch.empty(N, C, device=y.device)
+        check(lib.b3d_cbn_act_bwd1(ptr(gout), ptr(y), ptr(scale), ptr(shift), ptr(sk) if has_skip else None,
+                                   sk.shape[2] if has_skip else 0, skip_off, ptr(mean), ptr(invstd), ptr(ga), ptr(gskip), gpitch,
+                                   skip_off, ptr(S1), ptr(S2), N, H, W, C, up, pad, 0.2, int(post_leaky), st))
+        dbeta, dgamma = S1, S2
+        if batch_stats:
+            red = torch.stack(((gt * S1).sum(0), (gt * S2).sum(0)))            # [2, C]
+            M = N * H * W
+            if sync:
+                import torch.distributed as dist
+                dist.all_reduce(red)
+                M *= dist.get_world_size()
+            red = (red / M).contiguous()
+            m1, m2 = red[0].contiguous(), red[1].contiguous()
+        else:
+            m1 = m2 = torch.zeros(C, device=y.device)
+        check(lib.b3d_cbn_act_bwd2(ptr(ga), ptr(y), ptr(gt), ptr(mean), ptr(invstd), ptr(m1), ptr(m2), N, H, W, C, st))
+        return ga, dgamma, dbeta, None, None, gskip, None, None, None, None, None, None
+
+
+def cbn_act_pad(y_nchw, cbn, z, skip_nchw=None, skip_off=0, up=1, pad=1, post_leaky=False):
+    """ConditionalBatchNorm2d(y, z) -> LeakyReLU(0.2) [-> + skip] [-> LeakyReLU] [-> x2 upsample] -> replicate pad, fused.
+    `cbn` is a models.gan.ConditionalBatchNorm2d whose .norm is a (Synchronized)BatchNorm2d without affine; statistics and
+    running buffers follow F.batch_norm (single process) or the reference's SyncBN formulas (torch.distributed)."""
+    bn = cbn.norm
+    y = y_nchw.permute(0, 2, 3, 1)
+    C = y.shape[3]
+    gamma_t = 1 + cbn.fc_gamma(z)
+    beta = cbn.fc_beta(z)
+    sync = False
+    if bn.training:
+        yv = y_nchw.detach()
+        n = yv.numel() // C
+        mean, invstd = torch.batch_norm_stats(yv, bn.eps)
+        var_b = invstd.pow(-2) - bn.eps
+        if _dist_world() > 1 and bn.__class__.__name__.startswith("Synchronized"):
+            import torch.distributed as dist
+            sync = True
+            stats = torch.stack((mean * n, (var_b + mean * mean) * n))
+            dist.all_reduce(stats)
+            n = n * dist.get_world_size()
+            mean = stats[0] / n
+            var_b = stats[1] / n - mean * mean
+            invstd = var_b.clamp(min=bn.eps).pow(-0.5)                       # sync_batchnorm/batchnorm.py:150
+        if bn.track_running_stats:
+            with torch.no_grad():
+                bn.running_mean.mul_(1 - bn.momentum).add_(mean, alpha=bn.momentum)
+                bn.running_var.mul_(1 - bn.momentum).add_(var_b * (n / max(n - 1, 1)), alpha=bn.momentum)
+                bn.num_batches_tracked += 1
+        batch_stats = True
+    else:
+        mean, invstd = bn.running_mean, (bn.running_var + bn.eps).rsqrt()
+        batch_stats = False
+    skip = skip_nchw.permute(0, 2, 3, 1) if skip_nchw is not None else None
+    out = _CBNActPad.apply(y, gamma_t, beta, mean.contiguous(), invstd.contiguous(), skip, int(skip_off), int(up), int(pad),
+                           bool(post_leaky), batch_stats, sync)
+    return out.permute(0, 3, 1, 2)

@@ -102,3 +102,173 @@ int b3d_leaky_bwd(const float* gy, const float* y, float* out, long long n, floa
     return B3D_OK;
 }
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Fused generator glue (models/gan.py:282-286 ConditionalBatchNorm2d, :309-311 LeakyReLU + residual, :319 nearest x2
+// upsample, :329 replicate pad): one pass from a conv output y [N,H,W,C] to the NEXT conv's padded input
+//     out[n, yo, xo, c] = post( leaky(y[n,ys,xs,c] * scale[n,c] + shift[n,c]) + skip[n,ys,xs,c] )
+// with (ys, xs) = (yo / up, clamp(xo - pad, 0, up*W - 1) / up), scale = inv_std * (1 + gamma), shift = beta - mean*scale.
+// The reference runs ~8 full-tensor kernels for this chain, each an HBM round trip.
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+struct CbnGeom {
+    int N, H, W, C4;             // input y [N,H,W,4*C4]
+    int up, pad;                 // output [N, up*H, up*W + 2*pad, C]
+    int skip_pitch, skip_off;    // skip pixel (y,x) lives at row (y*skip_pitch + x + skip_off); pitch 0 = no skip
+    float slope;                 // LeakyReLU slope of the first activation
+    int post_leaky;              // apply LeakyReLU again after the residual add (blk6 / mesh head)
+};
+
+__device__ __forceinline__ float lk(float v, float s) { return v >= 0.f ? v : v * s; }
+
+__global__ void __launch_bounds__(NT)
+cbn_act_fwd_kernel(const float4* __restrict__ y, const float4* __restrict__ scale, const float4* __restrict__ shift,
+                   const float4* __restrict__ skip, float4* __restrict__ out, const CbnGeom g) {
+    const int Wo = g.up * g.W + 2 * g.pad, Ho = g.up * g.H;
+    const long long total = (long long)g.N * Ho * Wo * g.C4;
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+        const int c = (int)(i % g.C4);
+        long long t = i / g.C4;
+        const int xo = (int)(t % Wo);
+        t /= Wo;
+        const int yo = (int)(t % Ho);
+        const int n = (int)(t / Ho);
+        int xs = xo - g.pad;
+        xs = xs < 0 ? 0 : (xs >= g.up * g.W ? g.up * g.W - 1 : xs);
+        const int ys = yo / g.up;
+        xs /= g.up;
+        const float4 v = __ldg(y + (((long long)n * g.H + ys) * g.W + xs) * g.C4 + c);
+        const float4 sc = __ldg(scale + (long long)n * g.C4 + c), sh = __ldg(shift + (long long)n * g.C4 + c);
+        float4 o = make_float4(lk(fmaf(v.x, sc.x, sh.x), g.slope), lk(fmaf(v.y, sc.y, sh.y), g.slope),
+                               lk(fmaf(v.z, sc.z, sh.z), g.slope), lk(fmaf(v.w, sc.w, sh.w), g.slope));
+        if (g.skip_pitch) {
+            const float4 k = __ldg(skip + (((long long)n * g.H + ys) * g.skip_pitch + xs + g.skip_off) * g.C4 + c);
+            o.x += k.x; o.y += k.y; o.z += k.z; o.w += k.w;
+        }
+        if (g.post_leaky) o = make_float4(lk(o.x, g.slope), lk(o.y, g.slope), lk(o.z, g.slope), lk(o.w, g.slope));
+        out[i] = o;
+    }
+}
+
+// Backward pass 1.  Per input pixel: gather the gradient of its up x up children (+ the replicate-pad columns), undo the
+// activations, write ga = d/d(pre-activation) and (optionally) gskip; accumulate S1[n,c] = sum ga, S2[n,c] = sum ga * xhat
+// with xhat = (y - mean) * inv_std.  One CTA walks `rows_per_cta` image rows of one sample, threads own channel quads.
+__global__ void __launch_bounds__(NT)
+cbn_act_bwd1_kernel(const float4* __restrict__ gout, const float4* __restrict__ y, const float4* __restrict__ scale,
+                    const float4* __restrict__ shift, const float4* __restrict__ skip, const float4* __restrict__ mean,
+                    const float4* __restrict__ invstd, float4* __restrict__ ga, float4* __restrict__ gskip, int gskip_pitch,
+                    int gskip_off, float* __restrict__ S1, float* __restrict__ S2, const CbnGeom g, int rows_per_cta) {
+    const int n = blockIdx.y;
+    const int y0 = blockIdx.x * rows_per_cta, y1 = min(y0 + rows_per_cta, g.H);
+    const int Wo = g.up * g.W + 2 * g.pad;
+    for (int c = threadIdx.x % g.C4, lane_px = threadIdx.x / g.C4, px_step = NT / g.C4; c < g.C4; c += g.C4) {
+        const float4 sc = __ldg(scale + (long long)n * g.C4 + c), sh = __ldg(shift + (long long)n * g.C4 + c);
+        const float4 mu = __ldg(mean + c), is = __ldg(invstd + c);
+        float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a1;
+        for (int p = y0 * g.W + lane_px; p < y1 * g.W; p += px_step) {
+            const int ys = p / g.W, xs = p % g.W;
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < g.up; ++i) {
+                const float4* row = gout + (((long long)n * g.up * g.H + g.up * ys + i) * Wo) * g.C4 + c;
+                int lo = g.up * xs + g.pad, hi = lo + g.up;          // children columns [lo, hi)
+                if (xs == 0) lo = 0;                                  // left pad columns replicate column 0
+                if (xs == g.W - 1) hi = Wo;                           // right pad columns replicate the last column
+                for (int xo = lo; xo < hi; ++xo) {
+                    const float4 v = __ldg(row + (long long)xo * g.C4);
+                    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+                }
+            }
+            const long long idx = (((long long)n * g.H + ys) * g.W + xs) * g.C4 + c;
+            const float4 v = __ldg(y + idx);
+            const float4 pre = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
+            if (g.post_leaky) {                                       // sign of (leaky(pre) + skip)
+                float4 k = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g.skip_pitch) k = __ldg(skip + (((long long)n * g.H + ys) * g.skip_pitch + xs + g.skip_off) * g.C4 + c);
+                s.x = (lk(pre.x, g.slope) + k.x) >= 0.f ? s.x : s.x * g.slope;
+                s.y = (lk(pre.y, g.slope) + k.y) >= 0.f ? s.y : s.y * g.slope;
+                s.z = (lk(pre.z, g.slope) + k.z) >= 0.f ? s.z : s.z * g.slope;
+                s.w = (lk(pre.w, g.slope) + k.w) >= 0.f ? s.w : s.w * g.slope;
+            }
+            if (gskip) gskip[(((long long)n * g.H + ys) * gskip_pitch + xs + gskip_off) * g.C4 + c] = s;
+            const float4 a = make_float4(pre.x >= 0.f ? s.x : s.x * g.slope, pre.y >= 0.f ? s.y : s.y * g.slope,
+                                         pre.z >= 0.f ? s.z : s.z * g.slope, pre.w >= 0.f ? s.w : s.w * g.slope);
+            ga[idx] = a;
+            a1.x += a.x; a1.y += a.y; a1.z += a.z; a1.w += a.w;
+            a2.x = fmaf(a.x, (v.x - mu.x) * is.x, a2.x); a2.y = fmaf(a.y, (v.y - mu.y) * is.y, a2.y);
+            a2.z = fmaf(a.z, (v.z - mu.z) * is.z, a2.z); a2.w = fmaf(a.w, (v.w - mu.w) * is.w, a2.w);
+        }
+        float* s1 = S1 + ((long long)n * g.C4 + c) * 4;
+        float* s2 = S2 + ((long long)n * g.C4 + c) * 4;
+        atomicAdd(s1 + 0, a1.x); atomicAdd(s1 + 1, a1.y); atomicAdd(s1 + 2, a1.z); atomicAdd(s1 + 3, a1.w);
+        atomicAdd(s2 + 0, a2.x); atomicAdd(s2 + 1, a2.y); atomicAdd(s2 + 2, a2.z); atomicAdd(s2 + 3, a2.w);
+    }
+}
+
+// Backward pass 2 (in place on ga): dy = inv_std * (ga * gamma_t - m1 - xhat * m2)
+__global__ void __launch_bounds__(NT)
+cbn_act_bwd2_kernel(float4* __restrict__ ga, const float4* __restrict__ y, const float4* __restrict__ gamma_t,
+                    const float4* __restrict__ mean, const float4* __restrict__ invstd, const float4* __restrict__ m1,
+                    const float4* __restrict__ m2, long long per_n, int C4, long long total) {
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+        const int c = (int)(i % C4);
+        const long long n = i / per_n;
+        const float4 a = ga[i], v = __ldg(y + i), gt = __ldg(gamma_t + n * C4 + c);
+        const float4 mu = __ldg(mean + c), is = __ldg(invstd + c), q1 = __ldg(m1 + c), q2 = __ldg(m2 + c);
+        ga[i] = make_float4(is.x * (a.x * gt.x - q1.x - (v.x - mu.x) * is.x * q2.x), is.y * (a.y * gt.y - q1.y - (v.y - mu.y) * is.y * q2.y),
+                            is.z * (a.z * gt.z - q1.z - (v.z - mu.z) * is.z * q2.z), is.w * (a.w * gt.w - q1.w - (v.w - mu.w) * is.w * q2.w));
+    }
+}
+}  // namespace
+
+extern "C" {
+int b3d_cbn_act_fwd(const float* y, const float* scale, const float* shift, const float* skip, int skip_pitch, int skip_off,
+                    float* out, int N, int H, int W, int C, int up, int pad, float slope, int post_leaky, void* stream) {
+    B3D_REQUIRE(N >= 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0 && (up == 1 || up == 2) && pad >= 0, B3D_EINVAL,
+                "b3d_cbn_act_fwd: bad arguments");
+    if (N == 0) return B3D_OK;
+    B3D_REQUIRE(y && scale && shift && out && (skip != nullptr) == (skip_pitch != 0), B3D_EINVAL, "b3d_cbn_act_fwd: null pointer");
+    CbnGeom g{N, H, W, C / 4, up, pad, skip_pitch, skip_off, slope, post_leaky};
+    const long long total = (long long)N * up * H * (up * W + 2 * pad) * (C / 4);
+    cbn_act_fwd_kernel<<<grid_for(total), NT, 0, (cudaStream_t)stream>>>((const float4*)y, (const float4*)scale, (const float4*)shift,
+                                                                       (const float4*)skip, (float4*)out, g);
+    B3D_LAUNCH_OK();
+    return B3D_OK;
+}
+
+// S1, S2 [N,C] are zeroed by the call; gskip (nullable) is written at pixel offset gskip_off with row pitch gskip_pitch
+// (its pad columns are NOT touched: the caller zeroes the buffer when gskip_pitch != W)
+int b3d_cbn_act_bwd1(const float* gout, const float* y, const float* scale, const float* shift, const float* skip, int skip_pitch,
+                     int skip_off, const float* mean, const float* invstd, float* ga, float* gskip, int gskip_pitch, int gskip_off,
+                     float* S1, float* S2, int N, int H, int W, int C, int up, int pad, float slope, int post_leaky, void* stream) {
+    B3D_REQUIRE(N >= 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0 && C / 4 <= NT && NT % (C / 4) == 0 && (up == 1 || up == 2), B3D_EINVAL,
+                "b3d_cbn_act_bwd1: bad arguments (C/4 must divide %d)", NT);
+    if (N == 0) return B3D_OK;
+    B3D_REQUIRE(gout && y && scale && shift && mean && invstd && ga && S1 && S2, B3D_EINVAL, "b3d_cbn_act_bwd1: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    B3D_CUDA_OK(cudaMemsetAsync(S1, 0, sizeof(float) * (size_t)N * C, st));
+    B3D_CUDA_OK(cudaMemsetAsync(S2, 0, sizeof(float) * (size_t)N * C, st));
+    CbnGeom g{N, H, W, C / 4, up, pad, skip_pitch, skip_off, slope, post_leaky};
+    // enough CTAs to fill the GPU a few times, each with >= 1 row
+    int rows = (int)(((long long)N * H + 148 * 8 - 1) / (148 * 8));
+    rows = rows < 1 ? 1 : rows;
+    dim3 grid(b3d::ceil_div(H, rows), N);
+    cbn_act_bwd1_kernel<<<grid, NT, 0, st>>>((const float4*)gout, (const float4*)y, (const float4*)scale, (const float4*)shift,
+                                            (const float4*)skip, (const float4*)mean, (const float4*)invstd, (float4*)ga,
+                                            (float4*)gskip, gskip_pitch, gskip_off, S1, S2, g, rows);
+    B3D_LAUNCH_OK();
+    return B3D_OK;
+}
+
+int b3d_cbn_act_bwd2(float* ga, const float* y, const float* gamma_t, const float* mean, const float* invstd, const float* m1,
+                     const float* m2, int N, int H, int W, int C, void* stream) {
+    B3D_REQUIRE(N >= 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, B3D_EINVAL, "b3d_cbn_act_bwd2: bad arguments");
+    if (N == 0) return B3D_OK;
+    B3D_REQUIRE(ga && y && gamma_t && mean && invstd && m1 && m2, B3D_EINVAL, "b3d_cbn_act_bwd2: null pointer");
+    const long long per_n = (long long)H * W * (C / 4), total = per_n * N;
+    cbn_act_bwd2_kernel<<<grid_for(total), NT, 0, (cudaStream_t)stream>>>((float4*)ga, (const float4*)y, (const float4*)gamma_t,
+                                                                         (const float4*)mean, (const float4*)invstd,
+                                                                         (const float4*)m1, (const float4*)m2, per_n, C / 4, total);
+    B3D_LAUNCH_OK();
+    return B3D_OK;
+}
+}

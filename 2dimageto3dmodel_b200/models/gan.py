@@ -18,7 +18,7 @@ import torch.nn.functional as F
 
 from b3d import B3DError
 from b3d.conv import conv2d as _tc_conv2d
-from b3d.ew import CIRCULAR, REPLICATE, pad_x
+from b3d.ew import CIRCULAR, REPLICATE, cbn_act_pad, pad_x
 from rendering.utils import adjust_poles, circpad, symmetrize_texture
 
 
@@ -252,6 +252,23 @@ class ResBlockUp(nn.Module):
         h = self.relu(self.norm2(self.conv2(self.pad(h, 1)), z))
         return h + skip
 
+    def fusable(self):
+        from torch.nn.modules.batchnorm import _BatchNorm
+        return isinstance(self.norm1.norm, _BatchNorm) and isinstance(self.norm2.norm, _BatchNorm)
+
+    def forward_fused(self, xp, z, up, pad_next, post_leaky=False):
+        """Same block on an input that is ALREADY replicate-padded by 1 (xp = pad(x, 1)); returns the padded input of the
+        consumer: pad(up(out), pad_next) with out = [LeakyReLU](h + skip).  Every conv output goes through exactly one fused
+        elementwise kernel (b3d.ew.cbn_act_pad) instead of BN, affine, LeakyReLU, add, upsample and pad kernels."""
+        y1 = self.conv1(xp)
+        a = cbn_act_pad(y1, self.norm1, z, up=1, pad=1)
+        y2 = self.conv2(a)
+        if isinstance(self.shortcut, nn.Module):
+            skip, off = self.shortcut(xp[..., 1:-1]), 0              # 1x1 conv on the unpadded input
+        else:
+            skip, off = xp, 1                                        # identity: read the interior of the padded input
+        return cbn_act_pad(y2, self.norm2, z, skip_nchw=skip, skip_off=off, up=up, pad=pad_next, post_leaky=post_leaky)
+
 
 class Generator(nn.Module):
     def __init__(self, args, emb_dim, symmetric=True, mesh_head=True):
@@ -309,6 +326,8 @@ class Generator(nn.Module):
 
         x = self.fc(z).view(z.shape[0], -1, self.height, self.width)
         x = x.contiguous(memory_format=torch.channels_last)
+        if self.symmetric and not a.conditional_text and self.blk1.fusable() and not getattr(self, 'disable_fusion', False):
+            return self._forward_fused(x, z, return_attention)
         x = self.up(self.blk1(x, z))
         x = self.blk2(x, z)
         attention_map = None
@@ -338,6 +357,25 @@ class Generator(nn.Module):
             if attention_map is not None:
                 attention_map = symmetrize_texture(attention_map)
         return (x_tex, x_mesh, attention_map) if return_attention else (x_tex, x_mesh)
+
+    def _forward_fused(self, x, z, return_attention):
+        """The same network with the inter-convolution glue fused (replicate-padded tensors flow between the blocks)."""
+        p = pad_x(x, 1, REPLICATE)
+        p = self.blk1.forward_fused(p, z, up=2, pad_next=1)
+        p = self.blk2.forward_fused(p, z, up=2, pad_next=1)          # blk2 -> up: shared by the texture and mesh branches
+        t = p
+        for name in ('blk3a', 'blk3b', 'blk3c'):
+            if hasattr(self, name):
+                t = getattr(self, name).forward_fused(t, z, up=2, pad_next=1)
+        t = self.blk4.forward_fused(t, z, up=2, pad_next=1)
+        t = self.blk5.forward_fused(t, z, up=2, pad_next=1)
+        t = self.blk6.forward_fused(t, z, up=1, pad_next=2, post_leaky=True)
+        x_tex = symmetrize_texture(torch.tanh(self.conv_final(t)))
+        x_mesh = None
+        if self.mesh_head:
+            m = self.blk3_mesh.forward_fused(p, z, up=1, pad_next=2, post_leaky=True)
+            x_mesh = symmetrize_texture(adjust_poles(self.conv_mesh(m)))
+        return (x_tex, x_mesh, None) if return_attention else (x_tex, x_mesh)
 
 
 class SpatialAttention(nn.Module):

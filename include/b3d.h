@@ -242,6 +242,23 @@ B3D_API int b3d_pad_x_fwd(const float* x, float* out, long long rows, int W, int
 B3D_API int b3d_pad_x_bwd(const float* gout, float* gx, long long rows, int W, int C, int amount, int mode, void* stream);
 B3D_API int b3d_leaky_bwd(const float* gy, const float* y, float* out, long long n, float slope, void* stream);
 
+/* Fused generator glue between two convolutions (models/gan.py:282-286 ConditionalBatchNorm2d, :309-311 LeakyReLU and
+ * residual add, :319 nearest x2 upsample, :329 replicate pad), NHWC, C % 4 == 0:
+ *   out[n, yo, xo, :] = post( leaky(y[n,ys,xs,:] * scale[n,:] + shift[n,:]) + skip[n,ys,xs,:] ),
+ *   (ys, xs) = (yo / up, clamp(xo - pad, 0, up*W-1) / up);  out [N, up*H, up*W + 2*pad, C];  scale = inv_std*(1+gamma),
+ *   shift = beta - mean*scale ([N,C]); skip (nullable) is read at row pitch skip_pitch, pixel offset skip_off.
+ * bwd1: gout -> ga = d/d(pre-activation) [N,H,W,C], gskip (nullable), S1[n,c] = sum ga, S2[n,c] = sum ga*xhat (zeroed by the call)
+ * bwd2 (in place on ga): dy = inv_std * (ga * gamma_t - m1 - xhat * m2), m1/m2 [C] = batch means of d xhat, d xhat * xhat   */
+B3D_API int b3d_cbn_act_fwd(const float* y, const float* scale, const float* shift, const float* skip, int skip_pitch,
+                            int skip_off, float* out, int N, int H, int W, int C, int up, int pad, float slope,
+                            int post_leaky, void* stream);
+B3D_API int b3d_cbn_act_bwd1(const float* gout, const float* y, const float* scale, const float* shift, const float* skip,
+                             int skip_pitch, int skip_off, const float* mean, const float* invstd, float* ga, float* gskip,
+                             int gskip_pitch, int gskip_off, float* S1, float* S2, int N, int H, int W, int C, int up, int pad,
+                             float slope, int post_leaky, void* stream);
+B3D_API int b3d_cbn_act_bwd2(float* ga, const float* y, const float* gamma_t, const float* mean, const float* invstd,
+                             const float* m1, const float* m2, int N, int H, int W, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
