@@ -164,7 +164,13 @@ def conv2d(x_nchw, weight, bias=None, pad_y=0, stride=1, leaky=1.0):
         # dimension — X'[n,y,x, s*Cin + c] = X[n,y,x+s,c] — so the tensor cores see kh taps of kw*Cin real channels
         # instead of kh*kw taps of Cin channels zero-padded to 32.
         Wout = x.shape[2] - kw + 1
-        x = torch.cat([x[:, :, s:s + Wout, :] for s in range(kw)], dim=3)
+        cpad = (-kw * Cin) % 32                            # ... and round up to the 32-channel K slice in the same pass
+        parts = [x[:, :, s:s + Wout, :] for s in range(kw)]
+        if cpad:
+            parts.append(x.new_zeros(x.shape[0], x.shape[1], Wout, cpad))
+        x = torch.cat(parts, dim=3)
         weight = weight.permute(0, 3, 1, 2).reshape(Cout, kw * Cin, kh, 1)          # [co, s*Cin + c, r, 0]
+        if cpad:
+            weight = torch.nn.functional.pad(weight, (0, 0, 0, 0, 0, cpad))
     y = _Conv2dNHWC.apply(x, weight, bias, int(pad_y), int(stride), float(leaky))
     return y.permute(0, 3, 1, 2)
