@@ -189,6 +189,8 @@ struct WgradParams {
     int kx, ky;                    // K slices along x and y per image
     int kh, kw, pad_y, st;
     int splits;                    // K splits (gridDim.z / taps)
+    int tstep;                     // taps of one CTA are s0, s0 + tstep, ... (1: adjacent taps of a stride-1 conv,
+                                   // 2: taps of equal parity of a stride-2 conv = adjacent rows of the strided window)
 };
 
 template <int BN, int T>
@@ -218,9 +220,10 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int co0 = blockIdx.x * BM, ci0 = blockIdx.y * BN;
-    const int groups = p.kh * (p.kw / T);                 // tap groups: T == 1 -> every tap, else one per kernel row
+    const int gpr = p.kw / T;                             // tap groups per kernel row
+    const int groups = p.kh * gpr;
     const int grp = blockIdx.z % groups, split = blockIdx.z / groups;
-    const int r = T == 1 ? grp / p.kw : grp, s = T == 1 ? grp % p.kw : 0;
+    const int r = grp / gpr, s = grp % gpr;               // first tap of the group (tstep 1: gpr is 1 or kw; tstep 2: parity)
     const int per_img = p.kx * p.ky;
     const long long ktotal = (long long)p.N * per_img;
     const long long k_lo = ktotal * split / p.splits, k_hi = ktotal * (split + 1) / p.splits;
@@ -295,7 +298,7 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int ci = ci0 + c + j;
-                        if (ci < p.Cin) atomicAdd(dw + (((size_t)co * p.Cin + ci) * p.kh + r) * p.kw + s + t, v[j]);
+                        if (ci < p.Cin) atomicAdd(dw + (((size_t)co * p.Cin + ci) * p.kh + r) * p.kw + s + t * p.tstep, v[j]);
                     }
                 }
             }
@@ -418,7 +421,11 @@ int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, int N, int
     p.kh = kh; p.kw = kw; p.pad_y = pad_y; p.st = stride;
     // a row of kw taps per CTA when the K slice is a 32-pixel row segment (Wout >= 32) of a stride-1 conv
     int T = 1;
-    if (stride == 1 && Wout >= BK && (kw == 3 || kw == 5) && !getenv("B3D_WGRAD_T1")) T = kw;
+    p.tstep = 1;
+    if (Wout >= BK && !getenv("B3D_WGRAD_T1")) {
+        if (stride == 1 && (kw == 3 || kw == 5)) T = kw;
+        if (stride == 2 && kw == 4) { T = 2; p.tstep = 2; }      // taps {0,2} and {1,3}: rows t of one strided window
+    }
     const int BN = (Cin > 64 && T != 5) ? 128 : 64;          // T * BN <= 512 TMEM columns
     const int base_ctas = b3d::ceil_div(Cout, BM) * b3d::ceil_div(Cin, BN) * kh * (kw / T);
     const long long ktotal = (long long)N * p.kx * p.ky;
@@ -437,13 +444,15 @@ int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, int N, int
     {
         const uint64_t dims[5] = {32, (uint64_t)W, (uint64_t)H, (uint64_t)N, (uint64_t)Cin / 32};
         const uint64_t strides[4] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4, 128};
-        const uint32_t box[5] = {32, (uint32_t)(T == 1 ? stride * (p.BWk - 1) + 1 : 36), (uint32_t)(stride * (p.BHk - 1) + 1), 1,
+        const uint32_t box[5] = {32, (uint32_t)(T == 1 ? stride * (p.BWk - 1) + 1 : stride * 35 + 1), (uint32_t)(stride * (p.BHk - 1) + 1), 1,
                                  (uint32_t)(BN / 32)};
         const uint32_t es[5] = {1, (uint32_t)stride, (uint32_t)stride, 1, 1};
         if (int rc = tc::make_tmap_f32(&mx, x, 5, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
     }
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(b3d::ceil_div(Cout, BM), b3d::ceil_div(Cin, BN), kh * (kw / T) * splits);
+    if (T == 2 && BN == 128) return launch_wgrad<128, 6, 2>(mdy, mx, p, dw, grid, st);
+    if (T == 2) return launch_wgrad<64, 8, 2>(mdy, mx, p, dw, grid, st);
     if (T == 3 && BN == 128) return launch_wgrad<128, 6, 3>(mdy, mx, p, dw, grid, st);
     if (T == 3) return launch_wgrad<64, 8, 3>(mdy, mx, p, dw, grid, st);
     if (T == 5) return launch_wgrad<64, 8, 5>(mdy, mx, p, dw, grid, st);
