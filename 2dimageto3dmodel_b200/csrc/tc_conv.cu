@@ -204,7 +204,7 @@ struct WgradSmem {
 // operands are views of ONE staged window of 32 + T - 1 (rounded to 36) pixels shifted by s rows — T accumulators of BN
 // columns in TMEM, ~T x fewer bytes per MAC through the L2 -> SM path that bounds this kernel (profiles/r1_conv_layers.md).
 template <int BN, int STAGES, int T>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS, (T * BN <= 256 && STAGES <= 4) ? 2 : 1)
 wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
                   const WgradParams p, float* __restrict__ dw) {
     constexpr int BLK = BK * 32 * 4;                      // dY: one [32 pixels][32 channels] box = 4 KB
@@ -429,7 +429,7 @@ int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, int N, int
     const int BN = (Cin > 64 && T != 5) ? 128 : 64;          // T * BN <= 512 TMEM columns
     const int base_ctas = b3d::ceil_div(Cout, BM) * b3d::ceil_div(Cin, BN) * kh * (kw / T);
     const long long ktotal = (long long)N * p.kx * p.ky;
-    int splits = (2 * 148 + base_ctas - 1) / base_ctas;          // aim at ~2 waves of CTAs
+    int splits = ((T <= 2 ? 4 : 2) * 148 + base_ctas - 1) / base_ctas;   // ~2 waves of CTAs per resident CTA slot
     if (splits > ktotal / 8) splits = (int)(ktotal / 8);         // at least 8 K slices per CTA
     if (splits < 1) splits = 1;
     p.splits = splits;
@@ -451,13 +451,14 @@ int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, int N, int
     }
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(b3d::ceil_div(Cout, BM), b3d::ceil_div(Cin, BN), kh * (kw / T) * splits);
-    if (T == 2 && BN == 128) return launch_wgrad<128, 6, 2>(mdy, mx, p, dw, grid, st);
-    if (T == 2) return launch_wgrad<64, 8, 2>(mdy, mx, p, dw, grid, st);
+    const bool two = !getenv("B3D_WGRAD_1CTA");           // two CTAs per SM (half-depth ring) where TMEM has room for both
+    if (T == 2 && BN == 128) return two ? launch_wgrad<128, 3, 2>(mdy, mx, p, dw, grid, st) : launch_wgrad<128, 6, 2>(mdy, mx, p, dw, grid, st);
+    if (T == 2) return two ? launch_wgrad<64, 4, 2>(mdy, mx, p, dw, grid, st) : launch_wgrad<64, 8, 2>(mdy, mx, p, dw, grid, st);
     if (T == 3 && BN == 128) return launch_wgrad<128, 6, 3>(mdy, mx, p, dw, grid, st);
     if (T == 3) return launch_wgrad<64, 8, 3>(mdy, mx, p, dw, grid, st);
     if (T == 5) return launch_wgrad<64, 8, 5>(mdy, mx, p, dw, grid, st);
-    if (BN == 128) return launch_wgrad<128, 6, 1>(mdy, mx, p, dw, grid, st);
-    return launch_wgrad<64, 8, 1>(mdy, mx, p, dw, grid, st);
+    if (BN == 128) return two ? launch_wgrad<128, 3, 1>(mdy, mx, p, dw, grid, st) : launch_wgrad<128, 6, 1>(mdy, mx, p, dw, grid, st);
+    return two ? launch_wgrad<64, 4, 1>(mdy, mx, p, dw, grid, st) : launch_wgrad<64, 8, 1>(mdy, mx, p, dw, grid, st);
 }
 
 }  // extern "C"
