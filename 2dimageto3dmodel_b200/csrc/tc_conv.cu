@@ -429,7 +429,7 @@ int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, int N, int
     const int BN = (Cin > 64 && T != 5) ? 128 : 64;          // T * BN <= 512 TMEM columns
     const int base_ctas = b3d::ceil_div(Cout, BM) * b3d::ceil_div(Cin, BN) * kh * (kw / T);
     const long long ktotal = (long long)N * p.kx * p.ky;
-    int splits = ((T <= 2 ? 4 : 2) * 148 + base_ctas - 1) / base_ctas;   // ~2 waves of CTAs per resident CTA slot
+    int splits = ((T == 2 ? 4 : 2) * 148 + base_ctas - 1) / base_ctas;   // ~2 waves of CTAs per resident CTA slot
     if (splits > ktotal / 8) splits = (int)(ktotal / 8);         // at least 8 K slices per CTA
     if (splits < 1) splits = 1;
     p.splits = splits;
@@ -457,8 +457,9 @@ int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, int N, int
     if (T == 3 && BN == 128) return launch_wgrad<128, 6, 3>(mdy, mx, p, dw, grid, st);
     if (T == 3) return launch_wgrad<64, 8, 3>(mdy, mx, p, dw, grid, st);
     if (T == 5) return launch_wgrad<64, 8, 5>(mdy, mx, p, dw, grid, st);
-    if (BN == 128) return two ? launch_wgrad<128, 3, 1>(mdy, mx, p, dw, grid, st) : launch_wgrad<128, 6, 1>(mdy, mx, p, dw, grid, st);
-    return two ? launch_wgrad<64, 4, 1>(mdy, mx, p, dw, grid, st) : launch_wgrad<64, 8, 1>(mdy, mx, p, dw, grid, st);
+    // single taps: the deep single-CTA ring measured faster (profiles/r1_conv_layers.md)
+    if (BN == 128) return launch_wgrad<128, 6, 1>(mdy, mx, p, dw, grid, st);
+    return launch_wgrad<64, 8, 1>(mdy, mx, p, dw, grid, st);
 }
 
 }  // extern "C"
