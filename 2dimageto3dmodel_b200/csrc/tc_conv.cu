@@ -30,6 +30,7 @@ struct ConvParams {
     int N, Hout, Wout, Cout;          // logical output extent covered by tiles (before the epilogue transform)
     int BW, BH, BI;                   // output box per CTA, BW*BH*BI == 128
     int tiles_x, tiles_y;             // tiles along W and H (tiles along N = gridDim.x / (tiles_x*tiles_y))
+    int xbase;                        // first output column of this launch (a strip launch covers the last few columns)
     int ntaps, kslices;               // filter taps, Cin / 32
     int sy, sx;                       // input coordinate = s * out + d[t]
     int dy[MAX_TAPS], dx[MAX_TAPS];
@@ -66,7 +67,7 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     t /= p.tiles_x;
     const int ty = t % p.tiles_y;
     const int tn = t / p.tiles_y;
-    const int x0 = tx * p.BW, y0 = ty * p.BH, n0 = tn * p.BI;
+    const int x0 = p.xbase + tx * p.BW, y0 = ty * p.BH, n0 = tn * p.BI;
     const int c0 = blockIdx.y * BN;
 
     if (warp == 0 && lane == 0) {
@@ -356,48 +357,56 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
     B3D_CHECK_ALIGNED(x);
     B3D_CHECK_ALIGNED(wt);
 
-    ConvParams p{};
-    p.N = N; p.Hout = Hout; p.Wout = Wout; p.Cout = Cout;
-    p.BW = pow2_floor(Wout < BM ? Wout : BM);
-    p.BH = pow2_floor(Hout < BM / p.BW ? Hout : BM / p.BW);
-    p.BI = BM / (p.BW * p.BH);
-    p.tiles_x = b3d::ceil_div(Wout, p.BW);
-    p.tiles_y = b3d::ceil_div(Hout, p.BH);
-    const int tiles = p.tiles_x * p.tiles_y * b3d::ceil_div(N, p.BI);
-    p.ntaps = ntaps; p.kslices = Cin / BK; p.sy = sy; p.sx = sx;
-    for (int t = 0; t < ntaps; ++t) { p.dy[t] = dy[t]; p.dx[t] = dx[t]; }
-    p.OH = OH; p.OW = OW; p.OC = OC; p.osy = osy; p.osx = osx; p.ooy = ooy; p.oox = oox;
-    p.leaky = leaky;
-    p.dbg_lbo = 4096; p.dbg_sbo = 512; p.dbg_lt = 1;     // 32-bit MN-major: SWIZZLE_128B_BASE32B, 4-row atoms
-
-    CUtensorMap mx, mw;
-    {
-        const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-        const uint64_t strides[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
-        const uint32_t box[4] = {(uint32_t)BK, (uint32_t)(sx * (p.BW - 1) + 1), (uint32_t)(sy * (p.BH - 1) + 1),
-                                 (uint32_t)p.BI};
-        const uint32_t es[4] = {1, (uint32_t)sx, (uint32_t)sy, 1};
-        if (int rc = tc::make_tmap_f32(&mx, x, 4, dims, strides, box, es)) return rc;
-    }
     const int BN = Cout > 64 ? 128 : 64;
     cudaStream_t st = (cudaStream_t)stream;
+    CUtensorMap mw;
     if (w_cin_major) {        // wt [ntaps, Cin, Cout]: the B operand is N-major (no weight transpose for dgrad)
         B3D_REQUIRE(Cout % 4 == 0, B3D_EINVAL, "b3d_conv2d_tf32: Cout=%d must be a multiple of 4 for cin-major weights", Cout);
         const uint64_t dims[3] = {(uint64_t)Cout, (uint64_t)Cin, (uint64_t)ntaps};
         const uint64_t strides[2] = {(uint64_t)Cout * 4, (uint64_t)Cout * Cin * 4};
         const uint32_t box[3] = {32, (uint32_t)BK, 1};
         if (int rc = tc::make_tmap_f32(&mw, wt, 3, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
-        if (BN == 128) return launch<128, 3, true>(mx, mw, p, bias, out, tiles, st);
-        return launch<64, 4, true>(mx, mw, p, bias, out, tiles, st);
-    }
-    {
+    } else {
         const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)ntaps};
         const uint64_t strides[2] = {(uint64_t)Cin * 4, (uint64_t)Cout * Cin * 4};
         const uint32_t box[3] = {(uint32_t)BK, (uint32_t)BN, 1};
         if (int rc = tc::make_tmap_f32(&mw, wt, 3, dims, strides, box)) return rc;
     }
-    if (BN == 128) return launch<128, 3, false>(mx, mw, p, bias, out, tiles, st);
-    return launch<64, 4, false>(mx, mw, p, bias, out, tiles, st);
+
+    // One launch covers output columns [xlo, xhi).  A width of "power of two + a few columns" (dgrad of an x-padded
+    // input: 130, 66, 34 ...; stride-2 parity classes: 129, 65 ...) would leave a second, almost empty 128-pixel tile in
+    // every row, so the remainder columns get a narrow strip launch of their own.
+    auto run = [&](int xlo, int xhi) -> int {
+        const int wspan = xhi - xlo;
+        ConvParams p{};
+        p.N = N; p.Hout = Hout; p.Wout = xhi; p.Cout = Cout; p.xbase = xlo;
+        p.BW = pow2_floor(wspan < BM ? wspan : BM);
+        p.BH = pow2_floor(Hout < BM / p.BW ? Hout : BM / p.BW);
+        p.BI = BM / (p.BW * p.BH);
+        p.tiles_x = b3d::ceil_div(wspan, p.BW);
+        p.tiles_y = b3d::ceil_div(Hout, p.BH);
+        const int tiles = p.tiles_x * p.tiles_y * b3d::ceil_div(N, p.BI);
+        p.ntaps = ntaps; p.kslices = Cin / BK; p.sy = sy; p.sx = sx;
+        for (int t = 0; t < ntaps; ++t) { p.dy[t] = dy[t]; p.dx[t] = dx[t]; }
+        p.OH = OH; p.OW = OW; p.OC = OC; p.osy = osy; p.osx = osx; p.ooy = ooy; p.oox = oox;
+        p.leaky = leaky;
+        p.dbg_lbo = 4096; p.dbg_sbo = 512; p.dbg_lt = 1;     // 32-bit MN-major: SWIZZLE_128B_BASE32B, 4-row atoms
+        CUtensorMap mx;
+        const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        const uint64_t strides[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
+        const uint32_t box[4] = {(uint32_t)BK, (uint32_t)(sx * (p.BW - 1) + 1), (uint32_t)(sy * (p.BH - 1) + 1), (uint32_t)p.BI};
+        const uint32_t es[4] = {1, (uint32_t)sx, (uint32_t)sy, 1};
+        if (int rc = tc::make_tmap_f32(&mx, x, 4, dims, strides, box, es)) return rc;
+        if (w_cin_major) return BN == 128 ? launch<128, 3, true>(mx, mw, p, bias, out, tiles, st) : launch<64, 4, true>(mx, mw, p, bias, out, tiles, st);
+        return BN == 128 ? launch<128, 3, false>(mx, mw, p, bias, out, tiles, st) : launch<64, 4, false>(mx, mw, p, bias, out, tiles, st);
+    };
+    const int bw_full = pow2_floor(Wout < BM ? Wout : BM);
+    const int rem = Wout % bw_full;
+    if (rem != 0 && rem * 8 <= bw_full && Wout > bw_full) {
+        if (int rc = run(0, Wout - rem)) return rc;
+        return run(Wout - rem, Wout);
+    }
+    return run(0, Wout);
 }
 
 // dy [N,Hout,Wout,Cout], x [N,H,W,Cin] NHWC (x already padded along x; Cin, Cout multiples of 4),
