@@ -134,6 +134,9 @@ _prof_records = None
 _prof_saved = {}
 
 
+_PROF_SHAPES = bool(int(os.environ.get("B3D_PROF_SHAPES", "0")))
+
+
 def prof_enable():
     global _prof_records
     if _prof_records is not None:
@@ -152,6 +155,8 @@ def prof_enable():
             e0.record()
             rc = _fn(*args)
             e1.record()
+            if _PROF_SHAPES and _name.startswith("b3d_conv2d"):        # B3D_PROF_SHAPES=1: one key per conv geometry
+                _name = _name + ":" + ",".join(str(a) for a in args if isinstance(a, int))
             _prof_records.append((_name, e0, e1))
             return rc
 

@@ -153,18 +153,35 @@ class _Conv2dNHWC(torch.autograd.Function):
         return gx, gw, gb, None, None, None
 
 
+_FOLD = os.environ.get("B3D_FOLD", "kh")
+
+
 def conv2d(x_nchw, weight, bias=None, pad_y=0, stride=1, leaky=1.0):
     """Drop-in for F.conv2d(x, w, b, stride, padding=(pad_y, 0)) on logically-NCHW tensors: runs on the tcgen05
     kernels over the channels-last storage (a no-copy view when x is already channels_last) and returns a
     logically-NCHW, channels-last tensor."""
     x = x_nchw.permute(0, 2, 3, 1)
     Cout, Cin, kh, kw = weight.shape
-    if stride == 1 and kw > 1 and Cin * kw <= 64:
-        # thin stems (discriminator conv1: 8 or 11 input channels, 5x5): fold the kw horizontal taps into the channel
-        # dimension — X'[n,y,x, s*Cin + c] = X[n,y,x+s,c] — so the tensor cores see kh taps of kw*Cin real channels
-        # instead of kh*kw taps of Cin channels zero-padded to 32.
+    if stride == 1 and kh > 1 and Cin * kh <= 64 and _FOLD == "kh":
+        # thin stems (discriminator conv1: 8 or 11 input channels, 5x5): fold the kh vertical taps into the channel
+        # dimension — X'[n,y,x, r*Cin + c] = X[n, y+r-pad_y, x, c] (zero rows = the y padding) — so the tensor cores see
+        # kw taps of kh*Cin real channels instead of kh*kw taps of Cin channels zero-padded to 32.  The remaining taps
+        # are horizontal: the weight-gradient kernel covers a whole row of taps per CTA (one pass over dY and X').
+        Hout = x.shape[1] + 2 * pad_y - kh + 1
+        cpad = (-kh * Cin) % 32                            # ... and round up to the 32-channel K slice in the same pass
+        xp = torch.nn.functional.pad(x, (0, 0, 0, 0, pad_y, pad_y)) if pad_y else x
+        parts = [xp[:, r:r + Hout] for r in range(kh)]
+        if cpad:
+            parts.append(x.new_zeros(x.shape[0], Hout, x.shape[2], cpad))
+        x = torch.cat(parts, dim=3)
+        weight = weight.permute(0, 2, 1, 3).reshape(Cout, kh * Cin, 1, kw)          # [co, r*Cin + c, 0, s]
+        if cpad:
+            weight = torch.nn.functional.pad(weight, (0, 0, 0, 0, 0, cpad))
+        pad_y = 0
+    elif stride == 1 and kw > 1 and Cin * kw <= 64:
+        # same fold along x (B3D_FOLD=kw): X'[n,y,x, s*Cin + c] = X[n,y,x+s,c], kh vertical taps remain
         Wout = x.shape[2] - kw + 1
-        cpad = (-kw * Cin) % 32                            # ... and round up to the 32-channel K slice in the same pass
+        cpad = (-kw * Cin) % 32
         parts = [x[:, :, s:s + Wout, :] for s in range(kw)]
         if cpad:
             parts.append(x.new_zeros(x.shape[0], x.shape[1], Wout, cpad))

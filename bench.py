@@ -313,6 +313,9 @@ def run_cuda(args):
     raw_prof = b3d.prof_disable()
     prof = {k: statistics.mean(v) for k, v in raw_prof.items()}
     prof_tot = {k: sum(v) / nprof for k, v in raw_prof.items()}     # ms per step per entry point
+    if os.environ.get("B3D_PROF_SHAPES") == "1" and rank == 0:      # development aid: per-geometry conv times to stderr
+        for k, v in sorted(prof_tot.items(), key=lambda kv: -kv[1])[:60]:
+            print(f"{v:8.3f} ms/step x{len(raw_prof[k]) // nprof:3d}  {k}", file=sys.stderr)
 
     def finish():
         """All ranks leave together; with NCCL captured in a CUDA graph the communicator teardown can block, so multi-rank
