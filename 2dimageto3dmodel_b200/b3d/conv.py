@@ -21,8 +21,10 @@ def taps_layout(weight):
     return weight.permute(2, 3, 0, 1).reshape(kh * kw, co, ci).contiguous()
 
 
-def conv2d_nhwc(x, weight, bias=None, pad_y=0, stride=1, leaky=1.0, wt=None, cin_major=False):
-    """x [N,H,W,Cin] (Cin % 32 == 0), weight [Cout,Cin,kh,kw] -> [N,Hout,Wout,Cout]; zero pad along y only."""
+def conv2d_nhwc(x, weight, bias=None, pad_y=0, stride=1, leaky=1.0, wt=None, cin_major=False, pad_out=0, pad_mode=1):
+    """x [N,H,W,Cin] (Cin % 32 == 0), weight [Cout,Cin,kh,kw] -> [N,Hout,Wout,Cout]; zero pad along y only.
+    pad_out > 0: the result is written into the interior of a [N,Hout,Wout + 2*pad_out,Cout] buffer whose pad columns
+    are then filled in place (replicate / circular) — the next convolution's padded input without a copy."""
     x = dev(x, "x")
     N, H, W, Cin = x.shape
     Cout, Cin_w, kh, kw = weight.shape
@@ -33,7 +35,11 @@ def conv2d_nhwc(x, weight, bias=None, pad_y=0, stride=1, leaky=1.0, wt=None, cin
     wt = dev(wt, "weight")
     Hout = (H + 2 * pad_y - kh) // stride + 1
     Wout = (W - kw) // stride + 1
-    out = torch.empty(N, Hout, Wout, Cout, device=x.device, dtype=torch.float32)
+    OW = Wout + 2 * pad_out
+    out = torch.empty(N, Hout, OW, Cout, device=x.device, dtype=torch.float32)
+    optr = ctypes.c_void_p(out.data_ptr() + 4 * pad_out * Cout)          # pixel (n, y, pad_out) of the padded buffer
+    if pad_out and Cout % 4:
+        raise B3DError("conv2d: pad_out needs Cout % 4 == 0")
     dy = [r - pad_y for r in range(kh) for _ in range(kw)]
     dx = [s for _ in range(kh) for s in range(kw)]
     b = dev(bias, "bias") if bias is not None else None
@@ -44,15 +50,16 @@ def conv2d_nhwc(x, weight, bias=None, pad_y=0, stride=1, leaky=1.0, wt=None, cin
         use_flat = stride == 1 and not cin_major and os.environ["B3D_CONV_FLAT"] == "1"
     if use_flat:
         # halo-staged kernel (tc_conv2.cu); falls through to the per-tap kernel when the halo does not fit in smem
-        rc = lib.b3d_conv2d_flat_tf32(ptr(x), ptr(wt), ptr(b), ptr(out), N, H, W, Cin, Hout, Wout, Cout, kh * kw,
-                                      _ints(dy), _ints(dx), Hout, Wout, Cout, float(leaky), stream_ptr(x))
-        if rc == 0:
-            return out
-        if b"does not fit" not in lib.b3d_last_error():
+        rc = lib.b3d_conv2d_flat_tf32(ptr(x), ptr(wt), ptr(b), optr, N, H, W, Cin, Hout, Wout, Cout, kh * kw,
+                                      _ints(dy), _ints(dx), Hout, OW, Cout, float(leaky), stream_ptr(x))
+        if rc != 0 and b"does not fit" not in lib.b3d_last_error():
             check(rc)
-    check(lib.b3d_conv2d_tf32(ptr(x), ptr(wt), ptr(b), ptr(out), N, H, W, Cin, Hout, Wout, Cout, kh * kw, _ints(dy),
-                              _ints(dx), stride, stride, Hout, Wout, Cout, 1, 1, 0, 0, float(leaky), int(cin_major),
-                              stream_ptr(x)))
+    if not use_flat or rc != 0:
+        check(lib.b3d_conv2d_tf32(ptr(x), ptr(wt), ptr(b), optr, N, H, W, Cin, Hout, Wout, Cout, kh * kw, _ints(dy),
+                                  _ints(dx), stride, stride, Hout, OW, Cout, 1, 1, 0, 0, float(leaky), int(cin_major),
+                                  stream_ptr(x)))
+    if pad_out:
+        check(lib.b3d_wrap_x_inplace(ptr(out), N * Hout, Wout, Cout, pad_out, pad_mode, stream_ptr(x)))
     return out
 
 
@@ -112,25 +119,39 @@ def _pad_last(t, mult):
 
 class _Conv2dNHWC(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, pad_y, stride, leaky=1.0):
+    def forward(ctx, x, weight, bias, pad_y, stride, leaky=1.0, pad_out=0, pad_mode=1):
+        """pad_out > 0 (needs Cout = 4 * power of two): also applies the NEXT layer's x padding — the result is
+        [N,Hout,Wout + 2*pad_out,Cout] — and the backward undoes padding, activation and bias in one fused pass."""
         x = dev(x.detach(), "x")
         w = weight.detach()
         Cin = x.shape[3]
         if Cin % 32:                                    # thin inputs (discriminator stems: 8 / 11 channels): zero-pad K
             x = _pad_last(x, 32)
             w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, x.shape[3] - Cin))
-        y = conv2d_nhwc(x, w, bias.detach() if bias is not None else None, pad_y=pad_y, stride=stride, leaky=leaky)
-        if leaky != 1.0:
+        y = conv2d_nhwc(x, w, bias.detach() if bias is not None else None, pad_y=pad_y, stride=stride, leaky=leaky,
+                        pad_out=pad_out, pad_mode=pad_mode)
+        if leaky != 1.0 or pad_out:
             ctx.save_for_backward(x, w, y)
         else:
             ctx.save_for_backward(x, w)
-        ctx.cfg = (pad_y, stride, Cin, bias is not None, leaky)
+        ctx.cfg = (pad_y, stride, Cin, bias is not None, leaky, pad_out, pad_mode)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        pad_y, stride, Cin, has_bias, leaky = ctx.cfg
-        if leaky != 1.0:                  # LeakyReLU was fused into the epilogue: mask the incoming gradient by sign(y)
+        pad_y, stride, Cin, has_bias, leaky, pad_out, pad_mode = ctx.cfg
+        gb = None
+        want_gb = has_bias and ctx.needs_input_grad[2]
+        if pad_out:                       # padding + LeakyReLU + bias gradient in one pass over the padded gradient
+            x, w, y = ctx.saved_tensors
+            gy = dev(gy, "grad_output")
+            N, Ho, OW, Co = y.shape
+            masked = torch.empty(N, Ho, OW - 2 * pad_out, Co, device=gy.device, dtype=torch.float32)
+            gb = torch.zeros(Co, device=gy.device, dtype=torch.float32) if want_gb else None
+            check(lib.b3d_pad_leaky_bias_bwd(ptr(gy), ptr(y), ptr(masked), ptr(gb), N * Ho, OW - 2 * pad_out, Co, pad_out,
+                                             pad_mode, float(leaky), stream_ptr(gy)))
+            gy = masked
+        elif leaky != 1.0:                # LeakyReLU was fused into the epilogue: mask the incoming gradient by sign(y)
             x, w, y = ctx.saved_tensors
             gy = dev(gy, "grad_output")
             masked = torch.empty_like(gy)
@@ -140,7 +161,8 @@ class _Conv2dNHWC(torch.autograd.Function):
             x, w = ctx.saved_tensors
         Cout, _, kh, kw = w.shape
         gy = dev(gy, "grad_output")
-        gb = gy.sum(dim=(0, 1, 2)) if has_bias and ctx.needs_input_grad[2] else None
+        if gb is None and want_gb:
+            gb = gy.sum(dim=(0, 1, 2))
         gyp, wp = gy, w
         if Cout % 32:                                   # heads with 1 / 3 output channels: zero-pad the reduction dim
             gyp = _pad_last(gy, 32)
@@ -150,13 +172,13 @@ class _Conv2dNHWC(torch.autograd.Function):
             gx = conv2d_dgrad_nhwc(gyp, wp, (x.shape[1], x.shape[2]), pad_y=pad_y, stride=stride)[..., :Cin]
         if ctx.needs_input_grad[1]:
             gw = conv2d_wgrad_nhwc(gyp, x, kh, kw, pad_y=pad_y, stride=stride)[:Cout, :Cin]
-        return gx, gw, gb, None, None, None
+        return gx, gw, gb, None, None, None, None, None
 
 
 _FOLD = os.environ.get("B3D_FOLD", "kh")
 
 
-def conv2d(x_nchw, weight, bias=None, pad_y=0, stride=1, leaky=1.0):
+def conv2d(x_nchw, weight, bias=None, pad_y=0, stride=1, leaky=1.0, pad_out=0, pad_mode=1):
     """Drop-in for F.conv2d(x, w, b, stride, padding=(pad_y, 0)) on logically-NCHW tensors: runs on the tcgen05
     kernels over the channels-last storage (a no-copy view when x is already channels_last) and returns a
     logically-NCHW, channels-last tensor."""
@@ -189,5 +211,5 @@ def conv2d(x_nchw, weight, bias=None, pad_y=0, stride=1, leaky=1.0):
         weight = weight.permute(0, 3, 1, 2).reshape(Cout, kw * Cin, kh, 1)          # [co, s*Cin + c, r, 0]
         if cpad:
             weight = torch.nn.functional.pad(weight, (0, 0, 0, 0, 0, cpad))
-    y = _Conv2dNHWC.apply(x, weight, bias, int(pad_y), int(stride), float(leaky))
+    y = _Conv2dNHWC.apply(x, weight, bias, int(pad_y), int(stride), float(leaky), int(pad_out), int(pad_mode))
     return y.permute(0, 3, 1, 2)

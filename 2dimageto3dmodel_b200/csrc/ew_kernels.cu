@@ -61,6 +61,74 @@ leaky_bwd_kernel(const float4* __restrict__ gy, const float4* __restrict__ y, fl
     }
 }
 
+// In-place wrap fill: buf [rows, W + 2a, 4*C4] whose interior columns a .. a+W-1 were written by a conv epilogue.
+__global__ void __launch_bounds__(NT)
+wrap_x_kernel(float4* __restrict__ buf, long long rows, int W, int C4, int a, int mode) {
+    const int Wo = W + 2 * a;
+    const long long total = rows * 2 * a * C4;
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+        const int c = (int)(i % C4);
+        const long long t = i / C4;
+        const int j = (int)(t % (2 * a));
+        const long long r = t / (2 * a);
+        const int wo = j < a ? j : W + j;                    // pad column: left a, then right a
+        buf[(r * Wo + wo) * C4 + c] = buf[(r * Wo + a + src_col(wo, a, W, mode)) * C4 + c];
+    }
+}
+
+// Backward of  conv -> (+bias) -> LeakyReLU -> pad_x  in one pass:  gy = pad_x^T(g_pad) * leaky'(y),  gb += sum gy.
+// Thread t owns channel group t % C4 for the pixels t / C4, t / C4 + PPB, ... of its block's slab, so the bias
+// partial sums stay in registers; one shared-memory tree + one atomicAdd per (block, channel).
+__global__ void __launch_bounds__(NT)
+pad_leaky_bias_bwd_kernel(const float4* __restrict__ go, const float4* __restrict__ ypad, float4* __restrict__ gy,
+                          float* __restrict__ gb, long long rows, int W, int C4, int a, int mode, float slope,
+                          long long pix_per_block) {
+    __shared__ float4 red[NT];
+    const int Wo = W + 2 * a;
+    const int c = threadIdx.x % C4, lane_p = threadIdx.x / C4, PPB = NT / C4;
+    const long long npix = rows * W;
+    const long long p0 = (long long)blockIdx.x * pix_per_block;
+    const long long p1 = p0 + pix_per_block < npix ? p0 + pix_per_block : npix;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long pix = p0 + lane_p; pix < p1; pix += PPB) {
+        const int w = (int)(pix % W);
+        const long long r = pix / W;
+        const float4* g = go + (r * Wo) * C4 + c;
+        float4 s = __ldg(g + (long long)(w + a) * C4);
+        if (a > 0) {
+            if (mode == 0) {
+                if (w == 0)
+                    for (int k = 0; k < a; ++k) { const float4 v = __ldg(g + (long long)k * C4); s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+                if (w == W - 1)
+                    for (int k = 0; k < a; ++k) { const float4 v = __ldg(g + (long long)(W + a + k) * C4); s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+            } else {
+                if (w < a) { const float4 v = __ldg(g + (long long)(w + a + W) * C4); s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+                if (w >= W - a) { const float4 v = __ldg(g + (long long)(w + a - W) * C4); s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+            }
+        }
+        const float4 v = __ldg(ypad + (r * Wo + w + a) * C4 + c);
+        s = make_float4(v.x >= 0.f ? s.x : s.x * slope, v.y >= 0.f ? s.y : s.y * slope, v.z >= 0.f ? s.z : s.z * slope,
+                        v.w >= 0.f ? s.w : s.w * slope);
+        gy[pix * C4 + c] = s;
+        acc.x += s.x; acc.y += s.y; acc.z += s.z; acc.w += s.w;
+    }
+    if (gb == nullptr) return;
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int h = PPB / 2; h >= 1; h >>= 1) {
+        if (lane_p < h) {
+            const float4 o = red[threadIdx.x + h * C4];
+            float4& m = red[threadIdx.x];
+            m.x += o.x; m.y += o.y; m.z += o.z; m.w += o.w;
+        }
+        __syncthreads();
+    }
+    if (lane_p == 0) {
+        const float4 m = red[threadIdx.x];
+        atomicAdd(gb + 4 * c + 0, m.x); atomicAdd(gb + 4 * c + 1, m.y); atomicAdd(gb + 4 * c + 2, m.z); atomicAdd(gb + 4 * c + 3, m.w);
+    }
+}
+
 int grid_for(long long n) {
     long long b = (n + NT - 1) / NT;
     const long long cap = 148LL * 16;
@@ -90,6 +158,38 @@ int b3d_pad_x_bwd(const float* gout, float* gx, long long rows, int W, int C, in
     B3D_CHECK_ALIGNED(gx);
     pad_x_bwd_kernel<<<grid_for(rows * W * (C / 4)), NT, 0, (cudaStream_t)stream>>>((const float4*)gout, (float4*)gx, rows, W,
                                                                                 C / 4, amount, mode);
+    B3D_LAUNCH_OK();
+    return B3D_OK;
+}
+int b3d_wrap_x_inplace(float* buf, long long rows, int W, int C, int amount, int mode, void* stream) {
+    B3D_REQUIRE(rows >= 0 && W > 0 && C > 0 && C % 4 == 0 && amount >= 0 && amount <= W && (mode == 0 || mode == 1), B3D_EINVAL,
+                "b3d_wrap_x_inplace: bad arguments (C=%d must be a multiple of 4, amount=%d <= W=%d)", C, amount, W);
+    if (rows == 0 || amount == 0) return B3D_OK;
+    B3D_REQUIRE(buf, B3D_EINVAL, "b3d_wrap_x_inplace: null pointer");
+    B3D_CHECK_ALIGNED(buf);
+    wrap_x_kernel<<<grid_for(rows * 2 * amount * (C / 4)), NT, 0, (cudaStream_t)stream>>>((float4*)buf, rows, W, C / 4, amount, mode);
+    B3D_LAUNCH_OK();
+    return B3D_OK;
+}
+int b3d_pad_leaky_bias_bwd(const float* gout_pad, const float* y_pad, float* gy, float* gbias, long long rows, int W, int C,
+                           int amount, int mode, float slope, void* stream) {
+    B3D_REQUIRE(rows >= 0 && W > 0 && C >= 4 && amount >= 0 && amount <= W && (mode == 0 || mode == 1), B3D_EINVAL,
+                "b3d_pad_leaky_bias_bwd: bad arguments");
+    B3D_REQUIRE(C % 4 == 0 && NT % (C / 4) == 0, B3D_EINVAL, "b3d_pad_leaky_bias_bwd: C=%d must be 4 * a power of two <= %d", C, 4 * NT);
+    if (rows == 0) return B3D_OK;
+    B3D_REQUIRE(gout_pad && y_pad && gy, B3D_EINVAL, "b3d_pad_leaky_bias_bwd: null pointer");
+    B3D_CHECK_ALIGNED(gout_pad);
+    B3D_CHECK_ALIGNED(y_pad);
+    B3D_CHECK_ALIGNED(gy);
+    const long long npix = rows * W;
+    const int ppb = NT / (C / 4);
+    long long blocks = (npix + ppb - 1) / ppb;
+    const long long cap = 148LL * 8;
+    if (blocks > cap) blocks = cap;
+    const long long per = ((npix + blocks - 1) / blocks + ppb - 1) / ppb * ppb;
+    blocks = (npix + per - 1) / per;
+    pad_leaky_bias_bwd_kernel<<<(int)blocks, NT, 0, (cudaStream_t)stream>>>((const float4*)gout_pad, (const float4*)y_pad, (float4*)gy,
+                                                                          gbias, rows, W, C / 4, amount, mode, slope, per);
     B3D_LAUNCH_OK();
     return B3D_OK;
 }

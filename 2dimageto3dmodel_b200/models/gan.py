@@ -25,13 +25,15 @@ from rendering.utils import adjust_poles, circpad, symmetrize_texture
 class TCConv2d(nn.Conv2d):
     """nn.Conv2d (same parameters / state dict) whose forward runs on the tensor-core kernels."""
 
-    def forward(self, x, leaky=1.0):
-        """`leaky` != 1 fuses LeakyReLU(leaky) into the convolution's epilogue (conv -> bias -> activation in one pass)."""
+    def forward(self, x, leaky=1.0, pad_out=0, pad_mode=CIRCULAR):
+        """`leaky` != 1 fuses LeakyReLU(leaky) into the convolution's epilogue (conv -> bias -> activation in one pass);
+        `pad_out` > 0 also applies the next layer's x padding (the epilogue writes into the padded buffer)."""
         if not x.is_cuda:
             raise B3DError("models.gan convolutions run on CUDA only (libb3d tcgen05 kernels); there is no CPU fallback")
         if self.padding[1] != 0 or self.stride[0] != self.stride[1] or self.dilation != (1, 1) or self.groups != 1:
             raise B3DError("TCConv2d supports zero padding along y only, square strides, no dilation / groups")
-        return _tc_conv2d(x, self.weight, self.bias, pad_y=self.padding[0], stride=self.stride[0], leaky=leaky)
+        return _tc_conv2d(x, self.weight, self.bias, pad_y=self.padding[0], stride=self.stride[0], leaky=leaky,
+                          pad_out=pad_out, pad_mode=pad_mode)
 
 
 def positional_encoding(Ny, Nx):
@@ -55,11 +57,12 @@ def _norm_and_bias(args):
     raise ValueError(f"norm_d={args.norm_d!r}")
 
 
-def _conv_norm_act(conv, norm, x):
-    """LeakyReLU(0.2)(norm(conv(x))): one fused kernel when there is no norm layer."""
-    if norm is None:
-        return conv(x, leaky=0.2)
-    return F.leaky_relu(norm(conv(x)), 0.2)
+def _conv_norm_act(conv, norm, x, pad_next=0):
+    """pad_x(LeakyReLU(0.2)(norm(conv(x))), pad_next, circular): one fused kernel when there is no norm layer."""
+    if norm is None and conv.out_channels in (16, 32, 64, 128, 256, 512, 1024):
+        return conv(x, leaky=0.2, pad_out=pad_next, pad_mode=CIRCULAR)
+    y = conv(x, leaky=0.2) if norm is None else F.leaky_relu(norm(conv(x)), 0.2)
+    return pad_x(y, pad_next, CIRCULAR) if pad_next else y
 
 
 class _DiscriminatorBase(nn.Module):
@@ -131,10 +134,12 @@ class MeshDiscriminator(_DiscriminatorBase):
         if self.args.mask_output:
             with torch.no_grad():
                 mask = F.avg_pool2d(x[:, 3:4], 4)
-        x = self.conv1(self.pad(x), leaky=0.2)
-        x = _conv_norm_act(self.conv2, self.bn2, self.pad2(x))
-        x = _conv_norm_act(self.conv3, self.bn3, self.pad2(x))
-        y = self._project(self.conv4(self.pad(x)), x, c, caption)
+        p1, p2 = (1, 2) if self.circular else (0, 0)       # x padding of the 4x4 / 5x5 layers, applied by the producer
+        x = _conv_norm_act(self.conv1, None, self.pad(x), p1)
+        x = _conv_norm_act(self.conv2, self.bn2, x, p1)
+        x = _conv_norm_act(self.conv3, self.bn3, x, p2)
+        feat = x[..., p2:x.shape[3] - p2]
+        y = self._project(self.conv4(x), feat, c, caption)
         return y, mask
 
 
@@ -180,11 +185,13 @@ class TextureDiscriminator(_DiscriminatorBase):
             with torch.no_grad():
                 mask = F.avg_pool2d(x[:, 3:4], 16 if self.stride_first else 8)
         x = self._with_positions(x)
-        x = self.conv1(self.padconv1(x), leaky=0.2)
-        x = _conv_norm_act(self.conv2, self.bn2, self.pad2(x))
-        x = _conv_norm_act(self.conv3, self.bn3, self.pad2(x))
-        x = _conv_norm_act(self.conv4, self.bn4, self.pad2(x))
-        y = self._project(self.conv5(self.pad(x)), x, c, caption)
+        p1, p2 = (1, 2) if self.circular else (0, 0)       # x padding of the 4x4 / 5x5 layers, applied by the producer
+        x = _conv_norm_act(self.conv1, None, self.padconv1(x), p1)
+        x = _conv_norm_act(self.conv2, self.bn2, x, p1)
+        x = _conv_norm_act(self.conv3, self.bn3, x, p1)
+        x = _conv_norm_act(self.conv4, self.bn4, x, p2)
+        feat = x[..., p2:x.shape[3] - p2]
+        y = self._project(self.conv5(x), feat, c, caption)
         return y, mask
 
 

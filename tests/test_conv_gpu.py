@@ -144,3 +144,37 @@ def test_fused_leaky_epilogue_autograd():
         res.append([y.detach()] + list(torch.autograd.grad(y, [x, w, b], gy)))
     for a, r in zip(res[1], res[0]):
         assert float((a - r).abs().max()) <= 2 * TOL * float(r.abs().max())
+
+
+@pytest.mark.parametrize("mode", ["replicate", "circular"])
+@pytest.mark.parametrize("N,Cin,H,W,Cout,k,pad_y,stride,pad_out,bias", [
+    (2, 64, 16, 18, 128, 4, 1, 2, 1, True),      # discriminator conv2 -> next 4x4 layer's padding
+    (3, 8, 24, 28, 64, 5, 2, 1, 1, True),        # folded stem -> padded by 1
+    (2, 128, 8, 10, 256, 4, 1, 2, 2, False),     # conv4 -> the 5x5 head's padding of 2
+    (1, 32, 140, 134, 64, 3, 1, 1, 2, True),     # wide rows: main + strip launches into the padded buffer
+])
+def test_conv_leaky_pad_fused_autograd(mode, N, Cin, H, W, Cout, k, pad_y, stride, pad_out, bias):
+    """conv -> bias -> LeakyReLU -> x padding in one op (epilogue writes the padded buffer, one fused backward pass)
+    against the same chain in plain torch fp32 (models/gan.py discriminators :163-177, :294-302)."""
+    from b3d.conv import conv2d
+    from b3d.ew import CIRCULAR, REPLICATE
+    g = torch.Generator().manual_seed(Cin * 3 + Cout + pad_out)
+    x0 = torch.randn(N, Cin, H, W, generator=g).cuda()
+    w0 = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).cuda()
+    b0 = torch.randn(Cout, generator=g).cuda() if bias else None
+    outs = []
+    for impl in ("torch", "b3d"):
+        x, w = x0.clone().requires_grad_(True), w0.clone().requires_grad_(True)
+        b = b0.clone().requires_grad_(True) if bias else None
+        if impl == "torch":
+            y = torch.nn.functional.leaky_relu(ref_conv(x, w, b, pad_y, stride), 0.2)
+            y = torch.nn.functional.pad(y, (pad_out, pad_out, 0, 0), mode=mode)
+        else:
+            y = conv2d(x.contiguous(memory_format=torch.channels_last), w, b, pad_y, stride, leaky=0.2, pad_out=pad_out,
+                       pad_mode=REPLICATE if mode == "replicate" else CIRCULAR)
+        gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(5)).cuda()
+        grads = torch.autograd.grad(y, [x, w] + ([b] if bias else []), gy)
+        outs.append([y.detach()] + list(grads))
+    for a, r in zip(outs[1], outs[0]):
+        assert a.shape == r.shape
+        assert float((a - r).abs().max()) <= TOL * float(r.abs().max()), (a.shape, float((a - r).abs().max()), float(r.abs().max()))
