@@ -162,19 +162,23 @@ def test_conv_leaky_pad_fused_autograd(mode, N, Cin, H, W, Cout, k, pad_y, strid
     x0 = torch.randn(N, Cin, H, W, generator=g).cuda()
     w0 = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).cuda()
     b0 = torch.randn(Cout, generator=g).cuda() if bias else None
-    outs = []
-    for impl in ("torch", "b3d"):
+    outs, mask = [], None
+    for impl in ("b3d", "torch"):
         x, w = x0.clone().requires_grad_(True), w0.clone().requires_grad_(True)
         b = b0.clone().requires_grad_(True) if bias else None
         if impl == "torch":
-            y = torch.nn.functional.leaky_relu(ref_conv(x, w, b, pad_y, stride), 0.2)
+            # pre-activations within tf32 rounding of zero may change sign between the two implementations; the
+            # reference chain takes the activation mask of the kernel's output so that gradients are comparable
+            z = ref_conv(x, w, b, pad_y, stride)
+            y = torch.where(mask, z, 0.2 * z)
             y = torch.nn.functional.pad(y, (pad_out, pad_out, 0, 0), mode=mode)
         else:
             y = conv2d(x.contiguous(memory_format=torch.channels_last), w, b, pad_y, stride, leaky=0.2, pad_out=pad_out,
                        pad_mode=REPLICATE if mode == "replicate" else CIRCULAR)
+            mask = y.detach()[..., pad_out:y.shape[3] - pad_out] >= 0
         gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(5)).cuda()
         grads = torch.autograd.grad(y, [x, w] + ([b] if bias else []), gy)
         outs.append([y.detach()] + list(grads))
-    for a, r in zip(outs[1], outs[0]):
+    for a, r in zip(outs[0], outs[1]):
         assert a.shape == r.shape
         assert float((a - r).abs().max()) <= TOL * float(r.abs().max()), (a.shape, float((a - r).abs().max()), float(r.abs().max()))
