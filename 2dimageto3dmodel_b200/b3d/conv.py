@@ -21,10 +21,12 @@ def taps_layout(weight):
     return weight.permute(2, 3, 0, 1).reshape(kh * kw, co, ci).contiguous()
 
 
-def conv2d_nhwc(x, weight, bias=None, pad_y=0, stride=1, leaky=1.0, wt=None, cin_major=False, pad_out=0, pad_mode=1):
+def conv2d_nhwc(x, weight, bias=None, pad_y=0, stride=1, leaky=1.0, wt=None, cin_major=False, pad_out=0, pad_mode=1,
+                x_crop=0):
     """x [N,H,W,Cin] (Cin % 32 == 0), weight [Cout,Cin,kh,kw] -> [N,Hout,Wout,Cout]; zero pad along y only.
     pad_out > 0: the result is written into the interior of a [N,Hout,Wout + 2*pad_out,Cout] buffer whose pad columns
-    are then filled in place (replicate / circular) — the next convolution's padded input without a copy."""
+    are then filled in place (replicate / circular) — the next convolution's padded input without a copy.
+    x_crop > 0 (stride 1): convolve x[:, :, x_crop:W - x_crop] without materialising the slice (taps are shifted)."""
     x = dev(x, "x")
     N, H, W, Cin = x.shape
     Cout, Cin_w, kh, kw = weight.shape
@@ -34,18 +36,20 @@ def conv2d_nhwc(x, weight, bias=None, pad_y=0, stride=1, leaky=1.0, wt=None, cin
         wt = weight.permute(2, 3, 1, 0).reshape(kh * kw, Cin, Cout).contiguous() if cin_major else taps_layout(weight)
     wt = dev(wt, "weight")
     Hout = (H + 2 * pad_y - kh) // stride + 1
-    Wout = (W - kw) // stride + 1
+    if x_crop and stride != 1:
+        raise B3DError("conv2d: x_crop needs stride 1")
+    Wout = (W - 2 * x_crop - kw) // stride + 1
     OW = Wout + 2 * pad_out
     out = torch.empty(N, Hout, OW, Cout, device=x.device, dtype=torch.float32)
     optr = ctypes.c_void_p(out.data_ptr() + 4 * pad_out * Cout)          # pixel (n, y, pad_out) of the padded buffer
     if pad_out and Cout % 4:
         raise B3DError("conv2d: pad_out needs Cout % 4 == 0")
     dy = [r - pad_y for r in range(kh) for _ in range(kw)]
-    dx = [s for _ in range(kh) for s in range(kw)]
+    dx = [s + x_crop for _ in range(kh) for s in range(kw)]
     b = dev(bias, "bias") if bias is not None else None
     # the halo-staged kernel wins on wide-N layers with enough tiles to fill the GPU twice; elsewhere the per-tap kernel
     # (2 CTAs / SM) is as fast or faster (profiles/r1_conv_layers.md)
-    use_flat = stride == 1 and not cin_major and Cout > 64 and N * Hout * W >= 2 * 148 * 384
+    use_flat = stride == 1 and not cin_major and Cout > 64 and N * Hout * W >= 2 * 148 * 384 and not x_crop
     if os.environ.get("B3D_CONV_FLAT"):
         use_flat = stride == 1 and not cin_major and os.environ["B3D_CONV_FLAT"] == "1"
     if use_flat:
@@ -63,7 +67,7 @@ def conv2d_nhwc(x, weight, bias=None, pad_y=0, stride=1, leaky=1.0, wt=None, cin
     return out
 
 
-def conv2d_dgrad_nhwc(dy_, weight, in_hw, pad_y=0, stride=1):
+def conv2d_dgrad_nhwc(dy_, weight, in_hw, pad_y=0, stride=1, x_crop=0):
     """Gradient w.r.t. the (x-padded) input [N,H,W,Cin] of conv2d_nhwc, from dy_ [N,Hout,Wout,Cout] (Cout % 32 == 0)."""
     g = dev(dy_, "grad_output")
     N, Hout, Wout, Cout = g.shape
@@ -74,12 +78,12 @@ def conv2d_dgrad_nhwc(dy_, weight, in_hw, pad_y=0, stride=1):
     if stride == 1:
         wt = weight.permute(2, 3, 1, 0).reshape(kh * kw, Cin, Cout).contiguous()        # [tap][Cin][Cout]
         dy = [pad_y - r for r in range(kh) for _ in range(kw)]
-        dx = [-s for _ in range(kh) for s in range(kw)]
+        dx = [-s - x_crop for _ in range(kh) for s in range(kw)]
         check(lib.b3d_conv2d_tf32(ptr(g), ptr(wt), None, ptr(dxo), N, Hout, Wout, Cout, H, W, Cin, kh * kw, _ints(dy),
                                   _ints(dx), 1, 1, H, W, Cin, 1, 1, 0, 0, 1.0, 0, st))
         return dxo
-    if stride != 2:
-        raise B3DError("conv2d_dgrad: stride must be 1 or 2")
+    if stride != 2 or x_crop:
+        raise B3DError("conv2d_dgrad: stride must be 1 or 2 (x_crop: stride 1 only)")
     # input row y' = 2*yo + r - pad_y  =>  for the class y' = 2*a + cy only taps with (cy + pad_y - r) even take part
     for cy in range(2):
         for cx in range(2):
@@ -96,7 +100,7 @@ def conv2d_dgrad_nhwc(dy_, weight, in_hw, pad_y=0, stride=1):
     return dxo
 
 
-def conv2d_wgrad_nhwc(dy_, x, kh, kw, pad_y=0, stride=1):
+def conv2d_wgrad_nhwc(dy_, x, kh, kw, pad_y=0, stride=1, x_crop=0):
     """dW [Cout,Cin,kh,kw] from dy_ [N,Hout,Wout,Cout] and the (x-padded) input x [N,H,W,Cin], both NHWC
     (channel counts that are not multiples of 32 are zero-padded here)."""
     co_real, ci_real = dy_.shape[3], x.shape[3]
@@ -105,7 +109,7 @@ def conv2d_wgrad_nhwc(dy_, x, kh, kw, pad_y=0, stride=1):
     _, H, W, Cin = x.shape
     dw = torch.zeros(Cout, Cin, kh, kw, device=g.device, dtype=torch.float32)
     check(lib.b3d_conv2d_wgrad_tf32(ptr(g), ptr(x), ptr(dw), N, H, W, Cin, Hout, Wout, Cout, kh, kw, pad_y, stride,
-                                    stream_ptr(g)))
+                                    x_crop, stream_ptr(g)))
     return dw if (co_real, ci_real) == (Cout, Cin) else dw[:co_real, :ci_real]
 
 
@@ -119,7 +123,7 @@ def _pad_last(t, mult):
 
 class _Conv2dNHWC(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, pad_y, stride, leaky=1.0, pad_out=0, pad_mode=1):
+    def forward(ctx, x, weight, bias, pad_y, stride, leaky=1.0, pad_out=0, pad_mode=1, x_crop=0):
         """pad_out > 0 (needs Cout = 4 * power of two): also applies the NEXT layer's x padding — the result is
         [N,Hout,Wout + 2*pad_out,Cout] — and the backward undoes padding, activation and bias in one fused pass."""
         x = dev(x.detach(), "x")
@@ -129,17 +133,17 @@ class _Conv2dNHWC(torch.autograd.Function):
             x = _pad_last(x, 32)
             w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, x.shape[3] - Cin))
         y = conv2d_nhwc(x, w, bias.detach() if bias is not None else None, pad_y=pad_y, stride=stride, leaky=leaky,
-                        pad_out=pad_out, pad_mode=pad_mode)
+                        pad_out=pad_out, pad_mode=pad_mode, x_crop=x_crop)
         if leaky != 1.0 or pad_out:
             ctx.save_for_backward(x, w, y)
         else:
             ctx.save_for_backward(x, w)
-        ctx.cfg = (pad_y, stride, Cin, bias is not None, leaky, pad_out, pad_mode)
+        ctx.cfg = (pad_y, stride, Cin, bias is not None, leaky, pad_out, pad_mode, x_crop)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        pad_y, stride, Cin, has_bias, leaky, pad_out, pad_mode = ctx.cfg
+        pad_y, stride, Cin, has_bias, leaky, pad_out, pad_mode, x_crop = ctx.cfg
         gb = None
         want_gb = has_bias and ctx.needs_input_grad[2]
         if pad_out:                       # padding + LeakyReLU + bias gradient in one pass over the padded gradient
@@ -169,16 +173,16 @@ class _Conv2dNHWC(torch.autograd.Function):
             wp = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, 0, 0, gyp.shape[3] - Cout))
         gx = gw = None
         if ctx.needs_input_grad[0]:
-            gx = conv2d_dgrad_nhwc(gyp, wp, (x.shape[1], x.shape[2]), pad_y=pad_y, stride=stride)[..., :Cin]
+            gx = conv2d_dgrad_nhwc(gyp, wp, (x.shape[1], x.shape[2]), pad_y=pad_y, stride=stride, x_crop=x_crop)[..., :Cin]
         if ctx.needs_input_grad[1]:
-            gw = conv2d_wgrad_nhwc(gyp, x, kh, kw, pad_y=pad_y, stride=stride)[:Cout, :Cin]
-        return gx, gw, gb, None, None, None, None, None
+            gw = conv2d_wgrad_nhwc(gyp, x, kh, kw, pad_y=pad_y, stride=stride, x_crop=x_crop)[:Cout, :Cin]
+        return gx, gw, gb, None, None, None, None, None, None
 
 
 _FOLD = os.environ.get("B3D_FOLD", "kh")
 
 
-def conv2d(x_nchw, weight, bias=None, pad_y=0, stride=1, leaky=1.0, pad_out=0, pad_mode=1):
+def conv2d(x_nchw, weight, bias=None, pad_y=0, stride=1, leaky=1.0, pad_out=0, pad_mode=1, x_crop=0):
     """Drop-in for F.conv2d(x, w, b, stride, padding=(pad_y, 0)) on logically-NCHW tensors: runs on the tcgen05
     kernels over the channels-last storage (a no-copy view when x is already channels_last) and returns a
     logically-NCHW, channels-last tensor."""
@@ -189,13 +193,9 @@ def conv2d(x_nchw, weight, bias=None, pad_y=0, stride=1, leaky=1.0, pad_out=0, p
         # dimension — X'[n,y,x, r*Cin + c] = X[n, y+r-pad_y, x, c] (zero rows = the y padding) — so the tensor cores see
         # kw taps of kh*Cin real channels instead of kh*kw taps of Cin channels zero-padded to 32.  The remaining taps
         # are horizontal: the weight-gradient kernel covers a whole row of taps per CTA (one pass over dY and X').
-        Hout = x.shape[1] + 2 * pad_y - kh + 1
+        from .ew import fold_rows
         cpad = (-kh * Cin) % 32                            # ... and round up to the 32-channel K slice in the same pass
-        xp = torch.nn.functional.pad(x, (0, 0, 0, 0, pad_y, pad_y)) if pad_y else x
-        parts = [xp[:, r:r + Hout] for r in range(kh)]
-        if cpad:
-            parts.append(x.new_zeros(x.shape[0], Hout, x.shape[2], cpad))
-        x = torch.cat(parts, dim=3)
+        x = fold_rows(x, kh, pad_y, kh * Cin + cpad)
         weight = weight.permute(0, 2, 1, 3).reshape(Cout, kh * Cin, 1, kw)          # [co, r*Cin + c, 0, s]
         if cpad:
             weight = torch.nn.functional.pad(weight, (0, 0, 0, 0, 0, cpad))
@@ -211,5 +211,5 @@ def conv2d(x_nchw, weight, bias=None, pad_y=0, stride=1, leaky=1.0, pad_out=0, p
         weight = weight.permute(0, 3, 1, 2).reshape(Cout, kw * Cin, kh, 1)          # [co, s*Cin + c, r, 0]
         if cpad:
             weight = torch.nn.functional.pad(weight, (0, 0, 0, 0, 0, cpad))
-    y = _Conv2dNHWC.apply(x, weight, bias, int(pad_y), int(stride), float(leaky), int(pad_out), int(pad_mode))
+    y = _Conv2dNHWC.apply(x, weight, bias, int(pad_y), int(stride), float(leaky), int(pad_out), int(pad_mode), int(x_crop))
     return y.permute(0, 3, 1, 2)

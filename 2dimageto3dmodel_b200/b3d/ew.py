@@ -26,6 +26,31 @@ class _PadX(torch.autograd.Function):
         return gx, None, None
 
 
+class _FoldRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_nhwc, kh, pad_y, Cp):
+        x = dev(x_nhwc.detach(), "x")
+        N, H, W, C = x.shape
+        out = torch.empty(N, H + 2 * pad_y - kh + 1, W, Cp, device=x.device, dtype=torch.float32)
+        check(lib.b3d_fold_rows_fwd(ptr(x), ptr(out), N, H, W, C, kh, pad_y, Cp, stream_ptr(x)))
+        ctx.cfg = (kh, pad_y, Cp, x.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        kh, pad_y, Cp, shape = ctx.cfg
+        N, H, W, C = shape
+        g = dev(g, "grad")
+        gx = torch.empty(shape, device=g.device, dtype=torch.float32)
+        check(lib.b3d_fold_rows_bwd(ptr(g), ptr(gx), N, H, W, C, kh, pad_y, Cp, stream_ptr(g)))
+        return gx, None, None, None
+
+
+def fold_rows(x_nhwc, kh, pad_y, Cp):
+    """[N,H,W,C] -> [N,H + 2*pad_y - kh + 1,W,Cp] with out[..., r*C + c] = x[n, y + r - pad_y, x, c] (zeros elsewhere)."""
+    return _FoldRows.apply(x_nhwc, int(kh), int(pad_y), int(Cp))
+
+
 def pad_x(x_nchw, amount, mode):
     """Padding along x of a logically-NCHW (channels-last) tensor; returns the same kind of tensor."""
     if amount == 0:

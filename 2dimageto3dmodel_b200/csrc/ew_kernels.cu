@@ -129,6 +129,49 @@ pad_leaky_bias_bwd_kernel(const float4* __restrict__ go, const float4* __restric
     }
 }
 
+// Thin-stem fold: out[n, y, x, r*C + c] = x[n, y + r - pad_y, x, c] (zero outside the image, zero for k >= kh*C).
+__global__ void __launch_bounds__(NT)
+fold_rows_fwd_kernel(const float* __restrict__ x, float4* __restrict__ out, int N, int H, int W, int C, int Hout, int Cp4,
+                     int kh, int pad_y) {
+    const long long total = (long long)N * Hout * W * Cp4;
+    const int K = kh * C;
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+        const int k4 = (int)(i % Cp4);
+        long long t = i / Cp4;
+        const int xx = (int)(t % W); t /= W;
+        const int y = (int)(t % Hout);
+        const int n = (int)(t / Hout);
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = 4 * k4 + j;
+            const int r = k / C, c = k - r * C;
+            const int yy = y + r - pad_y;
+            v[j] = (k < K && yy >= 0 && yy < H) ? __ldg(x + (((long long)n * H + yy) * W + xx) * C + c) : 0.f;
+        }
+        out[i] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+__global__ void __launch_bounds__(NT)
+fold_rows_bwd_kernel(const float* __restrict__ go, float* __restrict__ gx, int N, int H, int W, int C, int Hout, int Cp,
+                     int kh, int pad_y) {
+    const long long total = (long long)N * H * W * C;
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+        const int c = (int)(i % C);
+        long long t = i / C;
+        const int xx = (int)(t % W); t /= W;
+        const int yy = (int)(t % H);
+        const int n = (int)(t / H);
+        float s = 0.f;
+        for (int r = 0; r < kh; ++r) {
+            const int y = yy - r + pad_y;
+            if (y >= 0 && y < Hout) s += __ldg(go + (((long long)n * Hout + y) * W + xx) * Cp + r * C + c);
+        }
+        gx[i] = s;
+    }
+}
+
 int grid_for(long long n) {
     long long b = (n + NT - 1) / NT;
     const long long cap = 148LL * 16;
@@ -158,6 +201,28 @@ int b3d_pad_x_bwd(const float* gout, float* gx, long long rows, int W, int C, in
     B3D_CHECK_ALIGNED(gx);
     pad_x_bwd_kernel<<<grid_for(rows * W * (C / 4)), NT, 0, (cudaStream_t)stream>>>((const float4*)gout, (float4*)gx, rows, W,
                                                                                 C / 4, amount, mode);
+    B3D_LAUNCH_OK();
+    return B3D_OK;
+}
+int b3d_fold_rows_fwd(const float* x, float* out, int N, int H, int W, int C, int kh, int pad_y, int Cp, void* stream) {
+    B3D_REQUIRE(N >= 0 && H > 0 && W > 0 && C > 0 && kh >= 1 && pad_y >= 0 && H + 2 * pad_y >= kh, B3D_EINVAL, "b3d_fold_rows_fwd: bad sizes");
+    B3D_REQUIRE(Cp % 4 == 0 && Cp >= kh * C, B3D_EINVAL, "b3d_fold_rows_fwd: Cp=%d must be a multiple of 4 and >= kh*C=%d", Cp, kh * C);
+    if (N == 0) return B3D_OK;
+    B3D_REQUIRE(x && out, B3D_EINVAL, "b3d_fold_rows_fwd: null pointer");
+    B3D_CHECK_ALIGNED(out);
+    const int Hout = H + 2 * pad_y - kh + 1;
+    fold_rows_fwd_kernel<<<grid_for((long long)N * Hout * W * (Cp / 4)), NT, 0, (cudaStream_t)stream>>>(x, (float4*)out, N, H, W, C, Hout,
+                                                                                                  Cp / 4, kh, pad_y);
+    B3D_LAUNCH_OK();
+    return B3D_OK;
+}
+int b3d_fold_rows_bwd(const float* gout, float* gx, int N, int H, int W, int C, int kh, int pad_y, int Cp, void* stream) {
+    B3D_REQUIRE(N >= 0 && H > 0 && W > 0 && C > 0 && kh >= 1 && pad_y >= 0 && H + 2 * pad_y >= kh && Cp >= kh * C, B3D_EINVAL,
+                "b3d_fold_rows_bwd: bad sizes");
+    if (N == 0) return B3D_OK;
+    B3D_REQUIRE(gout && gx, B3D_EINVAL, "b3d_fold_rows_bwd: null pointer");
+    const int Hout = H + 2 * pad_y - kh + 1;
+    fold_rows_bwd_kernel<<<grid_for((long long)N * H * W * C), NT, 0, (cudaStream_t)stream>>>(gout, gx, N, H, W, C, Hout, Cp, kh, pad_y);
     B3D_LAUNCH_OK();
     return B3D_OK;
 }

@@ -189,6 +189,7 @@ struct WgradParams {
     int BWk, BHk;                  // pixel box of one K slice, BWk * BHk == 32
     int kx, ky;                    // K slices along x and y per image
     int kh, kw, pad_y, st;
+    int xoff;                      // the convolution reads x from column xoff on (a caller-side crop of the padded input)
     int splits;                    // K splits (gridDim.z / taps)
     int tstep;                     // taps of one CTA are s0, s0 + tstep, ... (1: adjacent taps of a stride-1 conv,
                                    // 2: taps of equal parity of a stride-2 conv = adjacent rows of the strided window)
@@ -262,7 +263,7 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
                 tc::mbar_arrive_expect_tx(full + st, S::STAGE_BYTES);
                 // channels are split as (32, C/32) in the tensor maps: ONE 5-D box lands all 32-channel blocks back to back
                 tc::tma_load_5d(a, &tmap_dy, full + st, 0, x0, y0, n, co0 / 32);
-                tc::tma_load_5d(b, &tmap_x, full + st, 0, p.st * x0 + s, p.st * y0 + r - p.pad_y, n, ci0 / 32);
+                tc::tma_load_5d(b, &tmap_x, full + st, 0, p.st * x0 + s + p.xoff, p.st * y0 + r - p.pad_y, n, ci0 / 32);
             }
         }
     } else if (warp == 1) {
@@ -412,10 +413,10 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
 // dy [N,Hout,Wout,Cout], x [N,H,W,Cin] NHWC (x already padded along x; Cin, Cout multiples of 4),
 // dw [Cout,Cin,kh,kw] (accumulated into)
 int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, int N, int H, int W, int Cin, int Hout, int Wout,
-                          int Cout, int kh, int kw, int pad_y, int stride, void* stream) {
+                          int Cout, int kh, int kw, int pad_y, int stride, int x_off, void* stream) {
     B3D_REQUIRE(N > 0 && Cin > 0 && Cout > 0 && H > 0 && W > 0 && Hout > 0 && Wout > 0, B3D_EINVAL,
                 "b3d_conv2d_wgrad_tf32: bad sizes");
-    B3D_REQUIRE(kh * kw <= MAX_TAPS && (stride == 1 || stride == 2), B3D_EINVAL, "b3d_conv2d_wgrad_tf32: bad kernel/stride");
+    B3D_REQUIRE(kh * kw <= MAX_TAPS && (stride == 1 || stride == 2) && x_off >= 0, B3D_EINVAL, "b3d_conv2d_wgrad_tf32: bad kernel/stride");
     B3D_REQUIRE(dy && x && dw, B3D_EINVAL, "b3d_conv2d_wgrad_tf32: null pointer");
     B3D_REQUIRE(Cin % 32 == 0 && Cout % 32 == 0, B3D_EINVAL,
                 "b3d_conv2d_wgrad_tf32: Cin=%d and Cout=%d must be multiples of 32 (pad the channels with zeros)", Cin, Cout);
@@ -427,7 +428,7 @@ int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, int N, int
     p.BHk = BK / p.BWk;
     p.kx = b3d::ceil_div(Wout, p.BWk);
     p.ky = b3d::ceil_div(Hout, p.BHk);
-    p.kh = kh; p.kw = kw; p.pad_y = pad_y; p.st = stride;
+    p.kh = kh; p.kw = kw; p.pad_y = pad_y; p.st = stride; p.xoff = x_off;
     // a row of kw taps per CTA when the K slice is a 32-pixel row segment (Wout >= 32) of a stride-1 conv
     int T = 1;
     p.tstep = 1;

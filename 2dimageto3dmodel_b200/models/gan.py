@@ -25,7 +25,7 @@ from rendering.utils import adjust_poles, circpad, symmetrize_texture
 class TCConv2d(nn.Conv2d):
     """nn.Conv2d (same parameters / state dict) whose forward runs on the tensor-core kernels."""
 
-    def forward(self, x, leaky=1.0, pad_out=0, pad_mode=CIRCULAR):
+    def forward(self, x, leaky=1.0, pad_out=0, pad_mode=CIRCULAR, x_crop=0):
         """`leaky` != 1 fuses LeakyReLU(leaky) into the convolution's epilogue (conv -> bias -> activation in one pass);
         `pad_out` > 0 also applies the next layer's x padding (the epilogue writes into the padded buffer)."""
         if not x.is_cuda:
@@ -33,7 +33,7 @@ class TCConv2d(nn.Conv2d):
         if self.padding[1] != 0 or self.stride[0] != self.stride[1] or self.dilation != (1, 1) or self.groups != 1:
             raise B3DError("TCConv2d supports zero padding along y only, square strides, no dilation / groups")
         return _tc_conv2d(x, self.weight, self.bias, pad_y=self.padding[0], stride=self.stride[0], leaky=leaky,
-                          pad_out=pad_out, pad_mode=pad_mode)
+                          pad_out=pad_out, pad_mode=pad_mode, x_crop=x_crop)
 
 
 def positional_encoding(Ny, Nx):
@@ -271,7 +271,7 @@ class ResBlockUp(nn.Module):
         a = cbn_act_pad(y1, self.norm1, z, up=1, pad=1)
         y2 = self.conv2(a)
         if isinstance(self.shortcut, nn.Module):
-            skip, off = self.shortcut(xp[..., 1:-1]), 0              # 1x1 conv on the unpadded input
+            skip, off = self.shortcut(xp, x_crop=1), 0               # 1x1 conv on the interior of the padded input
         else:
             skip, off = xp, 1                                        # identity: read the interior of the padded input
         return cbn_act_pad(y2, self.norm2, z, skip_nchw=skip, skip_off=off, up=up, pad=pad_next, post_leaky=post_leaky)

@@ -225,12 +225,12 @@ B3D_API int b3d_conv2d_flat_tf32(const float* x, const float* wt, const float* b
 
 /* Weight gradient of the same convolution (split-K tcgen05 GEMM over the output pixels, M/N-major operands
  * straight from the NHWC tensors):
- *   dw[co, ci, r, s] += sum_{n,y,x} dy[n, y, x, co] * x[n, stride*y + r - pad_y, stride*x + s, ci]
+ *   dw[co, ci, r, s] += sum_{n,y,x} dy[n, y, x, co] * x[n, stride*y + r - pad_y, stride*x + s + x_off, ci]
  * dy [N,Hout,Wout,Cout], x [N,H,W,Cin] (x already padded along x; Cin, Cout multiples of 4),
  * dw [Cout,Cin,kh,kw] is ACCUMULATED into (caller zeroes it).                                          */
 B3D_API int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, int N, int H, int W, int Cin,
                                   int Hout, int Wout, int Cout, int kh, int kw, int pad_y, int stride,
-                                  void* stream);
+                                  int x_off, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * One-pass NHWC helpers between the GAN's convolutions.
@@ -240,6 +240,12 @@ B3D_API int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, in
  * ------------------------------------------------------------------------------------------ */
 B3D_API int b3d_pad_x_fwd(const float* x, float* out, long long rows, int W, int C, int amount, int mode, void* stream);
 B3D_API int b3d_pad_x_bwd(const float* gout, float* gx, long long rows, int W, int C, int amount, int mode, void* stream);
+/* Thin-stem fold in front of the 5x5 discriminator stems (models/gan.py:163, :294 — 8 / 11 input channels): the kh
+ * vertical taps become channels, out [N, H + 2*pad_y - kh + 1, W, Cp][.., r*C + c] = x [N,H,W,C][n, y + r - pad_y, x, c]
+ * (zero rows = the y padding, zero channels up to Cp), so the tensor cores see kw taps of kh*C real channels.  _bwd is
+ * the adjoint (gx [N,H,W,C] from gout [N,Hout,W,Cp]). */
+B3D_API int b3d_fold_rows_fwd(const float* x, float* out, int N, int H, int W, int C, int kh, int pad_y, int Cp, void* stream);
+B3D_API int b3d_fold_rows_bwd(const float* gout, float* gx, int N, int H, int W, int C, int kh, int pad_y, int Cp, void* stream);
 /* In-place x padding of buf [rows, W + 2*amount, C] whose interior columns were written by a convolution epilogue
  * (b3d_conv2d_tf32 with OW = W + 2*amount, oox = amount): fills the 2*amount pad columns (mode 0 replicate / 1 circular).
  * Replaces circpad (rendering/utils.py:29-33) / F.pad (models/gan.py:329) after a conv without a full-tensor copy. */

@@ -182,3 +182,48 @@ def test_conv_leaky_pad_fused_autograd(mode, N, Cin, H, W, Cout, k, pad_y, strid
     for a, r in zip(outs[0], outs[1]):
         assert a.shape == r.shape
         assert float((a - r).abs().max()) <= TOL * float(r.abs().max()), (a.shape, float((a - r).abs().max()), float(r.abs().max()))
+
+
+@pytest.mark.parametrize("N,C,H,W,kh,pad_y", [(2, 8, 12, 9, 5, 2), (3, 11, 7, 5, 5, 2), (1, 4, 6, 6, 3, 0)])
+def test_fold_rows_matches_torch(N, C, H, W, kh, pad_y):
+    """b3d_fold_rows_fwd/_bwd (thin-stem fold of the vertical taps into channels) against slicing + cat."""
+    from b3d.ew import fold_rows
+    g = torch.Generator().manual_seed(N + C)
+    x0 = torch.randn(N, H, W, C, generator=g).cuda()
+    Cp = -(-kh * C // 32) * 32
+    Hout = H + 2 * pad_y - kh + 1
+    outs = []
+    for impl in (0, 1):
+        x = x0.clone().requires_grad_(True)
+        if impl == 0:
+            xp = torch.nn.functional.pad(x, (0, 0, 0, 0, pad_y, pad_y))
+            y = torch.cat([xp[:, r:r + Hout] for r in range(kh)] + [x.new_zeros(N, Hout, W, Cp - kh * C)], dim=3)
+        else:
+            y = fold_rows(x, kh, pad_y, Cp)
+        gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(6)).cuda()
+        gx, = torch.autograd.grad(y, x, gy)
+        outs.append((y.detach(), gx))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.allclose(outs[0][1], outs[1][1], atol=1e-5)
+
+
+@pytest.mark.parametrize("N,Cin,H,W,Cout,k,pad_y", [(2, 128, 16, 34, 64, 1, 0), (2, 64, 8, 20, 64, 3, 1)])
+def test_conv2d_x_crop_autograd(N, Cin, H, W, Cout, k, pad_y):
+    """conv2d(x, w, x_crop=1) == conv2d(x[..., 1:-1], w) with gradients w.r.t. the full padded input (the ResBlockUp
+    1x1 shortcut reads the interior of the replicate-padded block input, models/gan.py:233-246)."""
+    from b3d.conv import conv2d
+    g = torch.Generator().manual_seed(Cin + Cout + k)
+    x0 = torch.randn(N, Cin, H, W, generator=g).cuda()
+    w0 = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).cuda()
+    outs = []
+    for impl in ("torch", "b3d"):
+        x, w = x0.clone().requires_grad_(True), w0.clone().requires_grad_(True)
+        if impl == "torch":
+            y = ref_conv(x[..., 1:-1], w, None, pad_y, 1)
+        else:
+            y = conv2d(x.contiguous(memory_format=torch.channels_last), w, None, pad_y, 1, x_crop=1)
+        gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(7)).cuda()
+        outs.append([y.detach()] + list(torch.autograd.grad(y, [x, w], gy)))
+    for a, r in zip(outs[1], outs[0]):
+        assert a.shape == r.shape
+        assert float((a - r).abs().max()) <= TOL * float(r.abs().max()), (a.shape, float((a - r).abs().max()), float(r.abs().max()))
