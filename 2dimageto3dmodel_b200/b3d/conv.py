@@ -21,6 +21,10 @@ def taps_layout(weight):
     return weight.permute(2, 3, 0, 1).reshape(kh * kw, co, ci).contiguous()
 
 
+def _thin(Cout, Cin, kh, kw, stride):
+    return Cout <= 4 and Cin % 64 == 0 and kh == 5 and kw == 5 and stride == 1 and not os.environ.get("B3D_NO_THIN")
+
+
 def conv2d_nhwc(x, weight, bias=None, pad_y=0, stride=1, leaky=1.0, wt=None, cin_major=False, pad_out=0, pad_mode=1,
                 x_crop=0):
     """x [N,H,W,Cin] (Cin % 32 == 0), weight [Cout,Cin,kh,kw] -> [N,Hout,Wout,Cout]; zero pad along y only.
@@ -44,6 +48,13 @@ def conv2d_nhwc(x, weight, bias=None, pad_y=0, stride=1, leaky=1.0, wt=None, cin
     optr = ctypes.c_void_p(out.data_ptr() + 4 * pad_out * Cout)          # pixel (n, y, pad_out) of the padded buffer
     if pad_out and Cout % 4:
         raise B3DError("conv2d: pad_out needs Cout % 4 == 0")
+    if _thin(Cout, Cin, kh, kw, stride) and not cin_major:
+        # 1-4 output channels: fp32 CUDA-core reduction kernel (csrc/thin_kernels.cu), not a 64-wide MMA tile
+        check(lib.b3d_conv2d_thin_fwd(ptr(x), ptr(wt), ptr(dev(bias, "bias") if bias is not None else None), optr, N, H, W,
+                                      Cin, Hout, Wout, Cout, kh, kw, pad_y, x_crop, OW, Cout, float(leaky), stream_ptr(x)))
+        if pad_out:
+            check(lib.b3d_wrap_x_inplace(ptr(out), N * Hout, Wout, Cout, pad_out, pad_mode, stream_ptr(x)))
+        return out
     dy = [r - pad_y for r in range(kh) for _ in range(kw)]
     dx = [s + x_crop for _ in range(kh) for s in range(kw)]
     b = dev(bias, "bias") if bias is not None else None
@@ -104,6 +115,13 @@ def conv2d_wgrad_nhwc(dy_, x, kh, kw, pad_y=0, stride=1, x_crop=0):
     """dW [Cout,Cin,kh,kw] from dy_ [N,Hout,Wout,Cout] and the (x-padded) input x [N,H,W,Cin], both NHWC
     (channel counts that are not multiples of 32 are zero-padded here)."""
     co_real, ci_real = dy_.shape[3], x.shape[3]
+    if _thin(co_real, ci_real, kh, kw, stride):
+        g, x = dev(dy_, "grad_output"), dev(x, "input")
+        N, Hout, Wout, _ = g.shape
+        dw = torch.zeros(co_real, ci_real, kh, kw, device=g.device, dtype=torch.float32)
+        check(lib.b3d_conv2d_thin_wgrad(ptr(g), ptr(x), ptr(dw), N, x.shape[1], x.shape[2], ci_real, Hout, Wout, co_real, kh, kw,
+                                        pad_y, x_crop, stream_ptr(g)))
+        return dw
     g, x = dev(_pad_last(dy_, 32), "grad_output"), dev(_pad_last(x, 32), "input")
     N, Hout, Wout, Cout = g.shape
     _, H, W, Cin = x.shape
@@ -175,7 +193,8 @@ class _Conv2dNHWC(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = conv2d_dgrad_nhwc(gyp, wp, (x.shape[1], x.shape[2]), pad_y=pad_y, stride=stride, x_crop=x_crop)[..., :Cin]
         if ctx.needs_input_grad[1]:
-            gw = conv2d_wgrad_nhwc(gyp, x, kh, kw, pad_y=pad_y, stride=stride, x_crop=x_crop)[:Cout, :Cin]
+            gw = conv2d_wgrad_nhwc(gy if _thin(Cout, x.shape[3], kh, kw, stride) else gyp, x, kh, kw, pad_y=pad_y,
+                                   stride=stride, x_crop=x_crop)[:Cout, :Cin]
         return gx, gw, gb, None, None, None, None, None, None
 
 

@@ -90,27 +90,39 @@ pad_leaky_bias_bwd_kernel(const float4* __restrict__ go, const float4* __restric
     const long long p0 = (long long)blockIdx.x * pix_per_block;
     const long long p1 = p0 + pix_per_block < npix ? p0 + pix_per_block : npix;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (long long pix = p0 + lane_p; pix < p1; pix += PPB) {
-        const int w = (int)(pix % W);
-        const long long r = pix / W;
-        const float4* g = go + (r * Wo) * C4 + c;
-        float4 s = __ldg(g + (long long)(w + a) * C4);
-        if (a > 0) {
-            if (mode == 0) {
-                if (w == 0)
-                    for (int k = 0; k < a; ++k) { const float4 v = __ldg(g + (long long)k * C4); s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
-                if (w == W - 1)
-                    for (int k = 0; k < a; ++k) { const float4 v = __ldg(g + (long long)(W + a + k) * C4); s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
-            } else {
-                if (w < a) { const float4 v = __ldg(g + (long long)(w + a + W) * C4); s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
-                if (w >= W - a) { const float4 v = __ldg(g + (long long)(w + a - W) * C4); s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+    constexpr int U = 4;                                   // independent pixels in flight per thread
+    for (long long pb = p0 + lane_p; pb < p1; pb += (long long)U * PPB) {
+        float4 s[U], v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long pix = pb + (long long)u * PPB;
+            if (pix >= p1) continue;
+            const int w = (int)(pix % W);
+            const long long r = pix / W;
+            const float4* g = go + (r * Wo) * C4 + c;
+            s[u] = __ldg(g + (long long)(w + a) * C4);
+            v[u] = __ldg(ypad + (r * Wo + w + a) * C4 + c);
+            if (a > 0) {
+                if (mode == 0) {
+                    if (w == 0)
+                        for (int k = 0; k < a; ++k) { const float4 t = __ldg(g + (long long)k * C4); s[u].x += t.x; s[u].y += t.y; s[u].z += t.z; s[u].w += t.w; }
+                    if (w == W - 1)
+                        for (int k = 0; k < a; ++k) { const float4 t = __ldg(g + (long long)(W + a + k) * C4); s[u].x += t.x; s[u].y += t.y; s[u].z += t.z; s[u].w += t.w; }
+                } else {
+                    if (w < a) { const float4 t = __ldg(g + (long long)(w + a + W) * C4); s[u].x += t.x; s[u].y += t.y; s[u].z += t.z; s[u].w += t.w; }
+                    if (w >= W - a) { const float4 t = __ldg(g + (long long)(w + a - W) * C4); s[u].x += t.x; s[u].y += t.y; s[u].z += t.z; s[u].w += t.w; }
+                }
             }
         }
-        const float4 v = __ldg(ypad + (r * Wo + w + a) * C4 + c);
-        s = make_float4(v.x >= 0.f ? s.x : s.x * slope, v.y >= 0.f ? s.y : s.y * slope, v.z >= 0.f ? s.z : s.z * slope,
-                        v.w >= 0.f ? s.w : s.w * slope);
-        gy[pix * C4 + c] = s;
-        acc.x += s.x; acc.y += s.y; acc.z += s.z; acc.w += s.w;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long pix = pb + (long long)u * PPB;
+            if (pix >= p1) continue;
+            const float4 m = make_float4(v[u].x >= 0.f ? s[u].x : s[u].x * slope, v[u].y >= 0.f ? s[u].y : s[u].y * slope,
+                                         v[u].z >= 0.f ? s[u].z : s[u].z * slope, v[u].w >= 0.f ? s[u].w : s[u].w * slope);
+            gy[pix * C4 + c] = m;
+            acc.x += m.x; acc.y += m.y; acc.z += m.z; acc.w += m.w;
+        }
     }
     if (gb == nullptr) return;
     red[threadIdx.x] = acc;
@@ -249,7 +261,7 @@ int b3d_pad_leaky_bias_bwd(const float* gout_pad, const float* y_pad, float* gy,
     const long long npix = rows * W;
     const int ppb = NT / (C / 4);
     long long blocks = (npix + ppb - 1) / ppb;
-    const long long cap = 148LL * 8;
+    const long long cap = 148LL * 16;
     if (blocks > cap) blocks = cap;
     const long long per = ((npix + blocks - 1) / blocks + ppb - 1) / ppb * ppb;
     blocks = (npix + per - 1) / per;

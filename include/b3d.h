@@ -232,6 +232,17 @@ B3D_API int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, in
                                   int Hout, int Wout, int Cout, int kh, int kw, int pad_y, int stride,
                                   int x_off, void* stream);
 
+/* Thin heads: 5x5 / stride-1 convolutions with 1..4 output channels (generator conv_final, models/gan.py:359;
+ * discriminator heads :177, :302) on the fp32 CUDA cores, channels across the lanes of a warp.  Cin % 64 == 0.
+ *   _fwd:   x [N,H,W,Cin], wt [25][Cout][Cin] (tap-major, as b3d_conv2d_tf32), bias [Cout] or NULL ->
+ *           out[n, y, x, co] = leaky(bias + sum ...) written with pixel pitch OW and channel pitch OC.
+ *   _wgrad: dw [Cout,Cin,5,5] += sum dy[n,y,x,co] * x[n, y + r - pad_y, x + s + x_off, ci]   (dy dense [N,Hout,Wout,Cout]). */
+B3D_API int b3d_conv2d_thin_fwd(const float* x, const float* wt, const float* bias, float* out, int N, int H, int W, int Cin,
+                                int Hout, int Wout, int Cout, int kh, int kw, int pad_y, int x_off, int OW, int OC,
+                                float leaky, void* stream);
+B3D_API int b3d_conv2d_thin_wgrad(const float* dy, const float* x, float* dw, int N, int H, int W, int Cin, int Hout,
+                                  int Wout, int Cout, int kh, int kw, int pad_y, int x_off, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * One-pass NHWC helpers between the GAN's convolutions.
  * b3d_pad_x_*: padding along x of x [rows = N*H, W, C] -> out [rows, W + 2*amount, C]; mode 0 = replicate

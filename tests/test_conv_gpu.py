@@ -84,7 +84,10 @@ def test_wgrad(N, Cin, H, W, Cout, k, pad_y, stride):
     (2, 8, 32, 36, 64, 5, 2, 1, True),       # discriminator stem, 8 channels: kw folded into K
     (2, 11, 32, 36, 64, 5, 2, 1, True),      # mesh discriminator stem, 11 channels
     (2, 8, 32, 34, 64, 4, 1, 2, True),       # 512^2 stem: 4x4 / stride 2 (channels zero-padded to 32)
-    (2, 64, 16, 20, 3, 5, 2, 1, True),       # 3-channel head
+    (2, 64, 16, 20, 3, 5, 2, 1, True),       # 3-channel head (CUDA-core thin kernels for fprop / wgrad)
+    (3, 512, 9, 13, 1, 5, 2, 1, True),       # discriminator head 512 -> 1
+    (2, 256, 8, 12, 1, 5, 2, 1, False),      # mesh discriminator head 256 -> 1
+    (2, 128, 6, 9, 2, 5, 2, 1, True),
     (2, 256, 16, 18, 128, 3, 1, 1, False),
 ])
 def test_conv2d_autograd_matches_torch(N, Cin, H, W, Cout, k, pad_y, stride, bias):
