@@ -33,38 +33,42 @@ struct ThinGeom {
 };
 
 // wt [KS][KS][COUT][Cin]
+constexpr int OUTS = 8;                       // adjacent output pixels per warp
+
 template <int COUT, int VEC>
 __global__ void __launch_bounds__(NT)
 conv_thin_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wt, const float* __restrict__ bias,
                      float* __restrict__ out, const ThinGeom g) {
     const int lane = threadIdx.x & 31;
     const int warps_total = gridDim.x * (NT / 32);
-    const int xg = (g.Wout + 3) / 4;
+    const int xg = (g.Wout + OUTS - 1) / OUTS;
     const long long items = (long long)g.N * g.Hout * xg;
     for (long long it = (long long)blockIdx.x * (NT / 32) + (threadIdx.x >> 5); it < items; it += warps_total) {
-        const int x0 = (int)(it % xg) * 4;
+        const int x0 = (int)(it % xg) * OUTS;
         const int y = (int)((it / xg) % g.Hout);
         const int n = (int)(it / ((long long)xg * g.Hout));
-        float acc[4][COUT];
+        float acc[OUTS][COUT];
 #pragma unroll
-        for (int o = 0; o < 4; ++o)
+        for (int o = 0; o < OUTS; ++o)
 #pragma unroll
             for (int c = 0; c < COUT; ++c) acc[o][c] = 0.f;
         for (int c0 = 0; c0 < g.Cin; c0 += 32 * VEC) {
             const int ci = c0 + lane * VEC;
 #pragma unroll 1
             for (int r = 0; r < KS; ++r) {
+                // rows outside the image contribute zeros (the y padding): clamp the address, zero the values — no
+                // branch between the loads, so a whole row of requests is in flight at once
                 const int yy = y + r - g.pad_y;
-                if (yy < 0 || yy >= g.H) continue;
-                const float* row = x + (((long long)n * g.H + yy) * g.W) * g.Cin + ci;
-                float px[4 + KS - 1][VEC];
+                const float rv = (yy >= 0 && yy < g.H) ? 1.f : 0.f;
+                const int yc = yy < 0 ? 0 : (yy >= g.H ? g.H - 1 : yy);
+                const float* row = x + (((long long)n * g.H + yc) * g.W) * g.Cin + ci;
+                float px[OUTS + KS - 1][VEC];
 #pragma unroll
-                for (int j = 0; j < 4 + KS - 1; ++j) {
+                for (int j = 0; j < OUTS + KS - 1; ++j) {
                     const int xx = x0 + j + g.xoff;
-                    if (xx < g.W) ldv<VEC>(px[j], row + (long long)xx * g.Cin);
-                    else
+                    ldv<VEC>(px[j], row + (long long)(xx < g.W ? xx : g.W - 1) * g.Cin);     // columns >= W feed dropped outputs only
 #pragma unroll
-                        for (int v = 0; v < VEC; ++v) px[j][v] = 0.f;
+                    for (int v = 0; v < VEC; ++v) px[j][v] *= rv;
                 }
 #pragma unroll
                 for (int s = 0; s < KS; ++s) {
@@ -73,22 +77,24 @@ conv_thin_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wt, 
                         float wv[VEC];
                         ldv<VEC>(wv, wt + ((long long)((r * KS + s) * COUT + c)) * g.Cin + ci);
 #pragma unroll
-                        for (int o = 0; o < 4; ++o)
+                        for (int o = 0; o < OUTS; ++o)
 #pragma unroll
                             for (int v = 0; v < VEC; ++v) acc[o][c] = fmaf(px[o + s][v], wv[v], acc[o][c]);
                     }
                 }
             }
         }
+        // OUTS x COUT sums over the lanes: butterfly that leaves output o's sums in lane o
 #pragma unroll
-        for (int o = 0; o < 4; ++o)
+        for (int c = 0; c < COUT; ++c) {
+            float mine = 0.f;
 #pragma unroll
-            for (int c = 0; c < COUT; ++c) acc[o][c] = b3d::warp_sum(acc[o][c]);
-        if (lane < 4 && x0 + lane < g.Wout) {
-#pragma unroll
-            for (int c = 0; c < COUT; ++c) {
-                float v = lane == 0 ? acc[0][c] : lane == 1 ? acc[1][c] : lane == 2 ? acc[2][c] : acc[3][c];
-                if (bias) v += __ldg(bias + c);
+            for (int o = 0; o < OUTS; ++o) {
+                const float t = b3d::warp_sum(acc[o][c]);
+                if (lane == o) mine = t;
+            }
+            if (lane < OUTS && x0 + lane < g.Wout) {
+                float v = mine + (bias ? __ldg(bias + c) : 0.f);
                 v = v >= 0.f ? v : v * g.leaky;
                 out[(((long long)n * g.Hout + y) * g.OW + x0 + lane) * g.OC + c] = v;
             }
@@ -125,20 +131,28 @@ conv_thin_wgrad_kernel(const float* __restrict__ gy, const float* __restrict__ x
             float gv[COUT];
 #pragma unroll
             for (int c = 0; c < COUT; ++c) gv[c] = __ldg(gyr + xo * COUT + c);
+            // all 25 input pixels of this output pixel are requested before the first FMA (no branches in between:
+            // x + s + xoff < W by the geometry check; rows outside the image are clamped and masked)
+            float xv[KS * KS][VEC];
 #pragma unroll
             for (int r = 0; r < KS; ++r) {
                 const int yy = y + r - g.pad_y;
-                if (yy < 0 || yy >= g.H) continue;
-                const float* xr = x + (((long long)n * g.H + yy) * g.W + xo + g.xoff) * g.Cin + ci;
+                const int yc = yy < 0 ? 0 : (yy >= g.H ? g.H - 1 : yy);
+                const float* xr = x + (((long long)n * g.H + yc) * g.W + xo + g.xoff) * g.Cin + ci;
 #pragma unroll
-                for (int s = 0; s < KS; ++s) {
-                    if (xo + s + g.xoff >= g.W) continue;
-                    float xv[VEC];
-                    ldv<VEC>(xv, xr + (long long)s * g.Cin);
+                for (int s = 0; s < KS; ++s) ldv<VEC>(xv[r * KS + s], xr + (long long)s * g.Cin);
+            }
 #pragma unroll
-                    for (int c = 0; c < COUT; ++c)
+            for (int r = 0; r < KS; ++r) {
+                const int yy = y + r - g.pad_y;
+                const float rv = (yy >= 0 && yy < g.H) ? 1.f : 0.f;
 #pragma unroll
-                        for (int v = 0; v < VEC; ++v) acc[c][r * KS + s][v] = fmaf(gv[c], xv[v], acc[c][r * KS + s][v]);
+                for (int c = 0; c < COUT; ++c) {
+                    const float gm = gv[c] * rv;
+#pragma unroll
+                    for (int s = 0; s < KS; ++s)
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) acc[c][r * KS + s][v] = fmaf(gm, xv[r * KS + s][v], acc[c][r * KS + s][v]);
                 }
             }
         }
@@ -158,7 +172,7 @@ conv_thin_wgrad_kernel(const float* __restrict__ gy, const float* __restrict__ x
 
 template <int COUT, int VEC>
 int launch_fwd(const float* x, const float* wt, const float* bias, float* out, const ThinGeom& g, cudaStream_t st) {
-    const long long items = (long long)g.N * g.Hout * ((g.Wout + 3) / 4);
+    const long long items = (long long)g.N * g.Hout * ((g.Wout + OUTS - 1) / OUTS);
     long long blocks = (items + NT / 32 - 1) / (NT / 32);
     if (blocks > 148 * 16) blocks = 148 * 16;
     conv_thin_fwd_kernel<COUT, VEC><<<(int)blocks, NT, 0, st>>>(x, wt, bias, out, g);
