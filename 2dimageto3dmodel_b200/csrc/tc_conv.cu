@@ -24,7 +24,7 @@ constexpr int BM = 128;         // output pixels per CTA  (UMMA M)
 constexpr int BK = 32;          // fp32 channels per K slice = 128 B = one swizzle row
 constexpr int UMMA_K = 8;       // tf32
 constexpr int MAX_TAPS = 25;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 224;   // warp 0: A-operand TMA, warp 1: MMA issue, warps 2-5: epilogue, warp 6: B-operand TMA
 
 struct ConvParams {
     int N, Hout, Wout, Cout;          // logical output extent covered by tiles (before the epilogue transform)
@@ -89,6 +89,8 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const uint32_t tmem_acc = *tmem_slot;
     const int KI = p.ntaps * p.kslices;
 
+    // One elected lane spends ~200 cycles per TMA instruction (profiles/r1_conv_layers.md), about the tensor-core time of
+    // the K slice it feeds, so the two operands are issued by two different warps; both complete on the same barrier.
     if (warp == 0) {
         if (lane == 0) {
             for (int it = 0; it < KI; ++it) {
@@ -96,9 +98,17 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 tc::mbar_wait(empty + s, ph ^ 1);
                 const int tap = it / p.kslices, ks = it % p.kslices;
                 unsigned char* a = base + s * S::STAGE_BYTES;
-                unsigned char* b = a + S::A_BYTES;
                 tc::mbar_arrive_expect_tx(full + s, S::STAGE_BYTES);
                 tc::tma_load_4d(a, &tmap_x, full + s, ks * BK, p.sx * x0 + p.dx[tap], p.sy * y0 + p.dy[tap], n0);
+            }
+        }
+    } else if (warp == 6) {
+        if (lane == 0) {
+            for (int it = 0; it < KI; ++it) {
+                const int s = it % STAGES, ph = (it / STAGES) & 1;
+                tc::mbar_wait(empty + s, ph ^ 1);
+                const int tap = it / p.kslices, ks = it % p.kslices;
+                unsigned char* b = base + s * S::STAGE_BYTES + S::A_BYTES;
                 if constexpr (WMN) {      // weights [tap][Cin][Cout]: 32 cin rows x 32 cout per box (N-major B operand)
 #pragma unroll
                     for (int nb = 0; nb < BN / 32; ++nb) tc::tma_load_3d(b + nb * 4096, &tmap_w, full + s, c0 + nb * 32, ks * BK, tap);
@@ -250,7 +260,7 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
     tc::tc_fence_after();
     const uint32_t tmem_acc = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == 0 || warp == 6) {           // warp 0 streams dY, warp 6 streams X (two TMA issue lanes, one barrier)
         if (lane == 0) {
             for (int it = 0; it < KI; ++it) {
                 const int st = it % STAGES, ph = (it / STAGES) & 1;
@@ -259,11 +269,13 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
                 const int n = (int)(k / per_img), rem = (int)(k % per_img);
                 const int x0 = (rem % p.kx) * p.BWk, y0 = (rem / p.kx) * p.BHk;
                 unsigned char* a = base + st * S::STAGE_BYTES;
-                unsigned char* b = a + S::A_BYTES;
-                tc::mbar_arrive_expect_tx(full + st, S::STAGE_BYTES);
                 // channels are split as (32, C/32) in the tensor maps: ONE 5-D box lands all 32-channel blocks back to back
-                tc::tma_load_5d(a, &tmap_dy, full + st, 0, x0, y0, n, co0 / 32);
-                tc::tma_load_5d(b, &tmap_x, full + st, 0, p.st * x0 + s + p.xoff, p.st * y0 + r - p.pad_y, n, ci0 / 32);
+                if (warp == 0) {
+                    tc::mbar_arrive_expect_tx(full + st, S::STAGE_BYTES);
+                    tc::tma_load_5d(a, &tmap_dy, full + st, 0, x0, y0, n, co0 / 32);
+                } else {
+                    tc::tma_load_5d(a + S::A_BYTES, &tmap_x, full + st, 0, p.st * x0 + s + p.xoff, p.st * y0 + r - p.pad_y, n, ci0 / 32);
+                }
             }
         }
     } else if (warp == 1) {
