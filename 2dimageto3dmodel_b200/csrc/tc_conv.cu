@@ -48,8 +48,8 @@ struct Smem {
     static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, int STAGES, bool WMN>
-__global__ void __launch_bounds__(NTHREADS, 2)
+template <int BN, int STAGES, bool WMN, int MINB>
+__global__ void __launch_bounds__(NTHREADS, MINB)
 conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const ConvParams p, const float* __restrict__ bias, float* __restrict__ out) {
     using S = Smem<BN, STAGES>;
@@ -334,14 +334,14 @@ int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, const WgradParam
     return B3D_OK;
 }
 
-template <int BN, int STAGES, bool WMN>
+template <int BN, int STAGES, bool WMN, int MINB>
 int launch(const CUtensorMap& mx, const CUtensorMap& mw, const ConvParams& p, const float* bias, float* out,
            int tiles, cudaStream_t st) {
     using S = Smem<BN, STAGES>;
-    B3D_CUDA_OK(cudaFuncSetAttribute(conv_tf32_kernel<BN, STAGES, WMN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B3D_CUDA_OK(cudaFuncSetAttribute(conv_tf32_kernel<BN, STAGES, WMN, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      S::TOTAL));
     dim3 grid(tiles, b3d::ceil_div(p.Cout, BN));
-    conv_tf32_kernel<BN, STAGES, WMN><<<grid, NTHREADS, S::TOTAL, st>>>(mx, mw, p, bias, out);
+    conv_tf32_kernel<BN, STAGES, WMN, MINB><<<grid, NTHREADS, S::TOTAL, st>>>(mx, mw, p, bias, out);
     B3D_LAUNCH_OK();
     return B3D_OK;
 }
@@ -410,8 +410,18 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
         const uint32_t box[4] = {(uint32_t)BK, (uint32_t)(sx * (p.BW - 1) + 1), (uint32_t)(sy * (p.BH - 1) + 1), (uint32_t)p.BI};
         const uint32_t es[4] = {1, (uint32_t)sx, (uint32_t)sy, 1};
         if (int rc = tc::make_tmap_f32(&mx, x, 4, dims, strides, box, es)) return rc;
-        if (w_cin_major) return BN == 128 ? launch<128, 3, true>(mx, mw, p, bias, out, tiles, st) : launch<64, 4, true>(mx, mw, p, bias, out, tiles, st);
-        return BN == 128 ? launch<128, 3, false>(mx, mw, p, bias, out, tiles, st) : launch<64, 4, false>(mx, mw, p, bias, out, tiles, st);
+        // CTAs per SM x ring depth: short K loops (few taps x few channel slices) are dominated by pipeline fill, epilogue
+        // and store drain, which only OTHER resident CTAs can hide -> more, shallower CTAs (profiles/r1_c_*.md)
+        static const int occ_env = getenv("B3D_CONV_OCC") ? atoi(getenv("B3D_CONV_OCC")) : 0;
+        const int occ = occ_env ? occ_env : 2;
+        if (w_cin_major) {
+            if (BN == 128) return occ >= 3 ? launch<128, 2, true, 3>(mx, mw, p, bias, out, tiles, st) : launch<128, 3, true, 2>(mx, mw, p, bias, out, tiles, st);
+            return occ >= 4 ? launch<64, 2, true, 4>(mx, mw, p, bias, out, tiles, st)
+                 : occ == 3 ? launch<64, 3, true, 3>(mx, mw, p, bias, out, tiles, st) : launch<64, 4, true, 2>(mx, mw, p, bias, out, tiles, st);
+        }
+        if (BN == 128) return occ >= 3 ? launch<128, 2, false, 3>(mx, mw, p, bias, out, tiles, st) : launch<128, 3, false, 2>(mx, mw, p, bias, out, tiles, st);
+        return occ >= 4 ? launch<64, 2, false, 4>(mx, mw, p, bias, out, tiles, st)
+             : occ == 3 ? launch<64, 3, false, 3>(mx, mw, p, bias, out, tiles, st) : launch<64, 4, false, 2>(mx, mw, p, bias, out, tiles, st);
     };
     const int bw_full = pow2_floor(Wout < BM ? Wout : BM);
     const int rem = Wout % bw_full;
