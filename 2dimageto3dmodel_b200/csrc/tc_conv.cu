@@ -185,6 +185,168 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 }
 
 // ----------------------------------------------------------------------------------------------
+// Persistent variant: one CTA loops over (tile, channel block) work items with TWO accumulators in tensor memory, so the
+// epilogue of item j (TMEM -> registers -> global, then the store drain) overlaps the TMA / MMA main loop of item j+1
+// inside the same CTA, and barrier init / TMEM allocation / descriptor prefetch are paid once per CTA instead of once
+// per 128 output pixels.  ncu on the one-tile-per-CTA kernel (profiles/r1_c_conv_final_full.md): layers with short K
+// loops (folded stems: 10 K slices, stride-2 dgrad classes: 16) keep the tensor pipe 18-23 % busy with no memory
+// system above 60 % — the CTA lifetime is fill + epilogue + drain.
+// Barriers: full/empty ring shared by all items (global K-slice counter), acc_full[2] (MMA -> epilogue, tcgen05.commit),
+// acc_empty[2] (epilogue -> MMA, one arrival per epilogue warp).
+// ----------------------------------------------------------------------------------------------
+constexpr int PTHREADS = 192;   // warp 0: TMA, warp 1: MMA issue, warps 2-5: epilogue
+
+template <int BN, int STAGES, bool WMN>
+__global__ void __launch_bounds__(PTHREADS, 2)
+conv_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                            const ConvParams p, const float* __restrict__ bias, float* __restrict__ out, int tiles,
+                            int work_items) {
+    using S = Smem<BN, STAGES>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + STAGES * S::STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* acc_full = empty + STAGES;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    constexpr uint32_t TCOLS = 2 * BN < 32 ? 32 : 2 * BN;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tmap_x);
+        tc::tma_prefetch_desc(&tmap_w);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            tc::mbar_init(full + s, 1);
+            tc::mbar_init(empty + s, 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            tc::mbar_init(acc_full + b, 1);
+            tc::mbar_init(acc_empty + b, 4);
+        }
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) tc::tmem_alloc<TCOLS>(tmem_slot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot;
+    const int KI = p.ntaps * p.kslices;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t git = 0;
+            for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
+                int t = w % tiles;
+                const int c0 = (w / tiles) * BN;
+                const int tx = t % p.tiles_x;
+                t /= p.tiles_x;
+                const int x0 = p.xbase + tx * p.BW, y0 = (t % p.tiles_y) * p.BH, n0 = (t / p.tiles_y) * p.BI;
+                for (int it = 0; it < KI; ++it, ++git) {
+                    const int s = git % STAGES, ph = (git / STAGES) & 1;
+                    tc::mbar_wait(empty + s, ph ^ 1);
+                    const int tap = it / p.kslices, ks = it % p.kslices;
+                    unsigned char* a = base + s * S::STAGE_BYTES;
+                    unsigned char* b = a + S::A_BYTES;
+                    tc::mbar_arrive_expect_tx(full + s, S::STAGE_BYTES);
+                    tc::tma_load_4d(a, &tmap_x, full + s, ks * BK, p.sx * x0 + p.dx[tap], p.sy * y0 + p.dy[tap], n0);
+                    if constexpr (WMN) {
+#pragma unroll
+                        for (int nb = 0; nb < BN / 32; ++nb) tc::tma_load_3d(b + nb * 4096, &tmap_w, full + s, c0 + nb * 32, ks * BK, tap);
+                    } else {
+                        tc::tma_load_3d(b, &tmap_w, full + s, ks * BK, c0, tap);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc::umma_idesc_tf32(BM, BN, false, WMN);
+            uint32_t git = 0, j = 0;
+            for (int w = blockIdx.x; w < work_items; w += gridDim.x, ++j) {
+                const uint32_t buf = j & 1;
+                tc::mbar_wait(acc_empty + buf, ((j >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
+                tc::tc_fence_after();
+                const uint32_t acc = tmem_acc + buf * BN;
+                for (int it = 0; it < KI; ++it, ++git) {
+                    const int s = git % STAGES, ph = (git / STAGES) & 1;
+                    tc::mbar_wait(full + s, ph);
+                    tc::tc_fence_after();
+                    const uint32_t a = tc::smem_u32(base + s * S::STAGE_BYTES);
+                    const uint32_t b = a + S::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t da = tc::umma_desc_k128(a + k * UMMA_K * 4);
+                        const uint64_t db = WMN ? tc::umma_desc_mn128(b + k * 1024, p.dbg_lbo, p.dbg_sbo, p.dbg_lt) : tc::umma_desc_k128(b + k * UMMA_K * 4);
+                        tc::umma_tf32(acc, da, db, idesc, (it | k) ? 1u : 0u);
+                    }
+                    tc::umma_commit(empty + s);
+                }
+                tc::umma_commit(acc_full + buf);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int bx = r % p.BW, by = (r / p.BW) % p.BH, bi = r / (p.BW * p.BH);
+        uint32_t j = 0;
+        for (int w = blockIdx.x; w < work_items; w += gridDim.x, ++j) {
+            int t = w % tiles;
+            const int c0 = (w / tiles) * BN;
+            const int tx = t % p.tiles_x;
+            t /= p.tiles_x;
+            const int n = (t / p.tiles_y) * p.BI + bi, y = (t % p.tiles_y) * p.BH + by, x = p.xbase + tx * p.BW + bx;
+            const bool valid = n < p.N && y < p.Hout && x < p.Wout;
+            float* dst = out + (((size_t)n * p.OH + (size_t)(p.osy * y + p.ooy)) * p.OW + (size_t)(p.osx * x + p.oox)) * p.OC;
+            const uint32_t buf = j & 1;
+            tc::mbar_wait(acc_full + buf, (j >> 1) & 1);
+            tc::tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                float v[32];
+                tc::tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)c, v);
+                if (c + 32 >= BN) {                  // last read of this accumulator: hand it back before the stores
+                    tc::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(acc_empty + buf);
+                }
+                if (valid) {
+                    const int cb = c0 + c;
+                    if (cb + 32 <= p.Cout && (p.OC & 3) == 0) {
+#pragma unroll
+                        for (int jj = 0; jj < 32; jj += 4) {
+                            float4 o;
+                            o.x = v[jj] + (bias ? __ldg(bias + cb + jj) : 0.f);
+                            o.y = v[jj + 1] + (bias ? __ldg(bias + cb + jj + 1) : 0.f);
+                            o.z = v[jj + 2] + (bias ? __ldg(bias + cb + jj + 2) : 0.f);
+                            o.w = v[jj + 3] + (bias ? __ldg(bias + cb + jj + 3) : 0.f);
+                            o.x = o.x >= 0.f ? o.x : o.x * p.leaky;
+                            o.y = o.y >= 0.f ? o.y : o.y * p.leaky;
+                            o.z = o.z >= 0.f ? o.z : o.z * p.leaky;
+                            o.w = o.w >= 0.f ? o.w : o.w * p.leaky;
+                            *reinterpret_cast<float4*>(dst + cb + jj) = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj) {
+                            const int co = cb + jj;
+                            if (co < p.Cout) {
+                                float o = v[jj] + (bias ? __ldg(bias + co) : 0.f);
+                                dst[co] = o >= 0.f ? o : o * p.leaky;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tc::tmem_dealloc<TCOLS>(tmem_acc);
+}
+
+// ----------------------------------------------------------------------------------------------
 // wgrad:  dW[co, ci, r, s] += sum_{n,y,x} dY[n, y, x, co] * X[n, st*y + r - pad_y, st*x + s, ci]      (NHWC operands)
 // GEMM with M = Cout (128), N = Cin (BN), K = output pixels.  In NHWC the reduction index (pixel) is the SLOW index
 // of both operands, i.e. they are M/N-major: a K slice is a BWk x BHk box of 32 output pixels, loaded as 32-channel
@@ -346,6 +508,18 @@ int launch(const CUtensorMap& mx, const CUtensorMap& mw, const ConvParams& p, co
     return B3D_OK;
 }
 
+template <int BN, int STAGES, bool WMN>
+int launch_persistent(const CUtensorMap& mx, const CUtensorMap& mw, const ConvParams& p, const float* bias, float* out,
+                      int tiles, cudaStream_t st) {
+    constexpr int TOTAL = Smem<BN, STAGES>::TOTAL + 64;
+    B3D_CUDA_OK(cudaFuncSetAttribute(conv_tf32_persistent_kernel<BN, STAGES, WMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOTAL));
+    const int work = tiles * b3d::ceil_div(p.Cout, BN);
+    const int grid = work < 2 * 148 ? work : 2 * 148;
+    conv_tf32_persistent_kernel<BN, STAGES, WMN><<<grid, PTHREADS, TOTAL, st>>>(mx, mw, p, bias, out, tiles, work);
+    B3D_LAUNCH_OK();
+    return B3D_OK;
+}
+
 int pow2_floor(int v) {
     int p = 1;
     while (p * 2 <= v) p *= 2;
@@ -412,6 +586,11 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
         if (int rc = tc::make_tmap_f32(&mx, x, 4, dims, strides, box, es)) return rc;
         // CTAs per SM x ring depth: short K loops (few taps x few channel slices) are dominated by pipeline fill, epilogue
         // and store drain, which only OTHER resident CTAs can hide -> more, shallower CTAs (profiles/r1_c_*.md)
+        static const int persist = getenv("B3D_CONV_PERSIST") ? atoi(getenv("B3D_CONV_PERSIST")) : 0;
+        if (persist) {
+            if (w_cin_major) return BN == 128 ? launch_persistent<128, 3, true>(mx, mw, p, bias, out, tiles, st) : launch_persistent<64, 4, true>(mx, mw, p, bias, out, tiles, st);
+            return BN == 128 ? launch_persistent<128, 3, false>(mx, mw, p, bias, out, tiles, st) : launch_persistent<64, 4, false>(mx, mw, p, bias, out, tiles, st);
+        }
         static const int occ_env = getenv("B3D_CONV_OCC") ? atoi(getenv("B3D_CONV_OCC")) : 0;
         const int occ = occ_env ? occ_env : 2;
         if (w_cin_major) {
