@@ -197,7 +197,7 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 constexpr int PTHREADS = 192;   // warp 0: TMA, warp 1: MMA issue, warps 2-5: epilogue
 
 template <int BN, int STAGES, bool WMN>
-__global__ void __launch_bounds__(PTHREADS, 2)
+__global__ void __launch_bounds__(PTHREADS, BN <= 128 ? 2 : 1)
 conv_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                             const ConvParams p, const float* __restrict__ bias, float* __restrict__ out, int tiles,
                             int work_items) {
@@ -514,7 +514,8 @@ int launch_persistent(const CUtensorMap& mx, const CUtensorMap& mw, const ConvPa
     constexpr int TOTAL = Smem<BN, STAGES>::TOTAL + 64;
     B3D_CUDA_OK(cudaFuncSetAttribute(conv_tf32_persistent_kernel<BN, STAGES, WMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOTAL));
     const int work = tiles * b3d::ceil_div(p.Cout, BN);
-    const int grid = work < 2 * 148 ? work : 2 * 148;
+    const int slots = (BN <= 128 ? 2 : 1) * 148;         // resident CTAs: 2 per SM (1 for the 256-wide tile: all of TMEM)
+    const int grid = work < slots ? work : slots;
     conv_tf32_persistent_kernel<BN, STAGES, WMN><<<grid, PTHREADS, TOTAL, st>>>(mx, mw, p, bias, out, tiles, work);
     B3D_LAUNCH_OK();
     return B3D_OK;
@@ -544,7 +545,12 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
     B3D_CHECK_ALIGNED(x);
     B3D_CHECK_ALIGNED(wt);
 
-    const int BN = Cout > 64 ? 128 : 64;
+    static const int persist = getenv("B3D_CONV_PERSIST") ? atoi(getenv("B3D_CONV_PERSIST")) : 1;
+    static const int wide = getenv("B3D_CONV_BN256") ? atoi(getenv("B3D_CONV_BN256")) : 0;
+    // 256-wide output-channel tiles halve the input-tile bytes per FLOP through the L2 -> SM fabric (the bound of the
+    // per-tap formulation, profiles/r1_c_*.md) when there are >= 256 output channels and enough tiles to fill the GPU
+    const bool bn256 = persist && wide && Cout % 256 == 0 && (long long)N * Hout * Wout / BM * (Cout / 256) >= 148;
+    const int BN = bn256 ? 256 : Cout > 64 ? 128 : 64;
     cudaStream_t st = (cudaStream_t)stream;
     CUtensorMap mw;
     if (w_cin_major) {        // wt [ntaps, Cin, Cout]: the B operand is N-major (no weight transpose for dgrad)
@@ -586,8 +592,8 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
         if (int rc = tc::make_tmap_f32(&mx, x, 4, dims, strides, box, es)) return rc;
         // CTAs per SM x ring depth: short K loops (few taps x few channel slices) are dominated by pipeline fill, epilogue
         // and store drain, which only OTHER resident CTAs can hide -> more, shallower CTAs (profiles/r1_c_*.md)
-        static const int persist = getenv("B3D_CONV_PERSIST") ? atoi(getenv("B3D_CONV_PERSIST")) : 0;
         if (persist) {
+            if (BN == 256) return w_cin_major ? launch_persistent<256, 4, true>(mx, mw, p, bias, out, tiles, st) : launch_persistent<256, 4, false>(mx, mw, p, bias, out, tiles, st);
             if (w_cin_major) return BN == 128 ? launch_persistent<128, 3, true>(mx, mw, p, bias, out, tiles, st) : launch_persistent<64, 4, true>(mx, mw, p, bias, out, tiles, st);
             return BN == 128 ? launch_persistent<128, 3, false>(mx, mw, p, bias, out, tiles, st) : launch_persistent<64, 4, false>(mx, mw, p, bias, out, tiles, st);
         }
