@@ -196,12 +196,24 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 // ----------------------------------------------------------------------------------------------
 constexpr int PTHREADS = 192;   // warp 0: TMA, warp 1: MMA issue, warps 2-5: epilogue
 
-template <int BN, int STAGES, bool WMN>
-__global__ void __launch_bounds__(PTHREADS, BN <= 128 ? 2 : 1)
+// R = pixel tiles stacked per work item: they share every weight tile that arrives (R accumulators of BN columns per
+// TMEM buffer), which cuts the weight bytes per FLOP through the L2 -> SM fabric by R.
+template <int BN, int STAGES, int R>
+struct PSmem {
+    static constexpr int A_TILE = BM * BK * 4;
+    static constexpr int A_BYTES = R * A_TILE;
+    static constexpr int B_BYTES = BN * BK * 4;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 320 /*barriers*/;
+    static constexpr int CTAS_PER_SM = (2 * TOTAL <= 227 * 1024 && 4 * R * BN <= 512) ? 2 : 1;
+};
+
+template <int BN, int STAGES, bool WMN, int R>
+__global__ void __launch_bounds__(PTHREADS, PSmem<BN, STAGES, R>::CTAS_PER_SM)
 conv_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                             const ConvParams p, const float* __restrict__ bias, float* __restrict__ out, int tiles,
-                            int work_items) {
-    using S = Smem<BN, STAGES>;
+                            int groups, int work_items) {
+    using S = PSmem<BN, STAGES, R>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(base + STAGES * S::STAGE_BYTES);
@@ -209,7 +221,8 @@ conv_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
     uint64_t* acc_full = empty + STAGES;
     uint64_t* acc_empty = acc_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-    constexpr uint32_t TCOLS = 2 * BN < 32 ? 32 : 2 * BN;
+    constexpr uint32_t TCOLS = 2 * R * BN < 32 ? 32 : 2 * R * BN;
+    static_assert(TCOLS <= 512 && (TCOLS & (TCOLS - 1)) == 0, "TMEM: 2 buffers x R accumulators x BN columns");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -238,11 +251,17 @@ conv_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         if (lane == 0) {
             uint32_t git = 0;
             for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
-                int t = w % tiles;
-                const int c0 = (w / tiles) * BN;
-                const int tx = t % p.tiles_x;
-                t /= p.tiles_x;
-                const int x0 = p.xbase + tx * p.BW, y0 = (t % p.tiles_y) * p.BH, n0 = (t / p.tiles_y) * p.BI;
+                const int g = w % groups, c0 = (w / groups) * BN;
+                int x0[R], y0[R], n0[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    int t = g * R + r;
+                    t = t < tiles ? t : tiles - 1;           // a group past the end re-loads the last tile (its result is dropped)
+                    x0[r] = p.xbase + (t % p.tiles_x) * p.BW;
+                    t /= p.tiles_x;
+                    y0[r] = (t % p.tiles_y) * p.BH;
+                    n0[r] = (t / p.tiles_y) * p.BI;
+                }
                 for (int it = 0; it < KI; ++it, ++git) {
                     const int s = git % STAGES, ph = (git / STAGES) & 1;
                     tc::mbar_wait(empty + s, ph ^ 1);
@@ -250,7 +269,9 @@ conv_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                     unsigned char* a = base + s * S::STAGE_BYTES;
                     unsigned char* b = a + S::A_BYTES;
                     tc::mbar_arrive_expect_tx(full + s, S::STAGE_BYTES);
-                    tc::tma_load_4d(a, &tmap_x, full + s, ks * BK, p.sx * x0 + p.dx[tap], p.sy * y0 + p.dy[tap], n0);
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        tc::tma_load_4d(a + r * S::A_TILE, &tmap_x, full + s, ks * BK, p.sx * x0[r] + p.dx[tap], p.sy * y0[r] + p.dy[tap], n0[r]);
                     if constexpr (WMN) {
 #pragma unroll
                         for (int nb = 0; nb < BN / 32; ++nb) tc::tma_load_3d(b + nb * 4096, &tmap_w, full + s, c0 + nb * 32, ks * BK, tap);
@@ -266,9 +287,9 @@ conv_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
             uint32_t git = 0, j = 0;
             for (int w = blockIdx.x; w < work_items; w += gridDim.x, ++j) {
                 const uint32_t buf = j & 1;
-                tc::mbar_wait(acc_empty + buf, ((j >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
+                tc::mbar_wait(acc_empty + buf, ((j >> 1) & 1) ^ 1);      // the epilogue has drained this buffer
                 tc::tc_fence_after();
-                const uint32_t acc = tmem_acc + buf * BN;
+                const uint32_t acc = tmem_acc + buf * (R * BN);
                 for (int it = 0; it < KI; ++it, ++git) {
                     const int s = git % STAGES, ph = (git / STAGES) & 1;
                     tc::mbar_wait(full + s, ph);
@@ -277,9 +298,10 @@ conv_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                     const uint32_t b = a + S::A_BYTES;
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t da = tc::umma_desc_k128(a + k * UMMA_K * 4);
                         const uint64_t db = WMN ? tc::umma_desc_mn128(b + k * 1024, p.dbg_lbo, p.dbg_sbo, p.dbg_lt) : tc::umma_desc_k128(b + k * UMMA_K * 4);
-                        tc::umma_tf32(acc, da, db, idesc, (it | k) ? 1u : 0u);
+#pragma unroll
+                        for (int r = 0; r < R; ++r)
+                            tc::umma_tf32(acc + r * BN, tc::umma_desc_k128(a + r * S::A_TILE + k * UMMA_K * 4), db, idesc, (it | k) ? 1u : 0u);
                     }
                     tc::umma_commit(empty + s);
                 }
@@ -288,52 +310,56 @@ conv_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         }
     } else {
         const int q = warp & 3;
-        const int r = q * 32 + lane;
-        const int bx = r % p.BW, by = (r / p.BW) % p.BH, bi = r / (p.BW * p.BH);
+        const int row = q * 32 + lane;
+        const int bx = row % p.BW, by = (row / p.BW) % p.BH, bi = row / (p.BW * p.BH);
         uint32_t j = 0;
         for (int w = blockIdx.x; w < work_items; w += gridDim.x, ++j) {
-            int t = w % tiles;
-            const int c0 = (w / tiles) * BN;
-            const int tx = t % p.tiles_x;
-            t /= p.tiles_x;
-            const int n = (t / p.tiles_y) * p.BI + bi, y = (t % p.tiles_y) * p.BH + by, x = p.xbase + tx * p.BW + bx;
-            const bool valid = n < p.N && y < p.Hout && x < p.Wout;
-            float* dst = out + (((size_t)n * p.OH + (size_t)(p.osy * y + p.ooy)) * p.OW + (size_t)(p.osx * x + p.oox)) * p.OC;
+            const int g = w % groups, c0 = (w / groups) * BN;
             const uint32_t buf = j & 1;
             tc::mbar_wait(acc_full + buf, (j >> 1) & 1);
             tc::tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
-                float v[32];
-                tc::tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)c, v);
-                if (c + 32 >= BN) {                  // last read of this accumulator: hand it back before the stores
-                    tc::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(acc_empty + buf);
-                }
-                if (valid) {
-                    const int cb = c0 + c;
-                    if (cb + 32 <= p.Cout && (p.OC & 3) == 0) {
+            for (int r = 0; r < R; ++r) {
+                int t = g * R + r;
+                const bool tile_ok = t < tiles;
+                const int tx = t % p.tiles_x;
+                t /= p.tiles_x;
+                const int n = (t / p.tiles_y) * p.BI + bi, y = (t % p.tiles_y) * p.BH + by, x = p.xbase + tx * p.BW + bx;
+                const bool valid = tile_ok && n < p.N && y < p.Hout && x < p.Wout;
+                float* dst = out + (((size_t)n * p.OH + (size_t)(p.osy * y + p.ooy)) * p.OW + (size_t)(p.osx * x + p.oox)) * p.OC;
+#pragma unroll 1
+                for (int c = 0; c < BN; c += 32) {
+                    float v[32];
+                    tc::tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + buf * (R * BN) + r * BN + (uint32_t)c, v);
+                    if (r == R - 1 && c + 32 >= BN) {        // last read of this buffer: hand it back before the stores
+                        tc::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(acc_empty + buf);
+                    }
+                    if (valid) {
+                        const int cb = c0 + c;
+                        if (cb + 32 <= p.Cout && (p.OC & 3) == 0) {
 #pragma unroll
-                        for (int jj = 0; jj < 32; jj += 4) {
-                            float4 o;
-                            o.x = v[jj] + (bias ? __ldg(bias + cb + jj) : 0.f);
-                            o.y = v[jj + 1] + (bias ? __ldg(bias + cb + jj + 1) : 0.f);
-                            o.z = v[jj + 2] + (bias ? __ldg(bias + cb + jj + 2) : 0.f);
-                            o.w = v[jj + 3] + (bias ? __ldg(bias + cb + jj + 3) : 0.f);
-                            o.x = o.x >= 0.f ? o.x : o.x * p.leaky;
-                            o.y = o.y >= 0.f ? o.y : o.y * p.leaky;
-                            o.z = o.z >= 0.f ? o.z : o.z * p.leaky;
-                            o.w = o.w >= 0.f ? o.w : o.w * p.leaky;
-                            *reinterpret_cast<float4*>(dst + cb + jj) = o;
-                        }
-                    } else {
+                            for (int jj = 0; jj < 32; jj += 4) {
+                                float4 o;
+                                o.x = v[jj] + (bias ? __ldg(bias + cb + jj) : 0.f);
+                                o.y = v[jj + 1] + (bias ? __ldg(bias + cb + jj + 1) : 0.f);
+                                o.z = v[jj + 2] + (bias ? __ldg(bias + cb + jj + 2) : 0.f);
+                                o.w = v[jj + 3] + (bias ? __ldg(bias + cb + jj + 3) : 0.f);
+                                o.x = o.x >= 0.f ? o.x : o.x * p.leaky;
+                                o.y = o.y >= 0.f ? o.y : o.y * p.leaky;
+                                o.z = o.z >= 0.f ? o.z : o.z * p.leaky;
+                                o.w = o.w >= 0.f ? o.w : o.w * p.leaky;
+                                *reinterpret_cast<float4*>(dst + cb + jj) = o;
+                            }
+                        } else {
 #pragma unroll
-                        for (int jj = 0; jj < 32; ++jj) {
-                            const int co = cb + jj;
-                            if (co < p.Cout) {
-                                float o = v[jj] + (bias ? __ldg(bias + co) : 0.f);
-                                dst[co] = o >= 0.f ? o : o * p.leaky;
+                            for (int jj = 0; jj < 32; ++jj) {
+                                const int co = cb + jj;
+                                if (co < p.Cout) {
+                                    float o = v[jj] + (bias ? __ldg(bias + co) : 0.f);
+                                    dst[co] = o >= 0.f ? o : o * p.leaky;
+                                }
                             }
                         }
                     }
@@ -508,17 +534,27 @@ int launch(const CUtensorMap& mx, const CUtensorMap& mw, const ConvParams& p, co
     return B3D_OK;
 }
 
-template <int BN, int STAGES, bool WMN>
+template <int BN, int STAGES, bool WMN, int R>
 int launch_persistent(const CUtensorMap& mx, const CUtensorMap& mw, const ConvParams& p, const float* bias, float* out,
                       int tiles, cudaStream_t st) {
-    constexpr int TOTAL = Smem<BN, STAGES>::TOTAL + 64;
-    B3D_CUDA_OK(cudaFuncSetAttribute(conv_tf32_persistent_kernel<BN, STAGES, WMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOTAL));
-    const int work = tiles * b3d::ceil_div(p.Cout, BN);
-    const int slots = (BN <= 128 ? 2 : 1) * 148;         // resident CTAs: 2 per SM (1 for the 256-wide tile: all of TMEM)
+    using S = PSmem<BN, STAGES, R>;
+    static_assert(S::TOTAL <= 227 * 1024, "persistent conv pipeline does not fit shared memory");
+    B3D_CUDA_OK(cudaFuncSetAttribute(conv_tf32_persistent_kernel<BN, STAGES, WMN, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    const int groups = b3d::ceil_div(tiles, R);
+    const int work = groups * b3d::ceil_div(p.Cout, BN);
+    const int slots = S::CTAS_PER_SM * 148;
     const int grid = work < slots ? work : slots;
-    conv_tf32_persistent_kernel<BN, STAGES, WMN><<<grid, PTHREADS, TOTAL, st>>>(mx, mw, p, bias, out, tiles, work);
+    conv_tf32_persistent_kernel<BN, STAGES, WMN, R><<<grid, PTHREADS, S::TOTAL, st>>>(mx, mw, p, bias, out, tiles, groups, work);
     B3D_LAUNCH_OK();
     return B3D_OK;
+}
+
+template <bool WMN>
+int dispatch_persistent(int BN, int stack, const CUtensorMap& mx, const CUtensorMap& mw, const ConvParams& p, const float* bias,
+                        float* out, int tiles, cudaStream_t st) {
+    if (BN == 256) return launch_persistent<256, 4, WMN, 1>(mx, mw, p, bias, out, tiles, st);
+    if (BN == 128) return stack ? launch_persistent<128, 4, WMN, 2>(mx, mw, p, bias, out, tiles, st) : launch_persistent<128, 3, WMN, 1>(mx, mw, p, bias, out, tiles, st);
+    return stack ? launch_persistent<64, 3, WMN, 4>(mx, mw, p, bias, out, tiles, st) : launch_persistent<64, 4, WMN, 1>(mx, mw, p, bias, out, tiles, st);
 }
 
 int pow2_floor(int v) {
@@ -546,7 +582,7 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
     B3D_CHECK_ALIGNED(wt);
 
     static const int persist = getenv("B3D_CONV_PERSIST") ? atoi(getenv("B3D_CONV_PERSIST")) : 1;
-    static const int wide = getenv("B3D_CONV_BN256") ? atoi(getenv("B3D_CONV_BN256")) : 0;
+    static const int wide = getenv("B3D_CONV_BN256") ? atoi(getenv("B3D_CONV_BN256")) : 1;
     // 256-wide output-channel tiles halve the input-tile bytes per FLOP through the L2 -> SM fabric (the bound of the
     // per-tap formulation, profiles/r1_c_*.md) when there are >= 256 output channels and enough tiles to fill the GPU
     const bool bn256 = persist && wide && Cout % 256 == 0 && (long long)N * Hout * Wout / BM * (Cout / 256) >= 148;
@@ -593,9 +629,12 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
         // CTAs per SM x ring depth: short K loops (few taps x few channel slices) are dominated by pipeline fill, epilogue
         // and store drain, which only OTHER resident CTAs can hide -> more, shallower CTAs (profiles/r1_c_*.md)
         if (persist) {
-            if (BN == 256) return w_cin_major ? launch_persistent<256, 4, true>(mx, mw, p, bias, out, tiles, st) : launch_persistent<256, 4, false>(mx, mw, p, bias, out, tiles, st);
-            if (w_cin_major) return BN == 128 ? launch_persistent<128, 3, true>(mx, mw, p, bias, out, tiles, st) : launch_persistent<64, 4, true>(mx, mw, p, bias, out, tiles, st);
-            return BN == 128 ? launch_persistent<128, 3, false>(mx, mw, p, bias, out, tiles, st) : launch_persistent<64, 4, false>(mx, mw, p, bias, out, tiles, st);
+            // stacked pixel tiles (1 CTA / SM, deeper stages) once there is work for ~2 waves of them
+            static const int stack_env = getenv("B3D_CONV_STACK") ? atoi(getenv("B3D_CONV_STACK")) : 0;
+            const int R = BN == 128 ? 2 : 4;
+            const bool stack = stack_env && BN < 256 && (long long)b3d::ceil_div(tiles, R) * b3d::ceil_div(Cout, BN) >= 2 * 148;
+            return w_cin_major ? dispatch_persistent<true>(BN, stack, mx, mw, p, bias, out, tiles, st)
+                               : dispatch_persistent<false>(BN, stack, mx, mw, p, bias, out, tiles, st);
         }
         static const int occ_env = getenv("B3D_CONV_OCC") ? atoi(getenv("B3D_CONV_OCC")) : 0;
         const int occ = occ_env ? occ_env : 2;
