@@ -630,7 +630,7 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
         // and store drain, which only OTHER resident CTAs can hide -> more, shallower CTAs (profiles/r1_c_*.md)
         if (persist) {
             // stacked pixel tiles (1 CTA / SM, deeper stages) once there is work for ~2 waves of them
-            static const int stack_env = getenv("B3D_CONV_STACK") ? atoi(getenv("B3D_CONV_STACK")) : 0;
+            static const int stack_env = getenv("B3D_CONV_STACK") ? atoi(getenv("B3D_CONV_STACK")) : 1;
             const int R = BN == 128 ? 2 : 4;
             const bool stack = stack_env && BN < 256 && (long long)b3d::ceil_div(tiles, R) * b3d::ceil_div(Cout, BN) >= 2 * 148;
             return w_cin_major ? dispatch_persistent<true>(BN, stack, mx, mw, p, bias, out, tiles, st)
