@@ -86,42 +86,44 @@ pad_leaky_bias_bwd_kernel(const float4* __restrict__ go, const float4* __restric
     __shared__ float4 red[NT];
     const int Wo = W + 2 * a;
     const int c = threadIdx.x % C4, lane_p = threadIdx.x / C4, PPB = NT / C4;
-    const long long npix = rows * W;
-    const long long p0 = (long long)blockIdx.x * pix_per_block;
-    const long long p1 = p0 + pix_per_block < npix ? p0 + pix_per_block : npix;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     constexpr int U = 4;                                   // independent pixels in flight per thread
-    for (long long pb = p0 + lane_p; pb < p1; pb += (long long)U * PPB) {
-        float4 s[U], v[U];
+    // a block walks whole rows (32-bit index math only; `pix_per_block` = rows per block here)
+    const long long r0 = (long long)blockIdx.x * pix_per_block;
+    const long long r1 = r0 + pix_per_block < rows ? r0 + pix_per_block : rows;
+    for (long long r = r0; r < r1; ++r) {
+        const float4* g = go + (r * Wo) * C4 + c;
+        const float4* yr = ypad + (r * Wo + a) * C4 + c;
+        float4* gr = gy + (r * W) * C4 + c;
+        for (int wb = lane_p; wb < W; wb += U * PPB) {
+            float4 s[U], v[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long pix = pb + (long long)u * PPB;
-            if (pix >= p1) continue;
-            const int w = (int)(pix % W);
-            const long long r = pix / W;
-            const float4* g = go + (r * Wo) * C4 + c;
-            s[u] = __ldg(g + (long long)(w + a) * C4);
-            v[u] = __ldg(ypad + (r * Wo + w + a) * C4 + c);
-            if (a > 0) {
-                if (mode == 0) {
-                    if (w == 0)
-                        for (int k = 0; k < a; ++k) { const float4 t = __ldg(g + (long long)k * C4); s[u].x += t.x; s[u].y += t.y; s[u].z += t.z; s[u].w += t.w; }
-                    if (w == W - 1)
-                        for (int k = 0; k < a; ++k) { const float4 t = __ldg(g + (long long)(W + a + k) * C4); s[u].x += t.x; s[u].y += t.y; s[u].z += t.z; s[u].w += t.w; }
-                } else {
-                    if (w < a) { const float4 t = __ldg(g + (long long)(w + a + W) * C4); s[u].x += t.x; s[u].y += t.y; s[u].z += t.z; s[u].w += t.w; }
-                    if (w >= W - a) { const float4 t = __ldg(g + (long long)(w + a - W) * C4); s[u].x += t.x; s[u].y += t.y; s[u].z += t.z; s[u].w += t.w; }
+            for (int u = 0; u < U; ++u) {
+                const int w = wb + u * PPB;
+                if (w >= W) continue;
+                s[u] = __ldg(g + (w + a) * C4);
+                v[u] = __ldg(yr + w * C4);
+                if (a > 0) {
+                    if (mode == 0) {
+                        if (w == 0)
+                            for (int k = 0; k < a; ++k) { const float4 t = __ldg(g + k * C4); s[u].x += t.x; s[u].y += t.y; s[u].z += t.z; s[u].w += t.w; }
+                        if (w == W - 1)
+                            for (int k = 0; k < a; ++k) { const float4 t = __ldg(g + (W + a + k) * C4); s[u].x += t.x; s[u].y += t.y; s[u].z += t.z; s[u].w += t.w; }
+                    } else {
+                        if (w < a) { const float4 t = __ldg(g + (w + a + W) * C4); s[u].x += t.x; s[u].y += t.y; s[u].z += t.z; s[u].w += t.w; }
+                        if (w >= W - a) { const float4 t = __ldg(g + (w + a - W) * C4); s[u].x += t.x; s[u].y += t.y; s[u].z += t.z; s[u].w += t.w; }
+                    }
                 }
             }
-        }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long pix = pb + (long long)u * PPB;
-            if (pix >= p1) continue;
-            const float4 m = make_float4(v[u].x >= 0.f ? s[u].x : s[u].x * slope, v[u].y >= 0.f ? s[u].y : s[u].y * slope,
-                                         v[u].z >= 0.f ? s[u].z : s[u].z * slope, v[u].w >= 0.f ? s[u].w : s[u].w * slope);
-            gy[pix * C4 + c] = m;
-            acc.x += m.x; acc.y += m.y; acc.z += m.z; acc.w += m.w;
+            for (int u = 0; u < U; ++u) {
+                const int w = wb + u * PPB;
+                if (w >= W) continue;
+                const float4 m = make_float4(v[u].x >= 0.f ? s[u].x : s[u].x * slope, v[u].y >= 0.f ? s[u].y : s[u].y * slope,
+                                             v[u].z >= 0.f ? s[u].z : s[u].z * slope, v[u].w >= 0.f ? s[u].w : s[u].w * slope);
+                gr[w * C4] = m;
+                acc.x += m.x; acc.y += m.y; acc.z += m.z; acc.w += m.w;
+            }
         }
     }
     if (gb == nullptr) return;
@@ -142,26 +144,31 @@ pad_leaky_bias_bwd_kernel(const float4* __restrict__ go, const float4* __restric
 }
 
 // Thin-stem fold: out[n, y, x, r*C + c] = x[n, y + r - pad_y, x, c] (zero outside the image, zero for k >= kh*C).
+// One block = one output row (n, y); a thread owns one 16-byte channel group k4 for the pixels px, px + PPB, ...: the
+// (r, c) decomposition of its four channels is computed once, the inner loop is loads + one float4 store (no divisions).
 __global__ void __launch_bounds__(NT)
 fold_rows_fwd_kernel(const float* __restrict__ x, float4* __restrict__ out, int N, int H, int W, int C, int Hout, int Cp4,
                      int kh, int pad_y) {
-    const long long total = (long long)N * Hout * W * Cp4;
     const int K = kh * C;
-    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
-        const int k4 = (int)(i % Cp4);
-        long long t = i / Cp4;
-        const int xx = (int)(t % W); t /= W;
-        const int y = (int)(t % Hout);
-        const int n = (int)(t / Hout);
-        float v[4];
+    const int k4 = threadIdx.x % Cp4, px0 = threadIdx.x / Cp4, PPB = NT / Cp4;
+    if (px0 >= PPB) return;                                  // NT not a multiple of Cp4: the tail threads idle
+    for (int row = blockIdx.x; row < N * Hout; row += gridDim.x) {
+        const int n = row / Hout, y = row - n * Hout;
+        long long src[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int k = 4 * k4 + j;
             const int r = k / C, c = k - r * C;
             const int yy = y + r - pad_y;
-            v[j] = (k < K && yy >= 0 && yy < H) ? __ldg(x + (((long long)n * H + yy) * W + xx) * C + c) : 0.f;
+            src[j] = (k < K && yy >= 0 && yy < H) ? (((long long)n * H + yy) * W) * C + c : -1;
         }
-        out[i] = make_float4(v[0], v[1], v[2], v[3]);
+        float4* orow = out + (long long)row * W * Cp4 + k4;
+        for (int xx = px0; xx < W; xx += PPB) {
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = src[j] >= 0 ? __ldg(x + src[j] + (long long)xx * C) : 0.f;
+            orow[(long long)xx * Cp4] = make_float4(v[0], v[1], v[2], v[3]);
+        }
     }
 }
 
@@ -223,8 +230,10 @@ int b3d_fold_rows_fwd(const float* x, float* out, int N, int H, int W, int C, in
     B3D_REQUIRE(x && out, B3D_EINVAL, "b3d_fold_rows_fwd: null pointer");
     B3D_CHECK_ALIGNED(out);
     const int Hout = H + 2 * pad_y - kh + 1;
-    fold_rows_fwd_kernel<<<grid_for((long long)N * Hout * W * (Cp / 4)), NT, 0, (cudaStream_t)stream>>>(x, (float4*)out, N, H, W, C, Hout,
-                                                                                                  Cp / 4, kh, pad_y);
+    B3D_REQUIRE(Cp / 4 <= NT, B3D_EINVAL, "b3d_fold_rows_fwd: Cp=%d too wide (max %d)", Cp, 4 * NT);
+    const int rows = N * Hout;
+    fold_rows_fwd_kernel<<<rows < 148 * 16 ? rows : 148 * 16, NT, 0, (cudaStream_t)stream>>>(x, (float4*)out, N, H, W, C, Hout, Cp / 4,
+                                                                                       kh, pad_y);
     B3D_LAUNCH_OK();
     return B3D_OK;
 }
@@ -258,13 +267,9 @@ int b3d_pad_leaky_bias_bwd(const float* gout_pad, const float* y_pad, float* gy,
     B3D_CHECK_ALIGNED(gout_pad);
     B3D_CHECK_ALIGNED(y_pad);
     B3D_CHECK_ALIGNED(gy);
-    const long long npix = rows * W;
-    const int ppb = NT / (C / 4);
-    long long blocks = (npix + ppb - 1) / ppb;
-    const long long cap = 148LL * 16;
-    if (blocks > cap) blocks = cap;
-    const long long per = ((npix + blocks - 1) / blocks + ppb - 1) / ppb * ppb;
-    blocks = (npix + per - 1) / per;
+    long long blocks = rows < 148LL * 16 ? rows : 148LL * 16;
+    const long long per = (rows + blocks - 1) / blocks;          // rows per block
+    blocks = (rows + per - 1) / per;
     pad_leaky_bias_bwd_kernel<<<(int)blocks, NT, 0, (cudaStream_t)stream>>>((const float4*)gout_pad, (const float4*)y_pad, (float4*)gy,
                                                                           gbias, rows, W, C / 4, amount, mode, slope, per);
     B3D_LAUNCH_OK();
@@ -324,6 +329,38 @@ cbn_act_fwd_kernel(const float4* __restrict__ y, const float4* __restrict__ scal
         }
         if (g.post_leaky) o = make_float4(lk(o.x, g.slope), lk(o.y, g.slope), lk(o.z, g.slope), lk(o.w, g.slope));
         out[i] = o;
+    }
+}
+
+// Same pass with the index arithmetic hoisted: one block walks output rows (n, yo), a thread owns channel quad
+// c = tid % C4 for the pixels tid / C4, + NT / C4, ... (needs NT % C4 == 0) — no 64-bit divisions per element, the
+// per-sample scale / shift stay in registers along the row.
+__global__ void __launch_bounds__(NT)
+cbn_act_fwd_rows_kernel(const float4* __restrict__ y, const float4* __restrict__ scale, const float4* __restrict__ shift,
+                        const float4* __restrict__ skip, float4* __restrict__ out, const CbnGeom g) {
+    const int Wo = g.up * g.W + 2 * g.pad, Ho = g.up * g.H, Wu = g.up * g.W;
+    const int c = threadIdx.x % g.C4, px0 = threadIdx.x / g.C4, PPB = NT / g.C4;
+    for (int row = blockIdx.x; row < g.N * Ho; row += gridDim.x) {
+        const int n = row / Ho, yo = row - n * Ho;
+        const int ys = yo / g.up;
+        const float4 sc = __ldg(scale + (long long)n * g.C4 + c), sh = __ldg(shift + (long long)n * g.C4 + c);
+        const float4* yrow = y + (((long long)n * g.H + ys) * g.W) * g.C4 + c;
+        const float4* srow = g.skip_pitch ? skip + (((long long)n * g.H + ys) * g.skip_pitch + g.skip_off) * g.C4 + c : nullptr;
+        float4* orow = out + (long long)row * Wo * g.C4 + c;
+        for (int xo = px0; xo < Wo; xo += PPB) {
+            int xs = xo - g.pad;
+            xs = xs < 0 ? 0 : (xs >= Wu ? Wu - 1 : xs);
+            xs = g.up == 2 ? xs >> 1 : xs;
+            const float4 v = __ldg(yrow + (long long)xs * g.C4);
+            float4 o = make_float4(lk(fmaf(v.x, sc.x, sh.x), g.slope), lk(fmaf(v.y, sc.y, sh.y), g.slope),
+                                   lk(fmaf(v.z, sc.z, sh.z), g.slope), lk(fmaf(v.w, sc.w, sh.w), g.slope));
+            if (srow) {
+                const float4 k = __ldg(srow + (long long)xs * g.C4);
+                o.x += k.x; o.y += k.y; o.z += k.z; o.w += k.w;
+            }
+            if (g.post_leaky) o = make_float4(lk(o.x, g.slope), lk(o.y, g.slope), lk(o.z, g.slope), lk(o.w, g.slope));
+            orow[(long long)xo * g.C4] = o;
+        }
     }
 }
 
@@ -406,8 +443,14 @@ int b3d_cbn_act_fwd(const float* y, const float* scale, const float* shift, cons
     B3D_REQUIRE(y && scale && shift && out && (skip != nullptr) == (skip_pitch != 0), B3D_EINVAL, "b3d_cbn_act_fwd: null pointer");
     CbnGeom g{N, H, W, C / 4, up, pad, skip_pitch, skip_off, slope, post_leaky};
     const long long total = (long long)N * up * H * (up * W + 2 * pad) * (C / 4);
-    cbn_act_fwd_kernel<<<grid_for(total), NT, 0, (cudaStream_t)stream>>>((const float4*)y, (const float4*)scale, (const float4*)shift,
-                                                                       (const float4*)skip, (float4*)out, g);
+    if (g.C4 <= NT && NT % g.C4 == 0 && (up == 1 || up == 2)) {
+        const int rows = N * up * H;
+        cbn_act_fwd_rows_kernel<<<rows < 148 * 16 ? rows : 148 * 16, NT, 0, (cudaStream_t)stream>>>(
+            (const float4*)y, (const float4*)scale, (const float4*)shift, (const float4*)skip, (float4*)out, g);
+    } else {
+        cbn_act_fwd_kernel<<<grid_for(total), NT, 0, (cudaStream_t)stream>>>((const float4*)y, (const float4*)scale, (const float4*)shift,
+                                                                           (const float4*)skip, (float4*)out, g);
+    }
     B3D_LAUNCH_OK();
     return B3D_OK;
 }

@@ -11,6 +11,10 @@ KEYS = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram rd"),
         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram %"),
         ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm %"),
         ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor %"),
+        ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 %"),
+        ("lts__t_sector_hit_rate.pct", "L2 hit %"),
+        ("l1tex__m_xbar2l1tex_read_bytes.sum", "L2->SM bytes"),
+        ("l1tex__m_xbar2l1tex_read_bytes.sum.per_second", "L2->SM rate"),
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy %"),
         ("launch__registers_per_thread", "regs"), ("launch__grid_size", "grid"), ("launch__block_size", "block"),
         ("smsp__inst_executed.sum", "warp inst"),
@@ -28,7 +32,7 @@ def main(rep, out):
     seen, lines = {}, []
     for r in rows[2:]:
         name = r[ix["Kernel Name"]].split("(")[0].replace("void ", "").replace("<unnamed>::", "")
-        if seen.get(name, 0) >= 1:
+        if seen.get(name, 0) >= int(__import__('os').environ.get('NCU_PER_KERNEL', '1')):
             continue
         seen[name] = seen.get(name, 0) + 1
         lines.append(f"### {name}\n")
