@@ -10,6 +10,8 @@
 //          lane stay in registers along the row, a block folds its warps in shared memory, then one global atomicAdd
 //          per weight per block.
 // The input gradient of these layers stays on the tensor-core dgrad (N = Cin is wide there).
+#include <stdlib.h>
+
 #include "b3d_common.cuh"
 
 namespace {
@@ -170,6 +172,93 @@ conv_thin_wgrad_kernel(const float* __restrict__ gy, const float* __restrict__ x
     }
 }
 
+// Sliding-window variant: along an output row the 5x5 input window moves by one column per pixel, so only its new
+// column (5 loads) is fetched per pixel instead of all 25 taps; the window lives in registers (slots rotate mod 5, the
+// row loop is unrolled by 5 so every slot index is static) and the new column is requested before the 4/5 of the FMAs
+// that do not need it.  ncu on the 25-loads version: 62 % of the samples are FFMAs waiting on the long scoreboard at
+// 12 % occupancy (profiles/r1_c_conv_final_full.md).
+template <int COUT, int VEC>
+__global__ void __launch_bounds__(NT)
+conv_thin_wgrad_win_kernel(const float* __restrict__ gy, const float* __restrict__ x, float* __restrict__ dw, const ThinGeom g) {
+    extern __shared__ float red[];                 // [COUT][KS*KS][32*VEC]
+    const int lane = threadIdx.x & 31;
+    const int chunks = g.Cin / (32 * VEC);
+    const int blocks_per_chunk = gridDim.x / chunks;
+    const int chunk = blockIdx.x / blocks_per_chunk, blk = blockIdx.x % blocks_per_chunk;
+    const int ci = chunk * 32 * VEC + lane * VEC;
+    for (int i = threadIdx.x; i < COUT * KS * KS * 32 * VEC; i += NT) red[i] = 0.f;
+    __syncthreads();
+    float acc[COUT][KS * KS][VEC];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c)
+#pragma unroll
+        for (int t = 0; t < KS * KS; ++t)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[c][t][v] = 0.f;
+    const int rows = g.N * g.Hout;
+    const int wstride = blocks_per_chunk * (NT / 32);
+    for (int row = blk * (NT / 32) + (threadIdx.x >> 5); row < rows; row += wstride) {
+        const int n = row / g.Hout, y = row % g.Hout;
+        const float* gyr = gy + (long long)row * g.Wout * COUT;
+        const float* xr[KS];
+        float rv[KS];
+#pragma unroll
+        for (int r = 0; r < KS; ++r) {
+            const int yy = y + r - g.pad_y;
+            rv[r] = (yy >= 0 && yy < g.H) ? 1.f : 0.f;                      // rows outside the image: clamp + mask
+            const int yc = yy < 0 ? 0 : (yy >= g.H ? g.H - 1 : yy);
+            xr[r] = x + (((long long)n * g.H + yc) * g.W + g.xoff) * g.Cin + ci;
+        }
+        float win[KS][KS][VEC];                    // win[r][slot]: input column (xo + j) lives in slot (xo + j) % 5
+#pragma unroll
+        for (int r = 0; r < KS; ++r)
+#pragma unroll
+            for (int j = 0; j < KS - 1; ++j) {
+                ldv<VEC>(win[r][j], xr[r] + (long long)j * g.Cin);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) win[r][j][v] *= rv[r];
+            }
+#pragma unroll 1
+        for (int xb = 0; xb < g.Wout; xb += KS) {
+#pragma unroll
+            for (int u = 0; u < KS; ++u) {
+                const int xo = xb + u;
+                if (xo < g.Wout) {
+#pragma unroll
+                    for (int r = 0; r < KS; ++r) {                         // new column xo + 4 -> slot (u + 4) % 5
+                        ldv<VEC>(win[r][(u + KS - 1) % KS], xr[r] + (long long)(xo + KS - 1) * g.Cin);
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) win[r][(u + KS - 1) % KS][v] *= rv[r];
+                    }
+                    float gv[COUT];
+#pragma unroll
+                    for (int c = 0; c < COUT; ++c) gv[c] = __ldg(gyr + xo * COUT + c);
+#pragma unroll
+                    for (int s = 0; s < KS; ++s)
+#pragma unroll
+                        for (int r = 0; r < KS; ++r)
+#pragma unroll
+                            for (int c = 0; c < COUT; ++c)
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v)
+                                    acc[c][r * KS + s][v] = fmaf(gv[c], win[r][(u + s) % KS][v], acc[c][r * KS + s][v]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < COUT; ++c)
+#pragma unroll
+        for (int t = 0; t < KS * KS; ++t)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) atomicAdd(red + (c * KS * KS + t) * 32 * VEC + lane * VEC + v, acc[c][t][v]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < COUT * KS * KS * 32 * VEC; i += NT) {
+        const int cl = i % (32 * VEC), t = (i / (32 * VEC)) % (KS * KS), c = i / (32 * VEC * KS * KS);
+        atomicAdd(dw + ((long long)c * g.Cin + chunk * 32 * VEC + cl) * (KS * KS) + t, red[i]);
+    }
+}
+
 template <int COUT, int VEC>
 int launch_fwd(const float* x, const float* wt, const float* bias, float* out, const ThinGeom& g, cudaStream_t st) {
     const long long items = (long long)g.N * g.Hout * ((g.Wout + OUTS - 1) / OUTS);
@@ -188,7 +277,13 @@ int launch_wgrad(const float* gy, const float* x, float* dw, const ThinGeom& g, 
     if (bpc > (rows + NT / 32 - 1) / (NT / 32)) bpc = (rows + NT / 32 - 1) / (NT / 32);
     const size_t smem = (size_t)COUT * KS * KS * 32 * VEC * 4;
     B3D_CUDA_OK(cudaFuncSetAttribute(conv_thin_wgrad_kernel<COUT, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_thin_wgrad_kernel<COUT, VEC><<<bpc * chunks, NT, smem, st>>>(gy, x, dw, g);
+    static const bool plain = getenv("B3D_THIN_NOWIN") != nullptr;
+    if (COUT * VEC <= 6 && !plain) {               // window (25 * VEC) + accumulators (COUT * 25 * VEC) fit the register file
+        B3D_CUDA_OK(cudaFuncSetAttribute(conv_thin_wgrad_win_kernel<COUT, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_thin_wgrad_win_kernel<COUT, VEC><<<bpc * chunks, NT, smem, st>>>(gy, x, dw, g);
+    } else {
+        conv_thin_wgrad_kernel<COUT, VEC><<<bpc * chunks, NT, smem, st>>>(gy, x, dw, g);
+    }
     B3D_LAUNCH_OK();
     return B3D_OK;
 }

@@ -97,8 +97,10 @@ class GANTrainer:
             MultiScaleDiscriminator(args, 4)).to(device)
         g, d = self.trainer.generator, self.trainer.discriminator
         # betas=(0, 0.9) of main.py:588-589 (written as floats: the int 0 raises on torch >= 2)
-        self.optimizer_g = torch.optim.Adam(g.parameters(), lr=args.lr_g, betas=(0.0, 0.9), capturable=capturable)
-        self.optimizer_d = torch.optim.Adam(d.parameters(), lr=args.lr_d, betas=(0.0, 0.9), capturable=capturable)
+        # same update rule; on CUDA the multi-tensor "fused" implementation is one kernel per step instead of ~10
+        fused = torch.device(device).type == 'cuda'
+        self.optimizer_g = torch.optim.Adam(g.parameters(), lr=args.lr_g, betas=(0.0, 0.9), capturable=capturable, fused=fused)
+        self.optimizer_d = torch.optim.Adam(d.parameters(), lr=args.lr_d, betas=(0.0, 0.9), capturable=capturable, fused=fused)
         self.total_it = 0
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
