@@ -224,17 +224,14 @@ conv_thin_wgrad_win_kernel(const float* __restrict__ gy, const float* __restrict
             for (int u = 0; u < KS; ++u) {
                 const int xo = xb + u;
                 if (xo < g.Wout) {
+                    float nw[KS][VEC];                                      // new column xo + 4: requested first ...
 #pragma unroll
-                    for (int r = 0; r < KS; ++r) {                         // new column xo + 4 -> slot (u + 4) % 5
-                        ldv<VEC>(win[r][(u + KS - 1) % KS], xr[r] + (long long)(xo + KS - 1) * g.Cin);
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) win[r][(u + KS - 1) % KS][v] *= rv[r];
-                    }
+                    for (int r = 0; r < KS; ++r) ldv<VEC>(nw[r], xr[r] + (long long)(xo + KS - 1) * g.Cin);
                     float gv[COUT];
 #pragma unroll
                     for (int c = 0; c < COUT; ++c) gv[c] = __ldg(gyr + xo * COUT + c);
 #pragma unroll
-                    for (int s = 0; s < KS; ++s)
+                    for (int s = 0; s < KS - 1; ++s)                        // ... the taps that do not need it run meanwhile
 #pragma unroll
                         for (int r = 0; r < KS; ++r)
 #pragma unroll
@@ -242,6 +239,16 @@ conv_thin_wgrad_win_kernel(const float* __restrict__ gy, const float* __restrict
 #pragma unroll
                                 for (int v = 0; v < VEC; ++v)
                                     acc[c][r * KS + s][v] = fmaf(gv[c], win[r][(u + s) % KS][v], acc[c][r * KS + s][v]);
+#pragma unroll
+                    for (int r = 0; r < KS; ++r)                            // ... then it enters slot (u + 4) % 5
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) {
+                            const float m = nw[r][v] * rv[r];
+                            win[r][(u + KS - 1) % KS][v] = m;
+#pragma unroll
+                            for (int c = 0; c < COUT; ++c)
+                                acc[c][r * KS + KS - 1][v] = fmaf(gv[c], m, acc[c][r * KS + KS - 1][v]);
+                        }
                 }
             }
         }
