@@ -345,14 +345,18 @@ def run_cuda(args):
         gf_img = (3 * 17.09 + 2 * 14.76) + 2 * (17.09 + 6 * 14.76)
         conv_ms = sum(v for k, v in prof_tot.items() if k.startswith("b3d_conv2d"))
         tpeak = peaks.get("bf16_tflops_sustained", 1415.7) / 2.0      # tf32 = half the bf16 rate
-        tensor = {"kernel": "conv_tf32 + wgrad_tf32 (tcgen05 kind::tf32)", "bound": "tensor",
+        tensor = {"kernel": "all conv entry points: conv_tf32_persistent + wgrad_tf32 (tcgen05 kind::tf32) + thin-head CUDA-core kernels", "bound": "tensor",
                   "achieved": round(gf_img * B / (conv_ms * 1e-3) / 1e3, 1), "peak": round(tpeak, 1), "unit": "TFLOP/s",
                   "frac": round(gf_img * B / (conv_ms * 1e-3) / 1e3 / tpeak, 4), "traffic": None,
                   "peak_source": "measured bf16 sustained / 2 (tf32 dense = half the bf16 rate)",
                   "conv_ms_per_step": round(conv_ms, 3), "gflop_per_step": round(gf_img * B, 1)}
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {})
+        traffic = tj.get(top)
+        if tensor is not None and "conv_dominant" in tj:      # DRAM bytes of the most expensive single conv launch (ncu)
+            tensor["traffic"] = tj["conv_dominant"]["bytes"]
+            tensor["traffic_kernel"] = tj["conv_dominant"]["kernel"]
     except (OSError, ValueError):
         pass
     out = {
