@@ -31,6 +31,14 @@ for p in (PKG, ROOT):
 
 import torch  # noqa: E402
 
+_T0 = time.time()
+
+
+def stage(msg):
+    """Wall-clock breadcrumbs on stderr (rank 0): where a slow multi-GPU launch spends its time."""
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(f"[bench +{time.time() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
 N_PTS, V, H, TEX, FLAT_COEF = 8000, 128, 256, 128, 5e-4
 WORKLOADS = {
     # BASELINE.json configs[1]
@@ -213,9 +221,11 @@ def run_cuda(args):
         pass
     hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
 
+    stage("process group ready" if world > 1 else "start")
     cfg = WORKLOADS[args.workload]
     METRIC, WORKLOAD = cfg["metric"], cfg["name"]
     wl = CudaWorkload(dev, gan=cfg["gan"])
+    stage("workload built")
     B = cfg["batch"]
     iters_per_step = 3 if cfg["gan"] else 1
     host = host_inputs(B, seed=1234 + rank, pin=True)       # each rank owns its shard of the global batch
@@ -267,6 +277,7 @@ def run_cuda(args):
             for _ in range(3):
                 wl.step(fresh(resident))
         torch.cuda.current_stream().wait_stream(side)
+        stage("eager warm-up done, capturing the step")
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, capture_error_mode="thread_local" if world > 1 else "global"):
             g_loss, g_grads = wl.step(fresh(resident))
@@ -293,6 +304,7 @@ def run_cuda(args):
     time.sleep(0.3) if clocks else None
     n0 = b3d.launch_count()
     lo = clocks.mark() if clocks else 0
+    stage("timing (resident inputs)")
     total_ms = timed(step_resident, args.steps, args.warmup)
     hi = clocks.mark() if clocks else 0
     launches = (b3d.launch_count() - n0) // (args.steps + args.warmup)
@@ -300,10 +312,12 @@ def run_cuda(args):
         n1 = b3d.launch_count()
         wl.step(fresh(resident))
         launches = b3d.launch_count() - n1
+    stage("timing (end to end)")
     e2e_ms = timed(step_e2e, args.steps, args.warmup)
     clk = clocks.stop(lo, max(hi, lo + 1)) if clocks else None
 
     # per-entry-point device times (events on the launching stream), separate pass
+    stage("per-entry-point profile pass")
     b3d.prof_enable()
     for _ in range(max(3, args.steps // 2)):
         flush.zero_()
