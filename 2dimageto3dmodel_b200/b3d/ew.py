@@ -124,6 +124,19 @@ class _CBNActPad(torch.autograd.Function):
         return ga, dgamma, dbeta, None, None, gskip, None, None, None, None, None, None
 
 
+def bn_stats(y_nhwc, eps):
+    """(mean, invstd) per channel of an NHWC tensor = torch.batch_norm_stats on the NCHW view, one libb3d pass."""
+    y = dev(y_nhwc, "y")
+    C = y.shape[-1]
+    if C % 4 or 256 % (C // 4):                        # odd channel counts: stock op
+        return torch.batch_norm_stats(y.permute(0, 3, 1, 2), eps)
+    mean = torch.empty(C, device=y.device, dtype=torch.float32)
+    invstd = torch.empty_like(mean)
+    ws = torch.empty(2 * C, device=y.device, dtype=torch.float64)
+    check(lib.b3d_bn_stats(ptr(y), y.numel() // C, C, float(eps), ptr(mean), ptr(invstd), ptr(ws), stream_ptr(y)))
+    return mean, invstd
+
+
 def cbn_act_pad(y_nchw, cbn, z, skip_nchw=None, skip_off=0, up=1, pad=1, post_leaky=False):
     """ConditionalBatchNorm2d(y, z) -> LeakyReLU(0.2) [-> + skip] [-> LeakyReLU] [-> x2 upsample] -> replicate pad, fused.
     `cbn` is a models.gan.ConditionalBatchNorm2d whose .norm is a (Synchronized)BatchNorm2d without affine; statistics and
@@ -137,7 +150,7 @@ def cbn_act_pad(y_nchw, cbn, z, skip_nchw=None, skip_off=0, up=1, pad=1, post_le
     if bn.training:
         yv = y_nchw.detach()
         n = yv.numel() // C
-        mean, invstd = torch.batch_norm_stats(yv, bn.eps)
+        mean, invstd = bn_stats(y.detach(), bn.eps)
         var_b = invstd.pow(-2) - bn.eps
         if _dist_world() > 1 and bn.__class__.__name__.startswith("Synchronized"):
             import torch.distributed as dist

@@ -286,6 +286,74 @@ int b3d_leaky_bwd(const float* gy, const float* y, float* out, long long n, floa
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Batch statistics of an NHWC activation for the generator's (Sync)BatchNorm layers (models/gan.py:211-232 ->
+// F.batch_norm / sync_batchnorm/batchnorm.py:150): per-channel mean and 1/sqrt(biased var + eps) in one pass over the
+// tensor.  Threads own a channel quad and stride over the pixels (fp32 partial sums of ~50-100 values), a block folds its
+// pixel lanes in shared memory and adds into fp64 accumulators; a second tiny kernel finishes.
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(NT)
+bn_stats_partial_kernel(const float4* __restrict__ y, long long rows, int C4, double* __restrict__ ws) {
+    __shared__ float4 rs[NT], rq[NT];
+    const int c = threadIdx.x % C4, lane_p = threadIdx.x / C4, PPB = NT / C4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+    for (long long p = (long long)blockIdx.x * PPB + lane_p; p < rows; p += (long long)gridDim.x * PPB) {
+        const float4 v = __ldg(y + p * C4 + c);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+    }
+    rs[threadIdx.x] = s; rq[threadIdx.x] = q;
+    __syncthreads();
+    for (int h = PPB / 2; h >= 1; h >>= 1) {
+        if (lane_p < h) {
+            const float4 a = rs[threadIdx.x + h * C4], b = rq[threadIdx.x + h * C4];
+            float4& m = rs[threadIdx.x]; float4& n = rq[threadIdx.x];
+            m.x += a.x; m.y += a.y; m.z += a.z; m.w += a.w;
+            n.x += b.x; n.y += b.y; n.z += b.z; n.w += b.w;
+        }
+        __syncthreads();
+    }
+    if (lane_p == 0) {
+        const float4 m = rs[threadIdx.x], n = rq[threadIdx.x];
+        const int C = 4 * C4;
+        atomicAdd(ws + 4 * c + 0, (double)m.x); atomicAdd(ws + 4 * c + 1, (double)m.y);
+        atomicAdd(ws + 4 * c + 2, (double)m.z); atomicAdd(ws + 4 * c + 3, (double)m.w);
+        atomicAdd(ws + C + 4 * c + 0, (double)n.x); atomicAdd(ws + C + 4 * c + 1, (double)n.y);
+        atomicAdd(ws + C + 4 * c + 2, (double)n.z); atomicAdd(ws + C + 4 * c + 3, (double)n.w);
+    }
+}
+
+__global__ void bn_stats_finish_kernel(const double* __restrict__ ws, long long rows, int C, float eps, float* __restrict__ mean,
+                                       float* __restrict__ invstd) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double m = ws[c] / (double)rows;
+    double var = ws[C + c] / (double)rows - m * m;
+    var = var > 0.0 ? var : 0.0;
+    mean[c] = (float)m;
+    invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+}
+}  // namespace
+
+extern "C" int b3d_bn_stats(const float* y, long long rows, int C, float eps, float* mean, float* invstd, double* workspace,
+                            void* stream) {
+    B3D_REQUIRE(rows > 0 && C >= 4 && C % 4 == 0 && C / 4 <= NT && NT % (C / 4) == 0, B3D_EINVAL,
+                "b3d_bn_stats: C=%d must be 4 * a divisor of %d", C, NT);
+    B3D_REQUIRE(y && mean && invstd && workspace, B3D_EINVAL, "b3d_bn_stats: null pointer");
+    B3D_CHECK_ALIGNED(y);
+    cudaStream_t st = (cudaStream_t)stream;
+    B3D_CUDA_OK(cudaMemsetAsync(workspace, 0, sizeof(double) * 2 * (size_t)C, st));
+    const int ppb = NT / (C / 4);
+    long long blocks = (rows + ppb - 1) / ppb;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    bn_stats_partial_kernel<<<(int)blocks, NT, 0, st>>>((const float4*)y, rows, C / 4, workspace);
+    B3D_LAUNCH_OK();
+    bn_stats_finish_kernel<<<(C + 127) / 128, 128, 0, st>>>(workspace, rows, C, eps, mean, invstd);
+    B3D_LAUNCH_OK();
+    return B3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // Fused generator glue (models/gan.py:282-286 ConditionalBatchNorm2d, :309-311 LeakyReLU + residual, :319 nearest x2
 // upsample, :329 replicate pad): one pass from a conv output y [N,H,W,C] to the NEXT conv's padded input
 //     out[n, yo, xo, c] = post( leaky(y[n,ys,xs,c] * scale[n,c] + shift[n,c]) + skip[n,ys,xs,c] )

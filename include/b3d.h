@@ -268,6 +268,12 @@ B3D_API int b3d_pad_leaky_bias_bwd(const float* gout_pad, const float* y_pad, fl
                                    int C, int amount, int mode, float slope, void* stream);
 B3D_API int b3d_leaky_bwd(const float* gy, const float* y, float* out, long long n, float slope, void* stream);
 
+/* Batch-norm statistics of an NHWC activation y [rows = N*H*W, C] in one pass: mean[c] and invstd[c] = 1/sqrt(biased
+ * variance + eps) — what F.batch_norm / torch.batch_norm_stats compute for the generator's BatchNorm2d(affine=False)
+ * layers (models/gan.py:211-232).  workspace: 2*C doubles (zeroed by the call).  C = 4 * a divisor of 256. */
+B3D_API int b3d_bn_stats(const float* y, long long rows, int C, float eps, float* mean, float* invstd, double* workspace,
+                         void* stream);
+
 /* Fused generator glue between two convolutions (models/gan.py:282-286 ConditionalBatchNorm2d, :309-311 LeakyReLU and
  * residual add, :319 nearest x2 upsample, :329 replicate pad), NHWC, C % 4 == 0:
  *   out[n, yo, xo, :] = post( leaky(y[n,ys,xs,:] * scale[n,:] + shift[n,:]) + skip[n,ys,xs,:] ),

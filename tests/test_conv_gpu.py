@@ -230,3 +230,16 @@ def test_conv2d_x_crop_autograd(N, Cin, H, W, Cout, k, pad_y):
     for a, r in zip(outs[1], outs[0]):
         assert a.shape == r.shape
         assert float((a - r).abs().max()) <= TOL * float(r.abs().max()), (a.shape, float((a - r).abs().max()), float(r.abs().max()))
+
+
+@pytest.mark.parametrize("N,C,H,W", [(4, 64, 33, 17), (2, 512, 8, 4), (3, 128, 16, 10), (2, 12, 5, 7)])
+def test_bn_stats_matches_torch(N, C, H, W):
+    """b3d_bn_stats (one-pass NHWC mean / invstd) against torch.batch_norm_stats; C = 12 takes the stock-op fallback."""
+    from b3d.ew import bn_stats
+    g = torch.Generator().manual_seed(C + W)
+    x = (torch.randn(N, C, H, W, generator=g) * 1.7 + 0.3).cuda().contiguous(memory_format=torch.channels_last)
+    mean, invstd = bn_stats(x.permute(0, 2, 3, 1), 1e-5)
+    rm, ri = torch.batch_norm_stats(x, 1e-5)
+    torch.cuda.synchronize()
+    assert torch.allclose(mean, rm, atol=2e-6, rtol=1e-5)
+    assert torch.allclose(invstd, ri, atol=0, rtol=2e-5)
