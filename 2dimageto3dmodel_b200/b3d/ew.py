@@ -1,4 +1,6 @@
 """One-pass NHWC helper ops between the convolutions (libb3d csrc/ew_kernels.cu), with autograd."""
+import os
+
 import torch
 
 from . import check, dev, lib, ptr, stream_ptr
@@ -124,11 +126,14 @@ class _CBNActPad(torch.autograd.Function):
         return ga, dgamma, dbeta, None, None, gskip, None, None, None, None, None, None
 
 
+_BN_STATS_TORCH = os.environ.get("B3D_BN_STATS", "") == "torch"
+
+
 def bn_stats(y_nhwc, eps):
     """(mean, invstd) per channel of an NHWC tensor = torch.batch_norm_stats on the NCHW view, one libb3d pass."""
     y = dev(y_nhwc, "y")
     C = y.shape[-1]
-    if C % 4 or 256 % (C // 4):                        # odd channel counts: stock op
+    if C % 4 or 256 % (C // 4) or _BN_STATS_TORCH:     # odd channel counts (or B3D_BN_STATS=torch): stock op
         return torch.batch_norm_stats(y.permute(0, 3, 1, 2), eps)
     mean = torch.empty(C, device=y.device, dtype=torch.float32)
     invstd = torch.empty_like(mean)

@@ -297,10 +297,17 @@ bn_stats_partial_kernel(const float4* __restrict__ y, long long rows, int C4, do
     __shared__ float4 rs[NT], rq[NT];
     const int c = threadIdx.x % C4, lane_p = threadIdx.x / C4, PPB = NT / C4;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
-    for (long long p = (long long)blockIdx.x * PPB + lane_p; p < rows; p += (long long)gridDim.x * PPB) {
-        const float4 v = __ldg(y + p * C4 + c);
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-        q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+    constexpr int U = 4;                                    // independent 16-byte loads in flight per thread
+    const long long stride = (long long)gridDim.x * PPB;
+    for (long long p = (long long)blockIdx.x * PPB + lane_p; p < rows; p += U * stride) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = p + u * stride < rows ? __ldg(y + (p + u * stride) * C4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w;
+            q.x = fmaf(v[u].x, v[u].x, q.x); q.y = fmaf(v[u].y, v[u].y, q.y); q.z = fmaf(v[u].z, v[u].z, q.z); q.w = fmaf(v[u].w, v[u].w, q.w);
+        }
     }
     rs[threadIdx.x] = s; rq[threadIdx.x] = q;
     __syncthreads();
@@ -345,7 +352,7 @@ extern "C" int b3d_bn_stats(const float* y, long long rows, int C, float eps, fl
     B3D_CUDA_OK(cudaMemsetAsync(workspace, 0, sizeof(double) * 2 * (size_t)C, st));
     const int ppb = NT / (C / 4);
     long long blocks = (rows + ppb - 1) / ppb;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;                 // 8 resident blocks per SM
     bn_stats_partial_kernel<<<(int)blocks, NT, 0, st>>>((const float4*)y, rows, C / 4, workspace);
     B3D_LAUNCH_OK();
     bn_stats_finish_kernel<<<(C + 127) / 128, 128, 0, st>>>(workspace, rows, C, eps, mean, invstd);
