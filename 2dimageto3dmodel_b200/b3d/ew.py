@@ -126,14 +126,16 @@ class _CBNActPad(torch.autograd.Function):
         return ga, dgamma, dbeta, None, None, gskip, None, None, None, None, None, None
 
 
-_BN_STATS_TORCH = os.environ.get("B3D_BN_STATS", "") == "torch"
+_BN_STATS_IMPL = os.environ.get("B3D_BN_STATS", "torch")
 
 
-def bn_stats(y_nhwc, eps):
-    """(mean, invstd) per channel of an NHWC tensor = torch.batch_norm_stats on the NCHW view, one libb3d pass."""
+def bn_stats(y_nhwc, eps, impl=None):
+    """(mean, invstd) per channel of an NHWC tensor = torch.batch_norm_stats on the NCHW view.  impl "b3d" = the one-pass
+    libb3d kernel, "torch" = the stock op (default: B3D_BN_STATS, else "torch" — measured on B200: the stock channels-last
+    kernel is as fast inside the training step)."""
     y = dev(y_nhwc, "y")
     C = y.shape[-1]
-    if C % 4 or 256 % (C // 4) or _BN_STATS_TORCH:     # odd channel counts (or B3D_BN_STATS=torch): stock op
+    if C % 4 or 256 % (C // 4) or (impl or _BN_STATS_IMPL) != "b3d":     # odd channel counts: always the stock op
         return torch.batch_norm_stats(y.permute(0, 3, 1, 2), eps)
     mean = torch.empty(C, device=y.device, dtype=torch.float32)
     invstd = torch.empty_like(mean)

@@ -352,7 +352,7 @@ extern "C" int b3d_bn_stats(const float* y, long long rows, int C, float eps, fl
     B3D_CUDA_OK(cudaMemsetAsync(workspace, 0, sizeof(double) * 2 * (size_t)C, st));
     const int ppb = NT / (C / 4);
     long long blocks = (rows + ppb - 1) / ppb;
-    if (blocks > 148 * 8) blocks = 148 * 8;                 // 8 resident blocks per SM
+    if (blocks > 148 * 2) blocks = 148 * 2;                 // few blocks: every block ends with 2C same-address fp64 atomics
     bn_stats_partial_kernel<<<(int)blocks, NT, 0, st>>>((const float4*)y, rows, C / 4, workspace);
     B3D_LAUNCH_OK();
     bn_stats_finish_kernel<<<(C + 127) / 128, 128, 0, st>>>(workspace, rows, C, eps, mean, invstd);
