@@ -30,8 +30,10 @@ class TCConv2d(nn.Conv2d):
         `pad_out` > 0 also applies the next layer's x padding (the epilogue writes into the padded buffer)."""
         if not x.is_cuda:
             raise B3DError("models.gan convolutions run on CUDA only (libb3d tcgen05 kernels); there is no CPU fallback")
-        if self.padding[1] != 0 or self.stride[0] != self.stride[1] or self.dilation != (1, 1) or self.groups != 1:
-            raise B3DError("TCConv2d supports zero padding along y only, square strides, no dilation / groups")
+        if self.stride[0] != self.stride[1] or self.dilation != (1, 1) or self.groups != 1 or self.padding_mode != 'zeros':
+            raise B3DError("TCConv2d supports zero padding, square strides, no dilation / groups")
+        if self.padding[1] != 0:          # the kernels zero-pad along y (TMA fill); zero padding along x is materialised
+            x = F.pad(x, (self.padding[1], self.padding[1], 0, 0))
         return _tc_conv2d(x, self.weight, self.bias, pad_y=self.padding[0], stride=self.stride[0], leaky=leaky,
                           pad_out=pad_out, pad_mode=pad_mode, x_crop=x_crop)
 

@@ -23,6 +23,8 @@ CASES = [  # N, Cin, H, W(x-padded), Cout, k, pad_y, stride, bias, leaky
     (2, 32, 32, 34, 64, 4, 1, 2, True, 0.2),        # discriminator 4x4 / stride 2 + bias + LeakyReLU (gan.py:163)
     (1, 256, 64, 66, 128, 3, 1, 1, False, 1.0),     # multiple tiles along y
     (5, 96, 10, 20, 40, 3, 1, 1, True, 1.0),        # ragged: N, H, Cout not multiples of the tile
+    (2, 64, 32, 34, 128, 3, 1, 2, False, 1.0),      # reconstruction encoder: 3x3 / stride 2 (reconstruction.py:54-60)
+    (2, 32, 32, 36, 64, 5, 2, 2, False, 1.0),       # ... and its 5x5 / stride 2 stem (:52)
 ]
 
 
@@ -44,7 +46,7 @@ def test_fprop(N, Cin, H, W, Cout, k, pad_y, stride, bias, leaky):
 
 @pytest.mark.parametrize("N,Cin,H,W,Cout,k,pad_y,stride", [
     (2, 64, 16, 18, 128, 3, 1, 1), (2, 32, 32, 36, 64, 5, 2, 1), (2, 64, 16, 18, 64, 4, 1, 2), (3, 128, 8, 6, 256, 3, 1, 1),
-    (2, 96, 9, 12, 64, 1, 0, 1),
+    (2, 96, 9, 12, 64, 1, 0, 1), (2, 64, 32, 34, 128, 3, 1, 2), (2, 128, 16, 18, 256, 3, 1, 2), (2, 32, 16, 20, 64, 5, 2, 2),
 ])
 def test_dgrad(N, Cin, H, W, Cout, k, pad_y, stride):
     from b3d.conv import conv2d_dgrad_nhwc
@@ -64,6 +66,7 @@ def test_dgrad(N, Cin, H, W, Cout, k, pad_y, stride):
 @pytest.mark.parametrize("N,Cin,H,W,Cout,k,pad_y,stride", [
     (2, 64, 16, 18, 128, 3, 1, 1), (4, 128, 64, 66, 64, 3, 1, 1), (2, 32, 32, 36, 4, 5, 2, 1), (2, 64, 16, 18, 64, 4, 1, 2),
     (3, 512, 8, 6, 512, 3, 1, 1), (2, 96, 9, 12, 40, 1, 0, 1), (8, 32, 64, 66, 64, 4, 1, 2),
+    (2, 64, 32, 34, 128, 3, 1, 2), (2, 32, 32, 36, 64, 5, 2, 2), (4, 256, 4, 4, 512, 3, 1, 1),
 ])
 def test_wgrad(N, Cin, H, W, Cout, k, pad_y, stride):
     from b3d.conv import conv2d_wgrad_nhwc
@@ -89,6 +92,8 @@ def test_wgrad(N, Cin, H, W, Cout, k, pad_y, stride):
     (2, 256, 8, 12, 1, 5, 2, 1, False),      # mesh discriminator head 256 -> 1
     (2, 128, 6, 9, 2, 5, 2, 1, True),
     (2, 256, 16, 18, 128, 3, 1, 1, False),
+    (2, 4, 64, 68, 64, 5, 2, 2, False),      # reconstruction stem: 4 input channels, 5x5 / stride 2
+    (4, 256, 4, 4, 256, 3, 1, 1, False),     # decoder base resolution: 4x2 maps (x-padded to 4)
 ])
 def test_conv2d_autograd_matches_torch(N, Cin, H, W, Cout, k, pad_y, stride, bias):
     """b3d.conv.conv2d (the function models/gan.py calls) forward + all three gradients vs torch fp32."""

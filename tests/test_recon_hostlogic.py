@@ -1,0 +1,74 @@
+"""Host-side logic of the models.reconstruction drop-in (CPU): state-dict layout and same-seed initial values equal the
+reference's when /root/reference is present (authoring container); DatasetParams against the reference golden."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+sys.path.insert(0, GOLDEN)
+import recon_common as RC          # noqa: E402
+
+REF = "/root/reference/code"
+
+
+def test_dataset_params_match_reference_golden():
+    from models.reconstruction import DatasetParams
+    d = np.load(os.path.join(GOLDEN, "recon_reference.npz"))
+    dp = DatasetParams(RC.dataset_args(), 10)
+    with torch.no_grad():
+        st = torch.tensor(d["dp_state"])
+        dp.ds_translation.copy_(st[:, :2]); dp.ds_scale.copy_(st[:, 2:3]); dp.ds_z0.copy_(st[:, 3:4])
+    idx = torch.tensor(d["dp_idx"])
+    t, s = dp(idx, 'deltas')
+    assert np.array_equal(t.detach().numpy(), d["dp_t"]) and np.array_equal(s.detach().numpy(), d["dp_s"])
+    assert np.allclose(dp(idx, 'z0').detach().numpy(), d["dp_z0"], rtol=1e-6, atol=0)
+    t, s = dp(None, 'deltas')
+    assert np.allclose(t.detach().numpy(), d["dp_t_mean"], atol=1e-7) and np.allclose(s.detach().numpy(), d["dp_s_mean"], atol=1e-7)
+    assert np.allclose(dp(None, 'z0').detach().numpy(), d["dp_z0_mean"], rtol=1e-6)
+    with pytest.raises(ValueError):
+        dp(idx, 'nope')
+    # mirrored copies (indices >= N) flip the sign of the x translation only
+    a, _ = dp(torch.tensor([3]), 'deltas')
+    b, _ = dp(torch.tensor([13]), 'deltas')
+    assert float(a[0, 0]) == -float(b[0, 0]) and float(a[0, 1]) == float(b[0, 1]) and float(b[0, 2]) == 0.0
+
+
+def test_state_dict_layout():
+    from models.reconstruction import ReconstructionNetwork
+    net = RC.build(sys.modules["models.reconstruction"], texture_res=256)
+    sd = net.state_dict()
+    assert sd["conv1e.weight"].shape == (64, 4, 5, 5) and sd["fc1e.weight"].shape == (256, 4096)
+    assert sd["blk1.shortcut.weight"].shape == (512, 256, 1, 1) and "blk3.shortcut.weight" not in sd
+    assert sd["blk3c_tex.conv2.weight"].shape == (256, 256, 3, 3) and sd["conv_tex.bias"].shape == (3,)
+    assert sd["bnfc3e.running_var"].shape == (1024,) and sd["fc1_tex.weight"].shape == (4 * 2 * 256, 1024)
+    assert round(sum(p.numel() for p in ReconstructionNetwork(texture_res=128).parameters()) / 1e6, 2) == 15.11
+    with pytest.raises(ValueError):
+        ReconstructionNetwork(texture_res=100)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present (GPU box)")
+def test_same_seed_state_equals_reference():
+    import importlib
+    from conftest import PKG
+    from models import reconstruction as mine
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k.split('.')[0] in ("models", "rendering", "utils")}
+    sys.path.remove(PKG)
+    sys.path.insert(0, REF)
+    try:
+        ref = importlib.import_module("models.reconstruction")
+        assert ref.__file__.startswith(REF)
+        r = RC.build(ref).state_dict()
+    finally:
+        sys.path.remove(REF)
+        for k in [k for k in sys.modules if k.split('.')[0] in ("models", "rendering", "utils")]:
+            sys.modules.pop(k)
+        sys.path.insert(0, PKG)
+        sys.modules.update(saved)
+    m = RC.build(mine).state_dict()
+    assert list(m.keys()) == list(r.keys())
+    for k in m:
+        assert m[k].shape == r[k].shape and torch.equal(m[k], r[k]), k
