@@ -123,7 +123,7 @@ class ReconstructionNetwork(nn.Module):
 
         tex = self.up(self.blk4_tex(bb))
         tex = self.blk5_tex(tex)
-        tex = self.conv_tex(self.pad(self.relu(tex), 2)).tanh_()
+        tex = torch.tanh(self.conv_tex(self.pad(self.relu(tex), 2)))
         if self.symmetric:
             tex = symmetrize_texture(tex)
             mesh_map = symmetrize_texture(mesh_map)
