@@ -78,6 +78,21 @@ def conv2d_nhwc(x, weight, bias=None, pad_y=0, stride=1, leaky=1.0, wt=None, cin
     return out
 
 
+def stride2_classes(kh, kw, pad_y, H, W):
+    """Output-parity decomposition of the input gradient of a stride-2 convolution (pure index arithmetic, unit-tested on
+    the CPU): input pixel (y', x') = (2a + cy, 2b + cx) receives dY[a + dy_t, b + dx_t] * W[:, :, r_t, s_t] summed over the
+    taps t of its class.  From y' = 2*yo + r - pad_y: only taps with (cy + pad_y - r) even take part, at yo = a + (cy +
+    pad_y - r) / 2; likewise along x (no x padding: the input is pre-padded).  Returns one tuple per class:
+    (cy, cx, [(r, s)], [dy], [dx], Ha, Wa) with Ha x Wa the number of input pixels of that parity."""
+    out = []
+    for cy in range(2):
+        for cx in range(2):
+            rs = [(r, s) for r in range(kh) for s in range(kw) if (cy + pad_y - r) % 2 == 0 and (cx - s) % 2 == 0]
+            out.append((cy, cx, rs, [(cy + pad_y - r) // 2 for r, s in rs], [(cx - s) // 2 for r, s in rs],
+                        (H - cy + 1) // 2, (W - cx + 1) // 2))
+    return out
+
+
 def conv2d_dgrad_nhwc(dy_, weight, in_hw, pad_y=0, stride=1, x_crop=0):
     """Gradient w.r.t. the (x-padded) input [N,H,W,Cin] of conv2d_nhwc, from dy_ [N,Hout,Wout,Cout] (Cout % 32 == 0)."""
     g = dev(dy_, "grad_output")
@@ -95,19 +110,13 @@ def conv2d_dgrad_nhwc(dy_, weight, in_hw, pad_y=0, stride=1, x_crop=0):
         return dxo
     if stride != 2 or x_crop:
         raise B3DError("conv2d_dgrad: stride must be 1 or 2 (x_crop: stride 1 only)")
-    # input row y' = 2*yo + r - pad_y  =>  for the class y' = 2*a + cy only taps with (cy + pad_y - r) even take part
-    for cy in range(2):
-        for cx in range(2):
-            rs = [(r, s) for r in range(kh) for s in range(kw) if (cy + pad_y - r) % 2 == 0 and (cx - s) % 2 == 0]
-            Ha, Wa = (H - cy + 1) // 2, (W - cx + 1) // 2
-            if not rs:
-                dxo[:, cy::2, cx::2] = 0
-                continue
-            wt = torch.stack([weight[:, :, r, s].t() for r, s in rs]).contiguous()      # [taps][Cin][Cout]
-            dy = [(cy + pad_y - r) // 2 for r, s in rs]
-            dx = [(cx - s) // 2 for r, s in rs]
-            check(lib.b3d_conv2d_tf32(ptr(g), ptr(wt), None, ptr(dxo), N, Hout, Wout, Cout, Ha, Wa, Cin, len(rs),
-                                      _ints(dy), _ints(dx), 1, 1, H, W, Cin, 2, 2, cy, cx, 1.0, 0, st))
+    for cy, cx, rs, dy, dx, Ha, Wa in stride2_classes(kh, kw, pad_y, H, W):
+        if not rs:
+            dxo[:, cy::2, cx::2] = 0
+            continue
+        wt = torch.stack([weight[:, :, r, s].t() for r, s in rs]).contiguous()      # [taps][Cin][Cout]
+        check(lib.b3d_conv2d_tf32(ptr(g), ptr(wt), None, ptr(dxo), N, Hout, Wout, Cout, Ha, Wa, Cin, len(rs),
+                                  _ints(dy), _ints(dx), 1, 1, H, W, Cin, 2, 2, cy, cx, 1.0, 0, st))
     return dxo
 
 
@@ -198,6 +207,14 @@ class _Conv2dNHWC(torch.autograd.Function):
         return gx, gw, gb, None, None, None, None, None, None
 
 
+def fold_kh_weight(weight, cpad=0):
+    """[Cout,Cin,kh,kw] -> [Cout, kh*Cin + cpad, 1, kw] matching fold_rows: channel r*Cin + c of the folded input is
+    row tap r of input channel c (pure torch; unit-tested on the CPU against the unfolded convolution)."""
+    Cout, Cin, kh, kw = weight.shape
+    w = weight.permute(0, 2, 1, 3).reshape(Cout, kh * Cin, 1, kw)
+    return torch.nn.functional.pad(w, (0, 0, 0, 0, 0, cpad)) if cpad else w
+
+
 _FOLD = os.environ.get("B3D_FOLD", "kh")
 
 
@@ -215,9 +232,7 @@ def conv2d(x_nchw, weight, bias=None, pad_y=0, stride=1, leaky=1.0, pad_out=0, p
         from .ew import fold_rows
         cpad = (-kh * Cin) % 32                            # ... and round up to the 32-channel K slice in the same pass
         x = fold_rows(x, kh, pad_y, kh * Cin + cpad)
-        weight = weight.permute(0, 2, 1, 3).reshape(Cout, kh * Cin, 1, kw)          # [co, r*Cin + c, 0, s]
-        if cpad:
-            weight = torch.nn.functional.pad(weight, (0, 0, 0, 0, 0, cpad))
+        weight = fold_kh_weight(weight, cpad)
         pad_y = 0
     elif stride == 1 and kw > 1 and Cin * kw <= 64:
         # same fold along x (B3D_FOLD=kw): X'[n,y,x, s*Cin + c] = X[n,y,x+s,c], kh vertical taps remain
