@@ -2,12 +2,13 @@
 run_reconstruction.py trains through the renderer, and the per-image pose offsets.
 
 Module tree, parameter and buffer names equal the reference's (`conv1e.weight`, `bn1e.running_mean`, `blk1.conv1.weight`,
-`blk4_mesh.shortcut.weight`, `conv_tex.bias`, `fc1_tex.weight`, ... — its checkpoints load with strict=True); every
-nn.Conv2d is a models.gan.TCConv2d, i.e. runs on libb3d's tcgen05 / TMA implicit-GEMM kernels (fprop, dgrad and wgrad,
-tf32 inputs, fp32 accumulate; the 3-channel 5x5 heads on the thin-head kernels).  The encoder's zero padding along x is
-materialised, along y it is the TMA out-of-bounds fill; the decoder's replicate / circular x padding is explicit as in the
-reference.  Batch norms, the three linear layers, nearest upsampling and tanh are stock torch ops on channels-last
-tensors.  CUDA only: there is no CPU fallback (TCConv2d raises on CPU tensors).
+`blk4_mesh.shortcut.weight`, `conv_tex.bias`, `fc1_tex.weight`, ... — its checkpoints load with strict=True) and modules
+are created in the reference's order, so the same seed gives the same initial weights.  Every convolution is a
+models.gan.TCConv2d, i.e. runs on libb3d's tcgen05 / TMA implicit-GEMM kernels (fprop, dgrad and wgrad, tf32 inputs, fp32
+accumulate; the 3-channel 5x5 heads on the thin-head kernels).  The encoder's zero padding along x is materialised, along
+y it is the TMA out-of-bounds fill; the decoder's replicate / circular x padding is explicit as in the reference.  Batch
+norms, the three linear layers, nearest upsampling and tanh are stock torch ops on channels-last tensors.  CUDA only:
+there is no CPU fallback (TCConv2d raises on CPU tensors).
 """
 import torch
 import torch.nn as nn
@@ -17,6 +18,12 @@ from b3d.ew import CIRCULAR, REPLICATE, pad_x
 from models.gan import TCConv2d
 from rendering.utils import adjust_poles, symmetrize_texture
 
+# encoder stages (reference :52-64): name suffix, channels in -> out, kernel, padding; all stride 2, no bias, BN + ReLU
+_ENCODER = (("1e", 4, 64, 5, 2), ("2e", 64, 128, 3, 1), ("3e", 128, 256, 3, 1), ("4e", 256, 512, 3, 1), ("5e", 512, 64, 3, 1))
+# decoder blocks in creation order (reference :77-99): attribute, channels in -> out, smallest texture_res that has it
+_DECODER = (("blk1", 256, 512, 0), ("blk2", 512, 256, 0), ("blk3", 256, 256, 0), ("blk3b_tex", 256, 256, 128),
+            ("blk3c_tex", 256, 256, 256), ("blk4_tex", 256, 128, 0), ("blk5_tex", 128, 64, 0))
+
 
 class ResBlock(nn.Module):
     """conv3x3 -> BN -> ReLU -> conv3x3 -> BN -> ReLU, plus a 1x1 (or identity) shortcut (reference :7-26)."""
@@ -25,22 +32,21 @@ class ResBlock(nn.Module):
         super().__init__()
         self.conv1 = TCConv2d(ch_in, ch_in, 3, padding=(1, 0), bias=False)
         self.conv2 = TCConv2d(ch_in, ch_out, 3, padding=(1, 0), bias=False)
-        self.bn1 = nn.BatchNorm2d(ch_in)
-        self.bn2 = nn.BatchNorm2d(ch_out)
+        self.bn1, self.bn2 = nn.BatchNorm2d(ch_in), nn.BatchNorm2d(ch_out)
         self.relu = nn.ReLU(inplace=True)
         self.pad_fn = pad_fn
-        self.shortcut = TCConv2d(ch_in, ch_out, 1, bias=False) if ch_in != ch_out else (lambda x: x)
+        self.shortcut = TCConv2d(ch_in, ch_out, 1, bias=False) if ch_in != ch_out else (lambda t: t)
 
     def forward(self, x):
-        skip = self.shortcut(x)
-        h = self.relu(self.bn1(self.conv1(self.pad_fn(x, 1))))
-        h = self.relu(self.bn2(self.conv2(self.pad_fn(h, 1))))
-        return h + skip
+        h = x
+        for conv, bn in ((self.conv1, self.bn1), (self.conv2, self.bn2)):
+            h = self.relu(bn(conv(self.pad_fn(h, 1))))
+        return h + self.shortcut(x)
 
 
 class ReconstructionNetwork(nn.Module):
-    """RGBA image [B,4,128,128] -> (texture [B,3,R,R] in [-1,1], displacement map [B,3,32,32]) (reference :29-134).
-    `symmetric=True` predicts the left half of the UV map and mirrors it."""
+    """RGBA image [B,4,256,256] -> (texture [B,3,R,R] in [-1,1], displacement map [B,3,32,32]) (reference :29-134).
+    `symmetric=True` predicts one half of the UV map and mirrors it."""
 
     def __init__(self, symmetric=True, texture_res=64, mesh_res=32, interpolation_mode='nearest'):
         super().__init__()
@@ -48,46 +54,25 @@ class ReconstructionNetwork(nn.Module):
             raise ValueError("mesh_res must be >= 32 and texture_res one of 64 / 128 / 256")
         if interpolation_mode not in ('nearest', 'bilinear'):
             raise ValueError(f"interpolation_mode={interpolation_mode!r}")
-        self.symmetric = symmetric
-        self.texture_res = texture_res
-        mode = REPLICATE if symmetric else CIRCULAR
-        self.pad = lambda x, amount: pad_x(x, amount, mode)
+        self.symmetric, self.texture_res = symmetric, texture_res
+        x_mode = REPLICATE if symmetric else CIRCULAR
+        self.pad = lambda t, amount: pad_x(t, amount, x_mode)
         self.relu = nn.ReLU(inplace=True)
-        if interpolation_mode == 'nearest':
-            self.up = lambda x: F.interpolate(x, scale_factor=2, mode='nearest')
-        else:
-            self.up = lambda x: F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=False)
+        up_kw = dict(mode='nearest') if interpolation_mode == 'nearest' else dict(mode='bilinear', align_corners=False)
+        self.up = lambda t: F.interpolate(t, scale_factor=2, **up_kw)
 
-        # encoder: 128 -> 64 -> 32 -> 16 -> 8 -> 4 (stride-2 convolutions), then two linear layers
-        self.conv1e = TCConv2d(4, 64, 5, stride=2, padding=2, bias=False)
-        self.bn1e = nn.BatchNorm2d(64)
-        self.conv2e = TCConv2d(64, 128, 3, stride=2, padding=1, bias=False)
-        self.bn2e = nn.BatchNorm2d(128)
-        self.conv3e = TCConv2d(128, 256, 3, stride=2, padding=1, bias=False)
-        self.bn3e = nn.BatchNorm2d(256)
-        self.conv4e = TCConv2d(256, 512, 3, stride=2, padding=1, bias=False)
-        self.bn4e = nn.BatchNorm2d(512)
-        bottleneck_dim = 256
-        self.conv5e = TCConv2d(512, 64, 3, stride=2, padding=1, bias=False)
-        self.bn5e = nn.BatchNorm2d(64)
-        self.fc1e = nn.Linear(64 * 8 * 8, bottleneck_dim, bias=False)
-        self.bnfc1e = nn.BatchNorm1d(bottleneck_dim)
-        self.fc3e = nn.Linear(bottleneck_dim, 1024, bias=False)
-        self.bnfc3e = nn.BatchNorm1d(1024)
+        for tag, cin, cout, k, p in _ENCODER:                   # 256 -> 128 -> 64 -> 32 -> 16 -> 8
+            setattr(self, "conv" + tag, TCConv2d(cin, cout, k, stride=2, padding=p, bias=False))
+            setattr(self, "bn" + tag, nn.BatchNorm2d(cout))
+        bottleneck = 256
+        self.fc1e, self.bnfc1e = nn.Linear(64 * 8 * 8, bottleneck, bias=False), nn.BatchNorm1d(bottleneck)
+        self.fc3e, self.bnfc3e = nn.Linear(bottleneck, 1024, bias=False), nn.BatchNorm1d(1024)
 
-        # texture decoder
-        self.base_res_h = 4
-        self.base_res_w = 2 if symmetric else 4
+        self.base_res_h, self.base_res_w = 4, (2 if symmetric else 4)
         self.fc1_tex = nn.Linear(1024, self.base_res_h * self.base_res_w * 256)
-        self.blk1 = ResBlock(256, 512, self.pad)
-        self.blk2 = ResBlock(512, 256, self.pad)
-        self.blk3 = ResBlock(256, 256, self.pad)
-        if texture_res >= 128:
-            self.blk3b_tex = ResBlock(256, 256, self.pad)
-        if texture_res >= 256:
-            self.blk3c_tex = ResBlock(256, 256, self.pad)
-        self.blk4_tex = ResBlock(256, 128, self.pad)
-        self.blk5_tex = ResBlock(128, 64, self.pad)
+        for name, cin, cout, min_res in _DECODER:
+            if texture_res >= min_res:
+                setattr(self, name, ResBlock(cin, cout, self.pad))
         self.conv_tex = TCConv2d(64, 3, 5, padding=(2, 0))
 
         # mesh head, zero-initialised so that training starts from the undeformed template (reference :101-103)
@@ -98,35 +83,28 @@ class ReconstructionNetwork(nn.Module):
             self.conv_mesh.weight.zero_()
         print('Model parameters: {:.2f}M'.format(sum(p.nelement() for p in self.parameters()) / 1000000))
 
+    def encode(self, image):
+        h = image.contiguous(memory_format=torch.channels_last)
+        for tag, *_ in _ENCODER:
+            h = self.relu(getattr(self, "bn" + tag)(getattr(self, "conv" + tag)(h)))
+        z = h.reshape(h.shape[0], -1)                           # (C, H, W) order, as the reference's .view on NCHW storage
+        z = self.relu(self.bnfc1e(self.fc1e(z)))
+        return self.relu(self.bnfc3e(self.fc3e(z)))
+
     def forward(self, x):
-        x = x.contiguous(memory_format=torch.channels_last)
-        for conv, bn in ((self.conv1e, self.bn1e), (self.conv2e, self.bn2e), (self.conv3e, self.bn3e),
-                         (self.conv4e, self.bn4e), (self.conv5e, self.bn5e)):
-            x = self.relu(bn(conv(x)))
-        x = x.reshape(x.shape[0], -1)                       # flatten in (C, H, W) order, as the reference's .view
-        z = self.relu(self.bnfc1e(self.fc1e(x)))
-        z = self.relu(self.bnfc3e(self.fc3e(z)))
-
-        bb = self.fc1_tex(z).view(z.shape[0], -1, self.base_res_h, self.base_res_w)
-        bb = bb.contiguous(memory_format=torch.channels_last)
-        bb = self.up(self.blk1(bb))
-        bb = self.up(self.blk2(bb))
-        bb = self.up(self.blk3(bb))
-        bb_mesh = bb
-        if self.texture_res >= 128:
-            bb = self.up(self.blk3b_tex(bb))
-        if self.texture_res >= 256:
-            bb = self.up(self.blk3c_tex(bb))
-
-        mesh_map = self.blk4_mesh(bb_mesh)
-        mesh_map = adjust_poles(self.conv_mesh(self.pad(self.relu(mesh_map), 2)))
-
-        tex = self.up(self.blk4_tex(bb))
-        tex = self.blk5_tex(tex)
+        z = self.encode(x)
+        h = self.fc1_tex(z).view(z.shape[0], -1, self.base_res_h, self.base_res_w).contiguous(memory_format=torch.channels_last)
+        for name in ("blk1", "blk2", "blk3"):
+            h = self.up(getattr(self, name)(h))
+        shared = h                                              # 32 x 16: both heads branch from here
+        for name in ("blk3b_tex", "blk3c_tex"):
+            if hasattr(self, name):
+                h = self.up(getattr(self, name)(h))
+        tex = self.blk5_tex(self.up(self.blk4_tex(h)))
         tex = torch.tanh(self.conv_tex(self.pad(self.relu(tex), 2)))
+        mesh_map = adjust_poles(self.conv_mesh(self.pad(self.relu(self.blk4_mesh(shared)), 2)))
         if self.symmetric:
-            tex = symmetrize_texture(tex)
-            mesh_map = symmetrize_texture(mesh_map)
+            tex, mesh_map = symmetrize_texture(tex), symmetrize_texture(mesh_map)
         return tex, mesh_map
 
 

@@ -72,3 +72,33 @@ def test_same_seed_state_equals_reference():
     assert list(m.keys()) == list(r.keys())
     for k in m:
         assert m[k].shape == r[k].shape and torch.equal(m[k], r[k]), k
+
+
+def test_forward_wiring_matches_reference_golden_on_cpu(monkeypatch):
+    """The module's wiring (layer order, paddings, flatten order, upsampling, heads, symmetrisation) with the CUDA pieces
+    swapped for exact torch ops — TCConv2d -> nn.Conv2d.forward, pad_x -> F.pad / wrap-around cat — must reproduce the
+    reference golden to fp32 round-off, forward and backward.  (The same golden is the target of the CUDA test.)"""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from models import gan, reconstruction
+    d = np.load(os.path.join(GOLDEN, "recon_reference.npz"))
+
+    def pad_x_cpu(t, amount, mode):
+        if mode == reconstruction.REPLICATE:
+            return F.pad(t, (amount, amount, 0, 0), mode='replicate')
+        return torch.cat((t[..., -amount:], t, t[..., :amount]), dim=3)
+
+    monkeypatch.setattr(gan.TCConv2d, "forward", lambda self, x, **kw: nn.Conv2d.forward(self, x))
+    monkeypatch.setattr(reconstruction, "pad_x", pad_x_cpu)
+    torch.set_num_threads(8)
+    net = RC.build(reconstruction).train()
+    x, w_tex, w_mesh = RC.inputs()
+    tex, mesh_map = net(x)
+    RC.loss_of(tex, mesh_map, w_tex, w_mesh).backward()
+    assert np.abs(tex.detach()[:, :, ::8, ::8].numpy() - d["tex_probe"]).max() < 2e-4
+    assert np.abs(mesh_map.detach().numpy() - d["mesh_map"]).max() < 1e-4     # fp32 round-off (channels-last vs NCHW kernels)
+    params = dict(net.named_parameters())
+    for name, ref in zip(d["grad_names"], d["grad_norms"]):
+        got = float(params[str(name)].grad.norm())
+        assert abs(got - ref) <= 2e-3 * ref + 1e-6, (str(name), got, ref)
+    assert np.abs(net.bn4e.running_mean.numpy() - d["bn4e_mean"]).max() < 1e-5
