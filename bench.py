@@ -91,9 +91,8 @@ def host_inputs(B, seed, pin):
 
 
 def template_path():
-    from oracle import mesh as M          # only the OBJ writer (the shipped templates cannot travel)
-    path = os.path.join(tempfile.mkdtemp(), "uvsphere_16rings.obj")
-    return M.write_uvsphere_obj(path, rings=16)
+    from tools.uvsphere import write_uvsphere_obj          # synthetic input (the shipped templates cannot travel)
+    return write_uvsphere_obj(os.path.join(tempfile.mkdtemp(), "uvsphere_16rings.obj"), rings=16)
 
 
 # --------------------------------------------------------------------------------------------- CUDA arm
