@@ -19,7 +19,7 @@ import torch.nn.functional as F
 from b3d import B3DError
 from b3d.conv import conv2d as _tc_conv2d
 from b3d.ew import CIRCULAR, REPLICATE, cbn_act_pad, pad_x
-from rendering.utils import adjust_poles, circpad, symmetrize_texture
+from rendering.utils import adjust_poles, symmetrize_texture
 
 
 class TCConv2d(nn.Conv2d):

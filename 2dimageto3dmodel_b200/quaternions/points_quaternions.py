@@ -1,7 +1,6 @@
 """Drop-in for /root/reference/code/quaternions/points_quaternions.py (:11-81): points <-> pure quaternions and
 rotation of a cloud by a quaternion (q (x) p (x) q*, q normalised first).  The batch-size assert of the reference
 (:23, it tests len(batch) == 3) is not reproduced."""
-import torch
 import torch.nn.functional as F
 
 from .operations import QuaternionOperations

@@ -1,5 +1,5 @@
 """Which aten ops / kernels make up the non-conv time of one G step + two D steps (eager, B=32, 256^2)."""
-import os, sys, types
+import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "2dimageto3dmodel_b200")); sys.path.insert(0, ROOT)
 import torch
