@@ -19,7 +19,7 @@ def transform_vertices(vtx, gt_scale, gt_translation, gt_rot, gt_idx=None, datas
     if optimize_deltas:
         translation_delta, scale_delta = dataset_params(gt_idx, 'deltas')
     vtx = qrot(gt_rot, (gt_scale + scale_delta).unsqueeze(-1) * vtx) + (gt_translation + translation_delta).unsqueeze(1)
-    vtx = vtx * vtx.new_tensor([1.0, -1.0, -1.0])
+    vtx = torch.cat((vtx[..., :1], -vtx[..., 1:]), dim=-1)       # * (1, -1, -1) without a host constant (CUDA-graph safe)
     if optimize_z0:
         z0 = dataset_params(gt_idx, 'z0').unsqueeze(-1)
         z = vtx[:, :, 2:]
