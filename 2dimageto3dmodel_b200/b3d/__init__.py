@@ -27,6 +27,7 @@ def _load():
                        "There is no CPU fallback.")
     lib = ctypes.CDLL(LIB_PATH)
     lib.b3d_last_error.restype = ctypes.c_char_p
+    lib.b3d_last_variant.restype = ctypes.c_char_p
     lib.b3d_launch_count.restype = ctypes.c_uint64
     lib.b3d_pc_silhouette_workspace_bytes.restype = ctypes.c_size_t
     return lib
@@ -104,6 +105,11 @@ def check(rc):
         raise B3DError(f"libb3d error {rc}: {lib.b3d_last_error().decode()}")
 
 
+def last_variant():
+    """Kernel template instances launched by this thread's most recent convolution entry point (';'-joined)."""
+    return lib.b3d_last_variant().decode()
+
+
 def launch_count():
     return int(lib.b3d_launch_count())
 
@@ -152,7 +158,7 @@ def prof_enable():
     for name in [n for n in dir(lib) if n.startswith("b3d_")] + list(_TIMED):
         fn = getattr(lib, name)
         if name in _prof_saved or not hasattr(fn, "argtypes") or name in ("b3d_last_error", "b3d_launch_count",
-                                                                          "b3d_version"):
+                                                                          "b3d_version", "b3d_last_variant"):
             continue
         _prof_saved[name] = fn
 

@@ -8,7 +8,17 @@ import os
 
 import torch
 
-from . import B3DError, check, dev, lib, ptr, stream_ptr
+from . import B3DError, check, dev, last_variant, lib, ptr, stream_ptr
+
+VARIANT_LOG = None      # tests set this to a list: every kernel template instance the conv entry points launch is appended
+
+
+def _conv_call(fn, *args):
+    """One convolution entry point of libb3d; records which kernel instances it launched when VARIANT_LOG is a list."""
+    rc = fn(*args)
+    if VARIANT_LOG is not None and rc == 0:
+        VARIANT_LOG.extend(v for v in last_variant().split(";") if v)
+    return rc
 
 
 def _ints(v):
@@ -50,7 +60,7 @@ def conv2d_nhwc(x, weight, bias=None, pad_y=0, stride=1, leaky=1.0, wt=None, cin
         raise B3DError("conv2d: pad_out needs Cout % 4 == 0")
     if _thin(Cout, Cin, kh, kw, stride) and not cin_major:
         # 1-4 output channels: fp32 CUDA-core reduction kernel (csrc/thin_kernels.cu), not a 64-wide MMA tile
-        check(lib.b3d_conv2d_thin_fwd(ptr(x), ptr(wt), ptr(dev(bias, "bias") if bias is not None else None), optr, N, H, W,
+        check(_conv_call(lib.b3d_conv2d_thin_fwd, ptr(x), ptr(wt), ptr(dev(bias, "bias") if bias is not None else None), optr, N, H, W,
                                       Cin, Hout, Wout, Cout, kh, kw, pad_y, x_crop, OW, Cout, float(leaky), stream_ptr(x)))
         if pad_out:
             check(lib.b3d_wrap_x_inplace(ptr(out), N * Hout, Wout, Cout, pad_out, pad_mode, stream_ptr(x)))
@@ -65,12 +75,12 @@ def conv2d_nhwc(x, weight, bias=None, pad_y=0, stride=1, leaky=1.0, wt=None, cin
         use_flat = stride == 1 and not cin_major and os.environ["B3D_CONV_FLAT"] == "1"
     if use_flat:
         # halo-staged kernel (tc_conv2.cu); falls through to the per-tap kernel when the halo does not fit in smem
-        rc = lib.b3d_conv2d_flat_tf32(ptr(x), ptr(wt), ptr(b), optr, N, H, W, Cin, Hout, Wout, Cout, kh * kw,
+        rc = _conv_call(lib.b3d_conv2d_flat_tf32, ptr(x), ptr(wt), ptr(b), optr, N, H, W, Cin, Hout, Wout, Cout, kh * kw,
                                       _ints(dy), _ints(dx), Hout, OW, Cout, float(leaky), stream_ptr(x))
         if rc != 0 and b"does not fit" not in lib.b3d_last_error():
             check(rc)
     if not use_flat or rc != 0:
-        check(lib.b3d_conv2d_tf32(ptr(x), ptr(wt), ptr(b), optr, N, H, W, Cin, Hout, Wout, Cout, kh * kw, _ints(dy),
+        check(_conv_call(lib.b3d_conv2d_tf32, ptr(x), ptr(wt), ptr(b), optr, N, H, W, Cin, Hout, Wout, Cout, kh * kw, _ints(dy),
                                   _ints(dx), stride, stride, Hout, OW, Cout, 1, 1, 0, 0, float(leaky), int(cin_major),
                                   stream_ptr(x)))
     if pad_out:
@@ -105,7 +115,7 @@ def conv2d_dgrad_nhwc(dy_, weight, in_hw, pad_y=0, stride=1, x_crop=0):
         wt = weight.permute(2, 3, 1, 0).reshape(kh * kw, Cin, Cout).contiguous()        # [tap][Cin][Cout]
         dy = [pad_y - r for r in range(kh) for _ in range(kw)]
         dx = [-s - x_crop for _ in range(kh) for s in range(kw)]
-        check(lib.b3d_conv2d_tf32(ptr(g), ptr(wt), None, ptr(dxo), N, Hout, Wout, Cout, H, W, Cin, kh * kw, _ints(dy),
+        check(_conv_call(lib.b3d_conv2d_tf32, ptr(g), ptr(wt), None, ptr(dxo), N, Hout, Wout, Cout, H, W, Cin, kh * kw, _ints(dy),
                                   _ints(dx), 1, 1, H, W, Cin, 1, 1, 0, 0, 1.0, 0, st))
         return dxo
     if stride != 2 or x_crop:
@@ -115,7 +125,7 @@ def conv2d_dgrad_nhwc(dy_, weight, in_hw, pad_y=0, stride=1, x_crop=0):
             dxo[:, cy::2, cx::2] = 0
             continue
         wt = torch.stack([weight[:, :, r, s].t() for r, s in rs]).contiguous()      # [taps][Cin][Cout]
-        check(lib.b3d_conv2d_tf32(ptr(g), ptr(wt), None, ptr(dxo), N, Hout, Wout, Cout, Ha, Wa, Cin, len(rs),
+        check(_conv_call(lib.b3d_conv2d_tf32, ptr(g), ptr(wt), None, ptr(dxo), N, Hout, Wout, Cout, Ha, Wa, Cin, len(rs),
                                   _ints(dy), _ints(dx), 1, 1, H, W, Cin, 2, 2, cy, cx, 1.0, 0, st))
     return dxo
 
@@ -128,14 +138,14 @@ def conv2d_wgrad_nhwc(dy_, x, kh, kw, pad_y=0, stride=1, x_crop=0):
         g, x = dev(dy_, "grad_output"), dev(x, "input")
         N, Hout, Wout, _ = g.shape
         dw = torch.zeros(co_real, ci_real, kh, kw, device=g.device, dtype=torch.float32)
-        check(lib.b3d_conv2d_thin_wgrad(ptr(g), ptr(x), ptr(dw), N, x.shape[1], x.shape[2], ci_real, Hout, Wout, co_real, kh, kw,
+        check(_conv_call(lib.b3d_conv2d_thin_wgrad, ptr(g), ptr(x), ptr(dw), N, x.shape[1], x.shape[2], ci_real, Hout, Wout, co_real, kh, kw,
                                         pad_y, x_crop, stream_ptr(g)))
         return dw
     g, x = dev(_pad_last(dy_, 32), "grad_output"), dev(_pad_last(x, 32), "input")
     N, Hout, Wout, Cout = g.shape
     _, H, W, Cin = x.shape
     dw = torch.zeros(Cout, Cin, kh, kw, device=g.device, dtype=torch.float32)
-    check(lib.b3d_conv2d_wgrad_tf32(ptr(g), ptr(x), ptr(dw), N, H, W, Cin, Hout, Wout, Cout, kh, kw, pad_y, stride,
+    check(_conv_call(lib.b3d_conv2d_wgrad_tf32, ptr(g), ptr(x), ptr(dw), N, H, W, Cin, Hout, Wout, Cout, kh, kw, pad_y, stride,
                                     x_crop, stream_ptr(g)))
     return dw if (co_real, ci_real) == (Cout, Cin) else dw[:co_real, :ci_real]
 

@@ -11,6 +11,9 @@ namespace b3d {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// kernel-variant record of the calling thread's most recent convolution entry point (b3d_last_variant)
+void clear_variant();
+void add_variant(const char* fmt, ...);
 
 #define B3D_REQUIRE(cond, code, ...)      \
     do {                                  \

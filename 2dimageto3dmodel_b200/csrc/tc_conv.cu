@@ -519,6 +519,7 @@ int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, const WgradParam
     B3D_CUDA_OK(cudaFuncSetAttribute(wgrad_tf32_kernel<BN, STAGES, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOTAL));
     wgrad_tf32_kernel<BN, STAGES, T><<<grid, NTHREADS, TOTAL, st>>>(mdy, mx, p, dw);
     B3D_LAUNCH_OK();
+    b3d::add_variant("wgrad_tf32<%d,%d,%d>", BN, STAGES, T);
     return B3D_OK;
 }
 
@@ -531,6 +532,7 @@ int launch(const CUtensorMap& mx, const CUtensorMap& mw, const ConvParams& p, co
     dim3 grid(tiles, b3d::ceil_div(p.Cout, BN));
     conv_tf32_kernel<BN, STAGES, WMN, MINB><<<grid, NTHREADS, S::TOTAL, st>>>(mx, mw, p, bias, out);
     B3D_LAUNCH_OK();
+    b3d::add_variant("conv_tf32<%d,%d,%d,%d>", BN, STAGES, (int)WMN, MINB);
     return B3D_OK;
 }
 
@@ -546,6 +548,7 @@ int launch_persistent(const CUtensorMap& mx, const CUtensorMap& mw, const ConvPa
     const int grid = work < slots ? work : slots;
     conv_tf32_persistent_kernel<BN, STAGES, WMN, R><<<grid, PTHREADS, S::TOTAL, st>>>(mx, mw, p, bias, out, tiles, groups, work);
     B3D_LAUNCH_OK();
+    b3d::add_variant("conv_tf32_persistent<%d,%d,%d,%d>", BN, STAGES, (int)WMN, R);
     return B3D_OK;
 }
 
@@ -580,6 +583,7 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
     B3D_REQUIRE(sy >= 1 && sy <= 2 && sx >= 1 && sx <= 2, B3D_EINVAL, "b3d_conv2d_tf32: stride must be 1 or 2");
     B3D_CHECK_ALIGNED(x);
     B3D_CHECK_ALIGNED(wt);
+    b3d::clear_variant();
 
     static const int persist = getenv("B3D_CONV_PERSIST") ? atoi(getenv("B3D_CONV_PERSIST")) : 1;
     static const int wide = getenv("B3D_CONV_BN256") ? atoi(getenv("B3D_CONV_BN256")) : 1;
@@ -668,6 +672,7 @@ int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, int N, int
                 "b3d_conv2d_wgrad_tf32: Cin=%d and Cout=%d must be multiples of 32 (pad the channels with zeros)", Cin, Cout);
     B3D_CHECK_ALIGNED(dy);
     B3D_CHECK_ALIGNED(x);
+    b3d::clear_variant();
     WgradParams p{};
     p.N = N; p.Hout = Hout; p.Wout = Wout; p.Cout = Cout; p.Cin = Cin;
     p.BWk = pow2_floor(Wout < BK ? Wout : BK);

@@ -276,6 +276,8 @@ int b3d_conv2d_flat_tf32(const float* x, const float* wt, const float* bias, flo
         conv_flat_tf32_kernel<64><<<grid, NTHREADS, smem, st>>>(m_main, m_tail, m_w, p, bias, out, a_stage, log2c);
     }
     B3D_LAUNCH_OK();
+    b3d::clear_variant();
+    b3d::add_variant("conv_flat_tf32<%d>R%d", BN, R);
     return B3D_OK;
 }
 

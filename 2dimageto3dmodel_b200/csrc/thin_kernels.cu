@@ -273,6 +273,8 @@ int launch_fwd(const float* x, const float* wt, const float* bias, float* out, c
     if (blocks > 148 * 16) blocks = 148 * 16;
     conv_thin_fwd_kernel<COUT, VEC><<<(int)blocks, NT, 0, st>>>(x, wt, bias, out, g);
     B3D_LAUNCH_OK();
+    b3d::clear_variant();
+    b3d::add_variant("conv_thin_fwd<%d,%d>", COUT, VEC);
     return B3D_OK;
 }
 
@@ -292,6 +294,8 @@ int launch_wgrad(const float* gy, const float* x, float* dw, const ThinGeom& g, 
         conv_thin_wgrad_kernel<COUT, VEC><<<bpc * chunks, NT, smem, st>>>(gy, x, dw, g);
     }
     B3D_LAUNCH_OK();
+    b3d::clear_variant();
+    b3d::add_variant(COUT * VEC <= 6 && !plain ? "conv_thin_wgrad_win<%d,%d>" : "conv_thin_wgrad<%d,%d>", COUT, VEC);
     return B3D_OK;
 }
 

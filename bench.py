@@ -1,17 +1,20 @@
 #!/usr/bin/env python
-"""bench.py — render+loss images/sec on B200 (BASELINE.json metric), one JSON line on stdout.
+"""bench.py — render+loss(+GAN) images/sec on B200 (BASELINE.json metric), one JSON line on stdout.
 
-Workload = BASELINE.json configs[1]: "CUB 256x256, 8000-pt cloud, full render+loss, batch=16 on 1xB200"
-(SURVEY.md §8d cfg2), per step and per GPU, forward + backward:
-  (i)  point path : EffectiveLossFunction(V=128)(points[16,8000,3], q, scale) -> sum-MSE vs mask[16,128,128]
-  (ii) mesh path  : mesh_map[16,3,32,32] -> template vertices (482 v / 960 f) -> pose -> DIB-R render 256x256
-                    with a 128x128 texture -> RGBA MSE vs X_real[16,4,256,256] + 5e-4 * loss_flat (+ mIoU)
-Synthetic, seeded inputs (no dataset exists offline).  No network / optimiser on this config.
+Workloads:
+  cfg3 (default; BASELINE.json configs[2], the configuration the metric is quoted on): per step THREE training
+       iterations (G, D, D — main.py:691's 1 : d_steps_per_g alternation) at batch 32 per GPU, each iteration =
+       cfg2's render+loss forward/backward on a FRESH batch + one conv-GAN step at 256^2 (nd = 2, class-conditional,
+       SyncBN generator, hinge loss, Adam(0, 0.9), EMA generator).
+  cfg2 (configs[1]): render+loss only, batch 16: (i) EffectiveLossFunction(V=128)(points[16,8000,3], q, scale) ->
+       sum-MSE vs mask; (ii) mesh_map -> template vertices (482 v / 960 f) -> pose -> DIB-R render 256x256 with a
+       128x128 texture -> RGBA MSE + 5e-4 * loss_flat (+ mIoU).
+Synthetic, seeded inputs (no dataset exists offline).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
-N>1 is launched by torchrun (one rank per GPU, NCCL); the batch is sharded per rank with no data-path
-collective (weak scaling: 16 images per GPU).  `--impl reference` times the oracle port (the reference's
-algorithm on the CPU, torch, all host threads) on a bounded sample of the same workload.
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg2|cfg3]
+N>1 is launched by torchrun (one rank per GPU, NCCL); every rank owns its own shard of the global batch (weak scaling).
+cfg3's collectives: SyncBN statistics of the generator and the gradient all-reduce of G / D (captured in the step's CUDA
+graph).  `--impl reference` times the reference's algorithm on the host cores (oracle/, torch CPU) on the same config.
 """
 import argparse
 import json
@@ -112,13 +115,14 @@ class CudaWorkload:
             torch.manual_seed(4321)                      # identical replicas on every rank
             self.gan = GANTrainer(gan_args(), mesh_template=self.tpl, device=device, capturable=True)
 
-    def step(self, d):
-        """One training iteration.  cfg2: render+loss fwd+bwd.  cfg3: three iterations (G, D, D — the reference's
-        1 : d_steps_per_g alternation, main.py:691), each = render+loss fwd+bwd + one GAN step with its optimiser."""
+    def step(self, batches):
+        """One step over `batches` (one input dict per training iteration).  cfg2: render+loss fwd+bwd.  cfg3: three
+        iterations (G, D, D — the reference's 1 : d_steps_per_g alternation, main.py:691), each on its own batch =
+        render+loss fwd+bwd + one GAN step with its optimiser."""
         if self.gan is None:
-            return self.render_step(d)
+            return self.render_step(batches[0])
         loss = None
-        for it in range(3):
+        for it, d in enumerate(batches):
             rl, _ = self.render_step(d)
             if it == 0:
                 gl = self.gan.g_step(d["X_alpha"], d["C"])
@@ -182,6 +186,67 @@ class ClockSampler:
                 "power_w_max": max((f(r[2]) or 0) for r in rows), "samples": len(rows), "reasons": reasons}
 
 
+def measure_tf32_peak(dev, seconds=2.0):
+    """Dense tf32 tensor-core peak of THIS GPU, measured the way MEASURED_PEAKS.json measures bf16: torch.matmul (cuBLAS)
+    8192^3 with allow_tf32, fp32 storage.  burst = best of 10 single calls, sustained = back to back for `seconds`."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a, b = torch.randn(n, n, device=dev), torch.randn(n, n, device=dev)
+        c = torch.empty(n, n, device=dev)
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(a, b, out=c); e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(10, int(seconds * 1e3 / best))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize()
+        fl = 2.0 * n ** 3
+        return {"burst": round(fl / (best * 1e-3) / 1e12, 1), "sustained": round(fl * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12, 1),
+                "how": f"measured live: torch.matmul (cuBLAS) fp32 storage, allow_tf32, 8192^3; burst best of 10, sustained {reps} "
+                       f"back-to-back calls (~{seconds:.0f} s)"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def chamfer_report(dev, B=32, N=8000):
+    """Nearest-neighbour (chamfer) kernel on 8000 x 8000 point sets (north_star): CUDA events on the launching stream."""
+    from b3d.chamfer import nearest
+
+    def chamfer_nn(a, b):
+        nearest(a, b)
+        nearest(b, a)
+    g = torch.Generator().manual_seed(5)
+    a = (torch.rand(B, N, 3, generator=g) - 0.5).to(dev)
+    b = (torch.rand(B, N, 3, generator=g) - 0.5).to(dev)
+    for _ in range(3):
+        chamfer_nn(a, b)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        chamfer_nn(a, b)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    fl = 8.0 * N * N * B * 2                      # both directions: (3 sub, 3 fma-equivalents, compare) ~ 8 flop per pair
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12     # 148 SMs x 128 FMA lanes x 2 flop x 1.965 GHz
+    return {"kernel": "chamfer_nn_kernel (both directions)", "sets": f"{B} x ({N} vs {N})", "ms_per_launch_pair": round(ms, 4),
+            "achieved": round(fl / (ms * 1e-3) / 1e12, 2), "peak": round(fp32_peak, 1), "unit": "TFLOP/s (fp32 CUDA cores)",
+            "frac": round(fl / (ms * 1e-3) / 1e12 / fp32_peak, 4), "bound": "fp32 issue (8NM flop over 20(N+M) bytes)"}
+
+
 def algorithmic_bytes(B):
     """SURVEY.md §8(d) per-sample figures x the samples one launch processes (stated in DESIGN.md)."""
     pc_fwd = 8 * V**3 + 4 * V**2 + 12 * N_PTS
@@ -227,11 +292,14 @@ def run_cuda(args):
     stage("workload built")
     B = cfg["batch"]
     iters_per_step = 3 if cfg["gan"] else 1
-    host = host_inputs(B, seed=1234 + rank, pin=True)       # each rank owns its shard of the global batch
-    if cfg["gan"]:
-        host.update(gan_host_inputs(B, seed=1234 + rank, pin=True))
-    h2d = sum(t.numel() * t.element_size() for t in host.values())
-    resident = {k: v.to(dev) for k, v in host.items()}
+    host = []                                               # one pinned host batch per training iteration of the step;
+    for it in range(iters_per_step):                        # each rank owns its shard of the global batch
+        hb = host_inputs(B, seed=1234 + rank + 1000 * it, pin=True)
+        if cfg["gan"]:
+            hb.update(gan_host_inputs(B, seed=1234 + rank + 1000 * it, pin=True))
+        host.append(hb)
+    h2d = sum(t.numel() * t.element_size() for hb in host for t in hb.values())
+    resident = [{k: v.to(dev) for k, v in hb.items()} for hb in host]
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)  # > 126 MB L2
 
     def sync_all():
@@ -259,8 +327,8 @@ def run_cuda(args):
             total = float(t)
         return total
 
-    def fresh(d):
-        return {k: v.detach() for k, v in d.items()}
+    def fresh(batches):
+        return [{k: v.detach() for k, v in d.items()} for d in batches]
 
     host_loss = torch.empty(1).pin_memory()
     graph = None
@@ -289,16 +357,19 @@ def run_cuda(args):
 
     def step_e2e():
         if graph is not None:
-            for k, v in host.items():                        # pinned host -> the graph's static inputs
-                resident[k].copy_(v, non_blocking=True)
+            for hb, rb in zip(host, resident):               # pinned host -> the graph's static inputs, every iteration's batch
+                for k, v in hb.items():
+                    rb[k].copy_(v, non_blocking=True)
             graph.replay()
             loss = g_loss
         else:
-            loss, _ = wl.step({k: v.to(dev, non_blocking=True) for k, v in host.items()})
+            loss, _ = wl.step([{k: v.to(dev, non_blocking=True) for k, v in hb.items()} for hb in host])
         host_loss.copy_(loss.reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()            # the user reads the loss every step
         return loss
 
+    tf32 = measure_tf32_peak(dev) if cfg["gan"] and rank == 0 else None
+    stage("tf32 peak measured" if tf32 else "timing setup")
     clocks = ClockSampler(local) if rank == 0 else None
     time.sleep(0.3) if clocks else None
     n0 = b3d.launch_count()
@@ -355,13 +426,15 @@ def run_cuda(args):
         # counting only what is executed: G-step = fwd G+D, dgrad+wgrad G, dgrad D (the reference's discarded D wgrad is
         # skipped) = 3G + 2D; D-step = G fwd + D fwd/dgrad/wgrad on 2B images = G + 6D — over the time spent inside the
         # tcgen05 conv entry points
-        gf_img = (3 * 17.09 + 2 * 14.76) + 2 * (17.09 + 6 * 14.76)
+        # ... minus the input gradient of the discriminators' first layers in the D-step (their input needs no gradient, so
+        # it is not executed): d1.conv1 1.678 + d2.conv1 0.036 GF per image of the 2B batch
+        gf_img = (3 * 17.09 + 2 * 14.76) + 2 * (17.09 + 6 * 14.76 - 2 * (1.678 + 0.036))
         conv_ms = sum(v for k, v in prof_tot.items() if k.startswith("b3d_conv2d"))
-        tpeak = peaks.get("bf16_tflops_sustained", 1415.7) / 2.0      # tf32 = half the bf16 rate
+        tpeak, tpeak_src = tf32["sustained"], tf32["how"]
         tensor = {"kernel": "all conv entry points: conv_tf32_persistent + wgrad_tf32 (tcgen05 kind::tf32) + thin-head CUDA-core kernels", "bound": "tensor",
                   "achieved": round(gf_img * B / (conv_ms * 1e-3) / 1e3, 1), "peak": round(tpeak, 1), "unit": "TFLOP/s",
                   "frac": round(gf_img * B / (conv_ms * 1e-3) / 1e3 / tpeak, 4), "traffic": None,
-                  "peak_source": "measured bf16 sustained / 2 (tf32 dense = half the bf16 rate)",
+                  "peak_source": tpeak_src, "peak_burst": tf32["burst"],
                   "conv_ms_per_step": round(conv_ms, 3), "gflop_per_step": round(gf_img * B, 1)}
     traffic = None
     try:
@@ -379,7 +452,10 @@ def run_cuda(args):
         "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": world * B,
                    "iterations_per_step": iters_per_step, "points": N_PTS, "voxels": V,
                    "image": H, "faces": 960, "texture": TEX, "l2": "flushed between timed iterations (256 MB write)",
-                   "parallelism": f"dp{world} (batch shards, no data-path collective)", "semantics": "R",
+                   "parallelism": (f"dp{world}: batch shards; render/loss without collectives, GAN with SyncBN statistic "
+                                   "all-reduces + gradient all-reduce (NCCL, captured in the step graph)") if cfg["gan"]
+                   else f"dp{world} (batch shards, no data-path collective)", "semantics": "R",
+                   "fresh_batch_per_iteration": True,
                    "cuda_graph": graph is not None},
         "e2e": {"value": round(e2e_v, 2), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": round(e2e_ms / args.steps, 4)},
@@ -390,6 +466,10 @@ def run_cuda(args):
                      "algorithmic_bytes_per_launch": alg[top], "ms_per_launch": round(cand[top], 4)},
         "kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(prof_tot.items(), key=lambda kv: -kv[1])},
     }
+    try:
+        out["chamfer"] = chamfer_report(dev)
+    except Exception as e:                                   # reported, never fatal for the headline
+        out["chamfer"] = {"error": str(e)[:200]}
     if tensor is not None:
         # cfg3: the convolutions dominate the step -> the tensor-core roofline is the primary one; the HBM-class kernel
         # roofline (point-cloud backward) moves to roofline_hbm
@@ -404,11 +484,28 @@ def run_cuda(args):
 
 # --------------------------------------------------------------------------------------------- CPU arm
 def cpu_threads():
-    """torch's CPU kernels stop scaling (and regress) far below the 100+ hardware threads of the GPU hosts on these
-    small per-op tensors: use at most 32 and report that number as `cores`."""
-    n = min(os.cpu_count() or 1, 32)
-    torch.set_num_threads(n)
-    return n
+    """All the host threads torch can USE: its CPU kernels stop scaling (and regress) below the 100+ hardware threads of
+    the GPU hosts, so a one-second probe (a ResBlock-sized fp32 convolution, forward + backward) picks the fastest of
+    {32, 64, all} and that number is reported as `cores`."""
+    ncpu = os.cpu_count() or 1
+    cands = sorted({min(ncpu, 32), min(ncpu, 64), ncpu})
+    if len(cands) == 1:
+        torch.set_num_threads(cands[0])
+        return cands[0]
+    x = torch.randn(8, 64, 128, 66, requires_grad=True)
+    w = torch.randn(64, 64, 3, 3, requires_grad=True)
+    best, best_t = cands[0], 1e9
+    for n in cands:
+        torch.set_num_threads(n)
+        torch.nn.functional.conv2d(x, w, padding=(1, 0)).sum().backward()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            torch.nn.functional.conv2d(x, w, padding=(1, 0)).sum().backward()
+        t = time.perf_counter() - t0
+        if t < best_t:
+            best, best_t = n, t
+    torch.set_num_threads(best)
+    return best
 
 
 class OracleWorkload:
@@ -421,14 +518,9 @@ class OracleWorkload:
         self.T = M.TemplateData(M.load_obj(path), path)
         self.gan = None
         if gan:
-            from models import gan as gan_modules           # only to CONSTRUCT the initial state dicts on the CPU
-            from oracle import gan as OG
+            from oracle import gan as OG                    # the CPU arms never import the product package (libb3d.so)
             self.OG, self.args = OG, gan_args()
-            torch.manual_seed(4321)
-            G = gan_modules.Generator(self.args, 64, symmetric=True, mesh_head=True)
-            D = gan_modules.MultiScaleDiscriminator(self.args, 4)
-            self.sg = {k: v.clone() for k, v in G.state_dict().items()}
-            self.sd = {k: v.clone() for k, v in D.state_dict().items()}
+            self.sg, self.sd = OG.init_state(self.args, seed=4321)
             for sdict in (self.sg, self.sd):
                 for k in OG.trainable(sdict):
                     sdict[k].requires_grad_(True)
@@ -453,12 +545,12 @@ class OracleWorkload:
         loss.backward()
         return loss.detach()
 
-    def step(self, d):
+    def step(self, batches):
         if self.gan is None:
-            return self.render_step(d)
+            return self.render_step(batches[0])
         OG, M, T = self.OG, self.M, self.T
         total = 0.0
-        for it in range(3):
+        for it, d in enumerate(batches):
             total = total + self.render_step(d)
             B = d["C"].shape[0]
             z = torch.randn(B, 64)
@@ -479,10 +571,13 @@ class OracleWorkload:
 
 
 def cpu_inputs(cfg, sample_b):
-    d = host_inputs(sample_b, seed=1234, pin=False)
-    if cfg["gan"]:
-        d.update(gan_host_inputs(sample_b, seed=1234, pin=False))
-    return d
+    out = []
+    for it in range(3 if cfg["gan"] else 1):
+        d = host_inputs(sample_b, seed=1234 + 1000 * it, pin=False)
+        if cfg["gan"]:
+            d.update(gan_host_inputs(sample_b, seed=1234 + 1000 * it, pin=False))
+        out.append(d)
+    return out
 
 
 def cpu_baseline(cfg, budget_s, sample_b=2):
@@ -505,31 +600,37 @@ def cpu_baseline(cfg, budget_s, sample_b=2):
 
 
 def run_reference(args):
+    """The reference's own CPU implementation of the path (its algorithm restated in torch under oracle/ — the reference
+    tree itself cannot be installed or travel) on THIS arm's config: the same batch per step, the same
+    three iterations per step; bounded to one timed step (a step is ~100 s of CPU work at batch 32)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cfg = WORKLOADS[args.workload]
     cores = cpu_threads()
-    sample_b, iters = 2, (3 if cfg["gan"] else 1)
+    B, iters = cfg["batch"], (3 if cfg["gan"] else 1)
+    if os.environ.get("B3D_REF_BATCH"):                      # development aid
+        B = int(os.environ["B3D_REF_BATCH"])
     wl = OracleWorkload(gan=cfg["gan"])
-    d = cpu_inputs(cfg, sample_b)
-    warm = min(args.warmup, 1)
+    d = cpu_inputs(cfg, B)
+    warm = 0 if cfg["gan"] else min(args.warmup, 1)
     for _ in range(warm):
         wl.step(d)
-    steps = max(1, min(args.steps, 3 if cfg["gan"] else 6))
+    steps = 1 if cfg["gan"] else max(1, min(args.steps, 3))
     t0 = time.perf_counter()
     for _ in range(steps):
         wl.step(d)
     el = time.perf_counter() - t0
-    v = sample_b * iters * steps / el
-    sample = (f"{steps} steps ({iters} iteration(s) each) of batch {sample_b} (bounded sample of the batch-{cfg['batch']} "
-              f"workload) through oracle/ = the reference's algorithm in torch on the CPU, {cores} threads")
+    v = B * iters * steps / el
+    sample = (f"{steps} step(s) ({iters} iteration(s) each) of batch {B} (the workload's own batch) through oracle/ = the "
+              f"reference's algorithm in torch on the CPU, {cores} threads")
     print(json.dumps({
         "impl": "reference", "metric": cfg["metric"], "value": round(v, 4), "unit": "images/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": round(el / steps * 1e3, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg["name"], "batch_per_step": sample_b, "iterations_per_step": iters, "points": N_PTS,
-                   "voxels": V, "image": H, "faces": 960, "texture": TEX, "semantics": "R"},
+        "config": {"workload": cfg["name"], "batch_per_gpu": B, "global_batch": B, "iterations_per_step": iters,
+                   "points": N_PTS, "voxels": V, "image": H, "faces": 960, "texture": TEX, "semantics": "R",
+                   "fresh_batch_per_iteration": True},
         "cpu_baseline": {"value": round(v, 4), "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(v, 4), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))

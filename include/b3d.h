@@ -44,6 +44,10 @@ extern "C" {
 
 B3D_API const char* b3d_last_error(void);
 B3D_API int b3d_version(void);
+/* ';'-joined names of the kernel template instances launched by the calling thread's most recent convolution
+ * entry point (b3d_conv2d_tf32 / _flat_tf32 / _wgrad_tf32 / _thin_*), e.g. "conv_tf32_persistent<256,4,0,1>":
+ * the parity tests assert WHICH variant they exercised, so dispatch drift cannot silently un-test a kernel. */
+B3D_API const char* b3d_last_variant(void);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
 B3D_API uint64_t b3d_launch_count(void);
 

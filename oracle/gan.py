@@ -180,3 +180,77 @@ def d_loss(sg, sd_, args, z, c, alpha, tex_real, mesh_real, training=True):
 def trainable(sd):
     """names of the tensors a module would expose as parameters (everything float except buffers)."""
     return [k for k, v in sd.items() if torch.is_floating_point(v) and not k.endswith(("_u", "_v", "running_mean", "running_var"))]
+
+
+def init_state(args, seed=0):
+    """Random initial state dicts (generator, discriminators) with the reference's key names and shapes, built from
+    plain tensors — so that the CPU arms of bench.py never import the product package (models.gan loads libb3d.so).
+    Shapes follow models/gan.py:23-121,123-233,288-312,314-426 of the reference; values: N(0, 1/fan_in) weights, zero
+    biases, unit-norm spectral-norm vectors, fresh batch-norm buffers (enough for a timing baseline and for parity
+    tests that load explicit weights afterwards)."""
+    g = torch.Generator().manual_seed(seed)
+    R, nd = args.texture_resolution, args.num_discriminators
+
+    def w(*shape):
+        fan_in = 1
+        for s in shape[1:]:
+            fan_in *= s
+        return torch.randn(*shape, generator=g) / math.sqrt(fan_in)
+
+    def sn(sd, name, co, ci, k, bias):
+        sd[name + ".weight_orig"] = w(co, ci, k, k)
+        if bias:
+            sd[name + ".bias"] = torch.zeros(co)
+        sd[name + ".weight_u"] = F.normalize(torch.randn(co, generator=g), dim=0)
+        sd[name + ".weight_v"] = F.normalize(torch.randn(ci * k * k, generator=g), dim=0)
+
+    def cbn_(sd, name, ch, emb):
+        sd[name + ".norm.running_mean"], sd[name + ".norm.running_var"] = torch.zeros(ch), torch.ones(ch)
+        sd[name + ".norm.num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+        for fc in ("fc_gamma", "fc_beta"):
+            sd[f"{name}.{fc}.weight"], sd[f"{name}.{fc}.bias"] = w(ch, emb), torch.zeros(ch)
+
+    def block(sd, name, ci, co, emb):
+        mid = min(ci, co)
+        sn(sd, name + ".conv1", mid, ci, 3, False)
+        sn(sd, name + ".conv2", co, mid, 3, False)
+        cbn_(sd, name + ".norm1", mid, emb)
+        cbn_(sd, name + ".norm2", co, emb)
+        if ci != co:
+            sn(sd, name + ".shortcut", co, ci, 1, False)
+
+    sg, emb = {}, 128
+    sg["emb_class.weight"] = torch.randn(args.n_classes[0], 64, generator=g)
+    sg["fc.weight"], sg["fc.bias"] = w(16384, emb), torch.zeros(16384)
+    block(sg, "blk1", 512, 512, emb)
+    block(sg, "blk2", 512, 256, emb)
+    for name, need in (("blk3a", 256), ("blk3b", 512), ("blk3c", 1024)):
+        if R >= need:
+            block(sg, name, 256, 256, emb)
+    block(sg, "blk4", 256, 128, emb)
+    block(sg, "blk5", 128, 128, emb)
+    block(sg, "blk6", 128, 64, emb)
+    sg["conv_final.weight"], sg["conv_final.bias"] = w(3, 64, 5, 5), torch.zeros(3)
+    block(sg, "blk3_mesh", 256, 64, emb)
+    sg["conv_mesh.weight"], sg["conv_mesh.bias"] = w(3, 64, 5, 5) * 0.02, torch.zeros(3)
+
+    sd = {}
+
+    def texd(pre, downsample):
+        stride_first = (downsample == 1 and R >= 512) or R >= 1024
+        sn(sd, pre + "conv1", 64, 8, 4 if stride_first else 5, True)
+        sn(sd, pre + "conv2", 128, 64, 4, True)
+        sn(sd, pre + "conv3", 256, 128, 4, True)
+        sn(sd, pre + "conv4", 512, 256, 4, True)
+        sn(sd, pre + "conv5", 1, 512, 5, True)
+        sd[pre + "projector.weight"] = torch.randn(args.n_classes[0], 512, generator=g)
+
+    texd("d1.", 1)
+    sn(sd, "d2.conv1", 64, 11, 5, True)
+    sn(sd, "d2.conv2", 128, 64, 4, True)
+    sn(sd, "d2.conv3", 256, 128, 4, True)
+    sn(sd, "d2.conv4", 1, 256, 5, True)
+    sd["d2.projector.weight"] = torch.randn(args.n_classes[0], 256, generator=g)
+    if nd == 3:
+        texd("d3.", 4)
+    return sg, sd

@@ -19,23 +19,26 @@ from models import gan as ref_gan                           # noqa: E402  (refer
 from utils.losses import GANLoss                            # noqa: E402  (reference)
 
 
-def main():
+def make(fname, res, nd, B, probe):
+    """One generator step + one discriminator step of the reference modules -> tests/golden/<fname>.
+    probe: spatial stride of the stored activation probes (full tensors for the small B=2 golden)."""
     torch.set_num_threads(8)
-    args = GC.make_args(256, 2)
+    args = GC.make_args(res, nd)
     G, D = GC.build(ref_gan, args)
     G.train(); D.train()
     crit = GANLoss('hinge', tensor=torch.FloatTensor)
-    z, c, alpha, tex, mesh = GC.inputs(args)
-    out = {}
+    z, c, alpha, tex, mesh = GC.inputs(args, B=B)
+    out = {"res": np.int64(res), "nd": np.int64(nd), "B": np.int64(B), "probe": np.int64(probe)}
     # ---- generator step
     loss, pred_tex, pred_mesh, dout, mask = GC.g_step(G, D, crit, z, c, alpha)
     loss.mean().backward()
     out["g_loss"] = loss.detach().numpy()
     out["tex_probe"] = pred_tex.detach()[:, :, ::16, ::16].numpy()
     out["tex_sum"] = np.float64(pred_tex.detach().double().sum())
-    out["mesh"] = pred_mesh.detach().numpy()
-    out["d_out0"], out["d_out1"] = dout[0].detach().numpy(), dout[1].detach().numpy()
-    out["mask0"], out["mask1"] = mask[0].numpy(), mask[1].numpy()
+    out["mesh"] = pred_mesh.detach()[:, :, ::probe, ::probe].numpy()
+    for i in range(nd):
+        out[f"d_out{i}"] = dout[i].detach()[:, :, ::probe, ::probe].numpy()
+        out[f"mask{i}"] = mask[i][:, :, ::probe, ::probe].numpy()
     names = [n for n, p in G.named_parameters() if p.grad is not None]
     out["g_grad_names"] = np.array(names)
     out["g_grad_norms"] = np.array([float(dict(G.named_parameters())[n].grad.norm()) for n in names])
@@ -47,14 +50,42 @@ def main():
     lf, lr, dout = GC.d_step(G, D, crit, z, c, alpha, tex, mesh)
     (lf.mean() + lr.mean()).backward()
     out["d_loss_fake"], out["d_loss_real"] = lf.detach().numpy(), lr.detach().numpy()
-    out["dd_out0"] = dout[0].detach().numpy()
+    out["dd_out0"] = dout[0].detach()[:, :, ::probe, ::probe].numpy()
     names = [n for n, p in D.named_parameters() if p.grad is not None]
     out["d_grad_names"] = np.array(names)
     out["d_grad_norms"] = np.array([float(dict(D.named_parameters())[n].grad.norm()) for n in names])
-    path = os.path.join(HERE, "gan_reference.npz")
+    path = os.path.join(HERE, fname)
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes; g_loss", out["g_loss"], "d losses", out["d_loss_fake"], out["d_loss_real"])
 
 
+def checkpoint_kat():
+    """Known-answer test from the SHIPPED checkpoint: the reference Generator, eval mode, running-average
+    weights of gan_weights/pretrained_weights_cub/checkpoint_latest.pth -> probes.  The 52 MB checkpoint is not
+    committed; __graft_entry__.build() stages a copy under tests/golden/_ckpt/ (git-ignored) when /root/reference exists."""
+    ck = "/root/reference/code/gan_weights/pretrained_weights_cub/checkpoint_latest.pth"
+    args = GC.make_args(512, 3)
+    G = ref_gan.Generator(args, 64, symmetric=True, mesh_head=True)
+    G.load_state_dict(torch.load(ck, map_location="cpu")["generator_running_avg"], strict=True)
+    G.eval()
+    torch.manual_seed(1234)
+    z, c = torch.randn(2, 64), torch.tensor([[3], [77]])
+    with torch.no_grad():
+        tex, mesh = G(z, c)
+    out = {"z": z.numpy(), "c": c.numpy(), "tex_probe": tex[:, :, ::16, ::16].numpy(), "tex_px": tex[0, :, 100, 200].numpy(),
+           "mesh": mesh.numpy(), "tex_sum": np.float64(tex.double().sum())}
+    path = os.path.join(HERE, "gan_checkpoint_kat.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes; tex[0,:,100,200]", out["tex_px"], "sum", out["tex_sum"])
+
+
 if __name__ == "__main__":
-    main()
+    which = sys.argv[1:] or ["b2", "b32", "r512", "kat"]
+    if "b2" in which:
+        make("gan_reference.npz", 256, 2, 2, 1)            # the small golden (full tensors)
+    if "b32" in which:
+        make("gan_reference_b32.npz", 256, 2, 32, 4)       # cfg3's batch: reaches the kernels bench.py dispatches
+    if "r512" in which:
+        make("gan_reference_r512.npz", 512, 3, 2, 1)       # cfg5's architecture (512^2, three discriminators)
+    if "kat" in which:
+        checkpoint_kat()
