@@ -81,7 +81,7 @@ def conv2d_nhwc(x, weight, bias=None, pad_y=0, stride=1, leaky=1.0, wt=None, cin
             check(rc)
     if not use_flat or rc != 0:
         check(_conv_call(lib.b3d_conv2d_tf32, ptr(x), ptr(wt), ptr(b), optr, N, H, W, Cin, Hout, Wout, Cout, kh * kw, _ints(dy),
-                                  _ints(dx), stride, stride, Hout, OW, Cout, 1, 1, 0, 0, float(leaky), int(cin_major),
+                                  _ints(dx), stride, stride, Hout, OW, Cout, 1, 1, 0, 0, float(leaky), int(cin_major), None, 0,
                                   stream_ptr(x)))
     if pad_out:
         check(lib.b3d_wrap_x_inplace(ptr(out), N * Hout, Wout, Cout, pad_out, pad_mode, stream_ptr(x)))
@@ -116,7 +116,7 @@ def conv2d_dgrad_nhwc(dy_, weight, in_hw, pad_y=0, stride=1, x_crop=0):
         dy = [pad_y - r for r in range(kh) for _ in range(kw)]
         dx = [-s - x_crop for _ in range(kh) for s in range(kw)]
         check(_conv_call(lib.b3d_conv2d_tf32, ptr(g), ptr(wt), None, ptr(dxo), N, Hout, Wout, Cout, H, W, Cin, kh * kw, _ints(dy),
-                                  _ints(dx), 1, 1, H, W, Cin, 1, 1, 0, 0, 1.0, 0, st))
+                                  _ints(dx), 1, 1, H, W, Cin, 1, 1, 0, 0, 1.0, 0, None, 0, st))
         return dxo
     if stride != 2 or x_crop:
         raise B3DError("conv2d_dgrad: stride must be 1 or 2 (x_crop: stride 1 only)")
@@ -126,7 +126,7 @@ def conv2d_dgrad_nhwc(dy_, weight, in_hw, pad_y=0, stride=1, x_crop=0):
             continue
         wt = torch.stack([weight[:, :, r, s].t() for r, s in rs]).contiguous()      # [taps][Cin][Cout]
         check(_conv_call(lib.b3d_conv2d_tf32, ptr(g), ptr(wt), None, ptr(dxo), N, Hout, Wout, Cout, Ha, Wa, Cin, len(rs),
-                                  _ints(dy), _ints(dx), 1, 1, H, W, Cin, 2, 2, cy, cx, 1.0, 0, st))
+                                  _ints(dy), _ints(dx), 1, 1, H, W, Cin, 2, 2, cy, cx, 1.0, 0, None, 0, st))
     return dxo
 
 
@@ -139,14 +139,14 @@ def conv2d_wgrad_nhwc(dy_, x, kh, kw, pad_y=0, stride=1, x_crop=0):
         N, Hout, Wout, _ = g.shape
         dw = torch.zeros(co_real, ci_real, kh, kw, device=g.device, dtype=torch.float32)
         check(_conv_call(lib.b3d_conv2d_thin_wgrad, ptr(g), ptr(x), ptr(dw), N, x.shape[1], x.shape[2], ci_real, Hout, Wout, co_real, kh, kw,
-                                        pad_y, x_crop, stream_ptr(g)))
+                                        pad_y, x_crop, 0, stream_ptr(g)))
         return dw
     g, x = dev(_pad_last(dy_, 32), "grad_output"), dev(_pad_last(x, 32), "input")
     N, Hout, Wout, Cout = g.shape
     _, H, W, Cin = x.shape
     dw = torch.zeros(Cout, Cin, kh, kw, device=g.device, dtype=torch.float32)
     check(_conv_call(lib.b3d_conv2d_wgrad_tf32, ptr(g), ptr(x), ptr(dw), N, H, W, Cin, Hout, Wout, Cout, kh, kw, pad_y, stride,
-                                    x_crop, stream_ptr(g)))
+                                    x_crop, 0, stream_ptr(g)))
     return dw if (co_real, ci_real) == (Cout, Cin) else dw[:co_real, :ci_real]
 
 
@@ -256,4 +256,136 @@ def conv2d(x_nchw, weight, bias=None, pad_y=0, stride=1, leaky=1.0, pad_out=0, p
         if cpad:
             weight = torch.nn.functional.pad(weight, (0, 0, 0, 0, 0, cpad))
     y = _Conv2dNHWC.apply(x, weight, bias, int(pad_y), int(stride), float(leaky), int(pad_out), int(pad_mode), int(x_crop))
+    return y.permute(0, 3, 1, 2)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Banked convolution: the weights arrive from b3d.bank.WeightBank already normalised and laid out for the kernels
+# (F [T'][Cout][Cin'] for fprop, D [T'][Cin'][Cout'] for the input gradient); the weight gradient is accumulated
+# straight into the bank's F-layout gradient sink.  No per-call permute / contiguous / zeros.
+# ------------------------------------------------------------------------------------------------------------------
+class _ConvBanked(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, wf, bias, lw, pad_y, stride, leaky, pad_out, pad_mode, x_crop):
+        x = dev(x.detach(), "x")
+        N, H, W, Cx = x.shape
+        if Cx != lw.Cinp:
+            if lw.fold or Cx > lw.Cinp:
+                raise B3DError(f"banked conv: input has {Cx} channels, the layer expects {lw.Cinp}")
+            x = _pad_last(x, 32)                                      # thin un-folded inputs (512^2 stem): zero-pad K
+        kh, kw = (1, lw.kw) if lw.fold else (lw.kh, lw.kw)
+        if lw.fold:
+            pad_y = 0
+        Cout, Cin = lw.Cout, lw.Cinp
+        wt = dev(wf.detach(), "weight")
+        b = dev(bias.detach(), "bias") if bias is not None else None
+        Hout = (H + 2 * pad_y - kh) // stride + 1
+        if x_crop and stride != 1:
+            raise B3DError("conv2d: x_crop needs stride 1")
+        Wout = (W - 2 * x_crop - kw) // stride + 1
+        OW = Wout + 2 * pad_out
+        if pad_out and Cout % 4:
+            raise B3DError("conv2d: pad_out needs Cout % 4 == 0")
+        out = torch.empty(N, Hout, OW, Cout, device=x.device, dtype=torch.float32)
+        optr = ctypes.c_void_p(out.data_ptr() + 4 * pad_out * Cout)
+        st = stream_ptr(x)
+        thin = _thin(Cout, Cin, kh, kw, stride)
+        if thin:
+            check(_conv_call(lib.b3d_conv2d_thin_fwd, ptr(x), ptr(wt), ptr(b), optr, N, H, W, Cin, Hout, Wout, Cout, kh, kw, pad_y,
+                             x_crop, OW, Cout, float(leaky), st))
+        else:
+            dy = [r - pad_y for r in range(kh) for _ in range(kw)]
+            dx = [s + x_crop for _ in range(kh) for s in range(kw)]
+            use_flat = stride == 1 and Cout > 64 and N * Hout * W >= 2 * 148 * 384 and not x_crop
+            if os.environ.get("B3D_CONV_FLAT"):
+                use_flat = stride == 1 and os.environ["B3D_CONV_FLAT"] == "1"
+            rc = -1
+            if use_flat:
+                rc = _conv_call(lib.b3d_conv2d_flat_tf32, ptr(x), ptr(wt), ptr(b), optr, N, H, W, Cin, Hout, Wout, Cout, kh * kw,
+                                _ints(dy), _ints(dx), Hout, OW, Cout, float(leaky), st)
+                if rc != 0 and b"does not fit" not in lib.b3d_last_error():
+                    check(rc)
+            if rc != 0:
+                check(_conv_call(lib.b3d_conv2d_tf32, ptr(x), ptr(wt), ptr(b), optr, N, H, W, Cin, Hout, Wout, Cout, kh * kw,
+                                 _ints(dy), _ints(dx), stride, stride, Hout, OW, Cout, 1, 1, 0, 0, float(leaky), 0, None, 0, st))
+        if pad_out:
+            check(lib.b3d_wrap_x_inplace(ptr(out), N * Hout, Wout, Cout, pad_out, pad_mode, st))
+        ctx.save_for_backward(x, out if (leaky != 1.0 or pad_out) else None)
+        ctx.lw = lw
+        ctx.cfg = (pad_y, stride, Cx, bias is not None, leaky, pad_out, pad_mode, x_crop, kh, kw, thin)
+        return out
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, y = ctx.saved_tensors
+        lw = ctx.lw
+        pad_y, stride, Cx, has_bias, leaky, pad_out, pad_mode, x_crop, kh, kw, thin = ctx.cfg
+        Cout, Cin = lw.Cout, lw.Cinp
+        N, H, W, _ = x.shape
+        gy = dev(gy, "grad_output")
+        st = stream_ptr(gy)
+        gb = None
+        want_gb = has_bias and ctx.needs_input_grad[2]
+        if pad_out:
+            _, Ho, OW, _ = y.shape
+            masked = torch.empty(N, Ho, OW - 2 * pad_out, Cout, device=gy.device, dtype=torch.float32)
+            gb = torch.zeros(Cout, device=gy.device, dtype=torch.float32) if want_gb else None
+            check(lib.b3d_pad_leaky_bias_bwd(ptr(gy), ptr(y), ptr(masked), ptr(gb), N * Ho, OW - 2 * pad_out, Cout, pad_out,
+                                             pad_mode, float(leaky), st))
+            gy = masked
+        elif leaky != 1.0:
+            masked = torch.empty_like(gy)
+            check(lib.b3d_leaky_bwd(ptr(gy), ptr(y), ptr(masked), gy.numel(), float(leaky), st))
+            gy = masked
+        if gb is None and want_gb:
+            gb = gy.sum(dim=(0, 1, 2))
+        _, Hout, Wout, _ = gy.shape
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            if lw.wd is None:
+                raise B3DError("banked conv: this layer was registered without an input gradient (no_dgrad)")
+            gyp = _pad_last(gy, 32)                                    # heads with 1 / 3 output channels: zero-pad K
+            Cop = lw.Coutp
+            gx = torch.empty(N, H, W, Cin, device=gy.device, dtype=torch.float32)
+            wd = lw.wd
+            if stride == 1:
+                dy = [pad_y - r for r in range(kh) for _ in range(kw)]
+                dx = [-s - x_crop for _ in range(kh) for s in range(kw)]
+                check(_conv_call(lib.b3d_conv2d_tf32, ptr(gyp), ptr(wd), None, ptr(gx), N, Hout, Wout, Cop, H, W, Cin, kh * kw,
+                                 _ints(dy), _ints(dx), 1, 1, H, W, Cin, 1, 1, 0, 0, 1.0, 0, None, 0, st))
+            elif stride == 2 and not x_crop:
+                for cy, cx, rs, dy, dx, Ha, Wa in stride2_classes(kh, kw, pad_y, H, W):
+                    if not rs:
+                        gx[:, cy::2, cx::2] = 0
+                        continue
+                    taps = [r * kw + s for r, s in rs]                  # rows of the tap-major D array: no gathered copy
+                    check(_conv_call(lib.b3d_conv2d_tf32, ptr(gyp), ptr(wd), None, ptr(gx), N, Hout, Wout, Cop, Ha, Wa, Cin,
+                                     len(rs), _ints(dy), _ints(dx), 1, 1, H, W, Cin, 2, 2, cy, cx, 1.0, 0, _ints(taps), kh * kw, st))
+            else:
+                raise B3DError("conv2d_dgrad: stride must be 1 or 2 (x_crop: stride 1 only)")
+            if Cx != Cin:
+                gx = gx[..., :Cx]
+        if ctx.needs_input_grad[1]:
+            gw = lw.df                                                 # the bank's gradient sink (zeroed by the bank)
+            if gw is None:
+                raise B3DError("banked conv: weight gradient requested but the bank was run without gradients")
+            if thin:
+                check(_conv_call(lib.b3d_conv2d_thin_wgrad, ptr(gy), ptr(x), ptr(gw), N, H, W, Cin, Hout, Wout, Cout, kh, kw, pad_y,
+                                 x_crop, 1, st))
+            else:
+                if Cout % 32:
+                    raise B3DError(f"banked conv: weight gradient needs Cout % 32 == 0 or a thin head (Cout={Cout})")
+                check(_conv_call(lib.b3d_conv2d_wgrad_tf32, ptr(gy), ptr(x), ptr(gw), N, H, W, Cin, Hout, Wout, Cout, kh, kw, pad_y,
+                                 stride, x_crop, 1, st))
+        return gx, gw, gb, None, None, None, None, None, None, None
+
+
+def conv2d_banked(x_nchw, lw, pad_y=0, stride=1, leaky=1.0, pad_out=0, pad_mode=1, x_crop=0):
+    """conv2d for a layer whose weights come from a WeightBank (`lw` = its LayerWeights).  Thin stems registered with
+    fold=True get their kh taps folded into the channels here (b3d.ew.fold_rows), as in conv2d()."""
+    x = x_nchw.permute(0, 2, 3, 1)
+    if lw.fold:
+        from .ew import fold_rows
+        x = fold_rows(x, lw.kh, pad_y, lw.Cinp)
+    y = _ConvBanked.apply(x, lw.wf, lw.bias, lw, int(pad_y), int(stride), float(leaky), int(pad_out), int(pad_mode), int(x_crop))
     return y.permute(0, 3, 1, 2)

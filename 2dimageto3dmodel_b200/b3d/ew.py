@@ -1,9 +1,10 @@
 """One-pass NHWC helper ops between the convolutions (libb3d csrc/ew_kernels.cu), with autograd."""
+import ctypes
 import os
 
 import torch
 
-from . import check, dev, lib, ptr, stream_ptr
+from . import B3DError, check, dev, lib, ptr, stream_ptr
 
 REPLICATE, CIRCULAR = 0, 1
 
@@ -72,31 +73,81 @@ def _dist_world():
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
 
+class CBNBatch:
+    """fc_gamma / fc_beta of ALL ConditionalBatchNorm2d layers of a generator forward as one GEMM
+    (models/gan.py:264-286: gamma = fc_gamma(z), beta = fc_beta(z) per layer): gb [N, 2*sum(C)], row n holds layer l's
+    gamma at off[l] and beta at off[l] + C_l.  The layers' backward passes write d(gamma), d(beta) straight into one sink
+    buffer of the same shape, handed to autograd once (by the layer that runs last in the backward = first in the forward;
+    every other layer is downstream of it, so the data dependencies order this, not the scheduler)."""
+
+    def __init__(self, cbns, z):
+        self.offsets, off = {}, 0
+        ws, bs = [], []
+        for m in cbns:
+            C = m.fc_gamma.out_features
+            self.offsets[id(m)] = (off, off + C)
+            off += 2 * C
+            ws += [m.fc_gamma.weight, m.fc_beta.weight]
+            bs += [m.fc_gamma.bias, m.fc_beta.bias]
+        self.first = id(cbns[0])
+        self.n_layers, self.done = len(cbns), 0
+        self.gb = torch.nn.functional.linear(z, torch.cat(ws), torch.cat(bs))
+        self.sink = None
+
+    def grad_sink(self):
+        if self.sink is None:
+            self.sink = torch.empty_like(self.gb)
+        return self.sink
+
+
 class _CBNActPad(torch.autograd.Function):
-    """y [N,H,W,C] (conv output, NHWC), gamma_t = 1 + gamma [N,C], beta [N,C], mean / invstd [C] (already computed)
-    -> out [N, up*H, up*W + 2*pad, C].  `skip` (optional) [N,H,Ws,C] read at pixel offset skip_off.
-    `batch_stats`: the statistics were computed from y (training mode), so dy carries the batch-norm coupling terms."""
+    """y [N,H,W,C] (conv output, NHWC) -> out [N, up*H, up*W + 2*pad, C]; gb = CBNBatch.gb (gamma / beta of this layer at
+    column offsets goff / boff).  `skip` (optional) [N,H,Ws,C] read at pixel offset skip_off.  Statistics, running buffers
+    and the per-sample affine come from one b3d_cbn_prepare launch (modes: 0 eval, 1 batch statistics, 2 SyncBN)."""
 
     @staticmethod
-    def forward(ctx, y, gamma_t, beta, mean, invstd, skip, skip_off, up, pad, post_leaky, batch_stats, sync):
+    def forward(ctx, y, gb, cb, key, bn, skip, skip_off, up, pad, post_leaky):
         y = dev(y.detach(), "y")
         N, H, W, C = y.shape
-        gt, bt = gamma_t.detach().contiguous(), beta.detach().contiguous()
-        scale = (invstd[None, :] * gt).contiguous()
-        shift = (bt - mean[None, :] * scale).contiguous()
+        gbd = dev(gb.detach(), "gamma/beta")
+        P = gbd.shape[1]
+        goff, boff = cb.offsets[key]
+        st = stream_ptr(y)
+        mode, sums, count, sync = 0, None, 1.0, False
+        if bn.training:
+            sums = torch.empty(2 * C, device=y.device, dtype=torch.float64)
+            check(lib.b3d_bn_sums(ptr(y), N * H * W, C, ptr(sums), st))
+            mode, count = 1, float(N * H * W)
+            if _dist_world() > 1 and bn.__class__.__name__.startswith("Synchronized"):
+                import torch.distributed as dist
+                dist.all_reduce(sums)                       # one collective per layer: [sum x, sum x^2] in fp64
+                mode, count, sync = 2, count * dist.get_world_size(), True
+        mean = torch.empty(C, device=y.device, dtype=torch.float32)
+        invstd = torch.empty_like(mean)
+        scale = torch.empty(N, C, device=y.device, dtype=torch.float32)
+        shift, gt = torch.empty_like(scale), torch.empty_like(scale)
+        track = bn.training and bn.track_running_stats
+        check(lib.b3d_cbn_prepare(ptr(gbd), P, goff, boff, ptr(sums), count, float(bn.eps), float(bn.momentum or 0.0), mode,
+                                  ptr(bn.running_mean) if (track or mode == 0) else None,
+                                  ptr(bn.running_var) if (track or mode == 0) else None,
+                                  ptr(bn.num_batches_tracked) if track else None,
+                                  ptr(mean), ptr(invstd), ptr(scale), ptr(shift), ptr(gt), N, C, st))
         sk = dev(skip.detach(), "skip") if skip is not None else None
         pitch = sk.shape[2] if sk is not None else 0
         out = torch.empty(N, up * H, up * W + 2 * pad, C, device=y.device, dtype=torch.float32)
         check(lib.b3d_cbn_act_fwd(ptr(y), ptr(scale), ptr(shift), ptr(sk), pitch, skip_off, ptr(out), N, H, W, C, up, pad, 0.2,
-                                  int(post_leaky), stream_ptr(y)))
+                                  int(post_leaky), st))
         ctx.save_for_backward(y, gt, scale, shift, mean, invstd, sk if sk is not None else torch.empty(0))
-        ctx.cfg = (skip_off, up, pad, post_leaky, batch_stats, sync, sk is not None, skip.shape if skip is not None else None)
+        ctx.cb, ctx.key = cb, key
+        ctx.cfg = (skip_off, up, pad, post_leaky, mode != 0, sync, count, sk is not None, skip.shape if skip is not None else None,
+                   P, goff, boff)
         return out
 
     @staticmethod
     def backward(ctx, gout):
         y, gt, scale, shift, mean, invstd, sk = ctx.saved_tensors
-        skip_off, up, pad, post_leaky, batch_stats, sync, has_skip, skip_shape = ctx.cfg
+        skip_off, up, pad, post_leaky, batch_stats, sync, count, has_skip, skip_shape, P, goff, boff = ctx.cfg
+        cb = ctx.cb
         N, H, W, C = y.shape
         gout = dev(gout, "grad")
         st = stream_ptr(y)
@@ -105,25 +156,33 @@ class _CBNActPad(torch.autograd.Function):
         if has_skip and ctx.needs_input_grad[5]:
             gpitch = skip_shape[2]
             gskip = torch.zeros(skip_shape, device=y.device) if gpitch != W else torch.empty(skip_shape, device=y.device)
-        S1 = torch.empty(N, C, device=y.device)
-        S2 = torch.empty(N, C, device=y.device)
+        want_gb = ctx.needs_input_grad[1]
+        sink = cb.grad_sink() if want_gb else torch.empty(N, P, device=y.device)
+        s1 = ctypes.c_void_p(sink.data_ptr() + 4 * boff)        # d beta  = sum ga
+        s2 = ctypes.c_void_p(sink.data_ptr() + 4 * goff)        # d gamma = sum ga * xhat
         check(lib.b3d_cbn_act_bwd1(ptr(gout), ptr(y), ptr(scale), ptr(shift), ptr(sk) if has_skip else None,
                                    sk.shape[2] if has_skip else 0, skip_off, ptr(mean), ptr(invstd), ptr(ga), ptr(gskip), gpitch,
-                                   skip_off, ptr(S1), ptr(S2), N, H, W, C, up, pad, 0.2, int(post_leaky), st))
-        dbeta, dgamma = S1, S2
+                                   skip_off, s1, s2, P, N, H, W, C, up, pad, 0.2, int(post_leaky), st))
+        inv_m = 0.0
         if batch_stats:
-            red = torch.stack(((gt * S1).sum(0), (gt * S2).sum(0)))            # [2, C]
-            M = N * H * W
+            red = torch.empty(2 * C, device=y.device, dtype=torch.float32)
+            check(lib.b3d_cbn_bwd_reduce(s1, s2, P, ptr(gt), ptr(red), N, C, st))
             if sync:
                 import torch.distributed as dist
                 dist.all_reduce(red)
-                M *= dist.get_world_size()
-            red = (red / M).contiguous()
-            m1, m2 = red[0].contiguous(), red[1].contiguous()
+            inv_m = 1.0 / count
         else:
-            m1 = m2 = torch.zeros(C, device=y.device)
-        check(lib.b3d_cbn_act_bwd2(ptr(ga), ptr(y), ptr(gt), ptr(mean), ptr(invstd), ptr(m1), ptr(m2), N, H, W, C, st))
-        return ga, dgamma, dbeta, None, None, gskip, None, None, None, None, None, None
+            red = torch.zeros(2 * C, device=y.device, dtype=torch.float32)
+        check(lib.b3d_cbn_act_bwd2(ptr(ga), ptr(y), ptr(gt), ptr(mean), ptr(invstd), ptr(red), ctypes.c_void_p(red.data_ptr() + 4 * C),
+                                   inv_m, N, H, W, C, st))
+        ggb = None
+        if want_gb:
+            cb.done += 1
+            if ctx.key == cb.first:
+                if cb.done != cb.n_layers:
+                    raise RuntimeError(f"CBNBatch: {cb.done} of {cb.n_layers} layers ran their backward before the first layer's")
+                ggb = sink
+        return ga, ggb, None, None, None, gskip, None, None, None, None
 
 
 _BN_STATS_IMPL = os.environ.get("B3D_BN_STATS", "torch")
@@ -131,8 +190,7 @@ _BN_STATS_IMPL = os.environ.get("B3D_BN_STATS", "torch")
 
 def bn_stats(y_nhwc, eps, impl=None):
     """(mean, invstd) per channel of an NHWC tensor = torch.batch_norm_stats on the NCHW view.  impl "b3d" = the one-pass
-    libb3d kernel, "torch" = the stock op (default: B3D_BN_STATS, else "torch" — measured on B200: the stock channels-last
-    kernel is as fast inside the training step)."""
+    libb3d kernel, "torch" = the stock op."""
     y = dev(y_nhwc, "y")
     C = y.shape[-1]
     if C % 4 or 256 % (C // 4) or (impl or _BN_STATS_IMPL) != "b3d":     # odd channel counts: always the stock op
@@ -144,40 +202,17 @@ def bn_stats(y_nhwc, eps, impl=None):
     return mean, invstd
 
 
-def cbn_act_pad(y_nchw, cbn, z, skip_nchw=None, skip_off=0, up=1, pad=1, post_leaky=False):
+def cbn_act_pad(y_nchw, cbn, z, skip_nchw=None, skip_off=0, up=1, pad=1, post_leaky=False, cb=None):
     """ConditionalBatchNorm2d(y, z) -> LeakyReLU(0.2) [-> + skip] [-> LeakyReLU] [-> x2 upsample] -> replicate pad, fused.
     `cbn` is a models.gan.ConditionalBatchNorm2d whose .norm is a (Synchronized)BatchNorm2d without affine; statistics and
-    running buffers follow F.batch_norm (single process) or the reference's SyncBN formulas (torch.distributed)."""
-    bn = cbn.norm
+    running buffers follow F.batch_norm (single process) or the reference's SyncBN formulas (torch.distributed).
+    cb: the forward's CBNBatch (gamma / beta of all layers from one GEMM); None = a one-layer batch built here."""
+    if cb is None:
+        cb = CBNBatch([cbn], z)
     y = y_nchw.permute(0, 2, 3, 1)
     C = y.shape[3]
-    gamma_t = 1 + cbn.fc_gamma(z)
-    beta = cbn.fc_beta(z)
-    sync = False
-    if bn.training:
-        yv = y_nchw.detach()
-        n = yv.numel() // C
-        mean, invstd = bn_stats(y.detach(), bn.eps)
-        var_b = invstd.pow(-2) - bn.eps
-        if _dist_world() > 1 and bn.__class__.__name__.startswith("Synchronized"):
-            import torch.distributed as dist
-            sync = True
-            stats = torch.stack((mean * n, (var_b + mean * mean) * n))
-            dist.all_reduce(stats)
-            n = n * dist.get_world_size()
-            mean = stats[0] / n
-            var_b = stats[1] / n - mean * mean
-            invstd = var_b.clamp(min=bn.eps).pow(-0.5)                       # sync_batchnorm/batchnorm.py:150
-        if bn.track_running_stats:
-            with torch.no_grad():
-                bn.running_mean.mul_(1 - bn.momentum).add_(mean, alpha=bn.momentum)
-                bn.running_var.mul_(1 - bn.momentum).add_(var_b * (n / max(n - 1, 1)), alpha=bn.momentum)
-                bn.num_batches_tracked += 1
-        batch_stats = True
-    else:
-        mean, invstd = bn.running_mean, (bn.running_var + bn.eps).rsqrt()
-        batch_stats = False
+    if C % 4 or 256 % (C // 4):
+        raise B3DError(f"cbn_act_pad: C={C} must be 4 * a divisor of 256")
     skip = skip_nchw.permute(0, 2, 3, 1) if skip_nchw is not None else None
-    out = _CBNActPad.apply(y, gamma_t, beta, mean.contiguous(), invstd.contiguous(), skip, int(skip_off), int(up), int(pad),
-                           bool(post_leaky), batch_stats, sync)
+    out = _CBNActPad.apply(y, cb.gb, cb, id(cbn), cbn.norm, skip, int(skip_off), int(up), int(pad), bool(post_leaky))
     return out.permute(0, 3, 1, 2)

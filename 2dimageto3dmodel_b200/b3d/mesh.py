@@ -18,11 +18,13 @@ def _i32(t, name):
         return dev(t, name, torch.int32)
     key = (t.data_ptr(), tuple(t.shape), t._version, str(t.device))
     hit = _i32_cache.get(key)
-    if hit is None:
+    if hit is None or hit[0] is not t:
+        # the entry keeps the SOURCE tensor alive: its address cannot be recycled for another index tensor of the same
+        # shape while the converted copy is cached (a different tensor at the same key simply replaces the entry)
         if len(_i32_cache) > 64:
             _i32_cache.clear()
-        hit = _i32_cache[key] = dev(t.to(torch.int32), name, torch.int32)
-    return hit
+        hit = _i32_cache[key] = (t, dev(t.to(torch.int32), name, torch.int32))
+    return hit[1]
 
 
 def face_setup(verts, faces, uv=None, ft=None, want_normals=True):
@@ -58,7 +60,12 @@ class _Render(torch.autograd.Function):
         B, F = fgeo.shape[0], fgeo.shape[1]
         tex = dev(texture.detach(), "texture") if texture is not None else None
         Th, Tw = (tex.shape[2], tex.shape[3]) if tex is not None else (0, 0)
+        if tex is not None and (tex.dim() != 4 or tex.shape[1] != 3 or tex.shape[0] != B):
+            # the shader kernels are built for RGB textures (every reference call site passes 3 channels)
+            raise B3DError(f"render: texture must be [B={B},3,Th,Tw], got {tuple(tex.shape)}")
         bg = dev(background.detach(), "background_image") if background is not None else None
+        if bg is not None and tuple(bg.shape) != (B, H, W, 3):
+            raise B3DError(f"render: background_image must be [B={B},{H},{W},3], got {tuple(bg.shape)}")
         d = verts_d.device
         imidx = torch.empty(B, H, W, device=d, dtype=torch.int32)
         imwei = torch.empty(B, H, W, 3, device=d, dtype=torch.float32)

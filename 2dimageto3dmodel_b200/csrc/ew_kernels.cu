@@ -361,6 +361,65 @@ extern "C" int b3d_bn_stats(const float* y, long long rows, int C, float eps, fl
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Per-layer scalar math of ConditionalBatchNorm2d in ONE launch (was ~15 tiny torch kernels per layer and forward):
+// statistics -> mean / inv_std, running-buffer update, and the per-sample affine of the fused pass below,
+//   scale[n,c] = inv_std[c] * (1 + gamma[n,c]),   shift[n,c] = beta[n,c] - mean[c] * scale[n,c],   gt[n,c] = 1 + gamma[n,c].
+// mode 0: eval (running statistics).  mode 1: batch statistics from fp64 sums [2][C] over `count` values per channel with
+// F.batch_norm's formulas (biased variance + eps under the root; running variance unbiased).  mode 2: the reference's
+// SyncBN formulas on the (all-reduced) sums: inv_std = clamp(var, eps)^-1/2 (sync_batchnorm/batchnorm.py:133-150).
+__global__ void __launch_bounds__(NT)
+cbn_prepare_kernel(const float* __restrict__ gb, int gb_pitch, int gamma_off, int beta_off, const double* __restrict__ sums,
+                   double count, float eps, float momentum, int mode, float* __restrict__ running_mean,
+                   float* __restrict__ running_var, long long* __restrict__ nbt, float* __restrict__ mean_out,
+                   float* __restrict__ invstd_out, float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ gt,
+                   int N, int C) {
+    const int i = blockIdx.x * NT + threadIdx.x;
+    if (i >= N * C) return;
+    const int n = i / C, c = i - n * C;
+    float mean, invstd;
+    double var_b = 0.0;
+    if (mode == 0) {
+        mean = running_mean[c];
+        invstd = rsqrtf(running_var[c] + eps);
+    } else {
+        const double m = sums[c] / count;
+        var_b = mode == 1 ? sums[C + c] / count - m * m : (sums[C + c] - sums[c] * m) / count;
+        if (mode == 1) var_b = var_b > 0.0 ? var_b : 0.0;
+        mean = (float)m;
+        invstd = mode == 1 ? (float)(1.0 / sqrt(var_b + (double)eps)) : (float)(1.0 / sqrt(var_b > (double)eps ? var_b : (double)eps));
+    }
+    const float g1 = 1.f + gb[(long long)n * gb_pitch + gamma_off + c];
+    const float sc = invstd * g1;
+    scale[i] = sc;
+    shift[i] = gb[(long long)n * gb_pitch + beta_off + c] - mean * sc;
+    gt[i] = g1;
+    if (n == 0) {
+        mean_out[c] = mean;
+        invstd_out[c] = invstd;
+        if (mode != 0 && running_mean != nullptr) {      // all reads of the running buffers above happen in mode 0 only
+            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+            running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(var_b * (count / (count > 1.0 ? count - 1.0 : 1.0)));
+            if (c == 0 && nbt != nullptr) *nbt += 1;
+        }
+    }
+}
+
+// red[0][c] = sum_n gt[n,c] * S1[n,c],  red[1][c] = sum_n gt[n,c] * S2[n,c]   (batch-norm coupling terms of the backward)
+__global__ void __launch_bounds__(NT)
+cbn_bwd_reduce_kernel(const float* __restrict__ S1, const float* __restrict__ S2, int s_pitch, const float* __restrict__ gt,
+                      float* __restrict__ red, int N, int C) {
+    const int c = blockIdx.x * NT + threadIdx.x;
+    if (c >= C) return;
+    float a = 0.f, b = 0.f;
+    for (int n = 0; n < N; ++n) {
+        const float g = gt[(long long)n * C + c];
+        a = fmaf(g, S1[(long long)n * s_pitch + c], a);
+        b = fmaf(g, S2[(long long)n * s_pitch + c], b);
+    }
+    red[c] = a;
+    red[C + c] = b;
+}
+
 // Fused generator glue (models/gan.py:282-286 ConditionalBatchNorm2d, :309-311 LeakyReLU + residual, :319 nearest x2
 // upsample, :329 replicate pad): one pass from a conv output y [N,H,W,C] to the NEXT conv's padded input
 //     out[n, yo, xo, c] = post( leaky(y[n,ys,xs,c] * scale[n,c] + shift[n,c]) + skip[n,ys,xs,c] )
@@ -446,7 +505,7 @@ __global__ void __launch_bounds__(NT)
 cbn_act_bwd1_kernel(const float4* __restrict__ gout, const float4* __restrict__ y, const float4* __restrict__ scale,
                     const float4* __restrict__ shift, const float4* __restrict__ skip, const float4* __restrict__ mean,
                     const float4* __restrict__ invstd, float4* __restrict__ ga, float4* __restrict__ gskip, int gskip_pitch,
-                    int gskip_off, float* __restrict__ S1, float* __restrict__ S2, const CbnGeom g, int rows_per_cta) {
+                    int gskip_off, float* __restrict__ S1, float* __restrict__ S2, int s_pitch, const CbnGeom g, int rows_per_cta) {
     const int n = blockIdx.y;
     const int y0 = blockIdx.x * rows_per_cta, y1 = min(y0 + rows_per_cta, g.H);
     const int Wo = g.up * g.W + 2 * g.pad;
@@ -486,23 +545,26 @@ cbn_act_bwd1_kernel(const float4* __restrict__ gout, const float4* __restrict__ 
             a2.x = fmaf(a.x, (v.x - mu.x) * is.x, a2.x); a2.y = fmaf(a.y, (v.y - mu.y) * is.y, a2.y);
             a2.z = fmaf(a.z, (v.z - mu.z) * is.z, a2.z); a2.w = fmaf(a.w, (v.w - mu.w) * is.w, a2.w);
         }
-        float* s1 = S1 + ((long long)n * g.C4 + c) * 4;
-        float* s2 = S2 + ((long long)n * g.C4 + c) * 4;
+        float* s1 = S1 + (long long)n * s_pitch + c * 4;
+        float* s2 = S2 + (long long)n * s_pitch + c * 4;
         atomicAdd(s1 + 0, a1.x); atomicAdd(s1 + 1, a1.y); atomicAdd(s1 + 2, a1.z); atomicAdd(s1 + 3, a1.w);
         atomicAdd(s2 + 0, a2.x); atomicAdd(s2 + 1, a2.y); atomicAdd(s2 + 2, a2.z); atomicAdd(s2 + 3, a2.w);
     }
 }
 
-// Backward pass 2 (in place on ga): dy = inv_std * (ga * gamma_t - m1 - xhat * m2)
+// Backward pass 2 (in place on ga): dy = inv_std * (ga * gamma_t - m1 - xhat * m2), (m1, m2) = red[0 / 1] * inv_m
 __global__ void __launch_bounds__(NT)
 cbn_act_bwd2_kernel(float4* __restrict__ ga, const float4* __restrict__ y, const float4* __restrict__ gamma_t,
                     const float4* __restrict__ mean, const float4* __restrict__ invstd, const float4* __restrict__ m1,
-                    const float4* __restrict__ m2, long long per_n, int C4, long long total) {
+                    const float4* __restrict__ m2, float inv_m, long long per_n, int C4, long long total) {
     for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
         const int c = (int)(i % C4);
         const long long n = i / per_n;
         const float4 a = ga[i], v = __ldg(y + i), gt = __ldg(gamma_t + n * C4 + c);
-        const float4 mu = __ldg(mean + c), is = __ldg(invstd + c), q1 = __ldg(m1 + c), q2 = __ldg(m2 + c);
+        const float4 mu = __ldg(mean + c), is = __ldg(invstd + c);
+        float4 q1 = __ldg(m1 + c), q2 = __ldg(m2 + c);
+        q1.x *= inv_m; q1.y *= inv_m; q1.z *= inv_m; q1.w *= inv_m;
+        q2.x *= inv_m; q2.y *= inv_m; q2.z *= inv_m; q2.w *= inv_m;
         ga[i] = make_float4(is.x * (a.x * gt.x - q1.x - (v.x - mu.x) * is.x * q2.x), is.y * (a.y * gt.y - q1.y - (v.y - mu.y) * is.y * q2.y),
                             is.z * (a.z * gt.z - q1.z - (v.z - mu.z) * is.z * q2.z), is.w * (a.w * gt.w - q1.w - (v.w - mu.w) * is.w * q2.w));
     }
@@ -534,14 +596,16 @@ int b3d_cbn_act_fwd(const float* y, const float* scale, const float* shift, cons
 // (its pad columns are NOT touched: the caller zeroes the buffer when gskip_pitch != W)
 int b3d_cbn_act_bwd1(const float* gout, const float* y, const float* scale, const float* shift, const float* skip, int skip_pitch,
                      int skip_off, const float* mean, const float* invstd, float* ga, float* gskip, int gskip_pitch, int gskip_off,
-                     float* S1, float* S2, int N, int H, int W, int C, int up, int pad, float slope, int post_leaky, void* stream) {
+                     float* S1, float* S2, int s_pitch, int N, int H, int W, int C, int up, int pad, float slope, int post_leaky,
+                     void* stream) {
     B3D_REQUIRE(N >= 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0 && C / 4 <= NT && NT % (C / 4) == 0 && (up == 1 || up == 2), B3D_EINVAL,
                 "b3d_cbn_act_bwd1: bad arguments (C/4 must divide %d)", NT);
     if (N == 0) return B3D_OK;
     B3D_REQUIRE(gout && y && scale && shift && mean && invstd && ga && S1 && S2, B3D_EINVAL, "b3d_cbn_act_bwd1: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    B3D_CUDA_OK(cudaMemsetAsync(S1, 0, sizeof(float) * (size_t)N * C, st));
-    B3D_CUDA_OK(cudaMemsetAsync(S2, 0, sizeof(float) * (size_t)N * C, st));
+    B3D_REQUIRE(s_pitch >= C && s_pitch % 4 == 0, B3D_EINVAL, "b3d_cbn_act_bwd1: S pitch %d must be >= C and a multiple of 4", s_pitch);
+    B3D_CUDA_OK(cudaMemset2DAsync(S1, sizeof(float) * (size_t)s_pitch, 0, sizeof(float) * (size_t)C, (size_t)N, st));
+    B3D_CUDA_OK(cudaMemset2DAsync(S2, sizeof(float) * (size_t)s_pitch, 0, sizeof(float) * (size_t)C, (size_t)N, st));
     CbnGeom g{N, H, W, C / 4, up, pad, skip_pitch, skip_off, slope, post_leaky};
     // enough CTAs to fill the GPU a few times, each with >= 1 row
     int rows = (int)(((long long)N * H + 148 * 8 - 1) / (148 * 8));
@@ -549,20 +613,63 @@ int b3d_cbn_act_bwd1(const float* gout, const float* y, const float* scale, cons
     dim3 grid(b3d::ceil_div(H, rows), N);
     cbn_act_bwd1_kernel<<<grid, NT, 0, st>>>((const float4*)gout, (const float4*)y, (const float4*)scale, (const float4*)shift,
                                             (const float4*)skip, (const float4*)mean, (const float4*)invstd, (float4*)ga,
-                                            (float4*)gskip, gskip_pitch, gskip_off, S1, S2, g, rows);
+                                            (float4*)gskip, gskip_pitch, gskip_off, S1, S2, s_pitch, g, rows);
     B3D_LAUNCH_OK();
     return B3D_OK;
 }
 
 int b3d_cbn_act_bwd2(float* ga, const float* y, const float* gamma_t, const float* mean, const float* invstd, const float* m1,
-                     const float* m2, int N, int H, int W, int C, void* stream) {
+                     const float* m2, float inv_m, int N, int H, int W, int C, void* stream) {
     B3D_REQUIRE(N >= 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, B3D_EINVAL, "b3d_cbn_act_bwd2: bad arguments");
     if (N == 0) return B3D_OK;
     B3D_REQUIRE(ga && y && gamma_t && mean && invstd && m1 && m2, B3D_EINVAL, "b3d_cbn_act_bwd2: null pointer");
     const long long per_n = (long long)H * W * (C / 4), total = per_n * N;
     cbn_act_bwd2_kernel<<<grid_for(total), NT, 0, (cudaStream_t)stream>>>((float4*)ga, (const float4*)y, (const float4*)gamma_t,
                                                                          (const float4*)mean, (const float4*)invstd,
-                                                                         (const float4*)m1, (const float4*)m2, per_n, C / 4, total);
+                                                                         (const float4*)m1, (const float4*)m2, inv_m, per_n, C / 4, total);
+    B3D_LAUNCH_OK();
+    return B3D_OK;
+}
+
+// fp64 per-channel sums [2][C] (sum, sum of squares) of y [rows, C]: the first half of b3d_bn_stats, for callers that
+// all-reduce the sums across ranks (SyncBN) and finish in b3d_cbn_prepare.  `sums` is zeroed here.
+int b3d_bn_sums(const float* y, long long rows, int C, double* sums, void* stream) {
+    B3D_REQUIRE(rows > 0 && C >= 4 && C % 4 == 0 && C / 4 <= NT && NT % (C / 4) == 0, B3D_EINVAL,
+                "b3d_bn_sums: C=%d must be 4 * a divisor of %d", C, NT);
+    B3D_REQUIRE(y && sums, B3D_EINVAL, "b3d_bn_sums: null pointer");
+    B3D_CHECK_ALIGNED(y);
+    cudaStream_t st = (cudaStream_t)stream;
+    B3D_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)C, st));
+    const int ppb = NT / (C / 4);
+    long long blocks = (rows + ppb - 1) / ppb;
+    if (blocks > 148 * 2) blocks = 148 * 2;
+    bn_stats_partial_kernel<<<(int)blocks, NT, 0, st>>>((const float4*)y, rows, C / 4, sums);
+    B3D_LAUNCH_OK();
+    return B3D_OK;
+}
+
+// ConditionalBatchNorm2d scalar math in one launch (see cbn_prepare_kernel).  gb [N, gb_pitch]: row n holds gamma at
+// gamma_off + c and beta at beta_off + c (the batched fc_gamma / fc_beta outputs of all layers).  mode 0 eval, 1 batch
+// statistics (F.batch_norm formulas), 2 the reference's SyncBN formulas; sums [2][C] fp64 (modes 1, 2), count = values per
+// channel over the (global) batch.  running_mean / running_var / num_batches_tracked (nullable) are updated in modes 1, 2.
+// Outputs: mean, invstd [C]; scale, shift, gt [N, C].
+int b3d_cbn_prepare(const float* gb, int gb_pitch, int gamma_off, int beta_off, const double* sums, double count, float eps,
+                    float momentum, int mode, float* running_mean, float* running_var, long long* num_batches_tracked,
+                    float* mean, float* invstd, float* scale, float* shift, float* gt, int N, int C, void* stream) {
+    B3D_REQUIRE(N > 0 && C > 0 && gb && mean && invstd && scale && shift && gt, B3D_EINVAL, "b3d_cbn_prepare: bad arguments");
+    B3D_REQUIRE(mode == 0 ? (running_mean && running_var) : (sums != nullptr && count > 0), B3D_EINVAL,
+                "b3d_cbn_prepare: mode %d needs %s", mode, mode == 0 ? "running statistics" : "sums and a count");
+    cbn_prepare_kernel<<<(N * C + NT - 1) / NT, NT, 0, (cudaStream_t)stream>>>(gb, gb_pitch, gamma_off, beta_off, sums, count, eps,
+                                                                                momentum, mode, running_mean, running_var,
+                                                                                num_batches_tracked, mean, invstd, scale, shift, gt, N, C);
+    B3D_LAUNCH_OK();
+    return B3D_OK;
+}
+
+// red [2][C] from the per-sample sums of b3d_cbn_act_bwd1 (row pitch s_pitch) and gt [N,C]
+int b3d_cbn_bwd_reduce(const float* S1, const float* S2, int s_pitch, const float* gt, float* red, int N, int C, void* stream) {
+    B3D_REQUIRE(N > 0 && C > 0 && S1 && S2 && gt && red, B3D_EINVAL, "b3d_cbn_bwd_reduce: bad arguments");
+    cbn_bwd_reduce_kernel<<<(C + NT - 1) / NT, NT, 0, (cudaStream_t)stream>>>(S1, S2, s_pitch, gt, red, N, C);
     B3D_LAUNCH_OK();
     return B3D_OK;
 }

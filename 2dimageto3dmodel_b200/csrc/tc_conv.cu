@@ -34,6 +34,7 @@ struct ConvParams {
     int ntaps, kslices;               // filter taps, Cin / 32
     int sy, sx;                       // input coordinate = s * out + d[t]
     int dy[MAX_TAPS], dx[MAX_TAPS];
+    int wtap[MAX_TAPS];               // weight tap (row of the tap-major weight array) read for loop tap t
     // epilogue: out pixel (n, oy*y + ooy, ox*x + oox) of a tensor [N, OH, OW, OC], channel offset 0
     int OH, OW, OC, osy, osx, ooy, oox;
     float leaky;                      // 1.0 = identity
@@ -111,9 +112,9 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 unsigned char* b = base + s * S::STAGE_BYTES + S::A_BYTES;
                 if constexpr (WMN) {      // weights [tap][Cin][Cout]: 32 cin rows x 32 cout per box (N-major B operand)
 #pragma unroll
-                    for (int nb = 0; nb < BN / 32; ++nb) tc::tma_load_3d(b + nb * 4096, &tmap_w, full + s, c0 + nb * 32, ks * BK, tap);
+                    for (int nb = 0; nb < BN / 32; ++nb) tc::tma_load_3d(b + nb * 4096, &tmap_w, full + s, c0 + nb * 32, ks * BK, p.wtap[tap]);
                 } else {
-                    tc::tma_load_3d(b, &tmap_w, full + s, ks * BK, c0, tap);
+                    tc::tma_load_3d(b, &tmap_w, full + s, ks * BK, c0, p.wtap[tap]);
                 }
             }
         }
@@ -274,9 +275,9 @@ conv_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                         tc::tma_load_4d(a + r * S::A_TILE, &tmap_x, full + s, ks * BK, p.sx * x0[r] + p.dx[tap], p.sy * y0[r] + p.dy[tap], n0[r]);
                     if constexpr (WMN) {
 #pragma unroll
-                        for (int nb = 0; nb < BN / 32; ++nb) tc::tma_load_3d(b + nb * 4096, &tmap_w, full + s, c0 + nb * 32, ks * BK, tap);
+                        for (int nb = 0; nb < BN / 32; ++nb) tc::tma_load_3d(b + nb * 4096, &tmap_w, full + s, c0 + nb * 32, ks * BK, p.wtap[tap]);
                     } else {
-                        tc::tma_load_3d(b, &tmap_w, full + s, ks * BK, c0, tap);
+                        tc::tma_load_3d(b, &tmap_w, full + s, ks * BK, c0, p.wtap[tap]);
                     }
                 }
             }
@@ -389,6 +390,7 @@ struct WgradParams {
     int kh, kw, pad_y, st;
     int xoff;                      // the convolution reads x from column xoff on (a caller-side crop of the padded input)
     int splits;                    // K splits (gridDim.z / taps)
+    int tapmajor;                  // dW layout: 0 = [Cout][Cin][kh][kw], 1 = tap-major [kh*kw][Cout][Cin] (the F layout)
     int tstep;                     // taps of one CTA are s0, s0 + tstep, ... (1: adjacent taps of a stride-1 conv,
                                    // 2: taps of equal parity of a stride-2 conv = adjacent rows of the strided window)
 };
@@ -497,10 +499,17 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
                 float v[32];
                 tc::tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * BN + c), v);
                 if (co < p.Cout) {
+                    if (p.tapmajor) {       // 32 consecutive input channels of one (tap, co) row: 8 x 16-byte reductions
+                        float* row = dw + ((size_t)(r * p.kw + s + t * p.tstep) * p.Cout + co) * p.Cin + ci0 + c;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int ci = ci0 + c + j;
-                        if (ci < p.Cin) atomicAdd(dw + (((size_t)co * p.Cin + ci) * p.kh + r) * p.kw + s + t * p.tstep, v[j]);
+                        for (int j = 0; j < 32; j += 4)
+                            if (ci0 + c + j < p.Cin) atomicAdd(reinterpret_cast<float4*>(row + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int ci = ci0 + c + j;
+                            if (ci < p.Cin) atomicAdd(dw + (((size_t)co * p.Cin + ci) * p.kh + r) * p.kw + s + t * p.tstep, v[j]);
+                        }
                     }
                 }
             }
@@ -575,12 +584,17 @@ extern "C" {
 // out [N, OH, OW, OC]; the tile grid covers (Hout, Wout) logical outputs, written to (osy*y+ooy, osx*x+oox)
 int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* out, int N, int H, int W, int Cin,
                     int Hout, int Wout, int Cout, int ntaps, const int* dy, const int* dx, int sy, int sx, int OH,
-                    int OW, int OC, int osy, int osx, int ooy, int oox, float leaky, int w_cin_major, void* stream) {
+                    int OW, int OC, int osy, int osx, int ooy, int oox, float leaky, int w_cin_major, const int* wtap,
+                    int wtaps_total, void* stream) {
     B3D_REQUIRE(N > 0 && H > 0 && W > 0 && Hout > 0 && Wout > 0 && Cout > 0, B3D_EINVAL, "b3d_conv2d_tf32: bad sizes");
     B3D_REQUIRE(Cin > 0 && Cin % BK == 0, B3D_EINVAL, "b3d_conv2d_tf32: Cin=%d must be a multiple of %d", Cin, BK);
     B3D_REQUIRE(ntaps >= 1 && ntaps <= MAX_TAPS && dy && dx, B3D_EINVAL, "b3d_conv2d_tf32: bad taps");
     B3D_REQUIRE(x && wt && out, B3D_EINVAL, "b3d_conv2d_tf32: null pointer");
     B3D_REQUIRE(sy >= 1 && sy <= 2 && sx >= 1 && sx <= 2, B3D_EINVAL, "b3d_conv2d_tf32: stride must be 1 or 2");
+    if (!wtap) wtaps_total = ntaps;
+    B3D_REQUIRE(wtaps_total >= ntaps || wtap, B3D_EINVAL, "b3d_conv2d_tf32: bad weight tap count");
+    for (int t = 0; wtap && t < ntaps; ++t)
+        B3D_REQUIRE(wtap[t] >= 0 && wtap[t] < wtaps_total, B3D_EINVAL, "b3d_conv2d_tf32: weight tap %d out of range", wtap[t]);
     B3D_CHECK_ALIGNED(x);
     B3D_CHECK_ALIGNED(wt);
     b3d::clear_variant();
@@ -595,12 +609,12 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
     CUtensorMap mw;
     if (w_cin_major) {        // wt [ntaps, Cin, Cout]: the B operand is N-major (no weight transpose for dgrad)
         B3D_REQUIRE(Cout % 4 == 0, B3D_EINVAL, "b3d_conv2d_tf32: Cout=%d must be a multiple of 4 for cin-major weights", Cout);
-        const uint64_t dims[3] = {(uint64_t)Cout, (uint64_t)Cin, (uint64_t)ntaps};
+        const uint64_t dims[3] = {(uint64_t)Cout, (uint64_t)Cin, (uint64_t)wtaps_total};
         const uint64_t strides[2] = {(uint64_t)Cout * 4, (uint64_t)Cout * Cin * 4};
         const uint32_t box[3] = {32, (uint32_t)BK, 1};
         if (int rc = tc::make_tmap_f32(&mw, wt, 3, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
     } else {
-        const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)ntaps};
+        const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)wtaps_total};
         const uint64_t strides[2] = {(uint64_t)Cin * 4, (uint64_t)Cout * Cin * 4};
         const uint32_t box[3] = {(uint32_t)BK, (uint32_t)BN, 1};
         if (int rc = tc::make_tmap_f32(&mw, wt, 3, dims, strides, box)) return rc;
@@ -620,7 +634,7 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
         p.tiles_y = b3d::ceil_div(Hout, p.BH);
         const int tiles = p.tiles_x * p.tiles_y * b3d::ceil_div(N, p.BI);
         p.ntaps = ntaps; p.kslices = Cin / BK; p.sy = sy; p.sx = sx;
-        for (int t = 0; t < ntaps; ++t) { p.dy[t] = dy[t]; p.dx[t] = dx[t]; }
+        for (int t = 0; t < ntaps; ++t) { p.dy[t] = dy[t]; p.dx[t] = dx[t]; p.wtap[t] = wtap ? wtap[t] : t; }
         p.OH = OH; p.OW = OW; p.OC = OC; p.osy = osy; p.osx = osx; p.ooy = ooy; p.oox = oox;
         p.leaky = leaky;
         p.dbg_lbo = 4096; p.dbg_sbo = 512; p.dbg_lt = 1;     // 32-bit MN-major: SWIZZLE_128B_BASE32B, 4-row atoms
@@ -663,7 +677,7 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
 // dy [N,Hout,Wout,Cout], x [N,H,W,Cin] NHWC (x already padded along x; Cin, Cout multiples of 4),
 // dw [Cout,Cin,kh,kw] (accumulated into)
 int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, int N, int H, int W, int Cin, int Hout, int Wout,
-                          int Cout, int kh, int kw, int pad_y, int stride, int x_off, void* stream) {
+                          int Cout, int kh, int kw, int pad_y, int stride, int x_off, int tap_major, void* stream) {
     B3D_REQUIRE(N > 0 && Cin > 0 && Cout > 0 && H > 0 && W > 0 && Hout > 0 && Wout > 0, B3D_EINVAL,
                 "b3d_conv2d_wgrad_tf32: bad sizes");
     B3D_REQUIRE(kh * kw <= MAX_TAPS && (stride == 1 || stride == 2) && x_off >= 0, B3D_EINVAL, "b3d_conv2d_wgrad_tf32: bad kernel/stride");
@@ -679,7 +693,8 @@ int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, int N, int
     p.BHk = BK / p.BWk;
     p.kx = b3d::ceil_div(Wout, p.BWk);
     p.ky = b3d::ceil_div(Hout, p.BHk);
-    p.kh = kh; p.kw = kw; p.pad_y = pad_y; p.st = stride; p.xoff = x_off;
+    p.kh = kh; p.kw = kw; p.pad_y = pad_y; p.st = stride; p.xoff = x_off; p.tapmajor = tap_major ? 1 : 0;
+    if (tap_major) B3D_CHECK_ALIGNED(dw);
     // a row of kw taps per CTA when the K slice is a 32-pixel row segment (Wout >= 32) of a stride-1 conv
     int T = 1;
     p.tstep = 1;

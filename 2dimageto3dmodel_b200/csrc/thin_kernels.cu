@@ -32,6 +32,7 @@ struct ThinGeom {
     int N, H, W, Cin, Hout, Wout, pad_y, xoff;
     int OW, OC;              // output pixel pitch / channel pitch (fwd)
     float leaky;
+    int tapmajor;            // wgrad: dW layout 0 = [Cout][Cin][5][5], 1 = tap-major [25][Cout][Cin]
 };
 
 // wt [KS][KS][COUT][Cin]
@@ -168,7 +169,8 @@ conv_thin_wgrad_kernel(const float* __restrict__ gy, const float* __restrict__ x
     __syncthreads();
     for (int i = threadIdx.x; i < COUT * KS * KS * 32 * VEC; i += NT) {
         const int cl = i % (32 * VEC), t = (i / (32 * VEC)) % (KS * KS), c = i / (32 * VEC * KS * KS);
-        atomicAdd(dw + ((long long)c * g.Cin + chunk * 32 * VEC + cl) * (KS * KS) + t, red[i]);
+        const int ci = chunk * 32 * VEC + cl;
+        atomicAdd(g.tapmajor ? dw + ((long long)t * COUT + c) * g.Cin + ci : dw + ((long long)c * g.Cin + ci) * (KS * KS) + t, red[i]);
     }
 }
 
@@ -262,7 +264,8 @@ conv_thin_wgrad_win_kernel(const float* __restrict__ gy, const float* __restrict
     __syncthreads();
     for (int i = threadIdx.x; i < COUT * KS * KS * 32 * VEC; i += NT) {
         const int cl = i % (32 * VEC), t = (i / (32 * VEC)) % (KS * KS), c = i / (32 * VEC * KS * KS);
-        atomicAdd(dw + ((long long)c * g.Cin + chunk * 32 * VEC + cl) * (KS * KS) + t, red[i]);
+        const int ci = chunk * 32 * VEC + cl;
+        atomicAdd(g.tapmajor ? dw + ((long long)t * COUT + c) * g.Cin + ci : dw + ((long long)c * g.Cin + ci) * (KS * KS) + t, red[i]);
     }
 }
 
@@ -320,7 +323,7 @@ int b3d_conv2d_thin_fwd(const float* x, const float* wt, const float* bias, floa
     B3D_REQUIRE(OW >= Wout && OC >= Cout, B3D_EINVAL, "b3d_conv2d_thin_fwd: output pitch smaller than the output");
     B3D_CHECK_ALIGNED(x);
     B3D_CHECK_ALIGNED(wt);
-    ThinGeom g{N, H, W, Cin, Hout, Wout, pad_y, x_off, OW, OC, leaky};
+    ThinGeom g{N, H, W, Cin, Hout, Wout, pad_y, x_off, OW, OC, leaky, 0};
     cudaStream_t st = (cudaStream_t)stream;
     const bool v4 = Cin % 128 == 0;
     switch (Cout * 2 + (v4 ? 1 : 0)) {
@@ -336,11 +339,11 @@ int b3d_conv2d_thin_fwd(const float* x, const float* wt, const float* bias, floa
 }
 
 int b3d_conv2d_thin_wgrad(const float* dy, const float* x, float* dw, int N, int H, int W, int Cin, int Hout, int Wout, int Cout,
-                          int kh, int kw, int pad_y, int x_off, void* stream) {
+                          int kh, int kw, int pad_y, int x_off, int tap_major, void* stream) {
     if (int rc = check_geom("b3d_conv2d_thin_wgrad", N, H, W, Cin, Hout, Wout, Cout, kh, kw, pad_y, x_off)) return rc;
     B3D_REQUIRE(dy && x && dw, B3D_EINVAL, "b3d_conv2d_thin_wgrad: null pointer");
     B3D_CHECK_ALIGNED(x);
-    ThinGeom g{N, H, W, Cin, Hout, Wout, pad_y, x_off, Wout, Cout, 1.f};
+    ThinGeom g{N, H, W, Cin, Hout, Wout, pad_y, x_off, Wout, Cout, 1.f, tap_major ? 1 : 0};
     cudaStream_t st = (cudaStream_t)stream;
     // 4-wide lanes only where COUT * 25 * 4 accumulators fit the register file (Cout == 1)
     const bool v4 = Cin % 128 == 0 && Cout == 1;

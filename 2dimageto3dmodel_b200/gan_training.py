@@ -156,8 +156,10 @@ class GANTrainer:
         self.optimizer_d.step()
         return loss.detach()
 
-    def step(self, X_tex, X_alpha, X_mesh, C, noise=None):
+    def step(self, X_tex, X_alpha, X_mesh, C, noise=None, epoch=1000):
+        """epoch drives the warm-up of the running-average generator (main.py:431-438: alpha^100 for epoch < 10,
+        alpha^10 for epoch < 100)."""
         is_g = self.total_it % (1 + self.args.d_steps_per_g) == 0
-        out = self.g_step(X_alpha, C, noise) if is_g else self.d_step(X_tex, X_alpha, X_mesh, C, noise)
+        out = self.g_step(X_alpha, C, noise, epoch) if is_g else self.d_step(X_tex, X_alpha, X_mesh, C, noise)
         self.total_it += 1
         return out

@@ -17,8 +17,10 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from b3d import B3DError
+from b3d.bank import WeightBank
 from b3d.conv import conv2d as _tc_conv2d
-from b3d.ew import CIRCULAR, REPLICATE, cbn_act_pad, pad_x
+from b3d.conv import conv2d_banked
+from b3d.ew import CIRCULAR, REPLICATE, CBNBatch, cbn_act_pad, pad_x
 from rendering.utils import adjust_poles, symmetrize_texture
 
 
@@ -59,12 +61,27 @@ def _norm_and_bias(args):
     raise ValueError(f"norm_d={args.norm_d!r}")
 
 
-def _conv_norm_act(conv, norm, x, pad_next=0):
-    """pad_x(LeakyReLU(0.2)(norm(conv(x))), pad_next, circular): one fused kernel when there is no norm layer."""
+def _conv_norm_act(conv, norm, x, pad_next=0, lw=None):
+    """pad_x(LeakyReLU(0.2)(norm(conv(x))), pad_next, circular): one fused kernel when there is no norm layer.
+    lw: the layer's weights from the network's WeightBank (spectral norm + kernel layouts done for all layers at once);
+    None = the module's own forward (torch's spectral-norm hook)."""
+    if lw is not None:
+        run = lambda **kw: conv2d_banked(x, lw, pad_y=conv.padding[0], stride=conv.stride[0], **kw)
+    else:
+        run = lambda **kw: conv(x, **kw)
     if norm is None and conv.out_channels in (16, 32, 64, 128, 256, 512, 1024):
-        return conv(x, leaky=0.2, pad_out=pad_next, pad_mode=CIRCULAR)
-    y = conv(x, leaky=0.2) if norm is None else F.leaky_relu(norm(conv(x)), 0.2)
+        return run(leaky=0.2, pad_out=pad_next, pad_mode=CIRCULAR)
+    y = run(leaky=0.2) if norm is None else F.leaky_relu(norm(run()), 0.2)
     return pad_x(y, pad_next, CIRCULAR) if pad_next else y
+
+
+def _head(conv, x, lw):
+    return conv(x) if lw is None else conv2d_banked(x, lw, pad_y=conv.padding[0], stride=conv.stride[0])
+
+
+def _bankable(m):
+    """Layers a WeightBank can serve: circular variant (no zero padding along x), unit dilation / groups."""
+    return isinstance(m, TCConv2d) and m.padding[1] == 0 and m.dilation == (1, 1) and m.groups == 1 and m.stride[0] == m.stride[1]
 
 
 class _DiscriminatorBase(nn.Module):
@@ -129,7 +146,8 @@ class MeshDiscriminator(_DiscriminatorBase):
             if args.conditional_color:
                 self.projector_col1 = nn.Embedding(args.n_classes[1], 256)
 
-    def forward(self, texture, mesh_map, c=None, caption=None):
+    def forward(self, texture, mesh_map, c=None, caption=None, W=None, prefix="d2."):
+        W = W or {}
         x = F.avg_pool2d(texture, texture.shape[2] // mesh_map.shape[2])      # texture at mesh resolution (32x32)
         x = self._with_positions(x, (mesh_map,))
         mask = None
@@ -137,11 +155,11 @@ class MeshDiscriminator(_DiscriminatorBase):
             with torch.no_grad():
                 mask = F.avg_pool2d(x[:, 3:4], 4)
         p1, p2 = (1, 2) if self.circular else (0, 0)       # x padding of the 4x4 / 5x5 layers, applied by the producer
-        x = _conv_norm_act(self.conv1, None, self.pad(x), p1)
-        x = _conv_norm_act(self.conv2, self.bn2, x, p1)
-        x = _conv_norm_act(self.conv3, self.bn3, x, p2)
+        x = _conv_norm_act(self.conv1, None, self.pad(x), p1, W.get(prefix + "conv1"))
+        x = _conv_norm_act(self.conv2, self.bn2, x, p1, W.get(prefix + "conv2"))
+        x = _conv_norm_act(self.conv3, self.bn3, x, p2, W.get(prefix + "conv3"))
         feat = x[..., p2:x.shape[3] - p2]
-        y = self._project(self.conv4(x), feat, c, caption)
+        y = self._project(_head(self.conv4, x, W.get(prefix + "conv4")), feat, c, caption)
         return y, mask
 
 
@@ -179,7 +197,8 @@ class TextureDiscriminator(_DiscriminatorBase):
             if args.conditional_color:
                 self.projector_col1 = nn.Embedding(args.n_classes[1], 512)
 
-    def forward(self, x, c=None, caption=None):
+    def forward(self, x, c=None, caption=None, W=None, prefix="d1."):
+        W = W or {}
         if self.downsample > 1:
             x = F.avg_pool2d(x, self.downsample)
         mask = None
@@ -188,12 +207,12 @@ class TextureDiscriminator(_DiscriminatorBase):
                 mask = F.avg_pool2d(x[:, 3:4], 16 if self.stride_first else 8)
         x = self._with_positions(x)
         p1, p2 = (1, 2) if self.circular else (0, 0)       # x padding of the 4x4 / 5x5 layers, applied by the producer
-        x = _conv_norm_act(self.conv1, None, self.padconv1(x), p1)
-        x = _conv_norm_act(self.conv2, self.bn2, x, p1)
-        x = _conv_norm_act(self.conv3, self.bn3, x, p1)
-        x = _conv_norm_act(self.conv4, self.bn4, x, p2)
+        x = _conv_norm_act(self.conv1, None, self.padconv1(x), p1, W.get(prefix + "conv1"))
+        x = _conv_norm_act(self.conv2, self.bn2, x, p1, W.get(prefix + "conv2"))
+        x = _conv_norm_act(self.conv3, self.bn3, x, p1, W.get(prefix + "conv3"))
+        x = _conv_norm_act(self.conv4, self.bn4, x, p2, W.get(prefix + "conv4"))
         feat = x[..., p2:x.shape[3] - p2]
-        y = self._project(self.conv5(x), feat, c, caption)
+        y = self._project(_head(self.conv5, x, W.get(prefix + "conv5")), feat, c, caption)
         return y, mask
 
 
@@ -208,11 +227,39 @@ class MultiScaleDiscriminator(nn.Module):
         if args.num_discriminators == 3:
             self.d3 = TextureDiscriminator(args, nc, 4)
 
+    def _weights(self):
+        """Spectral norm + kernel layouts of every convolution of d1 / d2 / d3 in one WeightBank pass (b3d/bank.py)."""
+        if getattr(self, 'disable_bank', False):
+            return None
+        bank = self.__dict__.get('_bank')
+        if bank is None:
+            convs, fold = {}, []
+            for dn in ('d1', 'd2', 'd3'):
+                d = getattr(self, dn, None)
+                if d is None:
+                    continue
+                for cn in ('conv1', 'conv2', 'conv3', 'conv4', 'conv5'):
+                    m = getattr(d, cn, None)
+                    if m is None:
+                        continue
+                    if not _bankable(m):
+                        self.__dict__['_bank'] = False
+                        return None
+                    convs[f"{dn}.{cn}"] = m
+                    if cn == 'conv1' and m.stride[0] == 1 and m.kernel_size[0] > 1 and m.in_channels * m.kernel_size[0] <= 64:
+                        fold.append(f"{dn}.{cn}")               # thin stem: vertical taps folded into the channels
+            bank = self.__dict__['_bank'] = WeightBank(convs, fold=fold)
+        return bank.forward(self.training) if bank else None
+
     def forward(self, x, mesh_map=None, c=None, caption=None):
-        d1, m1 = self.d1(x, c, caption)
-        d2, m2 = self.d2(x, c, caption) if self.args.texture_only else self.d2(x, mesh_map, c, caption)
+        W = self._weights() if x.is_cuda else None
+        d1, m1 = self.d1(x, c, caption, W=W, prefix="d1.")
+        if self.args.texture_only:
+            d2, m2 = self.d2(x, c, caption, W=W, prefix="d2.")
+        else:
+            d2, m2 = self.d2(x, mesh_map, c, caption, W=W, prefix="d2.")
         if self.args.num_discriminators == 3:
-            d3, m3 = self.d3(x, c, caption)
+            d3, m3 = self.d3(x, c, caption, W=W, prefix="d3.")
             return [d1, d2, d3], [m1, m2, m3]
         return [d1, d2], [m1, m2]
 
@@ -265,18 +312,24 @@ class ResBlockUp(nn.Module):
         from torch.nn.modules.batchnorm import _BatchNorm
         return isinstance(self.norm1.norm, _BatchNorm) and isinstance(self.norm2.norm, _BatchNorm)
 
-    def forward_fused(self, xp, z, up, pad_next, post_leaky=False):
+    def forward_fused(self, xp, z, up, pad_next, post_leaky=False, W=None, prefix="", cb=None):
         """Same block on an input that is ALREADY replicate-padded by 1 (xp = pad(x, 1)); returns the padded input of the
         consumer: pad(up(out), pad_next) with out = [LeakyReLU](h + skip).  Every conv output goes through exactly one fused
         elementwise kernel (b3d.ew.cbn_act_pad) instead of BN, affine, LeakyReLU, add, upsample and pad kernels."""
-        y1 = self.conv1(xp)
-        a = cbn_act_pad(y1, self.norm1, z, up=1, pad=1)
-        y2 = self.conv2(a)
+        if W is not None:
+            c1 = lambda t: conv2d_banked(t, W[prefix + ".conv1"], pad_y=1)
+            c2 = lambda t: conv2d_banked(t, W[prefix + ".conv2"], pad_y=1)
+            sc = lambda t: conv2d_banked(t, W[prefix + ".shortcut"], x_crop=1)
+        else:
+            c1, c2, sc = self.conv1, self.conv2, (lambda t: self.shortcut(t, x_crop=1))
+        y1 = c1(xp)
+        a = cbn_act_pad(y1, self.norm1, z, up=1, pad=1, cb=cb)
+        y2 = c2(a)
         if isinstance(self.shortcut, nn.Module):
-            skip, off = self.shortcut(xp, x_crop=1), 0               # 1x1 conv on the interior of the padded input
+            skip, off = sc(xp), 0                                    # 1x1 conv on the interior of the padded input
         else:
             skip, off = xp, 1                                        # identity: read the interior of the padded input
-        return cbn_act_pad(y2, self.norm2, z, skip_nchw=skip, skip_off=off, up=up, pad=pad_next, post_leaky=post_leaky)
+        return cbn_act_pad(y2, self.norm2, z, skip_nchw=skip, skip_off=off, up=up, pad=pad_next, post_leaky=post_leaky, cb=cb)
 
 
 class Generator(nn.Module):
@@ -367,23 +420,52 @@ class Generator(nn.Module):
                 attention_map = symmetrize_texture(attention_map)
         return (x_tex, x_mesh, attention_map) if return_attention else (x_tex, x_mesh)
 
+    def _weights(self):
+        """Spectral norm + kernel layouts of every convolution of the generator in one WeightBank pass (b3d/bank.py)."""
+        if getattr(self, 'disable_bank', False):
+            return None
+        bank = self.__dict__.get('_bank')
+        if bank is None:
+            convs = {}
+            for bn in ('blk1', 'blk2', 'blk3a', 'blk3b', 'blk3c', 'blk4', 'blk5', 'blk6', 'blk3_mesh'):
+                blk = getattr(self, bn, None)
+                if blk is None:
+                    continue
+                convs[bn + ".conv1"], convs[bn + ".conv2"] = blk.conv1, blk.conv2
+                if isinstance(blk.shortcut, nn.Module):
+                    convs[bn + ".shortcut"] = blk.shortcut
+            convs["conv_final"] = self.conv_final
+            if self.mesh_head:
+                convs["conv_mesh"] = self.conv_mesh
+            bank = self.__dict__['_bank'] = WeightBank(convs)
+        return bank.forward(self.training)
+
     def _forward_fused(self, x, z, return_attention):
-        """The same network with the inter-convolution glue fused (replicate-padded tensors flow between the blocks)."""
+        """The same network with the inter-convolution glue fused (replicate-padded tensors flow between the blocks) and the
+        weights of all convolutions prepared by one WeightBank pass."""
+        W = self._weights()
+        names = [n for n in ('blk1', 'blk2', 'blk3a', 'blk3b', 'blk3c', 'blk4', 'blk5', 'blk6') if hasattr(self, n)]
+        if self.mesh_head:
+            names.append('blk3_mesh')
+        # gamma / beta of all conditional batch norms from one GEMM (blk1.norm1 first: it closes the gradient sink)
+        cb = CBNBatch([m for n in names for m in (getattr(self, n).norm1, getattr(self, n).norm2)], z)
+        blk = lambda name, inp, **kw: getattr(self, name).forward_fused(inp, z, W=W, prefix=name, cb=cb, **kw)
+        head = (lambda conv, name, inp: conv(inp)) if W is None else (lambda conv, name, inp: conv2d_banked(inp, W[name], pad_y=2))
         p = pad_x(x, 1, REPLICATE)
-        p = self.blk1.forward_fused(p, z, up=2, pad_next=1)
-        p = self.blk2.forward_fused(p, z, up=2, pad_next=1)          # blk2 -> up: shared by the texture and mesh branches
+        p = blk('blk1', p, up=2, pad_next=1)
+        p = blk('blk2', p, up=2, pad_next=1)                          # blk2 -> up: shared by the texture and mesh branches
         t = p
         for name in ('blk3a', 'blk3b', 'blk3c'):
             if hasattr(self, name):
-                t = getattr(self, name).forward_fused(t, z, up=2, pad_next=1)
-        t = self.blk4.forward_fused(t, z, up=2, pad_next=1)
-        t = self.blk5.forward_fused(t, z, up=2, pad_next=1)
-        t = self.blk6.forward_fused(t, z, up=1, pad_next=2, post_leaky=True)
-        x_tex = symmetrize_texture(torch.tanh(self.conv_final(t)))
+                t = blk(name, t, up=2, pad_next=1)
+        t = blk('blk4', t, up=2, pad_next=1)
+        t = blk('blk5', t, up=2, pad_next=1)
+        t = blk('blk6', t, up=1, pad_next=2, post_leaky=True)
+        x_tex = symmetrize_texture(torch.tanh(head(self.conv_final, "conv_final", t)))
         x_mesh = None
         if self.mesh_head:
-            m = self.blk3_mesh.forward_fused(p, z, up=1, pad_next=2, post_leaky=True)
-            x_mesh = symmetrize_texture(adjust_poles(self.conv_mesh(m)))
+            m = blk('blk3_mesh', p, up=1, pad_next=2, post_leaky=True)
+            x_mesh = symmetrize_texture(adjust_poles(head(self.conv_mesh, "conv_mesh", m)))
         return (x_tex, x_mesh, None) if return_attention else (x_tex, x_mesh)
 
 

@@ -26,13 +26,20 @@ class EffectiveLossFunction(nn.Module):
         self._taps_key = None
         self._taps = None
 
+    def __setattr__(self, name, value):
+        # the schedule assigns a fresh tensor to `sigma` every step (training_test_shape_net.py:29): drop the cached
+        # taps on every assignment (keying on id() would be wrong: CPython recycles ids)
+        if name == "sigma":
+            self.__dict__["_taps_key"] = None
+        super().__setattr__(name, value)
+
     def _current_taps(self):
         s = self.sigma
-        key = (id(s), s._version, self.kernel_size, self.semantics)
-        if key != self._taps_key:
+        key = (s._version, self.kernel_size, self.semantics)
+        if self._taps_key is None or key != self._taps_key[:3] or self._taps_key[3] is not s:
             # one host read per sigma change (the schedule changes it once per step at most)
             self._taps = smoothing_taps(float(s), self.kernel_size, self.semantics)
-            self._taps_key = key
+            self._taps_key = key + (s,)
         return self._taps
 
     def forward(self, point_cloud, rotation, scale=None):

@@ -217,7 +217,9 @@ B3D_API int b3d_chamfer_bwd(const float* query, const float* cand, const int32_t
 B3D_API int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* out, int N, int H, int W,
                             int Cin, int Hout, int Wout, int Cout, int ntaps, const int* dy, const int* dx,
                             int sy, int sx, int OH, int OW, int OC, int osy, int osx, int ooy, int oox,
-                            float leaky, int w_cin_major, void* stream);
+                            float leaky, int w_cin_major, const int* wtap, int wtaps_total, void* stream);
+/* wtap (nullable): loop tap t reads weight tap wtap[t] of a tap-major array that holds wtaps_total taps — the stride-2
+ * input-gradient parity classes address their tap subsets of the full weight array without a gathered copy.           */
 
 /* Stride-1 variant with a halo-staged input and R stacked accumulators (csrc/tc_conv2.cu): x [N,H,P,Cin] with P the
  * padded width (row pitch), taps (dy, dx >= 0); same weights / bias / LeakyReLU semantics as b3d_conv2d_tf32, output
@@ -234,7 +236,9 @@ B3D_API int b3d_conv2d_flat_tf32(const float* x, const float* wt, const float* b
  * dw [Cout,Cin,kh,kw] is ACCUMULATED into (caller zeroes it).                                          */
 B3D_API int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, int N, int H, int W, int Cin,
                                   int Hout, int Wout, int Cout, int kh, int kw, int pad_y, int stride,
-                                  int x_off, void* stream);
+                                  int x_off, int tap_major, void* stream);
+/* tap_major != 0: dw is the tap-major array [kh*kw][Cout][Cin] (the layout b3d_conv2d_tf32 reads, 16-byte vector
+ * reductions) instead of [Cout][Cin][kh][kw].                                                                        */
 
 /* Thin heads: 5x5 / stride-1 convolutions with 1..4 output channels (generator conv_final, models/gan.py:359;
  * discriminator heads :177, :302) on the fp32 CUDA cores, channels across the lanes of a warp.  Cin % 64 == 0.
@@ -245,7 +249,22 @@ B3D_API int b3d_conv2d_thin_fwd(const float* x, const float* wt, const float* bi
                                 int Hout, int Wout, int Cout, int kh, int kw, int pad_y, int x_off, int OW, int OC,
                                 float leaky, void* stream);
 B3D_API int b3d_conv2d_thin_wgrad(const float* dy, const float* x, float* dw, int N, int H, int W, int Cin, int Hout,
-                                  int Wout, int Cout, int kh, int kw, int pad_y, int x_off, void* stream);
+                                  int Wout, int Cout, int kh, int kw, int pad_y, int x_off, int tap_major, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Weight bank (csrc/sn_kernels.cu): spectral normalisation (torch.nn.utils.spectral_norm as applied at
+ * models/gan.py:57-65,163-177,294-302: one power iteration in training mode, sigma = u.(W v), W / sigma) and the
+ * kernel weight layouts of ALL convolutions of a network in four launches; backward maps the tap-major weight
+ * gradients back to weight_orig's layout through d(W / sigma).  `layers` is a device array of records of
+ * b3d_bank_layer_bytes() bytes each (field order: csrc/sn_kernels.cu BankLayer; packed by b3d/bank.py), `items_*` device
+ * arrays of int4 work items, `scratch` a per-bank buffer (zeroed here), `out` / `df` / `dw` per-call flat buffers.
+ * ------------------------------------------------------------------------------------------ */
+B3D_API int b3d_bank_layer_bytes(void);
+B3D_API int b3d_bank_forward(const void* layers, const void* items_wtu, int n_wtu, const void* items_wv, int n_wv,
+                             const void* items_emit, int n_emit, float* scratch, size_t scratch_bytes, float* out,
+                             int training, void* stream);
+B3D_API int b3d_bank_backward(const void* layers, const void* items_dot, int n_dot, const void* items_emit, int n_emit,
+                              float* out, const float* df, float* dw, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * One-pass NHWC helpers between the GAN's convolutions.
@@ -283,17 +302,27 @@ B3D_API int b3d_bn_stats(const float* y, long long rows, int C, float eps, float
  *   out[n, yo, xo, :] = post( leaky(y[n,ys,xs,:] * scale[n,:] + shift[n,:]) + skip[n,ys,xs,:] ),
  *   (ys, xs) = (yo / up, clamp(xo - pad, 0, up*W-1) / up);  out [N, up*H, up*W + 2*pad, C];  scale = inv_std*(1+gamma),
  *   shift = beta - mean*scale ([N,C]); skip (nullable) is read at row pitch skip_pitch, pixel offset skip_off.
- * bwd1: gout -> ga = d/d(pre-activation) [N,H,W,C], gskip (nullable), S1[n,c] = sum ga, S2[n,c] = sum ga*xhat (zeroed by the call)
- * bwd2 (in place on ga): dy = inv_std * (ga * gamma_t - m1 - xhat * m2), m1/m2 [C] = batch means of d xhat, d xhat * xhat   */
+ * bwd1: gout -> ga = d/d(pre-activation) [N,H,W,C], gskip (nullable), S1[n,c] = sum ga, S2[n,c] = sum ga*xhat: rows of
+ *       pitch s_pitch floats (>= C; slices of the batched d(gamma, beta) buffer), zeroed by the call
+ * bwd2 (in place on ga): dy = inv_std * (ga * gamma_t - m1 - xhat * m2), (m1, m2) [C] = inv_m * (sums of d xhat, d xhat * xhat)
+ * b3d_cbn_prepare / b3d_cbn_bwd_reduce / b3d_bn_sums: the per-layer scalar math around these passes, one launch each
+ *       (statistics -> mean / inv_std / running buffers / scale / shift; coupling-term reduction; fp64 channel sums).       */
 B3D_API int b3d_cbn_act_fwd(const float* y, const float* scale, const float* shift, const float* skip, int skip_pitch,
                             int skip_off, float* out, int N, int H, int W, int C, int up, int pad, float slope,
                             int post_leaky, void* stream);
 B3D_API int b3d_cbn_act_bwd1(const float* gout, const float* y, const float* scale, const float* shift, const float* skip,
                              int skip_pitch, int skip_off, const float* mean, const float* invstd, float* ga, float* gskip,
-                             int gskip_pitch, int gskip_off, float* S1, float* S2, int N, int H, int W, int C, int up, int pad,
-                             float slope, int post_leaky, void* stream);
+                             int gskip_pitch, int gskip_off, float* S1, float* S2, int s_pitch, int N, int H, int W, int C,
+                             int up, int pad, float slope, int post_leaky, void* stream);
 B3D_API int b3d_cbn_act_bwd2(float* ga, const float* y, const float* gamma_t, const float* mean, const float* invstd,
-                             const float* m1, const float* m2, int N, int H, int W, int C, void* stream);
+                             const float* m1, const float* m2, float inv_m, int N, int H, int W, int C, void* stream);
+B3D_API int b3d_bn_sums(const float* y, long long rows, int C, double* sums, void* stream);
+B3D_API int b3d_cbn_prepare(const float* gb, int gb_pitch, int gamma_off, int beta_off, const double* sums, double count,
+                            float eps, float momentum, int mode, float* running_mean, float* running_var,
+                            long long* num_batches_tracked, float* mean, float* invstd, float* scale, float* shift, float* gt,
+                            int N, int C, void* stream);
+B3D_API int b3d_cbn_bwd_reduce(const float* S1, const float* S2, int s_pitch, const float* gt, float* red, int N, int C,
+                               void* stream);
 
 #ifdef __cplusplus
 }
