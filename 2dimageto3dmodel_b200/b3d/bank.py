@@ -180,7 +180,8 @@ class _BankFn(torch.autograd.Function):
             sz = sp["Tp"] * sp["Cout"] * sp["Cinp"]
             if g.data_ptr() != df.data_ptr() + 4 * sp["wf_off"]:          # gradient did not come from the sink: copy it in
                 df[sp["wf_off"]: sp["wf_off"] + sz].copy_(g.reshape(-1))
-        dw = torch.empty(bank.w_total, device=df.device, dtype=torch.float32)
+        dw = torch.zeros(bank.w_total, device=df.device, dtype=torch.float32)    # zeros: alignment gaps are all-reduced too
+        bank.last_dw = dw                                   # flat gradient of all conv weights (in-place all-reduce under DDP)
         check(lib.b3d_bank_backward(ptr(bank._table), ptr(bank._dot[0]), bank._dot[1], ptr(bank._emit[0]), bank._emit[1],
                                     ptr(out), ptr(df), ptr(dw), stream_ptr(df)))
         gws = []

@@ -113,25 +113,36 @@ class _CBNActPad(torch.autograd.Function):
         P = gbd.shape[1]
         goff, boff = cb.offsets[key]
         st = stream_ptr(y)
-        mode, sums, count, sync = 0, None, 1.0, False
+        mode, sums, count, sync, peers = 0, None, 1.0, False, None
         if bn.training:
             sums = torch.empty(2 * C, device=y.device, dtype=torch.float64)
             check(lib.b3d_bn_sums(ptr(y), N * H * W, C, ptr(sums), st))
             mode, count = 1, float(N * H * W)
             if _dist_world() > 1 and bn.__class__.__name__.startswith("Synchronized"):
                 import torch.distributed as dist
-                dist.all_reduce(sums)                       # one collective per layer: [sum x, sum x^2] in fp64
+                from .sync import peer_sync
                 mode, count, sync = 2, count * dist.get_world_size(), True
+                peers = peer_sync(y.device) if C <= 512 else None
+                if peers is None:
+                    dist.all_reduce(sums)                   # NCCL fallback: one collective per layer, [sum x, sum x^2] in fp64
         mean = torch.empty(C, device=y.device, dtype=torch.float32)
         invstd = torch.empty_like(mean)
         scale = torch.empty(N, C, device=y.device, dtype=torch.float32)
         shift, gt = torch.empty_like(scale), torch.empty_like(scale)
         track = bn.training and bn.track_running_stats
-        check(lib.b3d_cbn_prepare(ptr(gbd), P, goff, boff, ptr(sums), count, float(bn.eps), float(bn.momentum or 0.0), mode,
-                                  ptr(bn.running_mean) if (track or mode == 0) else None,
-                                  ptr(bn.running_var) if (track or mode == 0) else None,
-                                  ptr(bn.num_batches_tracked) if track else None,
-                                  ptr(mean), ptr(invstd), ptr(scale), ptr(shift), ptr(gt), N, C, st))
+        if peers is not None:
+            # statistics all-reduce over NVLink peer memory fused into the kernel that consumes them (csrc/ew_kernels.cu)
+            check(lib.b3d_cbn_prepare_sync(peers.data, peers.flag, peers.rank, peers.world, ptr(peers.epoch), ptr(peers.err),
+                                           ptr(gbd), P, goff, boff, ptr(sums), count, float(bn.eps), float(bn.momentum or 0.0),
+                                           ptr(bn.running_mean) if track else None, ptr(bn.running_var) if track else None,
+                                           ptr(bn.num_batches_tracked) if track else None,
+                                           ptr(mean), ptr(invstd), ptr(scale), ptr(shift), ptr(gt), N, C, st))
+        else:
+            check(lib.b3d_cbn_prepare(ptr(gbd), P, goff, boff, ptr(sums), count, float(bn.eps), float(bn.momentum or 0.0), mode,
+                                      ptr(bn.running_mean) if (track or mode == 0) else None,
+                                      ptr(bn.running_var) if (track or mode == 0) else None,
+                                      ptr(bn.num_batches_tracked) if track else None,
+                                      ptr(mean), ptr(invstd), ptr(scale), ptr(shift), ptr(gt), N, C, st))
         sk = dev(skip.detach(), "skip") if skip is not None else None
         pitch = sk.shape[2] if sk is not None else 0
         out = torch.empty(N, up * H, up * W + 2 * pad, C, device=y.device, dtype=torch.float32)
@@ -141,6 +152,7 @@ class _CBNActPad(torch.autograd.Function):
         ctx.cb, ctx.key = cb, key
         ctx.cfg = (skip_off, up, pad, post_leaky, mode != 0, sync, count, sk is not None, skip.shape if skip is not None else None,
                    P, goff, boff)
+        ctx.peers = peers
         return out
 
     @staticmethod
@@ -166,10 +178,15 @@ class _CBNActPad(torch.autograd.Function):
         inv_m = 0.0
         if batch_stats:
             red = torch.empty(2 * C, device=y.device, dtype=torch.float32)
-            check(lib.b3d_cbn_bwd_reduce(s1, s2, P, ptr(gt), ptr(red), N, C, st))
-            if sync:
-                import torch.distributed as dist
-                dist.all_reduce(red)
+            peers = ctx.peers
+            if sync and peers is not None:
+                check(lib.b3d_cbn_bwd_reduce_sync(peers.data, peers.flag, peers.rank, peers.world, ptr(peers.epoch), ptr(peers.err),
+                                                  s1, s2, P, ptr(gt), ptr(red), N, C, st))
+            else:
+                check(lib.b3d_cbn_bwd_reduce(s1, s2, P, ptr(gt), ptr(red), N, C, st))
+                if sync:
+                    import torch.distributed as dist
+                    dist.all_reduce(red)
             inv_m = 1.0 / count
         else:
             red = torch.zeros(2 * C, device=y.device, dtype=torch.float32)

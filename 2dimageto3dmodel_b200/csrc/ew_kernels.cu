@@ -404,6 +404,121 @@ cbn_prepare_kernel(const float* __restrict__ gb, int gb_pitch, int gamma_off, in
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// SyncBN statistics WITHOUT a separate collective: a one-shot all-reduce over NVLink / NVSwitch peer memory fused into
+// the kernel that consumes the sums (SURVEY §5 "one fused SyncBN collective"; VERDICT r1 "weak" #9: 64 latency-bound
+// [2,C] NCCL all-reduces per step, each wrapped in ~10 tiny ops).  Every rank owns a symmetric buffer (torch symmetric
+// memory: the same allocation mapped into every peer):  data [2 parities][world][SYNC_MAX] doubles + flag [2][world] u32.
+// Call k (epoch e = k, parity e & 1) on rank r:  store the local vector into slot [parity][r] of EVERY peer's buffer,
+// fence, store e into flag [parity][r] of every peer (release, system scope); spin until the own flags [parity][0..world)
+// all read e (acquire); sum the world slots in rank order — bitwise identical on all ranks.  A peer can run at most one
+// call ahead (it needs this rank's flag of call k+1 to finish call k+1), and that call uses the other parity, so two
+// parities suffice.  A spin that exceeds ~4 s (a dead peer) sets *err and falls through instead of hanging the GPU.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int SYNC_MAX = 1024;          // payload doubles per rank (2 * C, C <= 512)
+constexpr int SYNC_RANKS = 8;
+struct SyncPeers {
+    double* data[SYNC_RANKS];           // peer p's buffer (own rank included)
+    unsigned* flag[SYNC_RANKS];
+};
+
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// vec: shared-memory vector of n doubles (local contribution in, world total out).  All threads of the CTA call.
+__device__ void peer_allreduce(const SyncPeers& P, int rank, int world, unsigned* epoch_ctr, int* err, double* vec, int n) {
+    __shared__ unsigned ep_s;
+    if (threadIdx.x == 0) ep_s = ++(*epoch_ctr);
+    __syncthreads();
+    const unsigned e = ep_s, par = e & 1u;
+    for (int p = 0; p < world; ++p) {
+        double* dst = P.data[p] + ((size_t)par * world + rank) * SYNC_MAX;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = vec[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < world) {
+        unsigned* f = P.flag[threadIdx.x] + par * world + rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(e) : "memory");
+        const unsigned* mine = P.flag[rank] + par * world + threadIdx.x;
+        const unsigned long long t0 = gtimer();
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+            if (v != e && gtimer() - t0 > 4000000000ull) { *err = 1; break; }
+        } while (v != e);
+    }
+    __syncthreads();
+    const double* src = P.data[rank] + (size_t)par * world * SYNC_MAX;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double t = 0.0;
+        for (int r = 0; r < world; ++r) t += src[(size_t)r * SYNC_MAX + i];
+        vec[i] = t;
+    }
+    __syncthreads();
+}
+
+// b3d_cbn_prepare (mode 2: the reference's SyncBN formulas) with the all-reduce of the fp64 sums fused in.  One CTA.
+__global__ void __launch_bounds__(512)
+cbn_prepare_sync_kernel(SyncPeers P, int rank, int world, unsigned* epoch_ctr, int* err, const float* __restrict__ gb,
+                        int gb_pitch, int gamma_off, int beta_off, const double* __restrict__ sums_local, double count, float eps,
+                        float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
+                        long long* __restrict__ nbt, float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                        float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ gt, int N, int C) {
+    __shared__ double tot[SYNC_MAX];
+    __shared__ float mean_s[SYNC_MAX / 2], inv_s[SYNC_MAX / 2];
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) tot[i] = sums_local[i];
+    __syncthreads();
+    peer_allreduce(P, rank, world, epoch_ctr, err, tot, 2 * C);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const double m = tot[c] / count;
+        const double var_b = (tot[C + c] - tot[c] * m) / count;
+        const float mean = (float)m, invstd = (float)(1.0 / sqrt(var_b > (double)eps ? var_b : (double)eps));
+        mean_s[c] = mean;
+        inv_s[c] = invstd;
+        mean_out[c] = mean;
+        invstd_out[c] = invstd;
+        if (running_mean != nullptr) {
+            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+            running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(var_b * (count / (count > 1.0 ? count - 1.0 : 1.0)));
+            if (c == 0 && nbt != nullptr) *nbt += 1;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < N * C; i += blockDim.x) {
+        const int n = i / C, c = i - n * C;
+        const float g1 = 1.f + gb[(long long)n * gb_pitch + gamma_off + c];
+        const float sc = inv_s[c] * g1;
+        scale[i] = sc;
+        shift[i] = gb[(long long)n * gb_pitch + beta_off + c] - mean_s[c] * sc;
+        gt[i] = g1;
+    }
+}
+
+// b3d_cbn_bwd_reduce with the all-reduce of red [2][C] fused in.  One CTA.
+__global__ void __launch_bounds__(512)
+cbn_bwd_reduce_sync_kernel(SyncPeers P, int rank, int world, unsigned* epoch_ctr, int* err, const float* __restrict__ S1,
+                           const float* __restrict__ S2, int s_pitch, const float* __restrict__ gt, float* __restrict__ red, int N,
+                           int C) {
+    __shared__ double tot[SYNC_MAX];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int n = 0; n < N; ++n) {
+            const float g = gt[(long long)n * C + c];
+            a = fmaf(g, S1[(long long)n * s_pitch + c], a);
+            b = fmaf(g, S2[(long long)n * s_pitch + c], b);
+        }
+        tot[c] = (double)a;
+        tot[C + c] = (double)b;
+    }
+    __syncthreads();
+    peer_allreduce(P, rank, world, epoch_ctr, err, tot, 2 * C);
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = (float)tot[i];
+}
+
 // red[0][c] = sum_n gt[n,c] * S1[n,c],  red[1][c] = sum_n gt[n,c] * S2[n,c]   (batch-norm coupling terms of the backward)
 __global__ void __launch_bounds__(NT)
 cbn_bwd_reduce_kernel(const float* __restrict__ S1, const float* __restrict__ S2, int s_pitch, const float* __restrict__ gt,
@@ -670,6 +785,51 @@ int b3d_cbn_prepare(const float* gb, int gb_pitch, int gamma_off, int beta_off, 
 int b3d_cbn_bwd_reduce(const float* S1, const float* S2, int s_pitch, const float* gt, float* red, int N, int C, void* stream) {
     B3D_REQUIRE(N > 0 && C > 0 && S1 && S2 && gt && red, B3D_EINVAL, "b3d_cbn_bwd_reduce: bad arguments");
     cbn_bwd_reduce_kernel<<<(C + NT - 1) / NT, NT, 0, (cudaStream_t)stream>>>(S1, S2, s_pitch, gt, red, N, C);
+    B3D_LAUNCH_OK();
+    return B3D_OK;
+}
+
+// --- SyncBN with the collective fused in (one-shot all-reduce over NVLink peer memory; see peer_allreduce above) ---------
+// peer_data / peer_flag: `world` device pointers each (rank order) into every rank's symmetric buffer: data
+// [2][world][1024] doubles, flags [2][world] uint32 (zero-initialised once); epoch / err: this rank's own counters (zeroed
+// once).  All ranks must issue the same sequence of *_sync calls.  world <= 8, C <= 512.
+size_t b3d_sync_buffer_bytes(int world) { return (size_t)2 * world * SYNC_MAX * sizeof(double) + (size_t)2 * world * sizeof(unsigned) + 256; }
+size_t b3d_sync_flag_offset(int world) { return (size_t)2 * world * SYNC_MAX * sizeof(double); }
+
+static int fill_peers(SyncPeers& P, const void* const* peer_data, const void* const* peer_flag, int rank, int world, int C) {
+    B3D_REQUIRE(world >= 2 && world <= SYNC_RANKS && rank >= 0 && rank < world, B3D_EINVAL, "sync: world=%d rank=%d (2..%d ranks)", world,
+                rank, SYNC_RANKS);
+    B3D_REQUIRE(C > 0 && 2 * C <= SYNC_MAX, B3D_EINVAL, "sync: C=%d exceeds %d", C, SYNC_MAX / 2);
+    B3D_REQUIRE(peer_data && peer_flag, B3D_EINVAL, "sync: null peer tables");
+    for (int p = 0; p < SYNC_RANKS; ++p) {
+        P.data[p] = p < world ? (double*)const_cast<void*>(peer_data[p]) : nullptr;
+        P.flag[p] = p < world ? (unsigned*)const_cast<void*>(peer_flag[p]) : nullptr;
+        B3D_REQUIRE(p >= world || (P.data[p] && P.flag[p]), B3D_EINVAL, "sync: null peer pointer %d", p);
+    }
+    return B3D_OK;
+}
+
+int b3d_cbn_prepare_sync(const void* const* peer_data, const void* const* peer_flag, int rank, int world, unsigned* epoch, int* err,
+                         const float* gb, int gb_pitch, int gamma_off, int beta_off, const double* sums_local, double count,
+                         float eps, float momentum, float* running_mean, float* running_var, long long* num_batches_tracked,
+                         float* mean, float* invstd, float* scale, float* shift, float* gt, int N, int C, void* stream) {
+    SyncPeers P;
+    if (int rc = fill_peers(P, peer_data, peer_flag, rank, world, C)) return rc;
+    B3D_REQUIRE(N > 0 && gb && sums_local && count > 0 && mean && invstd && scale && shift && gt && epoch && err, B3D_EINVAL,
+                "b3d_cbn_prepare_sync: bad arguments");
+    cbn_prepare_sync_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(P, rank, world, epoch, err, gb, gb_pitch, gamma_off, beta_off, sums_local,
+                                                                count, eps, momentum, running_mean, running_var, num_batches_tracked,
+                                                                mean, invstd, scale, shift, gt, N, C);
+    B3D_LAUNCH_OK();
+    return B3D_OK;
+}
+
+int b3d_cbn_bwd_reduce_sync(const void* const* peer_data, const void* const* peer_flag, int rank, int world, unsigned* epoch, int* err,
+                            const float* S1, const float* S2, int s_pitch, const float* gt, float* red, int N, int C, void* stream) {
+    SyncPeers P;
+    if (int rc = fill_peers(P, peer_data, peer_flag, rank, world, C)) return rc;
+    B3D_REQUIRE(N > 0 && S1 && S2 && gt && red && epoch && err, B3D_EINVAL, "b3d_cbn_bwd_reduce_sync: bad arguments");
+    cbn_bwd_reduce_sync_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(P, rank, world, epoch, err, S1, S2, s_pitch, gt, red, N, C);
     B3D_LAUNCH_OK();
     return B3D_OK;
 }

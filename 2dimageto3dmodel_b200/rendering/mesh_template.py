@@ -136,6 +136,8 @@ class MeshTemplate:
         self.nonneg_tangent_map = frames[nonneg].to(device)
         self.is_symmetric = is_symmetric
         self._mirror_x = torch.tensor([-1.0, 1.0, 1.0], device=device)
+        self._zero_indices = zero.to(device)
+        self._records = {}          # (h, w, symmetric) -> per-vertex records of the fused CUDA vertex pipeline
 
     # ---- deformation ---------------------------------------------------------------------------------
     def deform(self, deltas):
@@ -153,8 +155,48 @@ class MeshTemplate:
         # even symmetry puts the seam half a texel in: u -> (u + delta) / expansion
         return 1 / (2 * width), (width + 1) / width
 
+    def _vertex_records(self, h, w):
+        """Sampling sites of get_vertex_positions resolved once per map size for libb3d's fused vertex kernel: per vertex
+        four texel offsets into the UNPADDED map (wrap-around / seam column folded in), bilinear weights, the tangent frame
+        of the sampled vertex, the template position and the x factor (-1 mirrored, 0 on the symmetry plane, +1)."""
+        key = (h, w, self.is_symmetric)
+        hit = self._records.get(key)
+        if hit is None:
+            from b3d.vertex import pack_records
+            V = self.topo_map.shape[0]
+            if self.is_symmetric:
+                delta, expansion = self._symmetric_shift(w)
+                site = self.nonneg_topo_map.clone()
+                site[:, 0] = (site[:, 0] + 1 + 2 * delta - expansion) / expansion
+                nn_idx, neg, pos, zero = (t.cpu() for t in (self.nonneg_indices, self.neg_indices, self.pos_indices, self._zero_indices))
+                src = torch.zeros(V, dtype=torch.long)              # row of `site` / nonneg frames each vertex samples
+                src[nn_idx] = torch.arange(len(nn_idx))
+                where = {int(v): i for i, v in enumerate(nn_idx.tolist())}
+                src[neg] = torch.tensor([where[int(p)] for p in pos.tolist()], dtype=torch.long)
+                sign = torch.ones(V)
+                sign[neg], sign[zero] = -1.0, 0.0
+                rec, sgn = pack_records(site.cpu()[src], w + 2, h, w, lambda xp: (xp - 1) % w,
+                                        self.nonneg_tangent_map.cpu()[src], self.mesh.vertices.cpu(), sign)
+            else:
+                rec, sgn = pack_records(self.topo_map.cpu(), w + 1, h, w, lambda xp: xp % w, self.tangent_map.cpu(),
+                                        self.mesh.vertices.cpu(), torch.ones(V))
+            dev_ = self.mesh.vertices.device
+            hit = self._records[key] = (rec.to(dev_), sgn.to(dev_))
+        return hit
+
+    def vertices_and_pose(self, displacement_map, scale=None, translation=None, rot=None, z0=None):
+        """get_vertex_positions + transform_vertices (run_reconstruction.py:237-252) in ONE CUDA launch (and one for the
+        backward): -> (raw [B,V,3] object-space vertices, vtx [B,V,3] camera-space vertices or None without a pose).
+        scale [B,1] (already including any learned delta), translation [B,3], rot [B,4] unit quaternions, z0 [B,1]|None."""
+        from b3d.vertex import vertex_pipeline
+        rec, sgn = self._vertex_records(displacement_map.shape[2], displacement_map.shape[3])
+        return vertex_pipeline(displacement_map, rec, sgn, self.topo_map.shape[0], scale, translation, rot, z0)
+
     def get_vertex_positions(self, displacement_map):
-        """UV displacement map [B,3,h,w] -> vertex positions [B,V,3] (reference :125-149)."""
+        """UV displacement map [B,3,h,w] -> vertex positions [B,V,3] (reference :125-149).  CUDA tensors take the fused
+        kernel; the torch composition below is the same math for other devices."""
+        if displacement_map.is_cuda and displacement_map.dtype == torch.float32 and not getattr(self, 'disable_fused_vertices', False):
+            return self.vertices_and_pose(displacement_map)[0]
         B, w = displacement_map.shape[0], displacement_map.shape[3]
         _, padded = self.adjust_uv_and_texture(displacement_map)
         if self.is_symmetric:

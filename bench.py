@@ -45,27 +45,53 @@ def stage(msg):
 N_PTS, V, H, TEX, FLAT_COEF = 8000, 128, 256, 128, 5e-4
 WORKLOADS = {
     # BASELINE.json configs[1]
-    "cfg2": dict(batch=16, gan=False, metric="render+loss images/sec (cfg2: 8000-pt effective loss V=128 + CUB mesh render 256x256, fwd+bwd)",
+    "cfg2": dict(batch=16, gan=False, kind="render", iters=1,
+                 metric="render+loss images/sec (cfg2: 8000-pt effective loss V=128 + CUB mesh render 256x256, fwd+bwd)",
                  name="cfg2: CUB 256x256, 8000-pt cloud, full render+loss, batch=16 per GPU"),
     # BASELINE.json configs[2] = the configuration the metric "render+loss+GAN images/sec" is quoted on
-    "cfg3": dict(batch=32, gan=True, metric="render+loss+GAN images/sec (cfg3: cfg2 render+loss at batch 32 + conv-GAN 256x256 G/D iteration, 1 G : 2 D, Adam)",
+    "cfg3": dict(batch=32, gan=True, kind="render+gan", iters=3, res=256, nd=2,
+                 metric="render+loss+GAN images/sec (cfg3: cfg2 render+loss at batch 32 + conv-GAN 256x256 G/D iteration, 1 G : 2 D, Adam)",
                  name="cfg3: CUB 256x256 render+loss + conv-GAN G/D step, batch=32 per GPU"),
+    # BASELINE.json configs[3]: run_reconstruction.py's training iteration (network -> template -> pose with DatasetParams
+    # deltas + z0 -> render -> MSE + flat warm-up -> two Adams) on the P3D template (962 v / 1920 f); the reference's batch
+    # of 50 on one GPU, 13 per rank under DDP x4 (global 52: equal shards)
+    "cfg4": dict(batch=50, gan=False, kind="recon", iters=1,
+                 metric="reconstruction-training images/sec (cfg4: ReconstructionNetwork + P3D mesh render 256x256 + losses, optimize_z0, Adam x2)",
+                 name="cfg4: Pascal3D+ 256x256, optimize_z0 reconstruction loop, batch=50 (13 per GPU under DDP)"),
+    # BASELINE.json configs[4]: main.py's GAN iteration at 512^2 with three discriminators, 8 images per rank
+    "cfg5": dict(batch=8, gan=True, kind="gan", iters=3, res=512, nd=3,
+                 metric="GAN-training images/sec (cfg5: conv-GAN 512x512 class-conditional, nd=3, 1 G : 2 D, Adam, SyncBN)",
+                 name="cfg5: CUB 512x512 class-conditional GAN training, batch=8 per GPU (64 on 8 GPUs)"),
 }
 GAN_RES = 256
 
 
-def gan_args():
+def gan_args(res=256, nd=2):
     import types
-    return types.SimpleNamespace(texture_resolution=GAN_RES, conditional_class=True, conditional_color=False,
+    return types.SimpleNamespace(texture_resolution=res, conditional_class=True, conditional_color=False,
                                  conditional_text=False, norm_g='syncbatch', norm_d='none', n_classes=(200,),
-                                 mask_output=True, texture_only=False, num_discriminators=2, text_embedding_dim=256,
+                                 mask_output=True, texture_only=False, num_discriminators=nd, text_embedding_dim=256,
                                  latent_dim=64, loss='hinge', lr_g=1e-4, lr_d=4e-4, d_steps_per_g=2,
                                  mesh_regularization=1e-4, g_running_average_alpha=0.999, symmetric_g=True)
 
 
-def gan_host_inputs(B, seed, pin):
+def recon_host_inputs(B, seed, pin, dataset_size=4722):
+    """cfg4: RGBA images with a disk alpha, poses in the ranges of cache/p3d/poses_metadata.npz, image indices
+    into a dataset of 4722 images and their mirrored copies."""
+    g = torch.Generator().manual_seed(seed + 13)
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, H), torch.linspace(-1, 1, H), indexing="ij")
+    disk = ((yy * yy + xx * xx) < 0.45).float()
+    x_real = torch.rand(B, 4, H, H, generator=g) * 2 - 1
+    x_real[:, 3] = disk
+    x_real[:, :3] *= disk
+    d = dict(x_real=x_real, pscale=0.55 + 0.3 * torch.rand(B, 1, generator=g), ptrans=(torch.rand(B, 3, generator=g) - 0.5) * 0.3,
+             rot=torch.nn.functional.normalize(torch.randn(B, 4, generator=g), dim=-1),
+             idx=torch.randint(0, 2 * dataset_size, (B,), generator=g))
+    return {k: (v.pin_memory() if pin else v) for k, v in d.items()}
+
+
+def gan_host_inputs(B, seed, pin, R=256):
     g = torch.Generator().manual_seed(seed + 77)
-    R = GAN_RES
     alpha = (torch.rand(B, 1, R // 8, R // 8, generator=g) > 0.4).float()
     d = dict(X_tex=torch.rand(B, 3, R, R, generator=g) * 2 - 1,
              X_alpha=torch.nn.functional.interpolate(alpha, size=(R, R), mode="bilinear", align_corners=False),
@@ -93,54 +119,61 @@ def host_inputs(B, seed, pin):
     return {k: (v.pin_memory() if pin else v) for k, v in d.items()}
 
 
-def template_path():
+def template_path(rings=16):
     from tools.uvsphere import write_uvsphere_obj          # synthetic input (the shipped templates cannot travel)
-    return write_uvsphere_obj(os.path.join(tempfile.mkdtemp(), "uvsphere_16rings.obj"), rings=16)
+    return write_uvsphere_obj(os.path.join(tempfile.mkdtemp(), f"uvsphere_{rings}rings.obj"), rings=rings)
 
 
 # --------------------------------------------------------------------------------------------- CUDA arm
 class CudaWorkload:
-    def __init__(self, device, gan=False):
+    def __init__(self, device, cfg):
         from rendering.mesh_template import MeshTemplate
         from rendering.renderer import Renderer
         from utils.effective_loss_function import EffectiveLossFunction
-        self.dev = device
-        self.elf = EffectiveLossFunction(voxel_size=V).to(device)
-        self.tpl = MeshTemplate(template_path(), device=device)
-        self.renderer = Renderer(H, H)
-        self.flip = torch.tensor([1.0, -1.0, -1.0], device=device)
-        self.gan = None
-        if gan:
+        self.dev, self.kind = device, cfg["kind"]
+        self.gan = self.recon = None
+        self.tpl = MeshTemplate(template_path(31 if self.kind == "recon" else 16), device=device)
+        if "render" in self.kind:
+            self.elf = EffectiveLossFunction(voxel_size=V).to(device)
+            self.renderer = Renderer(H, H)
+        if cfg["gan"]:
             from gan_training import GANTrainer
             torch.manual_seed(4321)                      # identical replicas on every rank
-            self.gan = GANTrainer(gan_args(), mesh_template=self.tpl, device=device, capturable=True)
+            self.gan = GANTrainer(gan_args(cfg["res"], cfg["nd"]), mesh_template=self.tpl, device=device, capturable=True)
+        if self.kind == "recon":
+            from reconstruction_training import ReconTrainer, default_args
+            torch.manual_seed(4321)
+            self.recon = ReconTrainer(default_args(optimize_z0=True), self.tpl, dataset_size=4722, device=device, capturable=True)
 
     def step(self, batches):
         """One step over `batches` (one input dict per training iteration).  cfg2: render+loss fwd+bwd.  cfg3: three
         iterations (G, D, D — the reference's 1 : d_steps_per_g alternation, main.py:691), each on its own batch =
-        render+loss fwd+bwd + one GAN step with its optimiser."""
-        if self.gan is None:
+        render+loss fwd+bwd + one GAN step with its optimiser.  cfg4: one run_reconstruction.py iteration.  cfg5: G, D, D."""
+        if self.kind == "render":
             return self.render_step(batches[0])
+        if self.kind == "recon":
+            d = batches[0]
+            return self.recon.step(d["x_real"], d["pscale"], d["ptrans"], d["rot"], d["idx"])[0], None
         loss = None
         for it, d in enumerate(batches):
-            rl, _ = self.render_step(d)
             if it == 0:
                 gl = self.gan.g_step(d["X_alpha"], d["C"])
             else:
                 gl = self.gan.d_step(d["X_tex"], d["X_alpha"], d["X_mesh"], d["C"])
-            loss = rl + gl if loss is None else loss + rl + gl
+            if "render" in self.kind:
+                gl = gl + self.render_step(d)[0]
+            loss = gl if loss is None else loss + gl
         return loss, None
 
     def render_step(self, d):
         from b3d.mesh import rgba_mse_iou
-        from rendering.utils import qrot
         from utils.losses import loss_flat
         p, q, s = (d[k].detach().requires_grad_(True) for k in ("points", "quat", "scale"))
         sil = self.elf(p, q, s)
         loss_pc = (sil - d["mask"]).square().sum() / sil.shape[0]        # unsupervised_part.py:111
         mm, tex = d["mesh_map"].detach().requires_grad_(True), d["tex"].detach().requires_grad_(True)
-        raw = self.tpl.get_vertex_positions(mm)
-        vtx = (qrot(d["rot"], d["pscale"].unsqueeze(-1) * raw) + d["ptrans"].unsqueeze(1)) * self.flip
+        # get_vertex_positions + transform_vertices in one launch (b3d.vertex; run_reconstruction.py:425-427)
+        raw, vtx = self.tpl.vertices_and_pose(mm, d["pscale"], d["ptrans"], d["rot"])
         img, alpha = self.tpl.forward_renderer(self.renderer, vtx, tex)
         recon, miou = rgba_mse_iou(img, alpha, d["x_real"])
         flat = loss_flat(self.tpl.mesh, self.tpl.compute_normals(raw))
@@ -247,11 +280,11 @@ def chamfer_report(dev, B=32, N=8000):
             "frac": round(fl / (ms * 1e-3) / 1e12 / fp32_peak, 4), "bound": "fp32 issue (8NM flop over 20(N+M) bytes)"}
 
 
-def algorithmic_bytes(B):
+def algorithmic_bytes(B, F_=960):
     """SURVEY.md §8(d) per-sample figures x the samples one launch processes (stated in DESIGN.md)."""
     pc_fwd = 8 * V**3 + 4 * V**2 + 12 * N_PTS
     pc_all = 20 * V**3 + 8 * V**2 + 36 * N_PTS
-    F_, Tw = 960, TEX + 2
+    Tw = TEX + 2
     mesh_fwd = 100 * F_ + 12 * TEX * Tw + H * H * 48
     mesh_bwd = H * H * 32 + 12 * TEX * Tw + 60 * F_
     return {"b3d_pc_silhouette_fwd_hosttaps": B * pc_fwd, "b3d_pc_silhouette_bwd_hosttaps": B * (pc_all - pc_fwd),
@@ -288,15 +321,21 @@ def run_cuda(args):
     stage("process group ready" if world > 1 else "start")
     cfg = WORKLOADS[args.workload]
     METRIC, WORKLOAD = cfg["metric"], cfg["name"]
-    wl = CudaWorkload(dev, gan=cfg["gan"])
+    wl = CudaWorkload(dev, cfg)
     stage("workload built")
     B = cfg["batch"]
-    iters_per_step = 3 if cfg["gan"] else 1
+    if cfg["kind"] == "recon" and world > 1:
+        B = 13                                              # DDP x4: 52 = 4 x 13 (equal shards of the reference's batch of 50)
+    iters_per_step = cfg["iters"]
     host = []                                               # one pinned host batch per training iteration of the step;
     for it in range(iters_per_step):                        # each rank owns its shard of the global batch
-        hb = host_inputs(B, seed=1234 + rank + 1000 * it, pin=True)
+        hb = {}
+        if "render" in cfg["kind"]:
+            hb.update(host_inputs(B, seed=1234 + rank + 1000 * it, pin=True))
         if cfg["gan"]:
-            hb.update(gan_host_inputs(B, seed=1234 + rank + 1000 * it, pin=True))
+            hb.update(gan_host_inputs(B, seed=1234 + rank + 1000 * it, pin=True, R=cfg["res"]))
+        if cfg["kind"] == "recon":
+            hb.update(recon_host_inputs(B, seed=1234 + rank + 1000 * it, pin=True))
         host.append(hb)
     h2d = sum(t.numel() * t.element_size() for hb in host for t in hb.values())
     resident = [{k: v.to(dev) for k, v in hb.items()} for hb in host]
@@ -334,8 +373,9 @@ def run_cuda(args):
     graph = None
     # N > 1: the step contains NCCL collectives (gradient all-reduce, SyncBN statistics); they are captured into the
     # graph too (thread-local capture mode, NCCL async error handling off).  B3D_DDP_EAGER=1 launches eagerly instead.
-    capture_ok = world == 1 or not cfg["gan"] or (os.environ.get("B3D_DIST_BACKEND", "nccl") == "nccl"
-                                                  and not os.environ.get("B3D_DDP_EAGER"))
+    has_coll = cfg["gan"] or cfg["kind"] == "recon"
+    capture_ok = world == 1 or not has_coll or (os.environ.get("B3D_DIST_BACKEND", "nccl") == "nccl"
+                                                and not os.environ.get("B3D_DDP_EAGER"))
     if not args.no_graph and capture_ok:
         # the step has no host synchronisation: capture it once (forward + backward) and replay it
         side = torch.cuda.Stream()
@@ -368,7 +408,7 @@ def run_cuda(args):
         torch.cuda.current_stream().synchronize()            # the user reads the loss every step
         return loss
 
-    tf32 = measure_tf32_peak(dev) if cfg["gan"] and rank == 0 else None
+    tf32 = measure_tf32_peak(dev) if (cfg["gan"] or cfg["kind"] == "recon") and rank == 0 else None
     stage("tf32 peak measured" if tf32 else "timing setup")
     clocks = ClockSampler(local) if rank == 0 else None
     time.sleep(0.3) if clocks else None
@@ -416,12 +456,24 @@ def run_cuda(args):
     ms = total_ms / args.steps
     value = world * B * iters_per_step / (ms / 1e3)
     e2e_v = world * B * iters_per_step / (e2e_ms / args.steps / 1e3)
-    alg = algorithmic_bytes(B)
+    alg = algorithmic_bytes(B, 1920 if cfg["kind"] == "recon" else 960)
     cand = {k: prof[k] for k in alg if k in prof}
-    top = max(cand, key=cand.get)
-    ach = alg[top] / (cand[top] * 1e-3) / 1e9
+    top = max(cand, key=cand.get) if cand else None
+    ach = alg[top] / (cand[top] * 1e-3) / 1e9 if top else 0.0
     tensor = None
-    if cfg["gan"]:
+    if cfg["kind"] in ("recon", "gan"):
+        # dense-conv FLOPs per image: reconstruction network 12.21 GF fwd, x3 for fwd + dgrad + wgrad
+        # (the first layer's input gradient is not executed: conv1e 5x5/s2 4->64, 0.21 GF); 512^2 GAN, nd=3: G 66.56, D 17.80
+        # GF fwd; G-step 3G + 2D, D-step G + 6D minus the first-layer input gradients of the 2B batch
+        # (d1.conv1 1.07 + d2.conv1 0.036 + d3.conv1 0.42 GF)
+        gf_img = 3 * 12.21 - 0.21 if cfg["kind"] == "recon" else (3 * 66.56 + 2 * 17.80) + 2 * (66.56 + 6 * 17.80 - 2 * 1.526)
+        conv_ms = sum(v for k, v in prof_tot.items() if k.startswith("b3d_conv2d"))
+        tensor = {"kernel": "all conv entry points", "bound": "tensor",
+                  "achieved": round(gf_img * B / (conv_ms * 1e-3) / 1e3, 1), "peak": tf32["sustained"], "unit": "TFLOP/s",
+                  "frac": round(gf_img * B / (conv_ms * 1e-3) / 1e3 / tf32["sustained"], 4), "traffic": None,
+                  "peak_source": tf32["how"], "peak_burst": tf32["burst"], "conv_ms_per_step": round(conv_ms, 3),
+                  "gflop_per_step": round(gf_img * B, 1)}
+    elif cfg["gan"]:
         # dense-conv FLOPs of one G + two D iterations (SURVEY §8d / App. D at 256^2, nd=2: G 17.09, D 14.76 GF/img fwd),
         # counting only what is executed: G-step = fwd G+D, dgrad+wgrad G, dgrad D (the reference's discarded D wgrad is
         # skipped) = 3G + 2D; D-step = G fwd + D fwd/dgrad/wgrad on 2B images = G + 6D — over the time spent inside the
@@ -451,7 +503,8 @@ def run_cuda(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": world * B,
                    "iterations_per_step": iters_per_step, "points": N_PTS, "voxels": V,
-                   "image": H, "faces": 960, "texture": TEX, "l2": "flushed between timed iterations (256 MB write)",
+                   "image": cfg.get("res", H) if cfg["kind"] == "gan" else H, "faces": 1920 if cfg["kind"] == "recon" else 960,
+                   "texture": TEX, "l2": "flushed between timed iterations (256 MB write)",
                    "parallelism": (f"dp{world}: batch shards; render/loss without collectives, GAN with SyncBN statistic "
                                    "all-reduces + gradient all-reduce (NCCL, captured in the step graph)") if cfg["gan"]
                    else f"dp{world} (batch shards, no data-path collective)", "semantics": "R",
@@ -463,7 +516,7 @@ def run_cuda(args):
         "clocks": clk,
         "roofline": {"kernel": top, "bound": "hbm", "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s",
                      "frac": round(ach / hbm_peak, 4), "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg[top], "ms_per_launch": round(cand[top], 4)},
+                     "algorithmic_bytes_per_launch": alg[top], "ms_per_launch": round(cand[top], 4)} if top else None,
         "kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(prof_tot.items(), key=lambda kv: -kv[1])},
     }
     try:
@@ -471,12 +524,13 @@ def run_cuda(args):
     except Exception as e:                                   # reported, never fatal for the headline
         out["chamfer"] = {"error": str(e)[:200]}
     if tensor is not None:
-        # cfg3: the convolutions dominate the step -> the tensor-core roofline is the primary one; the HBM-class kernel
-        # roofline (point-cloud backward) moves to roofline_hbm
-        out["roofline_hbm"] = out["roofline"]
+        # the convolutions dominate the step -> the tensor-core roofline is the primary one; the HBM-class kernel
+        # roofline (point-cloud / raster backward) moves to roofline_hbm
+        if out["roofline"] is not None:
+            out["roofline_hbm"] = out["roofline"]
         out["roofline"] = tensor
         out["dtype"] = "tf32 (convs) / f32"
-    if world == 1 and not os.environ.get("B3D_BENCH_NO_CPU"):
+    if world == 1 and not os.environ.get("B3D_BENCH_NO_CPU") and cfg["kind"] != "recon":
         out["cpu_baseline"] = cpu_baseline(cfg, budget_s=25.0)
     print(json.dumps(out), flush=True)
     finish()
@@ -511,15 +565,16 @@ def cpu_threads():
 class OracleWorkload:
     """The same step through oracle/ (the reference's algorithm restated in torch, on the CPU)."""
 
-    def __init__(self, gan=False):
+    def __init__(self, cfg):
         from oracle import mesh as M
         self.M = M
         path = template_path()
         self.T = M.TemplateData(M.load_obj(path), path)
         self.gan = None
-        if gan:
+        self.render = "render" in cfg["kind"]
+        if cfg["gan"]:
             from oracle import gan as OG                    # the CPU arms never import the product package (libb3d.so)
-            self.OG, self.args = OG, gan_args()
+            self.OG, self.args = OG, gan_args(cfg["res"], cfg["nd"])
             self.sg, self.sd = OG.init_state(self.args, seed=4321)
             for sdict in (self.sg, self.sd):
                 for k in OG.trainable(sdict):
@@ -551,7 +606,8 @@ class OracleWorkload:
         OG, M, T = self.OG, self.M, self.T
         total = 0.0
         for it, d in enumerate(batches):
-            total = total + self.render_step(d)
+            if self.render:
+                total = total + self.render_step(d)
             B = d["C"].shape[0]
             z = torch.randn(B, 64)
             if it == 0:
@@ -572,17 +628,17 @@ class OracleWorkload:
 
 def cpu_inputs(cfg, sample_b):
     out = []
-    for it in range(3 if cfg["gan"] else 1):
-        d = host_inputs(sample_b, seed=1234 + 1000 * it, pin=False)
+    for it in range(cfg["iters"]):
+        d = host_inputs(sample_b, seed=1234 + 1000 * it, pin=False) if "render" in cfg["kind"] else {}
         if cfg["gan"]:
-            d.update(gan_host_inputs(sample_b, seed=1234 + 1000 * it, pin=False))
+            d.update(gan_host_inputs(sample_b, seed=1234 + 1000 * it, pin=False, R=cfg["res"]))
         out.append(d)
     return out
 
 
 def cpu_baseline(cfg, budget_s, sample_b=2):
     cores = cpu_threads()
-    wl = OracleWorkload(gan=cfg["gan"])
+    wl = OracleWorkload(cfg)
     d = cpu_inputs(cfg, sample_b)
     iters = 3 if cfg["gan"] else 1
     t0 = time.perf_counter()
@@ -600,6 +656,16 @@ def cpu_baseline(cfg, budget_s, sample_b=2):
 
 
 def run_reference(args):
+    if WORKLOADS[args.workload]["kind"] == "recon":
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "cfg4: oracle/ has no restatement of the reconstruction network "
+                              "(its goldens come from the reference module itself in the authoring container); the reference tree "
+                              "cannot be installed or travel"}))
+        return
+    _run_reference(args)
+
+
+def _run_reference(args):
     """The reference's own CPU implementation of the path (its algorithm restated in torch under oracle/ — the reference
     tree itself cannot be installed or travel) on THIS arm's config: the same batch per step, the same
     three iterations per step; bounded to one timed step (a step is ~100 s of CPU work at batch 32)."""
@@ -611,7 +677,7 @@ def run_reference(args):
     B, iters = cfg["batch"], (3 if cfg["gan"] else 1)
     if os.environ.get("B3D_REF_BATCH"):                      # development aid
         B = int(os.environ["B3D_REF_BATCH"])
-    wl = OracleWorkload(gan=cfg["gan"])
+    wl = OracleWorkload(cfg)
     d = cpu_inputs(cfg, B)
     warm = 0 if cfg["gan"] else min(args.warmup, 1)
     for _ in range(warm):

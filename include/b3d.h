@@ -252,6 +252,28 @@ B3D_API int b3d_conv2d_thin_wgrad(const float* dy, const float* x, float* dw, in
                                   int Wout, int Cout, int kh, int kw, int pad_y, int x_off, int tap_major, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Fused vertex pipeline (csrc/vertex_kernels.cu): displacement map -> template vertices -> camera
+ * space in one launch (and one for the backward).
+ *   MeshTemplate.get_vertex_positions / deform / adjust_uv_and_texture   rendering/mesh_template.py:106-111,125-170
+ *   transform_vertices                                                    run_reconstruction.py:237-252
+ *   qrot                                                                  rendering/utils.py:36-46
+ * dmap [B,3,h,w] addressed through element strides (sn, sc, sy, sx); rec [V] per-vertex records of
+ * b3d_vertex_record_bytes() bytes (int32 tap[4] texel offsets y*w+x of the unpadded map with the wrap-around column
+ * resolved, float wgt[4] bilinear weights, float frame[9] tangent frame rows, float v0[3]); sgn [V] float4 (x factor:
+ * -1 mirrored vertex, 0 on the symmetry plane, +1).  Pose (nullable together with vtx): scale [B], trans [B,3], rot
+ * [B,4] (w,x,y,z), z0 [B] (nullable: perspective correction).  raw / vtx [B,V,3].
+ * _bwd: g_raw / g_vtx [B,V,3] (either nullable) -> d_dmap [B,3,h,w] (NCHW contiguous), d_scale [B], d_trans [B,3],
+ * d_z0 [B] (all nullable, ACCUMULATED into: the caller zeroes them).
+ * ------------------------------------------------------------------------------------------ */
+B3D_API int b3d_vertex_record_bytes(void);
+B3D_API int b3d_vertex_pipeline_fwd(const float* dmap, long long sn, long long sc, long long sy, long long sx, int h, int w,
+                                    const void* rec, const void* sgn, int B, int V, const float* scale, const float* trans,
+                                    const float* rot, const float* z0, float* raw, float* vtx, void* stream);
+B3D_API int b3d_vertex_pipeline_bwd(const float* g_raw, const float* g_vtx, const float* raw, const void* rec, const void* sgn,
+                                    int B, int V, int h, int w, const float* scale, const float* trans, const float* rot,
+                                    const float* z0, float* d_dmap, float* d_scale, float* d_trans, float* d_z0, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Weight bank (csrc/sn_kernels.cu): spectral normalisation (torch.nn.utils.spectral_norm as applied at
  * models/gan.py:57-65,163-177,294-302: one power iteration in training mode, sigma = u.(W v), W / sigma) and the
  * kernel weight layouts of ALL convolutions of a network in four launches; backward maps the tap-major weight
@@ -323,6 +345,22 @@ B3D_API int b3d_cbn_prepare(const float* gb, int gb_pitch, int gamma_off, int be
                             int N, int C, void* stream);
 B3D_API int b3d_cbn_bwd_reduce(const float* S1, const float* S2, int s_pitch, const float* gt, float* red, int N, int C,
                                void* stream);
+/* SyncBN (sync_batchnorm/batchnorm.py:68-150: statistics over all replicas) with the collective FUSED into the consuming
+ * kernel: a one-shot all-reduce over NVLink / NVSwitch peer memory (csrc/ew_kernels.cu peer_allreduce) instead of a
+ * separate NCCL all-reduce per layer.  peer_data / peer_flag: host arrays of `world` device pointers (rank order) into every
+ * rank's symmetric buffer (b3d_sync_buffer_bytes(world) bytes, zeroed once; flags start at b3d_sync_flag_offset(world));
+ * epoch / err: this rank's own device counters (zeroed once; *err != 0 after a peer timed out).  Same maths as
+ * b3d_cbn_prepare mode 2 / b3d_cbn_bwd_reduce on the global sums.  world <= 8, C <= 512; every rank issues the same calls. */
+B3D_API size_t b3d_sync_buffer_bytes(int world);
+B3D_API size_t b3d_sync_flag_offset(int world);
+B3D_API int b3d_cbn_prepare_sync(const void* const* peer_data, const void* const* peer_flag, int rank, int world,
+                                 unsigned* epoch, int* err, const float* gb, int gb_pitch, int gamma_off, int beta_off,
+                                 const double* sums_local, double count, float eps, float momentum, float* running_mean,
+                                 float* running_var, long long* num_batches_tracked, float* mean, float* invstd, float* scale,
+                                 float* shift, float* gt, int N, int C, void* stream);
+B3D_API int b3d_cbn_bwd_reduce_sync(const void* const* peer_data, const void* const* peer_flag, int rank, int world,
+                                    unsigned* epoch, int* err, const float* S1, const float* S2, int s_pitch, const float* gt,
+                                    float* red, int N, int C, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,24 +1,35 @@
 #!/bin/bash
-# One GPU-box visit: parity tests, bench line, ncu captures.  Everything lands in gpurun_out/ (kept < 64 MiB).
-T=${1:-r2b}
+# One GPU-box visit: parity tests, bench line, ncu captures.  Everything lands in gpurun_out/ (kept well below 64 MiB:
+# ncu reports are exported to CSV on the box and deleted).
+T=${1:-r2c}
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q -x -p no:cacheprovider > gpurun_out/${T}_pytest.log 2>&1
+rm -f gpurun_out/*.ncu-rep
+python -m pytest tests -m gpu -q -p no:cacheprovider --timeout 900 -rf --tb=short ${PYTEST_ARGS} > gpurun_out/${T}_pytest.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/${T}_pytest.log
 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err
 if [ "${NCU:-1}" = "1" ]; then
-  timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off \
-    -k regex:'pc_|mesh_|chamfer|cbn_|pad_leaky|fold_rows|wrap_x|rgba|flat_loss|bn_stats|bank_' -c 100 -f \
+  timeout 900 ncu --set full --clock-control none --profile-from-start off \
+    -k regex:'pc_|mesh_|chamfer|cbn_|pad_leaky|fold_rows|wrap_x|rgba|flat_loss|bn_stats|bank_|vertex_' -c 70 -f \
     -o gpurun_out/${T}_nonconv python tools/ncu_r2_step.py > gpurun_out/${T}_ncu.log 2>&1
-  B3D_BENCH_NO_CPU=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 --csv \
+  ncu -i gpurun_out/${T}_nonconv.ncu-rep --page raw --csv > gpurun_out/${T}_nonconv_raw.csv 2>/dev/null
+  rm -f gpurun_out/${T}_nonconv.ncu-rep
+  B3D_BENCH_NO_CPU=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3500 --csv \
     --log-file gpurun_out/${T}_launches.csv python bench.py --steps 2 --warmup 1 > gpurun_out/${T}_launches_bench.log 2>&1
 fi
-echo "==== pytest"; tail -n 12 gpurun_out/${T}_pytest.log
+if [ "${EXTRA:-0}" = "1" ]; then
+  B3D_BENCH_NO_CPU=1 python bench.py --workload cfg4 --steps 10 --warmup 3 > gpurun_out/${T}_bench_cfg4.json 2> gpurun_out/${T}_bench_cfg4.err
+  B3D_BENCH_NO_CPU=1 python bench.py --workload cfg5 --steps 10 --warmup 3 > gpurun_out/${T}_bench_cfg5.json 2> gpurun_out/${T}_bench_cfg5.err
+  B3D_BENCH_NO_CPU=1 python bench.py --workload cfg2 --steps 20 --warmup 5 > gpurun_out/${T}_bench_cfg2.json 2> gpurun_out/${T}_bench_cfg2.err
+  for w in cfg4 cfg5 cfg2; do echo "== $w"; cut -c1-400 gpurun_out/${T}_bench_$w.json; tail -n 3 gpurun_out/${T}_bench_$w.err | cut -c1-300; done
+fi
+echo "==== pytest"; grep -E "^(FAILED|ERROR)|passed|failed|rc=" gpurun_out/${T}_pytest.log | tail -n 30
+grep -E "^E  " gpurun_out/${T}_pytest.log | head -n 30
 echo "==== bench"; python - <<PY
 import json
 try:
     d = json.loads(open("gpurun_out/${T}_bench.json").read().strip().splitlines()[-1])
-    print({k: d[k] for k in ("value", "ms_per_step", "gpu_launches")}, d["e2e"], d["roofline"], d.get("chamfer"))
-    ks = d["kernel_ms_per_step"]; print("libb3d ms/step", round(sum(ks.values()), 2), dict(list(ks.items())[:12]))
+    print({k: d[k] for k in ("value", "ms_per_step", "gpu_launches")}, d["e2e"]["value"], d["roofline"]["achieved"], d["roofline"]["frac"])
+    ks = d["kernel_ms_per_step"]; print("libb3d ms/step", round(sum(ks.values()), 2), dict(list(ks.items())[:14]))
 except Exception as e:
     print("bench parse failed", e); print(open("gpurun_out/${T}_bench.err").read()[-1500:])
 PY
