@@ -81,7 +81,7 @@ def conv2d_nhwc(x, weight, bias=None, pad_y=0, stride=1, leaky=1.0, wt=None, cin
             check(rc)
     if not use_flat or rc != 0:
         check(_conv_call(lib.b3d_conv2d_tf32, ptr(x), ptr(wt), ptr(b), optr, N, H, W, Cin, Hout, Wout, Cout, kh * kw, _ints(dy),
-                                  _ints(dx), stride, stride, Hout, OW, Cout, 1, 1, 0, 0, float(leaky), int(cin_major), None, 0,
+                                  _ints(dx), stride, stride, Hout, OW, Cout, 1, 1, 0, 0, float(leaky), int(cin_major), None, 0, None,
                                   stream_ptr(x)))
     if pad_out:
         check(lib.b3d_wrap_x_inplace(ptr(out), N * Hout, Wout, Cout, pad_out, pad_mode, stream_ptr(x)))
@@ -116,7 +116,7 @@ def conv2d_dgrad_nhwc(dy_, weight, in_hw, pad_y=0, stride=1, x_crop=0):
         dy = [pad_y - r for r in range(kh) for _ in range(kw)]
         dx = [-s - x_crop for _ in range(kh) for s in range(kw)]
         check(_conv_call(lib.b3d_conv2d_tf32, ptr(g), ptr(wt), None, ptr(dxo), N, Hout, Wout, Cout, H, W, Cin, kh * kw, _ints(dy),
-                                  _ints(dx), 1, 1, H, W, Cin, 1, 1, 0, 0, 1.0, 0, None, 0, st))
+                                  _ints(dx), 1, 1, H, W, Cin, 1, 1, 0, 0, 1.0, 0, None, 0, None, st))
         return dxo
     if stride != 2 or x_crop:
         raise B3DError("conv2d_dgrad: stride must be 1 or 2 (x_crop: stride 1 only)")
@@ -126,7 +126,7 @@ def conv2d_dgrad_nhwc(dy_, weight, in_hw, pad_y=0, stride=1, x_crop=0):
             continue
         wt = torch.stack([weight[:, :, r, s].t() for r, s in rs]).contiguous()      # [taps][Cin][Cout]
         check(_conv_call(lib.b3d_conv2d_tf32, ptr(g), ptr(wt), None, ptr(dxo), N, Hout, Wout, Cout, Ha, Wa, Cin, len(rs),
-                                  _ints(dy), _ints(dx), 1, 1, H, W, Cin, 2, 2, cy, cx, 1.0, 0, None, 0, st))
+                                  _ints(dy), _ints(dx), 1, 1, H, W, Cin, 2, 2, cy, cx, 1.0, 0, None, 0, None, st))
     return dxo
 
 
@@ -266,7 +266,7 @@ def conv2d(x_nchw, weight, bias=None, pad_y=0, stride=1, leaky=1.0, pad_out=0, p
 # ------------------------------------------------------------------------------------------------------------------
 class _ConvBanked(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, wf, bias, lw, pad_y, stride, leaky, pad_out, pad_mode, x_crop):
+    def forward(ctx, x, wf, bias, lw, pad_y, stride, leaky, pad_out, pad_mode, x_crop, stats=None):
         x = dev(x.detach(), "x")
         N, H, W, Cx = x.shape
         if Cx != lw.Cinp:
@@ -299,6 +299,10 @@ class _ConvBanked(torch.autograd.Function):
             use_flat = stride == 1 and Cout > 64 and N * Hout * W >= 2 * 148 * 384 and not x_crop
             if os.environ.get("B3D_CONV_FLAT"):
                 use_flat = stride == 1 and os.environ["B3D_CONV_FLAT"] == "1"
+            if stats is not None:                 # the statistics epilogue lives in the persistent / row-window kernels
+                use_flat = False
+                if bias is not None or leaky != 1.0 or stride != 1:
+                    raise B3DError("banked conv: output statistics are taken before bias / activation (plain stride-1 convs only)")
             rc = -1
             if use_flat:
                 rc = _conv_call(lib.b3d_conv2d_flat_tf32, ptr(x), ptr(wt), ptr(b), optr, N, H, W, Cin, Hout, Wout, Cout, kh * kw,
@@ -307,7 +311,7 @@ class _ConvBanked(torch.autograd.Function):
                     check(rc)
             if rc != 0:
                 check(_conv_call(lib.b3d_conv2d_tf32, ptr(x), ptr(wt), ptr(b), optr, N, H, W, Cin, Hout, Wout, Cout, kh * kw,
-                                 _ints(dy), _ints(dx), stride, stride, Hout, OW, Cout, 1, 1, 0, 0, float(leaky), 0, None, 0, st))
+                                 _ints(dy), _ints(dx), stride, stride, Hout, OW, Cout, 1, 1, 0, 0, float(leaky), 0, None, 0, ptr(stats), st))
         if pad_out:
             check(lib.b3d_wrap_x_inplace(ptr(out), N * Hout, Wout, Cout, pad_out, pad_mode, st))
         ctx.save_for_backward(x, out if (leaky != 1.0 or pad_out) else None)
@@ -352,7 +356,7 @@ class _ConvBanked(torch.autograd.Function):
                 dy = [pad_y - r for r in range(kh) for _ in range(kw)]
                 dx = [-s - x_crop for _ in range(kh) for s in range(kw)]
                 check(_conv_call(lib.b3d_conv2d_tf32, ptr(gyp), ptr(wd), None, ptr(gx), N, Hout, Wout, Cop, H, W, Cin, kh * kw,
-                                 _ints(dy), _ints(dx), 1, 1, H, W, Cin, 1, 1, 0, 0, 1.0, 0, None, 0, st))
+                                 _ints(dy), _ints(dx), 1, 1, H, W, Cin, 1, 1, 0, 0, 1.0, 0, None, 0, None, st))
             elif stride == 2 and not x_crop:
                 for cy, cx, rs, dy, dx, Ha, Wa in stride2_classes(kh, kw, pad_y, H, W):
                     if not rs:
@@ -360,7 +364,7 @@ class _ConvBanked(torch.autograd.Function):
                         continue
                     taps = [r * kw + s for r, s in rs]                  # rows of the tap-major D array: no gathered copy
                     check(_conv_call(lib.b3d_conv2d_tf32, ptr(gyp), ptr(wd), None, ptr(gx), N, Hout, Wout, Cop, Ha, Wa, Cin,
-                                     len(rs), _ints(dy), _ints(dx), 1, 1, H, W, Cin, 2, 2, cy, cx, 1.0, 0, _ints(taps), kh * kw, st))
+                                     len(rs), _ints(dy), _ints(dx), 1, 1, H, W, Cin, 2, 2, cy, cx, 1.0, 0, _ints(taps), kh * kw, None, st))
             else:
                 raise B3DError("conv2d_dgrad: stride must be 1 or 2 (x_crop: stride 1 only)")
             if Cx != Cin:
@@ -377,15 +381,17 @@ class _ConvBanked(torch.autograd.Function):
                     raise B3DError(f"banked conv: weight gradient needs Cout % 32 == 0 or a thin head (Cout={Cout})")
                 check(_conv_call(lib.b3d_conv2d_wgrad_tf32, ptr(gy), ptr(x), ptr(gw), N, H, W, Cin, Hout, Wout, Cout, kh, kw, pad_y,
                                  stride, x_crop, 1, st))
-        return gx, gw, gb, None, None, None, None, None, None, None
+        return gx, gw, gb, None, None, None, None, None, None, None, None
 
 
-def conv2d_banked(x_nchw, lw, pad_y=0, stride=1, leaky=1.0, pad_out=0, pad_mode=1, x_crop=0):
+def conv2d_banked(x_nchw, lw, pad_y=0, stride=1, leaky=1.0, pad_out=0, pad_mode=1, x_crop=0, stats=None):
     """conv2d for a layer whose weights come from a WeightBank (`lw` = its LayerWeights).  Thin stems registered with
-    fold=True get their kh taps folded into the channels here (b3d.ew.fold_rows), as in conv2d()."""
+    fold=True get their kh taps folded into the channels here (b3d.ew.fold_rows), as in conv2d().
+    stats: optional zeroed fp64 tensor [2*Cout]; the conv epilogue accumulates the output's per-channel sum / sum of
+    squares into it (the following batch norm's statistics without another pass over the tensor)."""
     x = x_nchw.permute(0, 2, 3, 1)
     if lw.fold:
         from .ew import fold_rows
         x = fold_rows(x, lw.kh, pad_y, lw.Cinp)
-    y = _ConvBanked.apply(x, lw.wf, lw.bias, lw, int(pad_y), int(stride), float(leaky), int(pad_out), int(pad_mode), int(x_crop))
+    y = _ConvBanked.apply(x, lw.wf, lw.bias, lw, int(pad_y), int(stride), float(leaky), int(pad_out), int(pad_mode), int(x_crop), stats)
     return y.permute(0, 3, 1, 2)

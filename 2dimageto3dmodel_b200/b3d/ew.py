@@ -93,6 +93,15 @@ class CBNBatch:
         self.n_layers, self.done = len(cbns), 0
         self.gb = torch.nn.functional.linear(z, torch.cat(ws), torch.cat(bs))
         self.sink = None
+        # fp64 [sum x | sum x^2] slots the conv epilogues accumulate into (one zero fill for all layers of the forward)
+        self.stats = torch.zeros(off, device=z.device, dtype=torch.float64) if z.is_cuda else None
+
+    def stats_slot(self, cbn):
+        """The layer's zeroed statistics slot [2*C] (handed to the producing convolution), or None in eval mode."""
+        if self.stats is None or not cbn.norm.training:
+            return None
+        goff, boff = self.offsets[id(cbn)]
+        return self.stats[goff: goff + 2 * (boff - goff)]
 
     def grad_sink(self):
         if self.sink is None:
@@ -106,7 +115,7 @@ class _CBNActPad(torch.autograd.Function):
     and the per-sample affine come from one b3d_cbn_prepare launch (modes: 0 eval, 1 batch statistics, 2 SyncBN)."""
 
     @staticmethod
-    def forward(ctx, y, gb, cb, key, bn, skip, skip_off, up, pad, post_leaky):
+    def forward(ctx, y, gb, cb, key, bn, skip, skip_off, up, pad, post_leaky, sums_in=None):
         y = dev(y.detach(), "y")
         N, H, W, C = y.shape
         gbd = dev(gb.detach(), "gamma/beta")
@@ -115,8 +124,11 @@ class _CBNActPad(torch.autograd.Function):
         st = stream_ptr(y)
         mode, sums, count, sync, peers = 0, None, 1.0, False, None
         if bn.training:
-            sums = torch.empty(2 * C, device=y.device, dtype=torch.float64)
-            check(lib.b3d_bn_sums(ptr(y), N * H * W, C, ptr(sums), st))
+            if sums_in is not None:                     # accumulated by the epilogue of the convolution that produced y
+                sums = sums_in
+            else:
+                sums = torch.empty(2 * C, device=y.device, dtype=torch.float64)
+                check(lib.b3d_bn_sums(ptr(y), N * H * W, C, ptr(sums), st))
             mode, count = 1, float(N * H * W)
             if _dist_world() > 1 and bn.__class__.__name__.startswith("Synchronized"):
                 import torch.distributed as dist
@@ -199,7 +211,7 @@ class _CBNActPad(torch.autograd.Function):
                 if cb.done != cb.n_layers:
                     raise RuntimeError(f"CBNBatch: {cb.done} of {cb.n_layers} layers ran their backward before the first layer's")
                 ggb = sink
-        return ga, ggb, None, None, None, gskip, None, None, None, None
+        return ga, ggb, None, None, None, gskip, None, None, None, None, None
 
 
 _BN_STATS_IMPL = os.environ.get("B3D_BN_STATS", "torch")
@@ -219,7 +231,7 @@ def bn_stats(y_nhwc, eps, impl=None):
     return mean, invstd
 
 
-def cbn_act_pad(y_nchw, cbn, z, skip_nchw=None, skip_off=0, up=1, pad=1, post_leaky=False, cb=None):
+def cbn_act_pad(y_nchw, cbn, z, skip_nchw=None, skip_off=0, up=1, pad=1, post_leaky=False, cb=None, sums=None):
     """ConditionalBatchNorm2d(y, z) -> LeakyReLU(0.2) [-> + skip] [-> LeakyReLU] [-> x2 upsample] -> replicate pad, fused.
     `cbn` is a models.gan.ConditionalBatchNorm2d whose .norm is a (Synchronized)BatchNorm2d without affine; statistics and
     running buffers follow F.batch_norm (single process) or the reference's SyncBN formulas (torch.distributed).
@@ -231,5 +243,5 @@ def cbn_act_pad(y_nchw, cbn, z, skip_nchw=None, skip_off=0, up=1, pad=1, post_le
     if C % 4 or 256 % (C // 4):
         raise B3DError(f"cbn_act_pad: C={C} must be 4 * a divisor of 256")
     skip = skip_nchw.permute(0, 2, 3, 1) if skip_nchw is not None else None
-    out = _CBNActPad.apply(y, cb.gb, cb, id(cbn), cbn.norm, skip, int(skip_off), int(up), int(pad), bool(post_leaky))
+    out = _CBNActPad.apply(y, cb.gb, cb, id(cbn), cbn.norm, skip, int(skip_off), int(up), int(pad), bool(post_leaky), sums)
     return out.permute(0, 3, 1, 2)

@@ -161,6 +161,56 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, bool a_mn =
            | ((uint32_t)(M >> 4) << 24);   // m_dim
 }
 
+// ---------------------------------------------------------------------------------------------- epilogue: BN statistics
+// Per-channel sum / sum of squares of a conv OUTPUT accumulated by the epilogue that already holds the values in
+// registers (SURVEY §5 / §7 step 7 "BN statistics in the conv epilogue"; replaces a separate pass over the tensor).
+// v[32]: this lane's pixel, 32 consecutive channels (zeros for pixels outside the tensor).  A transposing butterfly
+// (31 shuffles per quantity) leaves lane l with the warp's sum for channel l; the four epilogue warps fold into a CTA
+// shared-memory pair sm_stats[2][BN] and the CTA flushes it with fp64 global atomics once per work item.
+__device__ __forceinline__ void warp_channel_sums(const float (&v)[32], float& s, float& q) {
+    float a[32], b[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { a[i] = v[i]; b[i] = v[i] * v[i]; }
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int ofs = 16; ofs >= 1; ofs >>= 1) {
+        const bool up = (lane & ofs) != 0;
+#pragma unroll
+        for (int i = 0; i < ofs; ++i) {
+            const float sa = up ? a[i] : a[i + ofs], ka = up ? a[i + ofs] : a[i];
+            const float sb = up ? b[i] : b[i + ofs], kb = up ? b[i + ofs] : b[i];
+            a[i] = ka + __shfl_xor_sync(0xffffffffu, sa, ofs);
+            b[i] = kb + __shfl_xor_sync(0xffffffffu, sb, ofs);
+        }
+    }
+    s = a[0];
+    q = b[0];
+}
+// epilogue warps: add this chunk's 32 channel sums into sm_stats[0][c..c+32) / sm_stats[1][...]  (BN = row length)
+__device__ __forceinline__ void stats_accumulate(const float (&v)[32], bool valid, float* sm_stats, int BN_, int c) {
+    float z[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) z[i] = valid ? v[i] : 0.f;
+    float s, q;
+    warp_channel_sums(z, s, q);
+    const int lane = threadIdx.x & 31;
+    atomicAdd(sm_stats + c + lane, s);
+    atomicAdd(sm_stats + BN_ + c + lane, q);
+}
+// one epilogue warp after all four are done with the item (named barrier 1, 128 threads): flush + clear
+__device__ __forceinline__ void stats_flush(float* sm_stats, int BN_, double* gstats, int C, int c0, int ep_tid) {
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    for (int i = ep_tid; i < BN_; i += 128) {
+        if (c0 + i < C) {
+            atomicAdd(gstats + c0 + i, (double)sm_stats[i]);
+            atomicAdd(gstats + C + c0 + i, (double)sm_stats[BN_ + i]);
+        }
+        sm_stats[i] = 0.f;
+        sm_stats[BN_ + i] = 0.f;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
 // ---------------------------------------------------------------------------------------------- host: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

@@ -17,6 +17,7 @@
 // epilogue (TMEM -> registers -> bias / LeakyReLU -> global).  STAGES-deep mbarrier ring between producer
 // and MMA; tcgen05.commit frees a stage and finally signals the epilogue.
 #include "tc_common.cuh"
+#include "tc_rowwin.cuh"
 
 namespace {
 
@@ -39,6 +40,7 @@ struct ConvParams {
     int OH, OW, OC, osy, osx, ooy, oox;
     float leaky;                      // 1.0 = identity
     int dbg_lbo, dbg_sbo, dbg_lt;     // MN-major descriptor offsets (bytes), layout type
+    double* stats;                    // nullable: [2][Cout] fp64 sum / sum of squares of the (pre-bias) output, accumulated
 };
 
 template <int BN, int STAGES>
@@ -205,7 +207,7 @@ struct PSmem {
     static constexpr int A_BYTES = R * A_TILE;
     static constexpr int B_BYTES = BN * BK * 4;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 320 /*barriers*/;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 320 /*barriers*/ + 2 * BN * 4 /*BN statistics*/;
     static constexpr int CTAS_PER_SM = (2 * TOTAL <= 227 * 1024 && 4 * R * BN <= 512) ? 2 : 1;
 };
 
@@ -222,8 +224,10 @@ conv_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
     uint64_t* acc_full = empty + STAGES;
     uint64_t* acc_empty = acc_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float* sm_stats = reinterpret_cast<float*>(base + STAGES * S::STAGE_BYTES + 320);
     constexpr uint32_t TCOLS = 2 * R * BN < 32 ? 32 : 2 * R * BN;
     static_assert(TCOLS <= 512 && (TCOLS & (TCOLS - 1)) == 0, "TMEM: 2 buffers x R accumulators x BN columns");
+    for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) sm_stats[i] = 0.f;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -337,6 +341,7 @@ conv_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                         __syncwarp();
                         if (lane == 0) tc::mbar_arrive(acc_empty + buf);
                     }
+                    if (p.stats) tc::stats_accumulate(v, valid, sm_stats, BN, c);
                     if (valid) {
                         const int cb = c0 + c;
                         if (cb + 32 <= p.Cout && (p.OC & 3) == 0) {
@@ -366,6 +371,7 @@ conv_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                     }
                 }
             }
+            if (p.stats) tc::stats_flush(sm_stats, BN, p.stats, p.Cout, c0, threadIdx.x - 64);
         }
     }
     tc::tc_fence_before();
@@ -585,7 +591,7 @@ extern "C" {
 int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* out, int N, int H, int W, int Cin,
                     int Hout, int Wout, int Cout, int ntaps, const int* dy, const int* dx, int sy, int sx, int OH,
                     int OW, int OC, int osy, int osx, int ooy, int oox, float leaky, int w_cin_major, const int* wtap,
-                    int wtaps_total, void* stream) {
+                    int wtaps_total, double* stats, void* stream) {
     B3D_REQUIRE(N > 0 && H > 0 && W > 0 && Hout > 0 && Wout > 0 && Cout > 0, B3D_EINVAL, "b3d_conv2d_tf32: bad sizes");
     B3D_REQUIRE(Cin > 0 && Cin % BK == 0, B3D_EINVAL, "b3d_conv2d_tf32: Cin=%d must be a multiple of %d", Cin, BK);
     B3D_REQUIRE(ntaps >= 1 && ntaps <= MAX_TAPS && dy && dx, B3D_EINVAL, "b3d_conv2d_tf32: bad taps");
@@ -599,7 +605,9 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
     B3D_CHECK_ALIGNED(wt);
     b3d::clear_variant();
 
-    static const int persist = getenv("B3D_CONV_PERSIST") ? atoi(getenv("B3D_CONV_PERSIST")) : 1;
+    static const int persist_env = getenv("B3D_CONV_PERSIST") ? atoi(getenv("B3D_CONV_PERSIST")) : 1;
+    const int persist = persist_env || stats != nullptr;      // the statistics epilogue lives in the persistent kernels
+    B3D_REQUIRE(!stats || (osy == 1 && osx == 1), B3D_EINVAL, "b3d_conv2d_tf32: statistics need a dense output");
     static const int wide = getenv("B3D_CONV_BN256") ? atoi(getenv("B3D_CONV_BN256")) : 1;
     // 256-wide output-channel tiles halve the input-tile bytes per FLOP through the L2 -> SM fabric (the bound of the
     // per-tap formulation, profiles/r1_c_*.md) when there are >= 256 output channels and enough tiles to fill the GPU
@@ -623,8 +631,32 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
     // One launch covers output columns [xlo, xhi).  A width of "power of two + a few columns" (dgrad of an x-padded
     // input: 130, 66, 34 ...; stride-2 parity classes: 129, 65 ...) would leave a second, almost empty 128-pixel tile in
     // every row, so the remainder columns get a narrow strip launch of their own.
+    // filter-grid detection for the row-window kernel (tc_conv3.cu): kh rows of kw horizontally consecutive taps
+    int g_kw = 0, g_kh = 0, g_step = 0;
+    if (sy == 1 && sx == 1 && osy == 1 && osx == 1 && !w_cin_major && !wtap) {
+        int kw_ = 1;
+        while (kw_ < ntaps && dy[kw_] == dy[0]) ++kw_;
+        const int step = kw_ > 1 ? dx[1] - dx[0] : 1;
+        bool grid_ok = ntaps % kw_ == 0 && ntaps / kw_ <= 5 && (kw_ == 3 || kw_ == 5) && (step == 1 || step == -1);
+        for (int t = 0; grid_ok && t < ntaps; ++t)
+            grid_ok = dy[t] == dy[(t / kw_) * kw_] && dx[t] == dx[0] + (t % kw_) * step;
+        static const int rowwin_env = getenv("B3D_CONV_ROWWIN") ? atoi(getenv("B3D_CONV_ROWWIN")) : 1;
+        if (grid_ok && rowwin_env) { g_kw = kw_; g_kh = ntaps / kw_; g_step = step; }
+    }
     auto run = [&](int xlo, int xhi) -> int {
         const int wspan = xhi - xlo;
+        if (g_kw && wspan >= BM) {
+            b3d::RowWinArgs a{};
+            a.x = x; a.wt = wt; a.bias = bias; a.out = out;
+            a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Hout = Hout; a.Cout = Cout; a.xlo = xlo; a.xhi = xhi;
+            a.kh = g_kh; a.kw = g_kw;
+            for (int r = 0; r < g_kh; ++r) a.dy[r] = dy[r * g_kw];
+            a.dx0 = g_step > 0 ? dx[0] : dx[g_kw - 1];
+            for (int t = 0; t < g_kw; ++t) a.shift[t] = dx[t] - a.dx0;
+            a.OH = OH; a.OW = OW; a.OC = OC; a.ooy = ooy; a.oox = oox; a.leaky = leaky; a.stats = stats;
+            const int rc = b3d::conv_rowwin_launch(a, st);
+            if (rc <= 0) return rc;                           // launched (0) or a real error (< 0); 1 = not covered
+        }
         ConvParams p{};
         p.N = N; p.Hout = Hout; p.Wout = xhi; p.Cout = Cout; p.xbase = xlo;
         p.BW = pow2_floor(wspan < BM ? wspan : BM);
@@ -638,6 +670,7 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
         p.OH = OH; p.OW = OW; p.OC = OC; p.osy = osy; p.osx = osx; p.ooy = ooy; p.oox = oox;
         p.leaky = leaky;
         p.dbg_lbo = 4096; p.dbg_sbo = 512; p.dbg_lt = 1;     // 32-bit MN-major: SWIZZLE_128B_BASE32B, 4-row atoms
+        p.stats = stats;
         CUtensorMap mx;
         const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
         const uint64_t strides[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};

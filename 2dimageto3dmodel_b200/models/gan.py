@@ -316,20 +316,25 @@ class ResBlockUp(nn.Module):
         """Same block on an input that is ALREADY replicate-padded by 1 (xp = pad(x, 1)); returns the padded input of the
         consumer: pad(up(out), pad_next) with out = [LeakyReLU](h + skip).  Every conv output goes through exactly one fused
         elementwise kernel (b3d.ew.cbn_act_pad) instead of BN, affine, LeakyReLU, add, upsample and pad kernels."""
+        s1 = s2 = None
         if W is not None:
-            c1 = lambda t: conv2d_banked(t, W[prefix + ".conv1"], pad_y=1)
-            c2 = lambda t: conv2d_banked(t, W[prefix + ".conv2"], pad_y=1)
+            # the conv epilogues accumulate the batch-norm statistics of their output (no separate pass over y)
+            if cb is not None and not getattr(self, 'disable_epilogue_stats', False):
+                s1, s2 = cb.stats_slot(self.norm1), cb.stats_slot(self.norm2)
+            c1 = lambda t: conv2d_banked(t, W[prefix + ".conv1"], pad_y=1, stats=s1)
+            c2 = lambda t: conv2d_banked(t, W[prefix + ".conv2"], pad_y=1, stats=s2)
             sc = lambda t: conv2d_banked(t, W[prefix + ".shortcut"], x_crop=1)
         else:
             c1, c2, sc = self.conv1, self.conv2, (lambda t: self.shortcut(t, x_crop=1))
         y1 = c1(xp)
-        a = cbn_act_pad(y1, self.norm1, z, up=1, pad=1, cb=cb)
+        a = cbn_act_pad(y1, self.norm1, z, up=1, pad=1, cb=cb, sums=s1)
         y2 = c2(a)
         if isinstance(self.shortcut, nn.Module):
             skip, off = sc(xp), 0                                    # 1x1 conv on the interior of the padded input
         else:
             skip, off = xp, 1                                        # identity: read the interior of the padded input
-        return cbn_act_pad(y2, self.norm2, z, skip_nchw=skip, skip_off=off, up=up, pad=pad_next, post_leaky=post_leaky, cb=cb)
+        return cbn_act_pad(y2, self.norm2, z, skip_nchw=skip, skip_off=off, up=up, pad=pad_next, post_leaky=post_leaky, cb=cb,
+                           sums=s2)
 
 
 class Generator(nn.Module):

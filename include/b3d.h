@@ -217,9 +217,12 @@ B3D_API int b3d_chamfer_bwd(const float* query, const float* cand, const int32_t
 B3D_API int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* out, int N, int H, int W,
                             int Cin, int Hout, int Wout, int Cout, int ntaps, const int* dy, const int* dx,
                             int sy, int sx, int OH, int OW, int OC, int osy, int osx, int ooy, int oox,
-                            float leaky, int w_cin_major, const int* wtap, int wtaps_total, void* stream);
+                            float leaky, int w_cin_major, const int* wtap, int wtaps_total, double* stats, void* stream);
 /* wtap (nullable): loop tap t reads weight tap wtap[t] of a tap-major array that holds wtaps_total taps — the stride-2
- * input-gradient parity classes address their tap subsets of the full weight array without a gathered copy.           */
+ * input-gradient parity classes address their tap subsets of the full weight array without a gathered copy.
+ * stats (nullable): [2][Cout] fp64, ACCUMULATED into by the epilogue: per-channel sum and sum of squares of the output
+ * before bias / activation — the BatchNorm statistics of the generator's layers without a second pass over the tensor
+ * (models/gan.py:264-286; the caller zeroes the buffer; dense outputs only).                                              */
 
 /* Stride-1 variant with a halo-staged input and R stacked accumulators (csrc/tc_conv2.cu): x [N,H,P,Cin] with P the
  * padded width (row pitch), taps (dy, dx >= 0); same weights / bias / LeakyReLU semantics as b3d_conv2d_tf32, output

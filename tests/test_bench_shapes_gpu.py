@@ -92,12 +92,42 @@ def test_layer_at_bench_shape(name, N, Cin, H, W, Cout, k, pad_y, stride, x_crop
         assert err <= TOL * ref, (name, what, err, ref)
 
 
+@pytest.mark.parametrize("N,Cin,H,W,Cout", [(32, 64, 256, 130, 64),      # G.blk6.conv2: row-window kernel
+                                             (32, 128, 128, 66, 128),     # G.blk5: persistent, stacked 128-wide tiles
+                                             (32, 256, 32, 18, 256),      # G.blk3a: 256-wide tiles
+                                             (3, 512, 8, 6, 512),         # blk1: tiny maps, several images per tile
+                                             (2, 128, 16, 19, 96)])       # ragged channel count / width
+def test_epilogue_statistics(N, Cin, H, W, Cout):
+    """BatchNorm statistics accumulated by the conv epilogue (b3d_conv2d_tf32 `stats`) == sums of the stored output."""
+    import b3d.conv as C
+    from b3d.bank import WeightBank
+    from models.gan import TCConv2d
+    torch.manual_seed(Cin + Cout)
+    conv = TCConv2d(Cin, Cout, 3, padding=(1, 0), bias=False).to(DEV)
+    W_ = WeightBank({"c": conv}).forward(True)
+    x = torch.randn(N, Cin, H, W, device=DEV).contiguous(memory_format=torch.channels_last)
+    stats = torch.zeros(2 * Cout, device=DEV, dtype=torch.float64)
+    C.VARIANT_LOG = []
+    with torch.no_grad():
+        y = C.conv2d_banked(x, W_["c"], pad_y=1, stats=stats)
+    torch.cuda.synchronize()
+    SEEN.update(C.VARIANT_LOG)
+    C.VARIANT_LOG = None
+    yd = y.double()
+    ref = torch.cat((yd.sum(dim=(0, 2, 3)), (yd * yd).sum(dim=(0, 2, 3))))
+    scale = float(yd.abs().sum(dim=(0, 2, 3)).max())
+    assert float((stats[:Cout] - ref[:Cout]).abs().max()) <= 2e-6 * scale
+    assert float((stats[Cout:] - ref[Cout:]).abs().max()) <= 2e-6 * float(ref[Cout:].max())
+
+
 def test_every_dispatched_variant_was_exercised():
     """The kernel instances cfg3 dispatches at batch 32 / 64 (profiles/r2_launches.md) all ran in the cases above."""
     need = {
         # fprop / dgrad: wide-N, stacked and small persistent tiles, the halo-staged kernel, N-major weights in the dgrad
         "conv_tf32_persistent<256,4,0,1>", "conv_tf32_persistent<128,4,0,2>", "conv_tf32_persistent<64,3,0,4>",
         "conv_tf32_persistent<128,3,0,1>", "conv_tf32_persistent<64,4,0,1>",
+        # row-window kernel (tc_conv3.cu): 128-pixel row tiles of the 64-wide layers (3x3, 1x5 / 5x5) and blk6.conv1's dgrad
+        "conv_rowwin_tf32<64,3,4,2>", "conv_rowwin_tf32<64,5,4,2>", "conv_rowwin_tf32<128,3,2,2>",
         # weight gradients: row-of-taps (T = 3, 5), stride-2 tap pairs (T = 2), single taps, both Cin tile widths
         "wgrad_tf32<128,6,3>", "wgrad_tf32<64,8,3>", "wgrad_tf32<64,8,5>", "wgrad_tf32<128,3,2>", "wgrad_tf32<64,4,2>",
         "wgrad_tf32<128,6,1>", "wgrad_tf32<64,8,1>",
