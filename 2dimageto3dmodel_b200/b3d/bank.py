@@ -38,12 +38,14 @@ class LayerWeights:
 
 
 class WeightBank:
-    def __init__(self, convs, fold=(), no_dgrad=()):
+    def __init__(self, convs, fold=(), no_dgrad=(), round_tf32=True):
         """convs: ordered {name: conv module} (spectral-normalised modules expose weight_orig / weight_u / weight_v, plain
         ones weight).  fold: names whose kh vertical taps are folded into the channel dimension (thin stems).
         no_dgrad: names that never need an input gradient (no D layout is written)."""
         self.names = list(convs)
         self.mods = [convs[n] for n in self.names]
+        # emitted weights rounded to the nearest tf32 value (the tensor cores would otherwise truncate the fp32 words)
+        self.round_tf32 = bool(round_tf32)
         self.specs = []
         off_out = off_scr = off_w = 0
         for n, m in zip(self.names, self.mods):
@@ -155,7 +157,7 @@ class _BankFn(torch.autograd.Function):
         st = stream_ptr(weights[0])
         check(lib.b3d_bank_forward(ptr(bank._table), ptr(bank._wtu[0]), bank._wtu[1], ptr(bank._wv[0]), bank._wv[1],
                                    ptr(bank._emit[0]), bank._emit[1], ptr(bank._scratch), bank._scratch.numel() * 4,
-                                   ptr(out), int(training), st))
+                                   ptr(out), int(training) | (2 if bank.round_tf32 else 0), st))
         wfs, wds = [], []
         for sp in bank.specs:
             wfs.append(out[sp["wf_off"]: sp["wf_off"] + sp["Tp"] * sp["Cout"] * sp["Cinp"]].view(sp["Tp"], sp["Cout"], sp["Cinp"]))

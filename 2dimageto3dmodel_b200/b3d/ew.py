@@ -103,10 +103,26 @@ class CBNBatch:
         goff, boff = self.offsets[id(cbn)]
         return self.stats[goff: goff + 2 * (boff - goff)]
 
-    def grad_sink(self):
+    shared = False                                  # per-sample gamma / beta rows
+
+    def grad_sink(self, N=None):
         if self.sink is None:
-            self.sink = torch.empty_like(self.gb)
+            self.sink = torch.empty_like(self.gb) if not self.shared else torch.empty(N, self.gb.shape[1], device=self.gb.device)
         return self.sink
+
+
+class BNAffine(CBNBatch):
+    """A plain BatchNorm2d (affine weight / bias shared by all samples; models/reconstruction.py:7-26, :52-64) expressed in
+    the fused kernels' terms: one row gb = [weight - 1 | bias] read by every sample (row pitch 0); the per-sample
+    d(gamma), d(beta) rows of the backward are summed over the batch."""
+    shared = True
+
+    def __init__(self, bn):
+        C = bn.num_features
+        self.offsets = {id(bn): (0, C)}
+        self.first, self.n_layers, self.done = id(bn), 1, 0
+        self.gb = torch.cat((bn.weight - 1, bn.bias)).view(1, 2 * C)
+        self.sink, self.stats = None, None
 
 
 class _CBNActPad(torch.autograd.Function):
@@ -115,11 +131,12 @@ class _CBNActPad(torch.autograd.Function):
     and the per-sample affine come from one b3d_cbn_prepare launch (modes: 0 eval, 1 batch statistics, 2 SyncBN)."""
 
     @staticmethod
-    def forward(ctx, y, gb, cb, key, bn, skip, skip_off, up, pad, post_leaky, sums_in=None):
+    def forward(ctx, y, gb, cb, key, bn, skip, skip_off, up, pad, post_leaky, sums_in=None, slope=0.2):
         y = dev(y.detach(), "y")
         N, H, W, C = y.shape
         gbd = dev(gb.detach(), "gamma/beta")
         P = gbd.shape[1]
+        gp = 0 if cb.shared else P                          # row pitch of gamma / beta (0: one row for all samples)
         goff, boff = cb.offsets[key]
         st = stream_ptr(y)
         mode, sums, count, sync, peers = 0, None, 1.0, False, None
@@ -145,12 +162,12 @@ class _CBNActPad(torch.autograd.Function):
         if peers is not None:
             # statistics all-reduce over NVLink peer memory fused into the kernel that consumes them (csrc/ew_kernels.cu)
             check(lib.b3d_cbn_prepare_sync(peers.data, peers.flag, peers.rank, peers.world, ptr(peers.epoch), ptr(peers.err),
-                                           ptr(gbd), P, goff, boff, ptr(sums), count, float(bn.eps), float(bn.momentum or 0.0),
+                                           ptr(gbd), gp, goff, boff, ptr(sums), count, float(bn.eps), float(bn.momentum or 0.0),
                                            ptr(bn.running_mean) if track else None, ptr(bn.running_var) if track else None,
                                            ptr(bn.num_batches_tracked) if track else None,
                                            ptr(mean), ptr(invstd), ptr(scale), ptr(shift), ptr(gt), N, C, st))
         else:
-            check(lib.b3d_cbn_prepare(ptr(gbd), P, goff, boff, ptr(sums), count, float(bn.eps), float(bn.momentum or 0.0), mode,
+            check(lib.b3d_cbn_prepare(ptr(gbd), gp, goff, boff, ptr(sums), count, float(bn.eps), float(bn.momentum or 0.0), mode,
                                       ptr(bn.running_mean) if (track or mode == 0) else None,
                                       ptr(bn.running_var) if (track or mode == 0) else None,
                                       ptr(bn.num_batches_tracked) if track else None,
@@ -158,19 +175,19 @@ class _CBNActPad(torch.autograd.Function):
         sk = dev(skip.detach(), "skip") if skip is not None else None
         pitch = sk.shape[2] if sk is not None else 0
         out = torch.empty(N, up * H, up * W + 2 * pad, C, device=y.device, dtype=torch.float32)
-        check(lib.b3d_cbn_act_fwd(ptr(y), ptr(scale), ptr(shift), ptr(sk), pitch, skip_off, ptr(out), N, H, W, C, up, pad, 0.2,
+        check(lib.b3d_cbn_act_fwd(ptr(y), ptr(scale), ptr(shift), ptr(sk), pitch, skip_off, ptr(out), N, H, W, C, up, pad, float(slope),
                                   int(post_leaky), st))
         ctx.save_for_backward(y, gt, scale, shift, mean, invstd, sk if sk is not None else torch.empty(0))
         ctx.cb, ctx.key = cb, key
         ctx.cfg = (skip_off, up, pad, post_leaky, mode != 0, sync, count, sk is not None, skip.shape if skip is not None else None,
-                   P, goff, boff)
+                   P, goff, boff, float(slope))
         ctx.peers = peers
         return out
 
     @staticmethod
     def backward(ctx, gout):
         y, gt, scale, shift, mean, invstd, sk = ctx.saved_tensors
-        skip_off, up, pad, post_leaky, batch_stats, sync, count, has_skip, skip_shape, P, goff, boff = ctx.cfg
+        skip_off, up, pad, post_leaky, batch_stats, sync, count, has_skip, skip_shape, P, goff, boff, slope = ctx.cfg
         cb = ctx.cb
         N, H, W, C = y.shape
         gout = dev(gout, "grad")
@@ -181,12 +198,12 @@ class _CBNActPad(torch.autograd.Function):
             gpitch = skip_shape[2]
             gskip = torch.zeros(skip_shape, device=y.device) if gpitch != W else torch.empty(skip_shape, device=y.device)
         want_gb = ctx.needs_input_grad[1]
-        sink = cb.grad_sink() if want_gb else torch.empty(N, P, device=y.device)
+        sink = cb.grad_sink(N) if want_gb else torch.empty(N, P, device=y.device)
         s1 = ctypes.c_void_p(sink.data_ptr() + 4 * boff)        # d beta  = sum ga
         s2 = ctypes.c_void_p(sink.data_ptr() + 4 * goff)        # d gamma = sum ga * xhat
         check(lib.b3d_cbn_act_bwd1(ptr(gout), ptr(y), ptr(scale), ptr(shift), ptr(sk) if has_skip else None,
                                    sk.shape[2] if has_skip else 0, skip_off, ptr(mean), ptr(invstd), ptr(ga), ptr(gskip), gpitch,
-                                   skip_off, s1, s2, P, N, H, W, C, up, pad, 0.2, int(post_leaky), st))
+                                   skip_off, s1, s2, P, N, H, W, C, up, pad, slope, int(post_leaky), st))
         inv_m = 0.0
         if batch_stats:
             red = torch.empty(2 * C, device=y.device, dtype=torch.float32)
@@ -210,8 +227,8 @@ class _CBNActPad(torch.autograd.Function):
             if ctx.key == cb.first:
                 if cb.done != cb.n_layers:
                     raise RuntimeError(f"CBNBatch: {cb.done} of {cb.n_layers} layers ran their backward before the first layer's")
-                ggb = sink
-        return ga, ggb, None, None, None, gskip, None, None, None, None, None
+                ggb = sink.sum(dim=0, keepdim=True) if cb.shared else sink
+        return ga, ggb, None, None, None, gskip, None, None, None, None, None, None
 
 
 _BN_STATS_IMPL = os.environ.get("B3D_BN_STATS", "torch")
@@ -229,6 +246,19 @@ def bn_stats(y_nhwc, eps, impl=None):
     ws = torch.empty(2 * C, device=y.device, dtype=torch.float64)
     check(lib.b3d_bn_stats(ptr(y), y.numel() // C, C, float(eps), ptr(mean), ptr(invstd), ptr(ws), stream_ptr(y)))
     return mean, invstd
+
+
+def bn_act_pad(y_nchw, bn, skip_nchw=None, skip_off=0, up=1, pad=1, post_relu=False, slope=0.0):
+    """BatchNorm2d(y) (affine, batch or running statistics, SyncBN under torch.distributed) -> ReLU [-> + skip] [-> ReLU]
+    [-> x2 nearest upsample] -> replicate pad in one pass (models/reconstruction.py:7-26 ResBlock glue), NHWC."""
+    cb = BNAffine(bn)
+    y = y_nchw.permute(0, 2, 3, 1)
+    C = y.shape[3]
+    if C % 4 or 256 % (C // 4):
+        raise B3DError(f"bn_act_pad: C={C} must be 4 * a divisor of 256")
+    skip = skip_nchw.permute(0, 2, 3, 1) if skip_nchw is not None else None
+    out = _CBNActPad.apply(y, cb.gb, cb, id(bn), bn, skip, int(skip_off), int(up), int(pad), bool(post_relu), None, float(slope))
+    return out.permute(0, 3, 1, 2)
 
 
 def cbn_act_pad(y_nchw, cbn, z, skip_nchw=None, skip_off=0, up=1, pad=1, post_leaky=False, cb=None, sums=None):

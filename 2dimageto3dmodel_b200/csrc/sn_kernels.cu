@@ -100,6 +100,14 @@ bank_wv_kernel(const BankLayer* __restrict__ layers, const Item* __restrict__ it
     if (lane == 0) scratch[L.s_off + row] = acc * inv;
 }
 
+// fp32 -> nearest tf32 value (ties away from zero), kept in an fp32 word: what the tensor core then reads exactly
+__device__ __forceinline__ float tf32_rna(float x, int on) {
+    if (!on) return x;
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
 __device__ __forceinline__ float layer_sigma(const BankLayer& L, const float* sv, int training, float* red, float* inv_s) {
     // training: u_new = s / max(|s|, eps), sigma = u_new . s;  eval: sigma = u . s
     float p = 0.f;
@@ -118,7 +126,7 @@ __device__ __forceinline__ float layer_sigma(const BankLayer& L, const float* sv
 // item: (layer, co chunk, ci' chunk)
 __global__ void __launch_bounds__(NT)
 bank_emit_kernel(const BankLayer* __restrict__ layers, const Item* __restrict__ items, const float* __restrict__ scratch,
-                 float* __restrict__ outb, int training) {
+                 float* __restrict__ outb, int training, int round_tf32) {
     __shared__ float red[NT / 32];
     const Item it = items[blockIdx.x];
     const BankLayer L = layers[it.layer];
@@ -162,7 +170,7 @@ bank_emit_kernel(const BankLayer* __restrict__ layers, const Item* __restrict__ 
             float val = 0.f;
             if (real) {
                 const int src = L.fold ? ((co * L.Cin + c) * L.kh + r_fix) * L.kw + tp : (co * L.Cin + c) * taps + tp;
-                val = __ldg(L.w + src) * rs;
+                val = tf32_rna(__ldg(L.w + src) * rs, round_tf32);
             }
             outb[L.wf_off + ((size_t)tp * L.Cout + co) * L.Cinp + ci] = val;
         }
@@ -180,7 +188,7 @@ bank_emit_kernel(const BankLayer* __restrict__ layers, const Item* __restrict__ 
             float val = 0.f;
             if (real) {
                 const int src = L.fold ? ((co * L.Cin + c) * L.kh + r_fix) * L.kw + tp : (co * L.Cin + c) * taps + tp;
-                val = __ldg(L.w + src) * rs;
+                val = tf32_rna(__ldg(L.w + src) * rs, round_tf32);
             }
             outb[L.wd_off + ((size_t)tp * L.Cinp + ci) * L.Coutp + co] = val;
         }
@@ -256,6 +264,8 @@ int b3d_bank_forward(const void* layers, const void* items_wtu, int n_wtu, const
     cudaStream_t st = (cudaStream_t)stream;
     B3D_CUDA_OK(cudaMemsetAsync(scratch, 0, scratch_bytes, st));
     const BankLayer* L = static_cast<const BankLayer*>(layers);
+    const int flags = training;
+    training &= 1;
     if (training && n_wtu > 0) {
         bank_wtu_kernel<<<n_wtu, NT, 0, st>>>(L, static_cast<const Item*>(items_wtu), scratch);
         B3D_LAUNCH_OK();
@@ -264,7 +274,8 @@ int b3d_bank_forward(const void* layers, const void* items_wtu, int n_wtu, const
         bank_wv_kernel<<<n_wv, NT, 0, st>>>(L, static_cast<const Item*>(items_wv), scratch, training);
         B3D_LAUNCH_OK();
     }
-    bank_emit_kernel<<<n_emit, NT, 0, st>>>(L, static_cast<const Item*>(items_emit), scratch, out, training);
+    const int round_tf32 = (flags >> 1) & 1;          // bit 1 of `training`: round the emitted weights to tf32
+    bank_emit_kernel<<<n_emit, NT, 0, st>>>(L, static_cast<const Item*>(items_emit), scratch, out, training, round_tf32);
     B3D_LAUNCH_OK();
     return B3D_OK;
 }

@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from b3d.ew import CIRCULAR, REPLICATE, pad_x
+from b3d.ew import CIRCULAR, REPLICATE, bn_act_pad, pad_x
 from models.gan import TCConv2d
 from rendering.utils import adjust_poles, symmetrize_texture
 
@@ -43,6 +43,18 @@ class ResBlock(nn.Module):
             h = self.relu(bn(conv(self.pad_fn(h, 1))))
         return h + self.shortcut(x)
 
+    def forward_fused(self, xp, up, pad_next, post_relu=False):
+        """The same block on an input that is ALREADY replicate-padded by 1; returns the consumer's padded input
+        pad(up([relu](h + skip)), pad_next).  Every conv output goes through ONE fused kernel (b3d.ew.bn_act_pad: batch
+        norm + ReLU + residual + upsample + pad) instead of BN, ReLU, add, interpolate and pad passes."""
+        a = bn_act_pad(self.conv1(xp), self.bn1, up=1, pad=1)
+        y2 = self.conv2(a)
+        if isinstance(self.shortcut, nn.Module):
+            skip, off = self.shortcut(xp, x_crop=1), 0
+        else:
+            skip, off = xp, 1
+        return bn_act_pad(y2, self.bn2, skip_nchw=skip, skip_off=off, up=up, pad=pad_next, post_relu=post_relu)
+
 
 class ReconstructionNetwork(nn.Module):
     """RGBA image [B,4,256,256] -> (texture [B,3,R,R] in [-1,1], displacement map [B,3,32,32]) (reference :29-134).
@@ -54,7 +66,7 @@ class ReconstructionNetwork(nn.Module):
             raise ValueError("mesh_res must be >= 32 and texture_res one of 64 / 128 / 256")
         if interpolation_mode not in ('nearest', 'bilinear'):
             raise ValueError(f"interpolation_mode={interpolation_mode!r}")
-        self.symmetric, self.texture_res = symmetric, texture_res
+        self.symmetric, self.texture_res, self.interpolation_mode = symmetric, texture_res, interpolation_mode
         x_mode = REPLICATE if symmetric else CIRCULAR
         self.pad = lambda t, amount: pad_x(t, amount, x_mode)
         self.relu = nn.ReLU(inplace=True)
@@ -91,9 +103,27 @@ class ReconstructionNetwork(nn.Module):
         z = self.relu(self.bnfc1e(self.fc1e(z)))
         return self.relu(self.bnfc3e(self.fc3e(z)))
 
+    def _decode_fused(self, h):
+        """Decoder with the inter-convolution glue fused (replicate-padded tensors flow between the blocks)."""
+        p = self.pad(h, 1)
+        for name in ("blk1", "blk2", "blk3"):
+            p = getattr(self, name).forward_fused(p, up=2, pad_next=1)
+        shared = p                                              # 32 x 16 (+ pad): both heads branch from here
+        for name in ("blk3b_tex", "blk3c_tex"):
+            if hasattr(self, name):
+                p = getattr(self, name).forward_fused(p, up=2, pad_next=1)
+        t = self.blk4_tex.forward_fused(p, up=2, pad_next=1)
+        t = self.blk5_tex.forward_fused(t, up=1, pad_next=2, post_relu=True)
+        tex = torch.tanh(self.conv_tex(t))
+        m = self.blk4_mesh.forward_fused(shared, up=1, pad_next=2, post_relu=True)
+        mesh_map = adjust_poles(self.conv_mesh(m))
+        return symmetrize_texture(tex), symmetrize_texture(mesh_map)
+
     def forward(self, x):
         z = self.encode(x)
         h = self.fc1_tex(z).view(z.shape[0], -1, self.base_res_h, self.base_res_w).contiguous(memory_format=torch.channels_last)
+        if self.symmetric and self.interpolation_mode == 'nearest' and h.is_cuda and not getattr(self, 'disable_fusion', False):
+            return self._decode_fused(h)
         for name in ("blk1", "blk2", "blk3"):
             h = self.up(getattr(self, name)(h))
         shared = h                                              # 32 x 16: both heads branch from here

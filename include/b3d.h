@@ -283,6 +283,7 @@ B3D_API int b3d_vertex_pipeline_bwd(const float* g_raw, const float* g_vtx, cons
  * gradients back to weight_orig's layout through d(W / sigma).  `layers` is a device array of records of
  * b3d_bank_layer_bytes() bytes each (field order: csrc/sn_kernels.cu BankLayer; packed by b3d/bank.py), `items_*` device
  * arrays of int4 work items, `scratch` a per-bank buffer (zeroed here), `out` / `df` / `dw` per-call flat buffers.
+ * `training`: bit 0 = training mode (power iteration), bit 1 = round the emitted weights to the nearest tf32 value.
  * ------------------------------------------------------------------------------------------ */
 B3D_API int b3d_bank_layer_bytes(void);
 B3D_API int b3d_bank_forward(const void* layers, const void* items_wtu, int n_wtu, const void* items_wv, int n_wv,

@@ -57,7 +57,7 @@ def test_bank_matches_spectral_norm_oracle(training):
     mods.train(training)
     sd = oracle_state(mods)
     fold = ("stem", "stem11")
-    bank = WeightBank(dict(mods.items()), fold=fold)
+    bank = WeightBank(dict(mods.items()), fold=fold, round_tf32=False)       # exact W / sigma for the comparison
     W = bank.forward(training)
     gs = {n: torch.randn(W[n].wf.shape, generator=torch.Generator().manual_seed(i)).to(DEV) for i, n in enumerate(W)}
     loss = sum((W[n].wf * gs[n]).sum() for n in W)
@@ -91,12 +91,25 @@ def test_bank_matches_spectral_norm_oracle(training):
         assert err <= 2e-5 * float(gref.abs().max()) + 1e-6, (n, err, float(gref.abs().max()))
 
 
+def test_bank_rounds_weights_to_tf32_by_default():
+    """The tensor cores read fp32 words as tf32 by dropping 13 mantissa bits (truncation: a bias towards zero).  The bank
+    therefore rounds the emitted weights to the nearest tf32 value (cvt.rna), which is what cuDNN's TF32 path does."""
+    from b3d.bank import WeightBank
+    mods = make_layers()
+    mods.train(False)
+    exact = WeightBank({"a": mods["a"]}, round_tf32=False).forward(False)["a"].wf
+    rnd = WeightBank({"a": mods["a"]}).forward(False)["a"].wf
+    assert int((rnd.view(torch.int32) & 0x1FFF).abs().max()) == 0               # low 13 mantissa bits cleared
+    assert float(((rnd - exact).abs() / exact.abs().clamp_min(1e-30)).max()) <= 2.0 ** -11 * 1.001  # round to nearest
+    assert float((rnd - exact).mean().abs()) < 1e-3 * float((rnd - exact).abs().mean()) + 1e-9      # unbiased
+
+
 def test_two_forwards_before_backward_do_not_alias():
     """torch's spectral_norm clones u / v for the graph; the bank keeps per-call copies in its output buffer."""
     from b3d.bank import WeightBank
     mods = make_layers()
     mods.train(True)
-    bank = WeightBank({"a": mods["a"]})
+    bank = WeightBank({"a": mods["a"]}, round_tf32=False)
     sd = oracle_state(nn.ModuleDict({"a": mods["a"]}))
     W1 = bank.forward(True)
     W2 = bank.forward(True)                       # second power iteration: u, v advance again
@@ -134,7 +147,7 @@ def test_banked_conv_matches_module_path():
     a, b = res
     for i in range(3):
         err, ref = float((a[i] - b[i]).abs().max()), float(a[i].abs().max())
-        assert err <= 2e-3 * ref, ("output", i, err, ref)
+        assert err <= 5e-3 * ref, ("output", i, err, ref)     # ~25 stacked tf32 convs on weights that differ by rounding
     assert a[3].keys() == b[3].keys()
     # both paths run the same tf32 kernels on weights that agree to 1 ulp; what differs is the order of the split-K
     # atomics in the weight gradients.  Cancelling sums (scalar biases) get the golden test's absolute floor.

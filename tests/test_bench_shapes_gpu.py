@@ -58,9 +58,9 @@ CASES = G_LAYERS + [(n, nb, ci, h, w, co, k, py, st, 0) for nb in (B, 2 * B) for
 
 
 def ref_conv(x, w, b, pad_y, stride):
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
-    return torch.nn.functional.conv2d(x, w, b, stride=stride, padding=(pad_y, 0))
+    """fp64 convolution (no TF32 / FFT / Winograd error on the reference side), returned as fp32."""
+    return torch.nn.functional.conv2d(x.double(), w.double(), b.double() if b is not None else None, stride=stride,
+                                      padding=(pad_y, 0)).float()
 
 
 @pytest.mark.parametrize("name,N,Cin,H,W,Cout,k,pad_y,stride,x_crop", CASES, ids=[f"{c[0]}-N{c[1]}" for c in CASES])
@@ -81,7 +81,7 @@ def test_layer_at_bench_shape(name, N, Cin, H, W, Cout, k, pad_y, stride, x_crop
             y = C.conv2d(x.contiguous(memory_format=torch.channels_last), w, b, pad_y, stride, x_crop=x_crop)
         gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(3)).to(DEV)
         grads = torch.autograd.grad(y, [x, w] + ([b] if b is not None else []), gy)
-        res[impl] = [y.detach()] + list(grads)
+        res[impl] = [y.detach().float()] + [g_.float() for g_ in grads]
         del x, w, y, gy, grads
     torch.cuda.synchronize()
     SEEN.update(C.VARIANT_LOG)
@@ -198,7 +198,8 @@ def test_mesh_bench_size_against_oracle():
         gvo, gto = torch.autograd.grad((img_o * wi[i:i + 1]).sum() + (alpha_o * wa[i:i + 1]).sum(), [vo, to])
         nbad = int((idx[i] != idx_o[0]).sum())
         assert nbad == 0, f"face-index buffer differs from the oracle in {nbad} of {idx_o.numel()} pixels"
-        assert float((img[i].cpu() - img_o[0]).abs().max()) < 2e-5
+        # colour: bilinear fetch from a 128-texel texture amplifies the fp32 rounding of the interpolated uv by ~T |d tex|
+        assert float((img[i].cpu() - img_o[0]).abs().max()) < 1e-4
         assert float((alpha[i].cpu() - alpha_o[0]).abs().max()) < 2e-5
         assert float((gv[i].cpu() - gvo[0]).abs().max()) < 2e-3 * float(gvo.abs().max())
         assert float((gt[i].cpu() - gto[0]).abs().max()) < 1e-4 * float(gto.abs().max())

@@ -13,14 +13,13 @@ if [ "${NCU:-1}" = "1" ]; then
     -o gpurun_out/${T}_nonconv python tools/ncu_r2_step.py > gpurun_out/${T}_ncu.log 2>&1
   ncu -i gpurun_out/${T}_nonconv.ncu-rep --page raw --csv > gpurun_out/${T}_nonconv_raw.csv 2>/dev/null
   rm -f gpurun_out/${T}_nonconv.ncu-rep
-  B3D_BENCH_NO_CPU=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3500 --csv \
+  [ "${LAUNCHES:-1}" = "1" ] && B3D_BENCH_NO_CPU=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3500 --csv \
     --log-file gpurun_out/${T}_launches.csv python bench.py --steps 2 --warmup 1 > gpurun_out/${T}_launches_bench.log 2>&1
 fi
 if [ "${EXTRA:-0}" = "1" ]; then
   B3D_BENCH_NO_CPU=1 python bench.py --workload cfg4 --steps 10 --warmup 3 > gpurun_out/${T}_bench_cfg4.json 2> gpurun_out/${T}_bench_cfg4.err
   B3D_BENCH_NO_CPU=1 python bench.py --workload cfg5 --steps 10 --warmup 3 > gpurun_out/${T}_bench_cfg5.json 2> gpurun_out/${T}_bench_cfg5.err
-  B3D_BENCH_NO_CPU=1 python bench.py --workload cfg2 --steps 20 --warmup 5 > gpurun_out/${T}_bench_cfg2.json 2> gpurun_out/${T}_bench_cfg2.err
-  for w in cfg4 cfg5 cfg2; do echo "== $w"; cut -c1-400 gpurun_out/${T}_bench_$w.json; tail -n 3 gpurun_out/${T}_bench_$w.err | cut -c1-300; done
+  for w in cfg4 cfg5; do echo "== $w"; cut -c1-400 gpurun_out/${T}_bench_$w.json; tail -n 3 gpurun_out/${T}_bench_$w.err | cut -c1-300; done
 fi
 echo "==== pytest"; grep -E "^(FAILED|ERROR)|passed|failed|rc=" gpurun_out/${T}_pytest.log | tail -n 30
 grep -E "^E  " gpurun_out/${T}_pytest.log | head -n 30

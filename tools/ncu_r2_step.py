@@ -14,7 +14,7 @@ import torch  # noqa: E402
 
 dev = torch.device("cuda:0")
 B = int(os.environ.get("B", 32))
-wl = bench.CudaWorkload(dev, gan=True)
+wl = bench.CudaWorkload(dev, bench.WORKLOADS["cfg3"])
 d = {k: v.to(dev) for k, v in bench.host_inputs(B, 1234, False).items()}
 d.update({k: v.to(dev) for k, v in bench.gan_host_inputs(B, 1234, False).items()})
 from b3d.chamfer import nearest  # noqa: E402
