@@ -147,7 +147,9 @@ def test_banked_conv_matches_module_path():
     a, b = res
     for i in range(3):
         err, ref = float((a[i] - b[i]).abs().max()), float(a[i].abs().max())
-        assert err <= 5e-3 * ref, ("output", i, err, ref)     # ~25 stacked tf32 convs on weights that differ by rounding
+        # ~25 stacked tf32 convs; the bank path feeds weights rounded to the nearest tf32, the module path lets the tensor
+        # core truncate them: the two differ by up to 2^-11 per weight
+        assert err <= 1e-2 * ref, ("output", i, err, ref)
     assert a[3].keys() == b[3].keys()
     # both paths run the same tf32 kernels on weights that agree to 1 ulp; what differs is the order of the split-K
     # atomics in the weight gradients.  Cancelling sums (scalar biases) get the golden test's absolute floor.
