@@ -163,11 +163,20 @@ fold_rows_fwd_kernel(const float* __restrict__ x, float4* __restrict__ out, int 
             src[j] = (k < K && yy >= 0 && yy < H) ? (((long long)n * H + yy) * W) * C + c : -1;
         }
         float4* orow = out + (long long)row * W * Cp4 + k4;
-        for (int xx = px0; xx < W; xx += PPB) {
-            float v[4];
+        constexpr int U = 4;                                 // independent pixels in flight per thread
+        for (int xb = px0; xb < W; xb += U * PPB) {
+            float v[U][4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = src[j] >= 0 ? __ldg(x + src[j] + (long long)xx * C) : 0.f;
-            orow[(long long)xx * Cp4] = make_float4(v[0], v[1], v[2], v[3]);
+            for (int u = 0; u < U; ++u) {
+                const int xx = xb + u * PPB;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[u][j] = (xx < W && src[j] >= 0) ? __ldg(x + src[j] + (long long)xx * C) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int xx = xb + u * PPB;
+                if (xx < W) orow[(long long)xx * Cp4] = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
+            }
         }
     }
 }
@@ -596,19 +605,29 @@ cbn_act_fwd_rows_kernel(const float4* __restrict__ y, const float4* __restrict__
         const float4* yrow = y + (((long long)n * g.H + ys) * g.W) * g.C4 + c;
         const float4* srow = g.skip_pitch ? skip + (((long long)n * g.H + ys) * g.skip_pitch + g.skip_off) * g.C4 + c : nullptr;
         float4* orow = out + (long long)row * Wo * g.C4 + c;
-        for (int xo = px0; xo < Wo; xo += PPB) {
-            int xs = xo - g.pad;
-            xs = xs < 0 ? 0 : (xs >= Wu ? Wu - 1 : xs);
-            xs = g.up == 2 ? xs >> 1 : xs;
-            const float4 v = __ldg(yrow + (long long)xs * g.C4);
-            float4 o = make_float4(lk(fmaf(v.x, sc.x, sh.x), g.slope), lk(fmaf(v.y, sc.y, sh.y), g.slope),
-                                   lk(fmaf(v.z, sc.z, sh.z), g.slope), lk(fmaf(v.w, sc.w, sh.w), g.slope));
-            if (srow) {
-                const float4 k = __ldg(srow + (long long)xs * g.C4);
-                o.x += k.x; o.y += k.y; o.z += k.z; o.w += k.w;
+        constexpr int U = 4;                                 // independent pixels in flight per thread
+        for (int xb = px0; xb < Wo; xb += U * PPB) {
+            float4 v[U], k[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int xo = xb + u * PPB;
+                if (xo >= Wo) continue;
+                int xs = xo - g.pad;
+                xs = xs < 0 ? 0 : (xs >= Wu ? Wu - 1 : xs);
+                xs = g.up == 2 ? xs >> 1 : xs;
+                v[u] = __ldg(yrow + (long long)xs * g.C4);
+                if (srow) k[u] = __ldg(srow + (long long)xs * g.C4);
             }
-            if (g.post_leaky) o = make_float4(lk(o.x, g.slope), lk(o.y, g.slope), lk(o.z, g.slope), lk(o.w, g.slope));
-            orow[(long long)xo * g.C4] = o;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int xo = xb + u * PPB;
+                if (xo >= Wo) continue;
+                float4 o = make_float4(lk(fmaf(v[u].x, sc.x, sh.x), g.slope), lk(fmaf(v[u].y, sc.y, sh.y), g.slope),
+                                       lk(fmaf(v[u].z, sc.z, sh.z), g.slope), lk(fmaf(v[u].w, sc.w, sh.w), g.slope));
+                if (srow) { o.x += k[u].x; o.y += k[u].y; o.z += k[u].z; o.w += k[u].w; }
+                if (g.post_leaky) o = make_float4(lk(o.x, g.slope), lk(o.y, g.slope), lk(o.z, g.slope), lk(o.w, g.slope));
+                orow[(long long)xo * g.C4] = o;
+            }
         }
     }
 }

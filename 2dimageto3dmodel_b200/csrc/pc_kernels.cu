@@ -34,6 +34,7 @@ constexpr float TERM_EPS = 1e-5f;      // effective_loss_function.py:18
 struct Taps {
     float w[MAX_TAPS + 1];
     int n;
+    int finite;     // every tap is finite: blocks of a column whose blur window holds no occupied cell can be skipped (0 * tap = 0)
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -238,9 +239,11 @@ constexpr int TILE_THREADS = 512;
 
 // Splat the points of the bins overlapping base cells [cy0-1, cy1] x [cx0-1, cx1] into a shared patch
 // covering cells [cy0, cy1] x [cx0, cx1] (row pitch `pitch`), depth-major.
+// zlo / zhi [ncol] (initialised to V / -1 by the caller): occupied depth range of every column — cells outside it are
+// exactly zero, so their blur, clamp and ray-march terms are constants (the sparsity skip of the fwd / bwd kernels).
 __device__ __forceinline__ void splat_bins(const float4* __restrict__ sorted, const int32_t* __restrict__ bs,
                                            int nbx, int nby, int cy0, int cy1, int cx0, int cx1, int pitch,
-                                           int ncol, int mode, float* A) {
+                                           int ncol, int mode, float* A, int* zlo, int* zhi) {
     const int by_lo = max(cy0 - 1, 0) / BIN_Y, by_hi = min(cy1 / BIN_Y, nby - 1);
     const int bx_lo = max(cx0 - 1, 0) / BIN_X, bx_hi = min(cx1 / BIN_X, nbx - 1);
     for (int by = by_lo; by <= by_hi; ++by) {
@@ -263,6 +266,8 @@ __device__ __forceinline__ void splat_bins(const float4* __restrict__ sorted, co
                 for (int k = 0; k < 2; ++k) {
                     const int cx = lx + k;
                     if (cx < 0 || cx > cx1 - cx0) continue;
+                    atomicMin(&zlo[cy * pitch + cx], fz);
+                    atomicMax(&zhi[cy * pitch + cx], fz + 1);
 #pragma unroll
                     for (int i = 0; i < 2; ++i)     // trilinear_interpolation.py:40-41: (gz_i*gy_j)*gx_k
                         atomicAdd(&A[(fz + i) * ncol + cy * pitch + cx], mul(mul(wz[i], wy[j]), wx[k]));
@@ -297,11 +302,14 @@ pc_sil_fwd_kernel(const float4* __restrict__ sorted, const int32_t* __restrict__
     float* A = sm;                       // [V][ncol]
     float* blkP = sm + V * ncol;         // [nzb][ncol] transmittance of the block
     float* blkS = blkP + nzb * ncol;     // [nzb][ncol] silhouette collected inside the block
+    int* zlo = reinterpret_cast<int*>(blkS + nzb * ncol);    // [ncol] first / last occupied depth of the column
+    int* zhi = zlo + ncol;
     const int tid = threadIdx.x;
     for (int i = tid; i < V * ncol; i += TILE_THREADS) A[i] = 0.f;
+    for (int i = tid; i < ncol; i += TILE_THREADS) { zlo[i] = V; zhi[i] = -1; }
     __syncthreads();
     splat_bins(sorted + (size_t)b * N, bin_start + (size_t)b * (nbx * nby + 1), nbx, nby, ty0,
-               min(ty0 + TY, V) - 1, tx0, min(tx0 + TX, V) - 1, TX, ncol, mode, A);
+               min(ty0 + TY, V) - 1, tx0, min(tx0 + TX, V) - 1, TX, ncol, mode, A, zlo, zhi);
     __syncthreads();
     clamp_patch(A, V * ncol);
     __syncthreads();
@@ -309,10 +317,18 @@ pc_sil_fwd_kernel(const float4* __restrict__ sorted, const int32_t* __restrict__
     const bool has_scale = scale != nullptr;
     const float sc = has_scale ? scale[b] : 1.f;
     const float c0 = (mode == B3D_MODE_REFERENCE) ? expf(TERM_EPS) : 1.f;   // D10 pad row
+    // sparsity skip: exact only when 0 * tap and 0 * scale are 0 (finite taps / scale; NaN must propagate)
+    const bool skip_ok = taps.finite && (!has_scale || fabsf(sc) <= 3.0e38f);
+    const int HB = (KT > 0 ? KT : taps.n) / 2;
     for (int it = tid; it < nzb * ncol; it += TILE_THREADS) {
         const int col = it % ncol, zb = (it / ncol) * ZB;
         float S[ZB];
-        blur_window<KT, false, true>(A + col, ncol, V, zb, taps, S);
+        if (skip_ok && (zb + ZB - 1 < zlo[col] - HB || zb > zhi[col] + HB)) {
+#pragma unroll
+            for (int j = 0; j < ZB; ++j) S[j] = 0.f;             // no occupied cell within the taps' reach: the blur is exactly 0
+        } else {
+            blur_window<KT, false, true>(A + col, ncol, V, zb, taps, S);
+        }
         float T = 1.f, acc = 0.f;
 #pragma unroll
         for (int j = 0; j < ZB; ++j) {
@@ -358,12 +374,15 @@ pc_sil_bwd_kernel(const float4* __restrict__ sorted, const int32_t* __restrict__
     float* blkA = A2 + V * ncol;         // [nzb][ncol] transmittance of the block
     float* blkB = blkA + nzb * ncol;     // [nzb][ncol] offset of the block's Q recurrence -> Q just after the block
     float* blkT = blkB + nzb * ncol;     // [nzb][ncol] transmittance at the start of the block
+    int* zlo = reinterpret_cast<int*>(blkT + nzb * ncol);    // [ncol] first / last occupied depth of the column
+    int* zhi = zlo + ncol;
     const int tid = threadIdx.x;
     for (int i = tid; i < V * ncol; i += TILE_THREADS) A1[i] = 0.f;
+    for (int i = tid; i < ncol; i += TILE_THREADS) { zlo[i] = V; zhi[i] = -1; }
     __syncthreads();
     const float4* sp = sorted + (size_t)b * N;
     const int32_t* bs = bin_start + (size_t)b * (nbx * nby + 1);
-    splat_bins(sp, bs, nbx, nby, ty0, cy1, tx0, cx1, EX, ncol, mode, A1);
+    splat_bins(sp, bs, nbx, nby, ty0, cy1, tx0, cx1, EX, ncol, mode, A1, zlo, zhi);
     __syncthreads();
     clamp_patch(A1, V * ncol);
     __syncthreads();
@@ -372,12 +391,21 @@ pc_sil_bwd_kernel(const float4* __restrict__ sorted, const int32_t* __restrict__
     const float sc = has_scale ? scale[b] : 1.f;
     const float c0 = (mode == B3D_MODE_REFERENCE) ? expf(TERM_EPS) : 1.f;
     const int nitems = nzb * ncol;
+    // sparsity skip (see the forward kernel): S == 0 exactly outside [zlo - H, zhi + H]; there o = eps is clamped, so
+    // d sil / d S == 0 as well, and the transposed blur of dS vanishes outside [zlo - 2H, zhi + 2H]
+    const bool skip_ok = taps.finite && (!has_scale || fabsf(sc) <= 3.0e38f);
+    const int HB = (KT > 0 ? KT : taps.n) / 2;
 
     // pass 1: S = blur_z(O); per block: a = prod(1-o), b = Q at block start for Q = 0 after the block
     for (int it = tid; it < nitems; it += TILE_THREADS) {
         const int col = it % ncol, zb = (it / ncol) * ZB;
         float S[ZB];
-        blur_window<KT, false, true>(A1 + col, ncol, V, zb, taps, S);
+        if (skip_ok && (zb + ZB - 1 < zlo[col] - HB || zb > zhi[col] + HB)) {
+#pragma unroll
+            for (int j = 0; j < ZB; ++j) S[j] = 0.f;
+        } else {
+            blur_window<KT, false, true>(A1 + col, ncol, V, zb, taps, S);
+        }
         float a = 1.f, q = 0.f;
 #pragma unroll
         for (int j = ZB - 1; j >= 0; --j) {
@@ -414,6 +442,7 @@ pc_sil_bwd_kernel(const float4* __restrict__ sorted, const int32_t* __restrict__
         const int cy = col / EX, cx = col % EX;
         const int y = ty0 + cy, x = tx0 + cx;
         if (y >= V || x >= V) continue;
+        if (skip_ok && (zb + ZB - 1 < zlo[col] - HB || zb > zhi[col] + HB)) continue;     // dS == 0 == what A2 already holds
         const bool owned = cy < TY && cx < TX;      // halo columns are owned by the neighbour patch
         const float go = dsil[((size_t)b * V + (V - 1 - y)) * V + x];
         float S[ZB], o[ZB], Tz[ZB];
@@ -452,6 +481,7 @@ pc_sil_bwd_kernel(const float4* __restrict__ sorted, const int32_t* __restrict__
     // pass 4: dG = mask * blur_z^T(dS)
     for (int it = tid; it < nitems; it += TILE_THREADS) {
         const int col = it % ncol, zb = (it / ncol) * ZB;
+        if (skip_ok && (zb + ZB - 1 < zlo[col] - 2 * HB || zb > zhi[col] + 2 * HB)) continue;   // dG == 0 == the empty cells of A1
         float D[ZB];
         blur_window<KT, true, false>(A2 + col, ncol, V, zb, taps, D);
 #pragma unroll
@@ -590,10 +620,10 @@ size_t patch_bytes(int V, int ty, bool bwd) {
     const size_t nzb = (V + ZB - 1) / ZB;
     if (bwd) {
         const size_t ncol = (size_t)(ty + 1) * (TX + 1);
-        return 4 * (2 * V * ncol + 3 * nzb * ncol);
+        return 4 * (2 * V * ncol + 3 * nzb * ncol + 2 * ncol);
     }
     const size_t ncol = (size_t)ty * TX;
-    return 4 * (V * ncol + 2 * nzb * ncol);
+    return 4 * (V * ncol + 2 * nzb * ncol + 2 * ncol);
 }
 
 int pick_ty(int V, bool bwd) {
@@ -611,6 +641,9 @@ int load_taps(const float* taps_dev, int ktaps, Taps& t, cudaStream_t st) {
     B3D_CUDA_OK(cudaMemcpyAsync(t.w, taps_dev, sizeof(float) * ktaps, cudaMemcpyDeviceToHost, st));
     B3D_CUDA_OK(cudaStreamSynchronize(st));
     t.n = ktaps;
+    t.finite = 1;
+    for (int i = 0; i < ktaps; ++i)
+        if (!(fabsf(t.w[i]) <= 3.0e38f)) t.finite = 0;
     return B3D_OK;
 }
 
@@ -674,7 +707,11 @@ int check_sil_args(const char* who, const void* sorted, const void* bin_start, c
 }
 
 void fill_taps(Taps& t, const float* host, int n) {
-    for (int i = 0; i < n; ++i) t.w[i] = host[i];
+    t.finite = 1;
+    for (int i = 0; i < n; ++i) {
+        t.w[i] = host[i];
+        if (!(fabsf(host[i]) <= 3.0e38f)) t.finite = 0;          // NaN / inf taps must propagate
+    }
     t.n = n;
 }
 

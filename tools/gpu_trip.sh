@@ -21,6 +21,11 @@ if [ "${EXTRA:-0}" = "1" ]; then
   B3D_BENCH_NO_CPU=1 python bench.py --workload cfg5 --steps 10 --warmup 3 > gpurun_out/${T}_bench_cfg5.json 2> gpurun_out/${T}_bench_cfg5.err
   for w in cfg4 cfg5; do echo "== $w"; cut -c1-400 gpurun_out/${T}_bench_$w.json; tail -n 3 gpurun_out/${T}_bench_$w.err | cut -c1-300; done
 fi
+if [ "${DIAG:-0}" = "1" ]; then
+  python tools/time_convs.py > gpurun_out/${T}_convs_rowwin1.txt 2>&1
+  B3D_CONV_ROWWIN=0 python tools/time_convs.py > gpurun_out/${T}_convs_rowwin0.txt 2>&1
+  echo "== conv layer times, row-window on / off"; paste -d'|' <(cut -c1-62 gpurun_out/${T}_convs_rowwin1.txt) <(cut -c24-62 gpurun_out/${T}_convs_rowwin0.txt) | head -24
+fi
 echo "==== pytest"; grep -E "^(FAILED|ERROR)|passed|failed|rc=" gpurun_out/${T}_pytest.log | tail -n 30
 grep -E "^E  " gpurun_out/${T}_pytest.log | head -n 30
 echo "==== bench"; python - <<PY
