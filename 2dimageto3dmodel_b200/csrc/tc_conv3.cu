@@ -244,6 +244,9 @@ int launch_rowwin(const b3d::RowWinArgs& a, cudaStream_t st) {
 namespace b3d {
 int conv_rowwin_launch(const RowWinArgs& a, cudaStream_t st) {
     if (a.xhi - a.xlo < BM || a.Cin % BK || a.kh < 1 || a.kh > 5) return 1;
+    // short K loops (folded stems: 1 filter row x 2 channel slices) cannot hide the two-stage ring's window loads behind
+    // MMA work: measured slower than the per-tap kernel (0.71 vs 0.62 ms, profiles/r2_e_conv_layers.md)
+    if (a.kh * (a.Cin / BK) < 4) return 1;
     // one CTA per SM: worth it only with >= ~2 waves of stacked work items
     const long long tiles = (long long)ceil_div(a.xhi - a.xlo, BM) * a.Hout * a.N;
     if (a.Cout == 64) {

@@ -127,7 +127,7 @@ def test_every_dispatched_variant_was_exercised():
         "conv_tf32_persistent<256,4,0,1>", "conv_tf32_persistent<128,4,0,2>", "conv_tf32_persistent<64,3,0,4>",
         "conv_tf32_persistent<128,3,0,1>", "conv_tf32_persistent<64,4,0,1>",
         # row-window kernel (tc_conv3.cu): 128-pixel row tiles of the 64-wide layers (3x3, 1x5 / 5x5) and blk6.conv1's dgrad
-        "conv_rowwin_tf32<64,3,4,2>", "conv_rowwin_tf32<64,5,4,2>", "conv_rowwin_tf32<128,3,2,2>",
+        "conv_rowwin_tf32<64,3,4,2>", "conv_rowwin_tf32<64,5,4,2>", "conv_rowwin_tf32<128,3,2,2>",     # <64,5,..>: conv_final dgrad
         # weight gradients: row-of-taps (T = 3, 5), stride-2 tap pairs (T = 2), single taps, both Cin tile widths
         "wgrad_tf32<128,6,3>", "wgrad_tf32<64,8,3>", "wgrad_tf32<64,8,5>", "wgrad_tf32<128,3,2>", "wgrad_tf32<64,4,2>",
         "wgrad_tf32<128,6,1>", "wgrad_tf32<64,8,1>",
