@@ -58,8 +58,10 @@ def conv2d_nhwc(x, weight, bias=None, pad_y=0, stride=1, leaky=1.0, wt=None, cin
     optr = ctypes.c_void_p(out.data_ptr() + 4 * pad_out * Cout)          # pixel (n, y, pad_out) of the padded buffer
     if pad_out and Cout % 4:
         raise B3DError("conv2d: pad_out needs Cout % 4 == 0")
-    if _thin(Cout, Cin, kh, kw, stride) and not cin_major:
+    wide_head = Wout >= 128 and N * Hout * (Wout // 128) >= 8 * 148 and not os.environ.get("B3D_THIN_HEAD_CUDA_CORES")
+    if _thin(Cout, Cin, kh, kw, stride) and not cin_major and not wide_head:
         # 1-4 output channels: fp32 CUDA-core reduction kernel (csrc/thin_kernels.cu), not a 64-wide MMA tile
+        # (wide heads — conv_final at 256 x 128 — take the row-window tensor-core kernel with N = 16 tiles instead)
         check(_conv_call(lib.b3d_conv2d_thin_fwd, ptr(x), ptr(wt), ptr(dev(bias, "bias") if bias is not None else None), optr, N, H, W,
                                       Cin, Hout, Wout, Cout, kh, kw, pad_y, x_crop, OW, Cout, float(leaky), stream_ptr(x)))
         if pad_out:
@@ -290,7 +292,9 @@ class _ConvBanked(torch.autograd.Function):
         optr = ctypes.c_void_p(out.data_ptr() + 4 * pad_out * Cout)
         st = stream_ptr(x)
         thin = _thin(Cout, Cin, kh, kw, stride)
-        if thin:
+        # wide thin heads (conv_final: 64 -> 3 at 256 x 128) go to the row-window tensor-core kernel with N = 16 tiles
+        thin_fwd = thin and not (Wout >= 128 and N * Hout * (Wout // 128) >= 8 * 148 and not os.environ.get("B3D_THIN_HEAD_CUDA_CORES"))
+        if thin_fwd:
             check(_conv_call(lib.b3d_conv2d_thin_fwd, ptr(x), ptr(wt), ptr(b), optr, N, H, W, Cin, Hout, Wout, Cout, kh, kw, pad_y,
                              x_crop, OW, Cout, float(leaky), st))
         else:

@@ -631,17 +631,22 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
     // One launch covers output columns [xlo, xhi).  A width of "power of two + a few columns" (dgrad of an x-padded
     // input: 130, 66, 34 ...; stride-2 parity classes: 129, 65 ...) would leave a second, almost empty 128-pixel tile in
     // every row, so the remainder columns get a narrow strip launch of their own.
-    // filter-grid detection for the row-window kernel (tc_conv3.cu): kh rows of kw horizontally consecutive taps
-    int g_kw = 0, g_kh = 0, g_step = 0;
-    if (sy == 1 && sx == 1 && osy == 1 && osx == 1 && !w_cin_major && !wtap) {
+    // filter-grid detection for the row-window kernel (tc_conv3.cu): kh rows of kw horizontally consecutive taps; the weight
+    // taps of a row form an arithmetic progression (identity, or the stride-2 dgrad parity classes' tap lists)
+    int g_kw = 0, g_kh = 0, g_step = 0, g_wstep = 1;
+    if (sy == 1 && sx == 1 && !w_cin_major) {
         int kw_ = 1;
         while (kw_ < ntaps && dy[kw_] == dy[0]) ++kw_;
         const int step = kw_ > 1 ? dx[1] - dx[0] : 1;
-        bool grid_ok = ntaps % kw_ == 0 && ntaps / kw_ <= 5 && (kw_ == 3 || kw_ == 5) && (step == 1 || step == -1);
-        for (int t = 0; grid_ok && t < ntaps; ++t)
+        const int wstep = (wtap && kw_ > 1) ? wtap[1] - wtap[0] : 1;
+        bool grid_ok = ntaps % kw_ == 0 && ntaps / kw_ <= 5 && (kw_ == 2 || kw_ == 3 || kw_ == 5) && (step == 1 || step == -1) &&
+                       wstep >= 1 && wstep <= 2 && (osy == osx) && (osy == 1 || osy == 2);
+        for (int t = 0; grid_ok && t < ntaps; ++t) {
             grid_ok = dy[t] == dy[(t / kw_) * kw_] && dx[t] == dx[0] + (t % kw_) * step;
+            if (wtap) grid_ok = grid_ok && wtap[t] == wtap[(t / kw_) * kw_] + (t % kw_) * wstep;
+        }
         static const int rowwin_env = getenv("B3D_CONV_ROWWIN") ? atoi(getenv("B3D_CONV_ROWWIN")) : 1;
-        if (grid_ok && rowwin_env) { g_kw = kw_; g_kh = ntaps / kw_; g_step = step; }
+        if (grid_ok && rowwin_env) { g_kw = kw_; g_kh = ntaps / kw_; g_step = step; g_wstep = wstep; }
     }
     auto run = [&](int xlo, int xhi) -> int {
         const int wspan = xhi - xlo;
@@ -654,6 +659,8 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
             a.dx0 = g_step > 0 ? dx[0] : dx[g_kw - 1];
             for (int t = 0; t < g_kw; ++t) a.shift[t] = dx[t] - a.dx0;
             a.OH = OH; a.OW = OW; a.OC = OC; a.ooy = ooy; a.oox = oox; a.leaky = leaky; a.stats = stats;
+            a.osy = osy; a.osx = osx; a.wtaps_total = wtaps_total; a.wtap_step = g_wstep;
+            for (int r = 0; r < g_kh; ++r) a.wtap0[r] = wtap ? wtap[r * g_kw] : r * g_kw;
             const int rc = b3d::conv_rowwin_launch(a, st);
             if (rc <= 0) return rc;                           // launched (0) or a real error (< 0); 1 = not covered
         }

@@ -23,7 +23,8 @@ struct RowParams {
     int tiles_x, tiles, groups, work;
     int kh, kslices;
     int dy[5], dx0, shift[5];
-    int OH, OW, OC, ooy, oox;
+    int OH, OW, OC, ooy, oox, osy, osx;
+    int wtap0[5];
     float leaky;
     double* stats;
 };
@@ -52,8 +53,9 @@ conv_rowwin_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     uint64_t* acc_empty = acc_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     float* sm_stats = reinterpret_cast<float*>(base + STAGES * S::STAGE_BYTES + 320);
-    constexpr uint32_t TCOLS = 2 * R * BN;
-    static_assert(TCOLS <= 512 && (TCOLS & (TCOLS - 1)) == 0, "TMEM: 2 buffers x R accumulators x BN columns");
+    // BN = 16 (thin heads): the epilogue reads 32-column groups, so the allocation keeps 32 spare columns behind the last one
+    constexpr uint32_t TCOLS = BN < 32 ? 4 * R * BN : 2 * R * BN;
+    static_assert(TCOLS <= 512 && (TCOLS & (TCOLS - 1)) == 0 && TCOLS >= 32, "TMEM: 2 buffers x R accumulators x BN columns");
     for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) sm_stats[i] = 0.f;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -103,7 +105,7 @@ conv_rowwin_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
 #pragma unroll
                     for (int r = 0; r < R; ++r)
                         tc::tma_load_4d(a + r * S::WIN_STRIDE, &tmap_x, full + s, ks * BK, x0[r] + p.dx0, y0[r] + p.dy[fr], n0[r]);
-                    tc::tma_load_3d(a + R * S::WIN_STRIDE, &tmap_w, full + s, ks * BK, c0, fr * KW);
+                    tc::tma_load_3d(a + R * S::WIN_STRIDE, &tmap_w, full + s, ks * BK, c0, p.wtap0[fr]);
                 }
             }
         }
@@ -156,7 +158,7 @@ conv_rowwin_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
                 t /= p.tiles_x;
                 const int y = t % p.Hout, n = t / p.Hout;
                 const bool valid = tile_ok && x < p.xhi;
-                float* dst = out + (((size_t)n * p.OH + (size_t)(y + p.ooy)) * p.OW + (size_t)(x + p.oox)) * p.OC;
+                float* dst = out + (((size_t)n * p.OH + (size_t)(p.osy * y + p.ooy)) * p.OW + (size_t)(p.osx * x + p.oox)) * p.OC;
 #pragma unroll 1
                 for (int c = 0; c < BN; c += 32) {
                     float v[32];
@@ -166,7 +168,7 @@ conv_rowwin_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
                         __syncwarp();
                         if (lane == 0) tc::mbar_arrive(acc_empty + buf);
                     }
-                    if (p.stats) tc::stats_accumulate(v, valid, sm_stats, BN, c);
+                    if (BN >= 32 && p.stats) tc::stats_accumulate(v, valid, sm_stats, BN, c);
                     if (valid) {
                         const int cb = c0 + c;
                         if (cb + 32 <= p.Cout && (p.OC & 3) == 0) {
@@ -196,7 +198,7 @@ conv_rowwin_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
                     }
                 }
             }
-            if (p.stats) tc::stats_flush(sm_stats, BN, p.stats, p.Cout, c0, threadIdx.x - 64);
+            if (BN >= 32 && p.stats) tc::stats_flush(sm_stats, BN, p.stats, p.Cout, c0, threadIdx.x - 64);
         }
     }
     tc::tc_fence_before();
@@ -218,6 +220,8 @@ int launch_rowwin(const b3d::RowWinArgs& a, cudaStream_t st) {
     for (int i = 0; i < 5; ++i) { p.dy[i] = a.dy[i]; p.shift[i] = a.shift[i]; }
     p.dx0 = a.dx0;
     p.OH = a.OH; p.OW = a.OW; p.OC = a.OC; p.ooy = a.ooy; p.oox = a.oox; p.leaky = a.leaky; p.stats = a.stats;
+    p.osy = a.osy; p.osx = a.osx;
+    for (int i = 0; i < 5; ++i) p.wtap0[i] = a.wtap0[i];
     CUtensorMap mx, mw;
     {
         const uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.N};
@@ -226,10 +230,12 @@ int launch_rowwin(const b3d::RowWinArgs& a, cudaStream_t st) {
         if (int rc = tc::make_tmap_f32(&mx, a.x, 4, dims, strides, box)) return rc;
     }
     {
-        const uint64_t dims[3] = {(uint64_t)a.Cin, (uint64_t)a.Cout, (uint64_t)(a.kh * a.kw)};
+        // one box = the KW weight tiles of a filter row: taps wtap0[r], wtap0[r] + step, ... (element stride on the tap dim)
+        const uint64_t dims[3] = {(uint64_t)a.Cin, (uint64_t)a.Cout, (uint64_t)a.wtaps_total};
         const uint64_t strides[2] = {(uint64_t)a.Cin * 4, (uint64_t)a.Cout * a.Cin * 4};
-        const uint32_t box[3] = {(uint32_t)BK, (uint32_t)BN, (uint32_t)KW};
-        if (int rc = tc::make_tmap_f32(&mw, a.wt, 3, dims, strides, box)) return rc;
+        const uint32_t box[3] = {(uint32_t)BK, (uint32_t)BN, (uint32_t)((KW - 1) * a.wtap_step + 1)};
+        const uint32_t es[3] = {1, 1, (uint32_t)a.wtap_step};
+        if (int rc = tc::make_tmap_f32(&mw, a.wt, 3, dims, strides, box, es)) return rc;
     }
     B3D_CUDA_OK(cudaFuncSetAttribute(conv_rowwin_tf32_kernel<BN, KW, R, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     const int grid = p.work < 148 ? p.work : 148;
@@ -249,14 +255,22 @@ int conv_rowwin_launch(const RowWinArgs& a, cudaStream_t st) {
     if (a.kh * (a.Cin / BK) < 4) return 1;
     // one CTA per SM: worth it only with >= ~2 waves of stacked work items
     const long long tiles = (long long)ceil_div(a.xhi - a.xlo, BM) * a.Hout * a.N;
+    if (a.Cout <= 16 && a.kw == 5 && a.stats == nullptr) {
+        // 1-16 output channels (conv_final 64 -> 3): N = 16 tensor-core tiles — 13 of 16 columns are padding, still ~2.5x the
+        // fp32 CUDA-core kernel (one window load feeds five taps)
+        if (tiles / 4 < 2 * 148) return 1;
+        return launch_rowwin<16, 5, 4, 2>(a, st);
+    }
     if (a.Cout == 64) {
         if (tiles / 4 < 2 * 148) return 1;
+        if (a.kw == 2) return launch_rowwin<64, 2, 4, 2>(a, st);        // stride-2 dgrad parity classes (2 x 2 taps)
         if (a.kw == 3) return launch_rowwin<64, 3, 4, 2>(a, st);
         if (a.kw == 5) return launch_rowwin<64, 5, 4, 2>(a, st);
         return 1;
     }
     if (a.Cout == 128) {
         if (tiles / 2 < 2 * 148) return 1;
+        if (a.kw == 2) return launch_rowwin<128, 2, 2, 2>(a, st);
         if (a.kw == 3) return launch_rowwin<128, 3, 2, 2>(a, st);
         return 1;
     }

@@ -16,6 +16,10 @@ struct RowWinArgs {
     int dx0;             // first input column of the staged window: x + dx0
     int shift[5];        // window row shift of tap s of a filter row (dx[s] - dx0)
     int OH, OW, OC, ooy, oox;
+    int osy, osx;        // output pixel (y, x) is written at (osy*y + ooy, osx*x + oox): 2 for the stride-2 dgrad parity classes
+    int wtap0[5];        // weight tap (row of the tap-major array) of the first tap of filter row r
+    int wtaps_total;     // taps in the weight array
+    int wtap_step;       // tap-index distance between consecutive taps of a filter row (1, or 2 for the parity classes)
     float leaky;
     double* stats;       // nullable: [2][Cout] fp64 sums of the output (BN statistics), accumulated
 };

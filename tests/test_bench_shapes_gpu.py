@@ -128,11 +128,13 @@ def test_every_dispatched_variant_was_exercised():
         "conv_tf32_persistent<128,3,0,1>", "conv_tf32_persistent<64,4,0,1>",
         # row-window kernel (tc_conv3.cu): 128-pixel row tiles of the 64-wide layers (3x3, 1x5 / 5x5) and blk6.conv1's dgrad
         "conv_rowwin_tf32<64,3,4,2>", "conv_rowwin_tf32<64,5,4,2>", "conv_rowwin_tf32<128,3,2,2>",     # <64,5,..>: conv_final dgrad
+        "conv_rowwin_tf32<64,2,4,2>",                                                                  # D1.conv2 dgrad parity classes
+        "conv_rowwin_tf32<16,5,4,2>",                                                                  # conv_final fprop (N = 16 tiles)
         # weight gradients: row-of-taps (T = 3, 5), stride-2 tap pairs (T = 2), single taps, both Cin tile widths
         "wgrad_tf32<128,6,3>", "wgrad_tf32<64,8,3>", "wgrad_tf32<64,8,5>", "wgrad_tf32<128,3,2>", "wgrad_tf32<64,4,2>",
         "wgrad_tf32<128,6,1>", "wgrad_tf32<64,8,1>",
         # 1-3 output channel heads on the CUDA-core kernels
-        "conv_thin_fwd<3,2>", "conv_thin_fwd<1,4>", "conv_thin_wgrad_win<3,2>", "conv_thin_wgrad_win<1,4>",
+        "conv_thin_fwd<3,2>", "conv_thin_fwd<1,4>", "conv_thin_wgrad_win<3,2>", "conv_thin_wgrad_win<1,4>",     # fwd<3,2>: conv_mesh
     }
     flat = {v for v in SEEN if v.startswith("conv_flat_tf32<128>")}
     assert flat, f"the halo-staged kernel never ran; seen: {sorted(SEEN)}"
