@@ -467,6 +467,33 @@ def run_cuda(args):
         for k, v in sorted(prof_tot.items(), key=lambda kv: -kv[1])[:60]:
             print(f"{v:8.3f} ms/step x{len(raw_prof[k]) // nprof:3d}  {k}", file=sys.stderr)
 
+    # collective work of one step (N > 1): the SyncBN statistic exchanges are libb3d entry points (timed above); the in-place
+    # gradient all-reduces of the flat conv-weight buffers are timed here with CUDA events (all ranks take part)
+    collectives = None
+    if dist is not None and cfg["gan"]:
+        import torch.distributed as tdist
+        G_, D_ = wl.gan.trainer.generator, wl.gan.trainer.discriminator
+        flats = [(n, getattr(m.__dict__.get('_bank'), 'last_dw', None)) for n, m in (("generator", G_), ("discriminator", D_))]
+        ar_ms, ar_bytes = 0.0, 0
+        if all(f is not None for _, f in flats) and tdist.get_backend() == "nccl":
+            plan = [flats[0][1], flats[1][1], flats[1][1]]             # G step, two D steps
+            for f in plan:
+                tdist.all_reduce(f, op=tdist.ReduceOp.AVG)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                for f in plan:
+                    tdist.all_reduce(f, op=tdist.ReduceOp.AVG)
+            e1.record()
+            torch.cuda.synchronize()
+            ar_ms, ar_bytes = e0.elapsed_time(e1) / 5, sum(f.numel() * 4 for f in plan)
+        sync_ms = sum(v for k, v in prof_tot.items() if k.endswith("_sync"))
+        sync_n = sum(len(v) for k, v in raw_prof.items() if k.endswith("_sync")) // nprof
+        collectives = {"syncbn_exchanges_per_step": sync_n, "syncbn_fused_kernels_ms_per_step": round(sync_ms, 3),
+                       "syncbn_path": "fused one-shot all-reduce over NVLink peer memory" if sync_n else "NCCL all-reduce per layer",
+                       "grad_allreduce_ms_per_step": round(ar_ms, 3), "grad_allreduce_bytes_per_step": ar_bytes}
+
     def finish():
         """All ranks leave together; with NCCL captured in a CUDA graph the communicator teardown can block, so multi-rank
         runs end with a barrier and a hard exit (the JSON line is flushed first)."""
@@ -551,6 +578,8 @@ def run_cuda(args):
         out["chamfer"] = chamfer_report(dev)
     except Exception as e:                                   # reported, never fatal for the headline
         out["chamfer"] = {"error": str(e)[:200]}
+    if collectives is not None:
+        out["collectives"] = collectives
     if tensor is not None:
         # the convolutions dominate the step -> the tensor-core roofline is the primary one; the HBM-class kernel
         # roofline (point-cloud / raster backward) moves to roofline_hbm

@@ -21,10 +21,20 @@ if [ "${EXTRA:-0}" = "1" ]; then
   B3D_BENCH_NO_CPU=1 python bench.py --workload cfg5 --steps 10 --warmup 3 > gpurun_out/${T}_bench_cfg5.json 2> gpurun_out/${T}_bench_cfg5.err
   for w in cfg4 cfg5; do echo "== $w"; cut -c1-400 gpurun_out/${T}_bench_$w.json; tail -n 3 gpurun_out/${T}_bench_$w.err | cut -c1-300; done
 fi
+if [ "${NCUCONV:-0}" = "1" ]; then
+  timeout 600 ncu --set full --clock-control none -k regex:'conv_|wgrad_' -c 40 -f -o gpurun_out/${T}_convs python tools/ncu_convs_r2.py > gpurun_out/${T}_ncu_convs.log 2>&1
+  ncu -i gpurun_out/${T}_convs.ncu-rep --page raw --csv > gpurun_out/${T}_convs_raw.csv 2>/dev/null; rm -f gpurun_out/${T}_convs.ncu-rep
+  timeout 600 ncu --set full --import-source on --clock-control none --profile-from-start off -k regex:'mesh_raster_bwd' -c 1 -f -o gpurun_out/${T}_meshbwd python tools/ncu_r2_step.py > gpurun_out/${T}_ncu_meshbwd.log 2>&1
+  ncu -i gpurun_out/${T}_meshbwd.ncu-rep --page source --csv > gpurun_out/${T}_meshbwd_source.csv 2>/dev/null; rm -f gpurun_out/${T}_meshbwd.ncu-rep
+fi
 if [ "${DIAG:-0}" = "1" ]; then
   python tools/time_convs.py > gpurun_out/${T}_convs_rowwin1.txt 2>&1
   B3D_CONV_ROWWIN=0 python tools/time_convs.py > gpurun_out/${T}_convs_rowwin0.txt 2>&1
   echo "== conv layer times, row-window on / off"; paste -d'|' <(cut -c1-62 gpurun_out/${T}_convs_rowwin1.txt) <(cut -c24-62 gpurun_out/${T}_convs_rowwin0.txt) | head -24
+fi
+if [ "${REFARM:-0}" = "1" ]; then
+  /usr/bin/time -v python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/${T}_bench_reference.json 2> gpurun_out/${T}_bench_reference.err
+  echo "== reference arm"; cut -c1-260 gpurun_out/${T}_bench_reference.json; grep -E "Elapsed|Maximum resident" gpurun_out/${T}_bench_reference.err
 fi
 echo "==== pytest"; grep -E "^(FAILED|ERROR)|passed|failed|rc=" gpurun_out/${T}_pytest.log | tail -n 30
 grep -E "^E  " gpurun_out/${T}_pytest.log | head -n 30
