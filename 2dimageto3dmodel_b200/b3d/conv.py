@@ -83,7 +83,7 @@ def conv2d_nhwc(x, weight, bias=None, pad_y=0, stride=1, leaky=1.0, wt=None, cin
             check(rc)
     if not use_flat or rc != 0:
         check(_conv_call(lib.b3d_conv2d_tf32, ptr(x), ptr(wt), ptr(b), optr, N, H, W, Cin, Hout, Wout, Cout, kh * kw, _ints(dy),
-                                  _ints(dx), stride, stride, Hout, OW, Cout, 1, 1, 0, 0, float(leaky), int(cin_major), None, 0, None,
+                                  _ints(dx), stride, stride, Hout, OW, Cout, 1, 1, 0, 0, float(leaky), int(cin_major), None, 0, None, 0, 0,
                                   stream_ptr(x)))
     if pad_out:
         check(lib.b3d_wrap_x_inplace(ptr(out), N * Hout, Wout, Cout, pad_out, pad_mode, stream_ptr(x)))
@@ -118,7 +118,7 @@ def conv2d_dgrad_nhwc(dy_, weight, in_hw, pad_y=0, stride=1, x_crop=0):
         dy = [pad_y - r for r in range(kh) for _ in range(kw)]
         dx = [-s - x_crop for _ in range(kh) for s in range(kw)]
         check(_conv_call(lib.b3d_conv2d_tf32, ptr(g), ptr(wt), None, ptr(dxo), N, Hout, Wout, Cout, H, W, Cin, kh * kw, _ints(dy),
-                                  _ints(dx), 1, 1, H, W, Cin, 1, 1, 0, 0, 1.0, 0, None, 0, None, st))
+                                  _ints(dx), 1, 1, H, W, Cin, 1, 1, 0, 0, 1.0, 0, None, 0, None, 0, 0, st))
         return dxo
     if stride != 2 or x_crop:
         raise B3DError("conv2d_dgrad: stride must be 1 or 2 (x_crop: stride 1 only)")
@@ -128,7 +128,7 @@ def conv2d_dgrad_nhwc(dy_, weight, in_hw, pad_y=0, stride=1, x_crop=0):
             continue
         wt = torch.stack([weight[:, :, r, s].t() for r, s in rs]).contiguous()      # [taps][Cin][Cout]
         check(_conv_call(lib.b3d_conv2d_tf32, ptr(g), ptr(wt), None, ptr(dxo), N, Hout, Wout, Cout, Ha, Wa, Cin, len(rs),
-                                  _ints(dy), _ints(dx), 1, 1, H, W, Cin, 2, 2, cy, cx, 1.0, 0, None, 0, None, st))
+                                  _ints(dy), _ints(dx), 1, 1, H, W, Cin, 2, 2, cy, cx, 1.0, 0, None, 0, None, 0, 0, st))
     return dxo
 
 
@@ -148,7 +148,7 @@ def conv2d_wgrad_nhwc(dy_, x, kh, kw, pad_y=0, stride=1, x_crop=0):
     _, H, W, Cin = x.shape
     dw = torch.zeros(Cout, Cin, kh, kw, device=g.device, dtype=torch.float32)
     check(_conv_call(lib.b3d_conv2d_wgrad_tf32, ptr(g), ptr(x), ptr(dw), N, H, W, Cin, Hout, Wout, Cout, kh, kw, pad_y, stride,
-                                    x_crop, 0, stream_ptr(g)))
+                                    x_crop, 0, 0, stream_ptr(g)))
     return dw if (co_real, ci_real) == (Cout, Cin) else dw[:co_real, :ci_real]
 
 
@@ -268,10 +268,17 @@ def conv2d(x_nchw, weight, bias=None, pad_y=0, stride=1, leaky=1.0, pad_out=0, p
 # ------------------------------------------------------------------------------------------------------------------
 class _ConvBanked(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, wf, bias, lw, pad_y, stride, leaky, pad_out, pad_mode, x_crop, stats=None):
+    def forward(ctx, x, wf, bias, lw, pad_y, stride, leaky, pad_out, pad_mode, x_crop, stats=None, fold_raw=0):
+        """fold_raw = kh > 0: x is the RAW 8-channel stem input [N,H,W,8]; the kernels fold the kh vertical taps into the K
+        dimension on the fly (TMA boxes of 4 rows x 8 channels) — the folded tensor never exists (pad_y = the fold's y padding)."""
         x = dev(x.detach(), "x")
         N, H, W, Cx = x.shape
-        if Cx != lw.Cinp:
+        fold_pad = 0
+        if fold_raw:
+            if not lw.fold or Cx != 8 or lw.Cin != 8 or stride != 1 or x_crop:
+                raise B3DError("banked conv: on-the-fly fold needs a folded 8-channel stride-1 stem")
+            fold_pad = pad_y
+        elif Cx != lw.Cinp:
             if lw.fold or Cx > lw.Cinp:
                 raise B3DError(f"banked conv: input has {Cx} channels, the layer expects {lw.Cinp}")
             x = _pad_last(x, 32)                                      # thin un-folded inputs (512^2 stem): zero-pad K
@@ -281,7 +288,7 @@ class _ConvBanked(torch.autograd.Function):
         Cout, Cin = lw.Cout, lw.Cinp
         wt = dev(wf.detach(), "weight")
         b = dev(bias.detach(), "bias") if bias is not None else None
-        Hout = (H + 2 * pad_y - kh) // stride + 1
+        Hout = (H + 2 * fold_pad - lw.kh + 1) if fold_raw else (H + 2 * pad_y - kh) // stride + 1
         if x_crop and stride != 1:
             raise B3DError("conv2d: x_crop needs stride 1")
         Wout = (W - 2 * x_crop - kw) // stride + 1
@@ -300,9 +307,9 @@ class _ConvBanked(torch.autograd.Function):
         else:
             dy = [r - pad_y for r in range(kh) for _ in range(kw)]
             dx = [s + x_crop for _ in range(kh) for s in range(kw)]
-            use_flat = stride == 1 and Cout > 64 and N * Hout * W >= 2 * 148 * 384 and not x_crop
+            use_flat = stride == 1 and Cout > 64 and N * Hout * W >= 2 * 148 * 384 and not x_crop and not fold_raw
             if os.environ.get("B3D_CONV_FLAT"):
-                use_flat = stride == 1 and os.environ["B3D_CONV_FLAT"] == "1"
+                use_flat = stride == 1 and os.environ["B3D_CONV_FLAT"] == "1" and not fold_raw
             if stats is not None:                 # the statistics epilogue lives in the persistent / row-window kernels
                 use_flat = False
                 if bias is not None or leaky != 1.0 or stride != 1:
@@ -315,19 +322,20 @@ class _ConvBanked(torch.autograd.Function):
                     check(rc)
             if rc != 0:
                 check(_conv_call(lib.b3d_conv2d_tf32, ptr(x), ptr(wt), ptr(b), optr, N, H, W, Cin, Hout, Wout, Cout, kh * kw,
-                                 _ints(dy), _ints(dx), stride, stride, Hout, OW, Cout, 1, 1, 0, 0, float(leaky), 0, None, 0, ptr(stats), st))
+                                 _ints(dy), _ints(dx), stride, stride, Hout, OW, Cout, 1, 1, 0, 0, float(leaky), 0, None, 0, ptr(stats),
+                                 fold_raw, fold_pad, st))
         if pad_out:
             check(lib.b3d_wrap_x_inplace(ptr(out), N * Hout, Wout, Cout, pad_out, pad_mode, st))
         ctx.save_for_backward(x, out if (leaky != 1.0 or pad_out) else None)
         ctx.lw = lw
-        ctx.cfg = (pad_y, stride, Cx, bias is not None, leaky, pad_out, pad_mode, x_crop, kh, kw, thin)
+        ctx.cfg = (pad_y, stride, Cx, bias is not None, leaky, pad_out, pad_mode, x_crop, kh, kw, thin, fold_raw, fold_pad)
         return out
 
     @staticmethod
     def backward(ctx, gy):
         x, y = ctx.saved_tensors
         lw = ctx.lw
-        pad_y, stride, Cx, has_bias, leaky, pad_out, pad_mode, x_crop, kh, kw, thin = ctx.cfg
+        pad_y, stride, Cx, has_bias, leaky, pad_out, pad_mode, x_crop, kh, kw, thin, fold_raw, fold_pad = ctx.cfg
         Cout, Cin = lw.Cout, lw.Cinp
         N, H, W, _ = x.shape
         gy = dev(gy, "grad_output")
@@ -354,13 +362,16 @@ class _ConvBanked(torch.autograd.Function):
                 raise B3DError("banked conv: this layer was registered without an input gradient (no_dgrad)")
             gyp = _pad_last(gy, 32)                                    # heads with 1 / 3 output channels: zero-pad K
             Cop = lw.Coutp
+            Hraw = H
+            if fold_raw:
+                H = Hout                                               # gradient w.r.t. the (virtual) folded tensor [N, Hout, W, Cin]
             gx = torch.empty(N, H, W, Cin, device=gy.device, dtype=torch.float32)
             wd = lw.wd
             if stride == 1:
                 dy = [pad_y - r for r in range(kh) for _ in range(kw)]
                 dx = [-s - x_crop for _ in range(kh) for s in range(kw)]
                 check(_conv_call(lib.b3d_conv2d_tf32, ptr(gyp), ptr(wd), None, ptr(gx), N, Hout, Wout, Cop, H, W, Cin, kh * kw,
-                                 _ints(dy), _ints(dx), 1, 1, H, W, Cin, 1, 1, 0, 0, 1.0, 0, None, 0, None, st))
+                                 _ints(dy), _ints(dx), 1, 1, H, W, Cin, 1, 1, 0, 0, 1.0, 0, None, 0, None, 0, 0, st))
             elif stride == 2 and not x_crop:
                 for cy, cx, rs, dy, dx, Ha, Wa in stride2_classes(kh, kw, pad_y, H, W):
                     if not rs:
@@ -368,10 +379,14 @@ class _ConvBanked(torch.autograd.Function):
                         continue
                     taps = [r * kw + s for r, s in rs]                  # rows of the tap-major D array: no gathered copy
                     check(_conv_call(lib.b3d_conv2d_tf32, ptr(gyp), ptr(wd), None, ptr(gx), N, Hout, Wout, Cop, Ha, Wa, Cin,
-                                     len(rs), _ints(dy), _ints(dx), 1, 1, H, W, Cin, 2, 2, cy, cx, 1.0, 0, _ints(taps), kh * kw, None, st))
+                                     len(rs), _ints(dy), _ints(dx), 1, 1, H, W, Cin, 2, 2, cy, cx, 1.0, 0, _ints(taps), kh * kw, None, 0, 0, st))
             else:
                 raise B3DError("conv2d_dgrad: stride must be 1 or 2 (x_crop: stride 1 only)")
-            if Cx != Cin:
+            if fold_raw:                                               # adjoint of the fold: back to the raw 8-channel layout
+                graw = torch.empty(N, Hraw, W, Cx, device=gy.device, dtype=torch.float32)
+                check(lib.b3d_fold_rows_bwd(ptr(gx), ptr(graw), N, Hraw, W, Cx, lw.kh, fold_pad, Cin, st))
+                gx, H = graw, Hraw
+            elif Cx != Cin:
                 gx = gx[..., :Cx]
         if ctx.needs_input_grad[1]:
             gw = lw.df                                                 # the bank's gradient sink (zeroed by the bank)
@@ -383,9 +398,9 @@ class _ConvBanked(torch.autograd.Function):
             else:
                 if Cout % 32:
                     raise B3DError(f"banked conv: weight gradient needs Cout % 32 == 0 or a thin head (Cout={Cout})")
-                check(_conv_call(lib.b3d_conv2d_wgrad_tf32, ptr(gy), ptr(x), ptr(gw), N, H, W, Cin, Hout, Wout, Cout, kh, kw, pad_y,
-                                 stride, x_crop, 1, st))
-        return gx, gw, gb, None, None, None, None, None, None, None, None
+                check(_conv_call(lib.b3d_conv2d_wgrad_tf32, ptr(gy), ptr(x), ptr(gw), N, H, W, Cin, Hout, Wout, Cout, kh, kw,
+                                 fold_pad if fold_raw else pad_y, stride, x_crop, 1, fold_raw, st))
+        return gx, gw, gb, None, None, None, None, None, None, None, None, None
 
 
 def conv2d_banked(x_nchw, lw, pad_y=0, stride=1, leaky=1.0, pad_out=0, pad_mode=1, x_crop=0, stats=None):
@@ -394,8 +409,15 @@ def conv2d_banked(x_nchw, lw, pad_y=0, stride=1, leaky=1.0, pad_out=0, pad_mode=
     stats: optional zeroed fp64 tensor [2*Cout]; the conv epilogue accumulates the output's per-channel sum / sum of
     squares into it (the following batch norm's statistics without another pass over the tensor)."""
     x = x_nchw.permute(0, 2, 3, 1)
+    fold_raw = 0
     if lw.fold:
-        from .ew import fold_rows
-        x = fold_rows(x, lw.kh, pad_y, lw.Cinp)
-    y = _ConvBanked.apply(x, lw.wf, lw.bias, lw, int(pad_y), int(stride), float(leaky), int(pad_out), int(pad_mode), int(x_crop), stats)
+        Wout = x.shape[2] - lw.kw + 1
+        if (lw.Cin == 8 and stride == 1 and not x_crop and Wout % 128 == 0 and x.shape[0] * x.shape[1] * (Wout // 128) >= 2 * 148
+                and not os.environ.get("B3D_FOLD_MATERIALIZE")):
+            fold_raw = lw.kh                # 8-channel stems of wide images: the kernels fold on the fly, no folded tensor
+        else:
+            from .ew import fold_rows
+            x = fold_rows(x, lw.kh, pad_y, lw.Cinp)
+    y = _ConvBanked.apply(x, lw.wf, lw.bias, lw, int(pad_y), int(stride), float(leaky), int(pad_out), int(pad_mode), int(x_crop), stats,
+                          fold_raw)
     return y.permute(0, 3, 1, 2)

@@ -41,6 +41,8 @@ struct ConvParams {
     float leaky;                      // 1.0 = identity
     int dbg_lbo, dbg_sbo, dbg_lt;     // MN-major descriptor offsets (bytes), layout type
     double* stats;                    // nullable: [2][Cout] fp64 sum / sum of squares of the (pre-bias) output, accumulated
+    int fold;                         // > 0: the A operand is folded on the fly from a raw [N,H,W,8] tensor (thin stems): K slice ks
+    int fold_y0;                      //      = image rows y + fold_y0 + 4 ks .. + 3 of the 8 channels (tensor map dims c, row, x, n)
 };
 
 template <int BN, int STAGES>
@@ -275,8 +277,12 @@ conv_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                     unsigned char* b = a + S::A_BYTES;
                     tc::mbar_arrive_expect_tx(full + s, S::STAGE_BYTES);
 #pragma unroll
-                    for (int r = 0; r < R; ++r)
-                        tc::tma_load_4d(a + r * S::A_TILE, &tmap_x, full + s, ks * BK, p.sx * x0[r] + p.dx[tap], p.sy * y0[r] + p.dy[tap], n0[r]);
+                    for (int r = 0; r < R; ++r) {
+                        if (p.fold)     // (c, row, x, n): four image rows of 8 channels become the 32 "channels" of the K slice
+                            tc::tma_load_4d(a + r * S::A_TILE, &tmap_x, full + s, 0, y0[r] + p.fold_y0 + 4 * ks, x0[r] + p.dx[tap], n0[r]);
+                        else
+                            tc::tma_load_4d(a + r * S::A_TILE, &tmap_x, full + s, ks * BK, p.sx * x0[r] + p.dx[tap], p.sy * y0[r] + p.dy[tap], n0[r]);
+                    }
                     if constexpr (WMN) {
 #pragma unroll
                         for (int nb = 0; nb < BN / 32; ++nb) tc::tma_load_3d(b + nb * 4096, &tmap_w, full + s, c0 + nb * 32, ks * BK, p.wtap[tap]);
@@ -396,6 +402,7 @@ struct WgradParams {
     int kh, kw, pad_y, st;
     int xoff;                      // the convolution reads x from column xoff on (a caller-side crop of the padded input)
     int splits;                    // K splits (gridDim.z / taps)
+    int fold;                      // > 0: X is the raw stem input [N,H,W,8]; 32-"channel" block b = image rows y - fold_pad + 4b .. + 3
     int tapmajor;                  // dW layout: 0 = [Cout][Cin][kh][kw], 1 = tap-major [kh*kw][Cout][Cin] (the F layout)
     int tstep;                     // taps of one CTA are s0, s0 + tstep, ... (1: adjacent taps of a stride-1 conv,
                                    // 2: taps of equal parity of a stride-2 conv = adjacent rows of the strided window)
@@ -469,6 +476,10 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
                 if (warp == 0) {
                     tc::mbar_arrive_expect_tx(full + st, S::STAGE_BYTES);
                     tc::tma_load_5d(a, &tmap_dy, full + st, 0, x0, y0, n, co0 / 32);
+                } else if (p.fold) {      // (c, row, x, n) boxes of 4 rows x 8 channels per pixel: one per 32-"channel" block
+#pragma unroll
+                    for (int blk = 0; blk < BN / 32; ++blk)
+                        tc::tma_load_4d(a + S::A_BYTES + blk * XBLK, &tmap_x, full + st, 0, y0 - p.pad_y + 4 * (ci0 / 32 + blk), x0 + s + p.xoff, n);
                 } else {
                     tc::tma_load_5d(a + S::A_BYTES, &tmap_x, full + st, 0, p.st * x0 + s + p.xoff, p.st * y0 + r - p.pad_y, n, ci0 / 32);
                 }
@@ -591,7 +602,7 @@ extern "C" {
 int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* out, int N, int H, int W, int Cin,
                     int Hout, int Wout, int Cout, int ntaps, const int* dy, const int* dx, int sy, int sx, int OH,
                     int OW, int OC, int osy, int osx, int ooy, int oox, float leaky, int w_cin_major, const int* wtap,
-                    int wtaps_total, double* stats, void* stream) {
+                    int wtaps_total, double* stats, int fold_kh, int fold_pad, void* stream) {
     B3D_REQUIRE(N > 0 && H > 0 && W > 0 && Hout > 0 && Wout > 0 && Cout > 0, B3D_EINVAL, "b3d_conv2d_tf32: bad sizes");
     B3D_REQUIRE(Cin > 0 && Cin % BK == 0, B3D_EINVAL, "b3d_conv2d_tf32: Cin=%d must be a multiple of %d", Cin, BK);
     B3D_REQUIRE(ntaps >= 1 && ntaps <= MAX_TAPS && dy && dx, B3D_EINVAL, "b3d_conv2d_tf32: bad taps");
@@ -606,7 +617,13 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
     b3d::clear_variant();
 
     static const int persist_env = getenv("B3D_CONV_PERSIST") ? atoi(getenv("B3D_CONV_PERSIST")) : 1;
-    const int persist = persist_env || stats != nullptr;      // the statistics epilogue lives in the persistent kernels
+    const int persist = persist_env || stats != nullptr || fold_kh > 0;   // statistics epilogue / on-the-fly fold: persistent kernels
+    if (fold_kh > 0) {
+        // x is the RAW stem input [N, H, W, 8]; the convolution is kh x kw with the kh rows folded into the K dimension:
+        // Cin = 32 * ceil(8 kh / 32) "channels", taps = the kw horizontal ones (dy ignored), zero rows = the y padding
+        B3D_REQUIRE(fold_kh <= 8 && Cin == 32 * ((8 * fold_kh + 31) / 32) && sy == 1 && sx == 1 && !w_cin_major && !wtap && Wout % BM == 0,
+                    B3D_EINVAL, "b3d_conv2d_tf32: on-the-fly fold needs 8 input channels, stride 1 and Wout %% 128 == 0 (Wout=%d)", Wout);
+    }
     B3D_REQUIRE(!stats || (osy == 1 && osx == 1), B3D_EINVAL, "b3d_conv2d_tf32: statistics need a dense output");
     static const int wide = getenv("B3D_CONV_BN256") ? atoi(getenv("B3D_CONV_BN256")) : 1;
     // 256-wide output-channel tiles halve the input-tile bytes per FLOP through the L2 -> SM fabric (the bound of the
@@ -634,7 +651,7 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
     // filter-grid detection for the row-window kernel (tc_conv3.cu): kh rows of kw horizontally consecutive taps; the weight
     // taps of a row form an arithmetic progression (identity, or the stride-2 dgrad parity classes' tap lists)
     int g_kw = 0, g_kh = 0, g_step = 0, g_wstep = 1;
-    if (sy == 1 && sx == 1 && !w_cin_major) {
+    if (sy == 1 && sx == 1 && !w_cin_major && fold_kh == 0) {
         int kw_ = 1;
         while (kw_ < ntaps && dy[kw_] == dy[0]) ++kw_;
         const int step = kw_ > 1 ? dx[1] - dx[0] : 1;
@@ -678,12 +695,21 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
         p.leaky = leaky;
         p.dbg_lbo = 4096; p.dbg_sbo = 512; p.dbg_lt = 1;     // 32-bit MN-major: SWIZZLE_128B_BASE32B, 4-row atoms
         p.stats = stats;
+        p.fold = fold_kh; p.fold_y0 = -fold_pad;
         CUtensorMap mx;
+        if (fold_kh > 0) {
+            B3D_REQUIRE(p.BH == 1, B3D_EINVAL, "b3d_conv2d_tf32: on-the-fly fold needs one-row tiles");
+            const uint64_t dims[4] = {8, (uint64_t)H, (uint64_t)W, (uint64_t)N};                    // (c, row, x, n)
+            const uint64_t strides[3] = {(uint64_t)W * 32, 32, (uint64_t)H * W * 32};
+            const uint32_t box[4] = {8, 4, (uint32_t)p.BW, (uint32_t)p.BI};
+            if (int rc = tc::make_tmap_f32(&mx, x, 4, dims, strides, box)) return rc;
+        } else {
         const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
         const uint64_t strides[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
         const uint32_t box[4] = {(uint32_t)BK, (uint32_t)(sx * (p.BW - 1) + 1), (uint32_t)(sy * (p.BH - 1) + 1), (uint32_t)p.BI};
         const uint32_t es[4] = {1, (uint32_t)sx, (uint32_t)sy, 1};
         if (int rc = tc::make_tmap_f32(&mx, x, 4, dims, strides, box, es)) return rc;
+        }
         // CTAs per SM x ring depth: short K loops (few taps x few channel slices) are dominated by pipeline fill, epilogue
         // and store drain, which only OTHER resident CTAs can hide -> more, shallower CTAs (profiles/r1_c_*.md)
         if (persist) {
@@ -717,7 +743,7 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
 // dy [N,Hout,Wout,Cout], x [N,H,W,Cin] NHWC (x already padded along x; Cin, Cout multiples of 4),
 // dw [Cout,Cin,kh,kw] (accumulated into)
 int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, int N, int H, int W, int Cin, int Hout, int Wout,
-                          int Cout, int kh, int kw, int pad_y, int stride, int x_off, int tap_major, void* stream) {
+                          int Cout, int kh, int kw, int pad_y, int stride, int x_off, int tap_major, int fold_kh, void* stream) {
     B3D_REQUIRE(N > 0 && Cin > 0 && Cout > 0 && H > 0 && W > 0 && Hout > 0 && Wout > 0, B3D_EINVAL,
                 "b3d_conv2d_wgrad_tf32: bad sizes");
     B3D_REQUIRE(kh * kw <= MAX_TAPS && (stride == 1 || stride == 2) && x_off >= 0, B3D_EINVAL, "b3d_conv2d_wgrad_tf32: bad kernel/stride");
@@ -734,6 +760,10 @@ int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, int N, int
     p.kx = b3d::ceil_div(Wout, p.BWk);
     p.ky = b3d::ceil_div(Hout, p.BHk);
     p.kh = kh; p.kw = kw; p.pad_y = pad_y; p.st = stride; p.xoff = x_off; p.tapmajor = tap_major ? 1 : 0;
+    p.fold = fold_kh;
+    if (fold_kh > 0)    // x raw [N,H,W,8]; (kh, kw) = (1, kw) of the folded conv, Cin = its folded channel count, pad_y = the fold's
+        B3D_REQUIRE(kh == 1 && stride == 1 && fold_kh <= 8 && Cin == 32 * ((8 * fold_kh + 31) / 32) && Wout >= BK, B3D_EINVAL,
+                    "b3d_conv2d_wgrad_tf32: on-the-fly fold needs a 1 x kw stride-1 geometry over 8 raw channels");
     if (tap_major) B3D_CHECK_ALIGNED(dw);
     // a row of kw taps per CTA when the K slice is a 32-pixel row segment (Wout >= 32) of a stride-1 conv
     int T = 1;
@@ -757,7 +787,12 @@ int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, int N, int
         const uint32_t box[5] = {32, (uint32_t)p.BWk, (uint32_t)p.BHk, 1, (uint32_t)(BM / 32)};
         if (int rc = tc::make_tmap_f32(&mdy, dy, 5, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
     }
-    {
+    if (fold_kh > 0) {
+        const uint64_t dims[4] = {8, (uint64_t)H, (uint64_t)W, (uint64_t)N};                        // (c, row, x, n)
+        const uint64_t strides[3] = {(uint64_t)W * 32, 32, (uint64_t)H * W * 32};
+        const uint32_t box[4] = {8, 4, (uint32_t)(T == 1 ? p.BWk : 36), 1};
+        if (int rc = tc::make_tmap_f32(&mx, x, 4, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+    } else {
         const uint64_t dims[5] = {32, (uint64_t)W, (uint64_t)H, (uint64_t)N, (uint64_t)Cin / 32};
         const uint64_t strides[4] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4, 128};
         const uint32_t box[5] = {32, (uint32_t)(T == 1 ? stride * (p.BWk - 1) + 1 : stride * 35 + 1), (uint32_t)(stride * (p.BHk - 1) + 1), 1,
@@ -771,7 +806,10 @@ int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, int N, int
     if (T == 2 && BN == 128) return two ? launch_wgrad<128, 3, 2>(mdy, mx, p, dw, grid, st) : launch_wgrad<128, 6, 2>(mdy, mx, p, dw, grid, st);
     if (T == 2) return two ? launch_wgrad<64, 4, 2>(mdy, mx, p, dw, grid, st) : launch_wgrad<64, 8, 2>(mdy, mx, p, dw, grid, st);
     if (T == 3 && BN == 128) return launch_wgrad<128, 6, 3>(mdy, mx, p, dw, grid, st);
-    if (T == 3) return launch_wgrad<64, 8, 3>(mdy, mx, p, dw, grid, st);
+    // Cout = Cin = 64 rows of three taps: nothing is saturated with one CTA per SM (ncu: tensor pipe 35 %, L2 14 %): two
+    // half-depth CTAs per SM overlap each other's TMA latency and epilogue (B3D_WGRAD_T3=1 restores the deep single ring)
+    static const int t3_one = getenv("B3D_WGRAD_T3") ? atoi(getenv("B3D_WGRAD_T3")) : 0;
+    if (T == 3) return t3_one ? launch_wgrad<64, 8, 3>(mdy, mx, p, dw, grid, st) : launch_wgrad<64, 4, 3>(mdy, mx, p, dw, grid, st);
     if (T == 5) return launch_wgrad<64, 8, 5>(mdy, mx, p, dw, grid, st);
     // single taps: the deep single-CTA ring measured faster (profiles/r1_conv_layers.md)
     if (BN == 128) return launch_wgrad<128, 6, 1>(mdy, mx, p, dw, grid, st);

@@ -13,6 +13,7 @@
 // warps 2-5 epilogue, two TMEM accumulator buffers of R x BN columns, mbarrier ring across work items.
 #include "tc_common.cuh"
 #include "tc_rowwin.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -264,7 +265,8 @@ int conv_rowwin_launch(const RowWinArgs& a, cudaStream_t st) {
     if (a.Cout == 64) {
         if (tiles / 4 < 2 * 148) return 1;
         if (a.kw == 2) return launch_rowwin<64, 2, 4, 2>(a, st);        // stride-2 dgrad parity classes (2 x 2 taps)
-        if (a.kw == 3) return launch_rowwin<64, 3, 4, 2>(a, st);
+        static const int r2 = getenv("B3D_ROWWIN_R2") ? atoi(getenv("B3D_ROWWIN_R2")) : 0;     // experiment: 2 tiles x 3 stages
+        if (a.kw == 3) return r2 ? launch_rowwin<64, 3, 2, 3>(a, st) : launch_rowwin<64, 3, 4, 2>(a, st);
         if (a.kw == 5) return launch_rowwin<64, 5, 4, 2>(a, st);
         return 1;
     }

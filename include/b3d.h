@@ -217,12 +217,17 @@ B3D_API int b3d_chamfer_bwd(const float* query, const float* cand, const int32_t
 B3D_API int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* out, int N, int H, int W,
                             int Cin, int Hout, int Wout, int Cout, int ntaps, const int* dy, const int* dx,
                             int sy, int sx, int OH, int OW, int OC, int osy, int osx, int ooy, int oox,
-                            float leaky, int w_cin_major, const int* wtap, int wtaps_total, double* stats, void* stream);
+                            float leaky, int w_cin_major, const int* wtap, int wtaps_total, double* stats, int fold_kh,
+                            int fold_pad, void* stream);
 /* wtap (nullable): loop tap t reads weight tap wtap[t] of a tap-major array that holds wtaps_total taps — the stride-2
  * input-gradient parity classes address their tap subsets of the full weight array without a gathered copy.
  * stats (nullable): [2][Cout] fp64, ACCUMULATED into by the epilogue: per-channel sum and sum of squares of the output
  * before bias / activation — the BatchNorm statistics of the generator's layers without a second pass over the tensor
- * (models/gan.py:264-286; the caller zeroes the buffer; dense outputs only).                                              */
+ * (models/gan.py:264-286; the caller zeroes the buffer; dense outputs only).
+ * fold_kh > 0: thin 8-channel stems (models/gan.py:163-166, 5x5 on 8 channels): x is the RAW input [N,H,W,8]; the kh vertical
+ * taps are folded into the K dimension ON THE FLY by the TMA boxes (four image rows x 8 channels = one 32-channel K slice, rows
+ * outside the image = the zero padding fold_pad) — Cin is the folded channel count (32 * ceil(8 kh / 32)), the taps are the kw
+ * horizontal ones, wt is the folded tap-major layout [kw][Cout][Cin] (b3d/bank.py `fold`).  Needs Wout % 128 == 0.            */
 
 /* Stride-1 variant with a halo-staged input and R stacked accumulators (csrc/tc_conv2.cu): x [N,H,P,Cin] with P the
  * padded width (row pitch), taps (dy, dx >= 0); same weights / bias / LeakyReLU semantics as b3d_conv2d_tf32, output
@@ -239,9 +244,10 @@ B3D_API int b3d_conv2d_flat_tf32(const float* x, const float* wt, const float* b
  * dw [Cout,Cin,kh,kw] is ACCUMULATED into (caller zeroes it).                                          */
 B3D_API int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, int N, int H, int W, int Cin,
                                   int Hout, int Wout, int Cout, int kh, int kw, int pad_y, int stride,
-                                  int x_off, int tap_major, void* stream);
+                                  int x_off, int tap_major, int fold_kh, void* stream);
 /* tap_major != 0: dw is the tap-major array [kh*kw][Cout][Cin] (the layout b3d_conv2d_tf32 reads, 16-byte vector
- * reductions) instead of [Cout][Cin][kh][kw].                                                                        */
+ * reductions) instead of [Cout][Cin][kh][kw].  fold_kh > 0: x is the raw 8-channel stem input, folded on the fly as in
+ * b3d_conv2d_tf32 (kh = 1, kw = the horizontal taps, Cin = folded channel count, pad_y = the fold's y padding).              */
 
 /* Thin heads: 5x5 / stride-1 convolutions with 1..4 output channels (generator conv_final, models/gan.py:359;
  * discriminator heads :177, :302) on the fp32 CUDA cores, channels across the lanes of a warp.  Cin % 64 == 0.

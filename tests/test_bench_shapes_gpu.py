@@ -120,6 +120,39 @@ def test_epilogue_statistics(N, Cin, H, W, Cout):
     assert float((stats[Cout:] - ref[Cout:]).abs().max()) <= 2e-6 * float(ref[Cout:].max())
 
 
+@pytest.mark.parametrize("N,H,W,need_dx", [(64, 256, 260, False), (32, 256, 260, True), (32, 128, 132, True)])
+def test_stem_fold_on_the_fly(N, H, W, need_dx):
+    """Discriminator stem (8 -> 64 channels, 5x5, models/gan.py:163-166) through the banked path: the kernels fold the five
+    vertical taps into the K dimension ON THE FLY from the raw 8-channel input (TMA boxes of 4 rows x 8 channels) — forward,
+    weight / bias gradient and (generator step) input gradient against an fp64 convolution."""
+    import b3d.conv as C
+    from b3d.bank import WeightBank
+    from models.gan import TCConv2d
+    torch.manual_seed(N + W)
+    conv = TCConv2d(8, 64, 5, padding=(2, 0)).to(DEV)
+    x0 = torch.randn(N, 8, H, W, device=DEV)
+    res = {}
+    for impl in ("ref", "b3d"):
+        x = x0.clone().requires_grad_(need_dx)
+        if impl == "ref":
+            y = ref_conv(x, conv.weight, conv.bias, 2, 1)
+        else:
+            W_ = WeightBank({"c": conv}, fold=("c",), round_tf32=False).forward(True)
+            C.VARIANT_LOG = []
+            y = C.conv2d_banked(x, W_["c"], pad_y=2)
+        gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(3)).to(DEV)
+        grads = torch.autograd.grad(y, ([x] if need_dx else []) + [conv.weight, conv.bias], gy)
+        res[impl] = [y.detach().float()] + [g_.float() for g_ in grads]
+    torch.cuda.synchronize()
+    assert not any(v.startswith("fold") for v in C.VARIANT_LOG)
+    SEEN.update(C.VARIANT_LOG)
+    C.VARIANT_LOG = None
+    for a, r in zip(res["b3d"], res["ref"]):
+        assert a.shape == r.shape
+        err, ref = float((a - r).abs().max()), float(r.abs().max())
+        assert err <= TOL * ref, (tuple(a.shape), err, ref)
+
+
 def test_every_dispatched_variant_was_exercised():
     """The kernel instances cfg3 dispatches at batch 32 / 64 (profiles/r2_launches.md) all ran in the cases above."""
     need = {

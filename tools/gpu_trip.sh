@@ -29,12 +29,13 @@ if [ "${NCUCONV:-0}" = "1" ]; then
 fi
 if [ "${DIAG:-0}" = "1" ]; then
   python tools/time_convs.py > gpurun_out/${T}_convs_rowwin1.txt 2>&1
-  B3D_CONV_ROWWIN=0 python tools/time_convs.py > gpurun_out/${T}_convs_rowwin0.txt 2>&1
-  echo "== conv layer times, row-window on / off"; paste -d'|' <(cut -c1-62 gpurun_out/${T}_convs_rowwin1.txt) <(cut -c24-62 gpurun_out/${T}_convs_rowwin0.txt) | head -24
+  ${DIAG_ENV:-B3D_CONV_ROWWIN=0} python tools/time_convs.py > gpurun_out/${T}_convs_rowwin0.txt 2>&1
+  echo "== conv layer times, default | ${DIAG_ENV:-B3D_CONV_ROWWIN=0}"; paste -d'|' <(cut -c1-82 gpurun_out/${T}_convs_rowwin1.txt) <(cut -c24-82 gpurun_out/${T}_convs_rowwin0.txt) | head -24
 fi
 if [ "${REFARM:-0}" = "1" ]; then
-  /usr/bin/time -v python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/${T}_bench_reference.json 2> gpurun_out/${T}_bench_reference.err
-  echo "== reference arm"; cut -c1-260 gpurun_out/${T}_bench_reference.json; grep -E "Elapsed|Maximum resident" gpurun_out/${T}_bench_reference.err
+  SECONDS=0
+  python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/${T}_bench_reference.json 2> gpurun_out/${T}_bench_reference.err
+  echo "== reference arm: ${SECONDS} s wall"; cut -c1-260 gpurun_out/${T}_bench_reference.json; tail -n 2 gpurun_out/${T}_bench_reference.err
 fi
 echo "==== pytest"; grep -E "^(FAILED|ERROR)|passed|failed|rc=" gpurun_out/${T}_pytest.log | tail -n 30
 grep -E "^E  " gpurun_out/${T}_pytest.log | head -n 30
