@@ -413,7 +413,7 @@ def conv2d_banked(x_nchw, lw, pad_y=0, stride=1, leaky=1.0, pad_out=0, pad_mode=
     if lw.fold:
         Wout = x.shape[2] - lw.kw + 1
         if (lw.Cin == 8 and stride == 1 and not x_crop and Wout % 128 == 0 and x.shape[0] * x.shape[1] * (Wout // 128) >= 2 * 148
-                and not os.environ.get("B3D_FOLD_MATERIALIZE")):
+                and os.environ.get("B3D_FOLD_ONFLY")):            # experimental (off): see DESIGN.md §4
             fold_raw = lw.kh                # 8-channel stems of wide images: the kernels fold on the fly, no folded tensor
         else:
             from .ew import fold_rows

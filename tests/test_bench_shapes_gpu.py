@@ -120,6 +120,7 @@ def test_epilogue_statistics(N, Cin, H, W, Cout):
     assert float((stats[Cout:] - ref[Cout:]).abs().max()) <= 2e-6 * float(ref[Cout:].max())
 
 
+@pytest.mark.skipif(not os.environ.get("B3D_FOLD_ONFLY"), reason="on-the-fly stem fold is experimental (B3D_FOLD_ONFLY=1)")
 @pytest.mark.parametrize("N,H,W,need_dx", [(64, 256, 260, False), (32, 256, 260, True), (32, 128, 132, True)])
 def test_stem_fold_on_the_fly(N, H, W, need_dx):
     """Discriminator stem (8 -> 64 channels, 5x5, models/gan.py:163-166) through the banked path: the kernels fold the five
