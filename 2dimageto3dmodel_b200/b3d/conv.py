@@ -398,8 +398,10 @@ class _ConvBanked(torch.autograd.Function):
             else:
                 if Cout % 32:
                     raise B3DError(f"banked conv: weight gradient needs Cout % 32 == 0 or a thin head (Cout={Cout})")
+                if fold_raw:
+                    raise B3DError("banked conv: the on-the-fly fold has no weight-gradient kernel (materialise the fold)")
                 check(_conv_call(lib.b3d_conv2d_wgrad_tf32, ptr(gy), ptr(x), ptr(gw), N, H, W, Cin, Hout, Wout, Cout, kh, kw,
-                                 fold_pad if fold_raw else pad_y, stride, x_crop, 1, fold_raw, st))
+                                 pad_y, stride, x_crop, 1, 0, st))
         return gx, gw, gb, None, None, None, None, None, None, None, None, None
 
 
@@ -412,9 +414,12 @@ def conv2d_banked(x_nchw, lw, pad_y=0, stride=1, leaky=1.0, pad_out=0, pad_mode=
     fold_raw = 0
     if lw.fold:
         Wout = x.shape[2] - lw.kw + 1
+        need_wgrad = torch.is_grad_enabled() and lw.wf.requires_grad
         if (lw.Cin == 8 and stride == 1 and not x_crop and Wout % 128 == 0 and x.shape[0] * x.shape[1] * (Wout // 128) >= 2 * 148
-                and os.environ.get("B3D_FOLD_ONFLY")):            # experimental (off): see DESIGN.md §4
-            fold_raw = lw.kh                # 8-channel stems of wide images: the kernels fold on the fly, no folded tensor
+                and not need_wgrad and not os.environ.get("B3D_FOLD_MATERIALIZE")):
+            # 8-channel stems of wide images when no weight gradient is taken (generator step: the discriminator is frozen):
+            # the forward kernel folds the kh rows on the fly (TMA boxes of 4 rows x 8 channels), no folded tensor is written
+            fold_raw = lw.kh
         else:
             from .ew import fold_rows
             x = fold_rows(x, lw.kh, pad_y, lw.Cinp)

@@ -137,6 +137,19 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
     return d;
 }
 
+// K-major operand, 32-byte swizzle: rows of 32 B (8 fp32 = one UMMA_K step of tf32), 8-row atoms of 256 B stacked along
+// M/N.  What TMA writes for a box whose inner dimension is 8 floats under CU_TENSOR_MAP_SWIZZLE_32B (tools/probe/tma_probe.cu:
+// under the 128-byte modes such a box is padded to one 128-byte line per inner row instead).
+__device__ __forceinline__ uint64_t umma_desc_k32(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;                             // leading byte offset (unused: K extent = one atom)
+    d |= (uint64_t)(256 >> 4) << 32;                    // stride byte offset: 8 rows x 32 B
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;                             // layout type: SWIZZLE_32B
+    return d;
+}
+
 // MN-major operand, 128-byte swizzle: the tile is stored as [mn block of 32][k rows][32 fp32 along M/N]; one
 // swizzle atom = 8 k-rows x 128 B.  Leading byte offset = distance between consecutive 32-wide M/N blocks,
 // stride byte offset = distance between consecutive groups of 8 k-rows.

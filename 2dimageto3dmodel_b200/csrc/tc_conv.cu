@@ -278,8 +278,8 @@ conv_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                     tc::mbar_arrive_expect_tx(full + s, S::STAGE_BYTES);
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
-                        if (p.fold)     // (c, row, x, n): four image rows of 8 channels become the 32 "channels" of the K slice
-                            tc::tma_load_4d(a + r * S::A_TILE, &tmap_x, full + s, 0, y0[r] + p.fold_y0 + 4 * ks, x0[r] + p.dx[tap], n0[r]);
+                        if (p.fold)     // box {8 ch, BW px, 4 rows}: lands as [row][pixel][8 floats] = four 32-byte-swizzled K-step tiles
+                            tc::tma_load_4d(a + r * S::A_TILE, &tmap_x, full + s, 0, x0[r] + p.dx[tap], y0[r] + p.fold_y0 + 4 * ks, n0[r]);
                         else
                             tc::tma_load_4d(a + r * S::A_TILE, &tmap_x, full + s, ks * BK, p.sx * x0[r] + p.dx[tap], p.sy * y0[r] + p.dy[tap], n0[r]);
                     }
@@ -311,8 +311,12 @@ conv_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t db = WMN ? tc::umma_desc_mn128(b + k * 1024, p.dbg_lbo, p.dbg_sbo, p.dbg_lt) : tc::umma_desc_k128(b + k * UMMA_K * 4);
 #pragma unroll
-                        for (int r = 0; r < R; ++r)
-                            tc::umma_tf32(acc + r * BN, tc::umma_desc_k128(a + r * S::A_TILE + k * UMMA_K * 4), db, idesc, (it | k) ? 1u : 0u);
+                        for (int r = 0; r < R; ++r) {
+                            // on-the-fly fold: K step k = image row k of the 4-row box, a [128 px][32 B] tile of its own
+                            const uint64_t da = p.fold ? tc::umma_desc_k32(a + r * S::A_TILE + k * (BM * 32))
+                                                       : tc::umma_desc_k128(a + r * S::A_TILE + k * UMMA_K * 4);
+                            tc::umma_tf32(acc + r * BN, da, db, idesc, (it | k) ? 1u : 0u);
+                        }
                     }
                     tc::umma_commit(empty + s);
                 }
@@ -698,11 +702,11 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
         p.fold = fold_kh; p.fold_y0 = -fold_pad;
         CUtensorMap mx;
         if (fold_kh > 0) {
-            B3D_REQUIRE(p.BH == 1, B3D_EINVAL, "b3d_conv2d_tf32: on-the-fly fold needs one-row tiles");
-            const uint64_t dims[4] = {8, (uint64_t)H, (uint64_t)W, (uint64_t)N};                    // (c, row, x, n)
-            const uint64_t strides[3] = {(uint64_t)W * 32, 32, (uint64_t)H * W * 32};
-            const uint32_t box[4] = {8, 4, (uint32_t)p.BW, (uint32_t)p.BI};
-            if (int rc = tc::make_tmap_f32(&mx, x, 4, dims, strides, box)) return rc;
+            B3D_REQUIRE(p.BH == 1 && p.BI == 1, B3D_EINVAL, "b3d_conv2d_tf32: on-the-fly fold needs one-row tiles");
+            const uint64_t dims[4] = {8, (uint64_t)W, (uint64_t)H, (uint64_t)N};                    // the raw NHWC tensor
+            const uint64_t strides[3] = {32, (uint64_t)W * 32, (uint64_t)H * W * 32};
+            const uint32_t box[4] = {8, (uint32_t)p.BW, 4, 1};                                     // 4 image rows per K slice
+            if (int rc = tc::make_tmap_f32(&mx, x, 4, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_32B)) return rc;
         } else {
         const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
         const uint64_t strides[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
@@ -761,9 +765,9 @@ int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, int N, int
     p.ky = b3d::ceil_div(Hout, p.BHk);
     p.kh = kh; p.kw = kw; p.pad_y = pad_y; p.st = stride; p.xoff = x_off; p.tapmajor = tap_major ? 1 : 0;
     p.fold = fold_kh;
-    if (fold_kh > 0)    // x raw [N,H,W,8]; (kh, kw) = (1, kw) of the folded conv, Cin = its folded channel count, pad_y = the fold's
-        B3D_REQUIRE(kh == 1 && stride == 1 && fold_kh <= 8 && Cin == 32 * ((8 * fold_kh + 31) / 32) && Wout >= BK, B3D_EINVAL,
-                    "b3d_conv2d_wgrad_tf32: on-the-fly fold needs a 1 x kw stride-1 geometry over 8 raw channels");
+    B3D_REQUIRE(fold_kh == 0, B3D_EINVAL,
+                "b3d_conv2d_wgrad_tf32: the on-the-fly fold is not available for the weight gradient (TMA pads 32-byte inner boxes "
+                "to 128-byte lines under the 128B swizzles the MN-major tf32 operand needs): pass the materialised fold");
     if (tap_major) B3D_CHECK_ALIGNED(dw);
     // a row of kw taps per CTA when the K slice is a 32-pixel row segment (Wout >= 32) of a stride-1 conv
     int T = 1;

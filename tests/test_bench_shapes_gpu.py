@@ -120,17 +120,18 @@ def test_epilogue_statistics(N, Cin, H, W, Cout):
     assert float((stats[Cout:] - ref[Cout:]).abs().max()) <= 2e-6 * float(ref[Cout:].max())
 
 
-@pytest.mark.skipif(not os.environ.get("B3D_FOLD_ONFLY"), reason="on-the-fly stem fold is experimental (B3D_FOLD_ONFLY=1)")
 @pytest.mark.parametrize("N,H,W,need_dx", [(64, 256, 260, False), (32, 256, 260, True), (32, 128, 132, True)])
 def test_stem_fold_on_the_fly(N, H, W, need_dx):
-    """Discriminator stem (8 -> 64 channels, 5x5, models/gan.py:163-166) through the banked path: the kernels fold the five
-    vertical taps into the K dimension ON THE FLY from the raw 8-channel input (TMA boxes of 4 rows x 8 channels) — forward,
-    weight / bias gradient and (generator step) input gradient against an fp64 convolution."""
+    """Discriminator stem (8 -> 64 channels, 5x5, models/gan.py:163-166) through the banked path with FROZEN weights (the
+    generator step): the forward kernel folds the five vertical taps into the K dimension ON THE FLY from the raw 8-channel
+    input (TMA boxes of 4 rows x 8 channels, 32-byte swizzle) — forward and input gradient against an fp64 convolution."""
     import b3d.conv as C
     from b3d.bank import WeightBank
     from models.gan import TCConv2d
     torch.manual_seed(N + W)
     conv = TCConv2d(8, 64, 5, padding=(2, 0)).to(DEV)
+    for p_ in conv.parameters():
+        p_.requires_grad_(False)
     x0 = torch.randn(N, 8, H, W, device=DEV)
     res = {}
     for impl in ("ref", "b3d"):
@@ -142,10 +143,9 @@ def test_stem_fold_on_the_fly(N, H, W, need_dx):
             C.VARIANT_LOG = []
             y = C.conv2d_banked(x, W_["c"], pad_y=2)
         gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(3)).to(DEV)
-        grads = torch.autograd.grad(y, ([x] if need_dx else []) + [conv.weight, conv.bias], gy)
+        grads = torch.autograd.grad(y, [x], gy) if need_dx else []
         res[impl] = [y.detach().float()] + [g_.float() for g_ in grads]
     torch.cuda.synchronize()
-    assert not any(v.startswith("fold") for v in C.VARIANT_LOG)
     SEEN.update(C.VARIANT_LOG)
     C.VARIANT_LOG = None
     for a, r in zip(res["b3d"], res["ref"]):
@@ -165,7 +165,7 @@ def test_every_dispatched_variant_was_exercised():
         "conv_rowwin_tf32<64,2,4,2>",                                                                  # D1.conv2 dgrad parity classes
         "conv_rowwin_tf32<16,5,4,2>",                                                                  # conv_final fprop (N = 16 tiles)
         # weight gradients: row-of-taps (T = 3, 5), stride-2 tap pairs (T = 2), single taps, both Cin tile widths
-        "wgrad_tf32<128,6,3>", "wgrad_tf32<64,8,3>", "wgrad_tf32<64,8,5>", "wgrad_tf32<128,3,2>", "wgrad_tf32<64,4,2>",
+        "wgrad_tf32<128,6,3>", "wgrad_tf32<64,4,3>", "wgrad_tf32<64,8,5>", "wgrad_tf32<128,3,2>", "wgrad_tf32<64,4,2>",
         "wgrad_tf32<128,6,1>", "wgrad_tf32<64,8,1>",
         # 1-3 output channel heads on the CUDA-core kernels
         "conv_thin_fwd<3,2>", "conv_thin_fwd<1,4>", "conv_thin_wgrad_win<3,2>", "conv_thin_wgrad_win<1,4>",     # fwd<3,2>: conv_mesh
