@@ -84,7 +84,7 @@ def conv2d_nhwc(x, weight, bias=None, pad_y=0, stride=1, leaky=1.0, wt=None, cin
     if not use_flat or rc != 0:
         check(_conv_call(lib.b3d_conv2d_tf32, ptr(x), ptr(wt), ptr(b), optr, N, H, W, Cin, Hout, Wout, Cout, kh * kw, _ints(dy),
                                   _ints(dx), stride, stride, Hout, OW, Cout, 1, 1, 0, 0, float(leaky), int(cin_major), None, 0, None, 0, 0,
-                                  stream_ptr(x)))
+                                  None, stream_ptr(x)))
     if pad_out:
         check(lib.b3d_wrap_x_inplace(ptr(out), N * Hout, Wout, Cout, pad_out, pad_mode, stream_ptr(x)))
     return out
@@ -118,7 +118,7 @@ def conv2d_dgrad_nhwc(dy_, weight, in_hw, pad_y=0, stride=1, x_crop=0):
         dy = [pad_y - r for r in range(kh) for _ in range(kw)]
         dx = [-s - x_crop for _ in range(kh) for s in range(kw)]
         check(_conv_call(lib.b3d_conv2d_tf32, ptr(g), ptr(wt), None, ptr(dxo), N, Hout, Wout, Cout, H, W, Cin, kh * kw, _ints(dy),
-                                  _ints(dx), 1, 1, H, W, Cin, 1, 1, 0, 0, 1.0, 0, None, 0, None, 0, 0, st))
+                                  _ints(dx), 1, 1, H, W, Cin, 1, 1, 0, 0, 1.0, 0, None, 0, None, 0, 0, None, st))
         return dxo
     if stride != 2 or x_crop:
         raise B3DError("conv2d_dgrad: stride must be 1 or 2 (x_crop: stride 1 only)")
@@ -128,7 +128,7 @@ def conv2d_dgrad_nhwc(dy_, weight, in_hw, pad_y=0, stride=1, x_crop=0):
             continue
         wt = torch.stack([weight[:, :, r, s].t() for r, s in rs]).contiguous()      # [taps][Cin][Cout]
         check(_conv_call(lib.b3d_conv2d_tf32, ptr(g), ptr(wt), None, ptr(dxo), N, Hout, Wout, Cout, Ha, Wa, Cin, len(rs),
-                                  _ints(dy), _ints(dx), 1, 1, H, W, Cin, 2, 2, cy, cx, 1.0, 0, None, 0, None, 0, 0, st))
+                                  _ints(dy), _ints(dx), 1, 1, H, W, Cin, 2, 2, cy, cx, 1.0, 0, None, 0, None, 0, 0, None, st))
     return dxo
 
 
@@ -148,7 +148,7 @@ def conv2d_wgrad_nhwc(dy_, x, kh, kw, pad_y=0, stride=1, x_crop=0):
     _, H, W, Cin = x.shape
     dw = torch.zeros(Cout, Cin, kh, kw, device=g.device, dtype=torch.float32)
     check(_conv_call(lib.b3d_conv2d_wgrad_tf32, ptr(g), ptr(x), ptr(dw), N, H, W, Cin, Hout, Wout, Cout, kh, kw, pad_y, stride,
-                                    x_crop, 0, 0, stream_ptr(g)))
+                                    x_crop, 0, 0, 0, stream_ptr(g)))
     return dw if (co_real, ci_real) == (Cout, Cin) else dw[:co_real, :ci_real]
 
 
@@ -266,9 +266,31 @@ def conv2d(x_nchw, weight, bias=None, pad_y=0, stride=1, leaky=1.0, pad_out=0, p
 # (F [T'][Cout][Cin'] for fprop, D [T'][Cin'][Cout'] for the input gradient); the weight gradient is accumulated
 # straight into the bank's F-layout gradient sink.  No per-call permute / contiguous / zeros.
 # ------------------------------------------------------------------------------------------------------------------
+class _ConvOpts(ctypes.Structure):
+    """b3d_conv_opts (include/b3d.h)."""
+    _fields_ = [("mask", ctypes.c_void_p), ("mask_slope", ctypes.c_float), ("stats_sum_only", ctypes.c_int),
+                ("x_row_pitch", ctypes.c_int), ("nclass", ctypes.c_int), ("class_ooy", ctypes.c_int * 4), ("class_oox", ctypes.c_int * 4)]
+
+
+class ActLink:
+    """Hand-over between two chained banked convolutions  conv_L -> bias -> LeakyReLU -> x padding -> conv_L+1  (the
+    discriminators, models/gan.py:163-177,294-302) for the backward pass.  The producer (conv_L, `link_out`) records its
+    padded output; the consumer (conv_L+1, `link_in`), whose saved input IS that tensor, runs its input-gradient kernels
+    with the LeakyReLU adjoint in their epilogue (mask = the activated tensor), folds the pad columns back
+    (b3d_wrap_x_bwd_inplace) and leaves the bias gradient here — the producer's backward then reads the interior of the
+    padded gradient in place (row-pitch tensor maps) instead of running b3d_pad_leaky_bias_bwd over it.
+    Only valid when conv_L+1 is the ONLY consumer of conv_L's output: the caller creates a link exactly then."""
+    __slots__ = ("armed", "slope", "pad", "mode", "ptr", "shape", "want_gb", "gb", "done")
+
+    def __init__(self):
+        self.armed = self.done = False
+        self.gb = None
+
+
 class _ConvBanked(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, wf, bias, lw, pad_y, stride, leaky, pad_out, pad_mode, x_crop, stats=None, fold_raw=0):
+    def forward(ctx, x, wf, bias, lw, pad_y, stride, leaky, pad_out, pad_mode, x_crop, stats=None, fold_raw=0, link_in=None,
+                link_out=None):
         """fold_raw = kh > 0: x is the RAW 8-channel stem input [N,H,W,8]; the kernels fold the kh vertical taps into the K
         dimension on the fly (TMA boxes of 4 rows x 8 channels) — the folded tensor never exists (pad_y = the fold's y padding)."""
         x = dev(x.detach(), "x")
@@ -323,12 +345,21 @@ class _ConvBanked(torch.autograd.Function):
             if rc != 0:
                 check(_conv_call(lib.b3d_conv2d_tf32, ptr(x), ptr(wt), ptr(b), optr, N, H, W, Cin, Hout, Wout, Cout, kh * kw,
                                  _ints(dy), _ints(dx), stride, stride, Hout, OW, Cout, 1, 1, 0, 0, float(leaky), 0, None, 0, ptr(stats),
-                                 fold_raw, fold_pad, st))
+                                 fold_raw, fold_pad, None, st))
         if pad_out:
             check(lib.b3d_wrap_x_inplace(ptr(out), N * Hout, Wout, Cout, pad_out, pad_mode, st))
         ctx.save_for_backward(x, out if (leaky != 1.0 or pad_out) else None)
         ctx.lw = lw
         ctx.cfg = (pad_y, stride, Cx, bias is not None, leaky, pad_out, pad_mode, x_crop, kh, kw, thin, fold_raw, fold_pad)
+        # chained activation adjoint (ActLink): usable as a consumer when x is exactly the producer's padded output
+        ctx.link_in = link_in if (link_in is not None and link_in.armed and link_in.ptr == x.data_ptr() and link_in.shape == tuple(x.shape)
+                                  and Cx == Cin and Cin % 32 == 0 and not fold_raw and not thin) else None
+        ctx.link_out = None
+        if link_out is not None and pad_out and leaky != 1.0 and Cout % 32 == 0 and not thin:
+            link_out.armed, link_out.slope, link_out.pad, link_out.mode = True, float(leaky), int(pad_out), int(pad_mode)
+            link_out.ptr, link_out.shape, link_out.done = out.data_ptr(), tuple(out.shape), False
+            link_out.want_gb = bias is not None and bool(ctx.needs_input_grad[2])     # frozen discriminator (generator step): no bias sums
+            ctx.link_out = link_out
         return out
 
     @staticmethod
@@ -342,7 +373,19 @@ class _ConvBanked(torch.autograd.Function):
         st = stream_ptr(gy)
         gb = None
         want_gb = has_bias and ctx.needs_input_grad[2]
-        if pad_out:
+        g_pitch, g_off = 0, 0                                          # gy as a window of wider rows (pixels): pitch, first column
+        link_out = ctx.link_out
+        if link_out is not None and link_out.done:
+            # the consumer's input-gradient epilogue already applied LeakyReLU', folded the pad columns and summed the bias
+            # gradient: gy is the PADDED gradient [N,Ho,Wo + 2 pad,C]; its interior is read in place
+            link_out.done = False
+            if tuple(gy.shape) != tuple(y.shape):
+                raise B3DError("banked conv: chained gradient has the wrong shape")
+            g_pitch, g_off = y.shape[2], pad_out
+            gb = link_out.gb if want_gb else None
+            link_out.gb = None
+            gy = gy[:, :, pad_out:y.shape[2] - pad_out]                # a view: shapes below are the interior's
+        elif pad_out:
             _, Ho, OW, _ = y.shape
             masked = torch.empty(N, Ho, OW - 2 * pad_out, Cout, device=gy.device, dtype=torch.float32)
             gb = torch.zeros(Cout, device=gy.device, dtype=torch.float32) if want_gb else None
@@ -360,28 +403,58 @@ class _ConvBanked(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             if lw.wd is None:
                 raise B3DError("banked conv: this layer was registered without an input gradient (no_dgrad)")
-            gyp = _pad_last(gy, 32)                                    # heads with 1 / 3 output channels: zero-pad K
+            gyp = gy if g_pitch else _pad_last(gy, 32)                 # heads with 1 / 3 output channels: zero-pad K
+            gptr = ctypes.c_void_p(gy.data_ptr()) if g_pitch else ptr(gyp)     # (the view's data_ptr = first interior pixel)
             Cop = lw.Coutp
             Hraw = H
             if fold_raw:
                 H = Hout                                               # gradient w.r.t. the (virtual) folded tensor [N, Hout, W, Cin]
             gx = torch.empty(N, H, W, Cin, device=gy.device, dtype=torch.float32)
             wd = lw.wd
+            link_in = ctx.link_in if (stride == 1 or (stride == 2 and not x_crop)) else None
+            opts, sums = None, None
+            classes = stride2_classes(kh, kw, pad_y, H, W) if (stride == 2 and not x_crop) else []
+            # one launch for the four parity classes when they have the same extent and tap count (even H, W; 4x4 kernels)
+            merged = (len(classes) == 4 and all(c[2] for c in classes) and len({(len(c[2]), c[5], c[6]) for c in classes}) == 1
+                      and not os.environ.get("B3D_DGRAD_PER_CLASS"))
+            if g_pitch or link_in is not None or merged:
+                opts = _ConvOpts(None, 1.0, 0, g_pitch, 0)
+                if link_in is not None:                                # LeakyReLU adjoint of the PRODUCER of x in this epilogue
+                    if link_in.want_gb:
+                        sums = torch.zeros(2 * Cin, device=gy.device, dtype=torch.float64)
+                    opts.mask, opts.mask_slope, opts.stats_sum_only = x.data_ptr(), link_in.slope, 1
+            optr_ = ctypes.cast(ctypes.pointer(opts), ctypes.c_void_p) if opts is not None else None
             if stride == 1:
                 dy = [pad_y - r for r in range(kh) for _ in range(kw)]
                 dx = [-s - x_crop for _ in range(kh) for s in range(kw)]
-                check(_conv_call(lib.b3d_conv2d_tf32, ptr(gyp), ptr(wd), None, ptr(gx), N, Hout, Wout, Cop, H, W, Cin, kh * kw,
-                                 _ints(dy), _ints(dx), 1, 1, H, W, Cin, 1, 1, 0, 0, 1.0, 0, None, 0, None, 0, 0, st))
+                check(_conv_call(lib.b3d_conv2d_tf32, gptr, ptr(wd), None, ptr(gx), N, Hout, Wout, Cop, H, W, Cin, kh * kw,
+                                 _ints(dy), _ints(dx), 1, 1, H, W, Cin, 1, 1, 0, 0, 1.0, 0, None, 0, ptr(sums), 0, 0, optr_, st))
+            elif merged:
+                opts.nclass = 4
+                for i, c in enumerate(classes):
+                    opts.class_ooy[i], opts.class_oox[i] = c[0], c[1]
+                dy = [v for c in classes for v in c[3]]
+                dx = [v for c in classes for v in c[4]]
+                taps = [r * kw + s for c in classes for r, s in c[2]]   # rows of the tap-major D array: no gathered copy
+                check(_conv_call(lib.b3d_conv2d_tf32, gptr, ptr(wd), None, ptr(gx), N, Hout, Wout, Cop, classes[0][5], classes[0][6], Cin,
+                                 len(taps), _ints(dy), _ints(dx), 1, 1, H, W, Cin, 2, 2, 0, 0, 1.0, 0, _ints(taps), kh * kw,
+                                 ptr(sums), 0, 0, optr_, st))
             elif stride == 2 and not x_crop:
-                for cy, cx, rs, dy, dx, Ha, Wa in stride2_classes(kh, kw, pad_y, H, W):
+                for cy, cx, rs, dy, dx, Ha, Wa in classes:
                     if not rs:
                         gx[:, cy::2, cx::2] = 0
                         continue
                     taps = [r * kw + s for r, s in rs]                  # rows of the tap-major D array: no gathered copy
-                    check(_conv_call(lib.b3d_conv2d_tf32, ptr(gyp), ptr(wd), None, ptr(gx), N, Hout, Wout, Cop, Ha, Wa, Cin,
-                                     len(rs), _ints(dy), _ints(dx), 1, 1, H, W, Cin, 2, 2, cy, cx, 1.0, 0, _ints(taps), kh * kw, None, 0, 0, st))
+                    check(_conv_call(lib.b3d_conv2d_tf32, gptr, ptr(wd), None, ptr(gx), N, Hout, Wout, Cop, Ha, Wa, Cin,
+                                     len(rs), _ints(dy), _ints(dx), 1, 1, H, W, Cin, 2, 2, cy, cx, 1.0, 0, _ints(taps), kh * kw,
+                                     ptr(sums), 0, 0, optr_, st))
             else:
                 raise B3DError("conv2d_dgrad: stride must be 1 or 2 (x_crop: stride 1 only)")
+            if link_in is not None:
+                # gx = LeakyReLU'(x) * d(padded input), pad columns included: fold them back, hand the bias gradient over
+                check(lib.b3d_wrap_x_bwd_inplace(ptr(gx), N * H, W - 2 * link_in.pad, Cin, link_in.pad, link_in.mode, st))
+                link_in.gb = sums[:Cin].float() if sums is not None else None
+                link_in.done = True
             if fold_raw:                                               # adjoint of the fold: back to the raw 8-channel layout
                 graw = torch.empty(N, Hraw, W, Cx, device=gy.device, dtype=torch.float32)
                 check(lib.b3d_fold_rows_bwd(ptr(gx), ptr(graw), N, Hraw, W, Cx, lw.kh, fold_pad, Cin, st))
@@ -400,12 +473,12 @@ class _ConvBanked(torch.autograd.Function):
                     raise B3DError(f"banked conv: weight gradient needs Cout % 32 == 0 or a thin head (Cout={Cout})")
                 if fold_raw:
                     raise B3DError("banked conv: the on-the-fly fold has no weight-gradient kernel (materialise the fold)")
-                check(_conv_call(lib.b3d_conv2d_wgrad_tf32, ptr(gy), ptr(x), ptr(gw), N, H, W, Cin, Hout, Wout, Cout, kh, kw,
-                                 pad_y, stride, x_crop, 1, 0, st))
-        return gx, gw, gb, None, None, None, None, None, None, None, None, None
+                check(_conv_call(lib.b3d_conv2d_wgrad_tf32, ctypes.c_void_p(gy.data_ptr()), ptr(x), ptr(gw), N, H, W, Cin, Hout, Wout,
+                                 Cout, kh, kw, pad_y, stride, x_crop, 1, 0, g_pitch, st))
+        return gx, gw, gb, None, None, None, None, None, None, None, None, None, None, None
 
 
-def conv2d_banked(x_nchw, lw, pad_y=0, stride=1, leaky=1.0, pad_out=0, pad_mode=1, x_crop=0, stats=None):
+def conv2d_banked(x_nchw, lw, pad_y=0, stride=1, leaky=1.0, pad_out=0, pad_mode=1, x_crop=0, stats=None, link_in=None, link_out=None):
     """conv2d for a layer whose weights come from a WeightBank (`lw` = its LayerWeights).  Thin stems registered with
     fold=True get their kh taps folded into the channels here (b3d.ew.fold_rows), as in conv2d().
     stats: optional zeroed fp64 tensor [2*Cout]; the conv epilogue accumulates the output's per-channel sum / sum of
@@ -424,5 +497,5 @@ def conv2d_banked(x_nchw, lw, pad_y=0, stride=1, leaky=1.0, pad_out=0, pad_mode=
             from .ew import fold_rows
             x = fold_rows(x, lw.kh, pad_y, lw.Cinp)
     y = _ConvBanked.apply(x, lw.wf, lw.bias, lw, int(pad_y), int(stride), float(leaky), int(pad_out), int(pad_mode), int(x_crop), stats,
-                          fold_raw)
+                          fold_raw, link_in, link_out)
     return y.permute(0, 3, 1, 2)

@@ -76,6 +76,36 @@ wrap_x_kernel(float4* __restrict__ buf, long long rows, int W, int C4, int a, in
     }
 }
 
+// Adjoint of the wrap fill, in place: pad-column gradients are added to the interior columns they were copied from.
+// mode 1 (circular): one thread per (row, pad column, channel quad); mode 0 (replicate): one thread per (row, side, quad).
+__global__ void __launch_bounds__(NT)
+wrap_x_bwd_kernel(float4* __restrict__ g, long long rows, int W, int C4, int a, int mode) {
+    const int Wo = W + 2 * a;
+    const int per_row = mode ? 2 * a : 2;
+    const long long total = rows * per_row * C4;
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+        const int c = (int)(i % C4);
+        const long long t = i / C4;
+        const int j = (int)(t % per_row);
+        float4* row = g + (t / per_row) * Wo * C4 + c;
+        float4 s;
+        int dst;
+        if (mode) {
+            const int src = j < a ? j : W + j;               // pad column: left a, then right a
+            dst = j < a ? W + j : j;                         // left pad j = copy of interior W - a + j; right pad k = copy of interior k
+            s = row[(size_t)src * C4];
+        } else {
+            const int first = j == 0 ? 0 : W + a;
+            dst = j == 0 ? a : W + a - 1;
+            s = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k = 0; k < a; ++k) { const float4 v = row[(size_t)(first + k) * C4]; s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+        }
+        float4 d = row[(size_t)dst * C4];
+        d.x += s.x; d.y += s.y; d.z += s.z; d.w += s.w;
+        row[(size_t)dst * C4] = d;
+    }
+}
+
 // Backward of  conv -> (+bias) -> LeakyReLU -> pad_x  in one pass:  gy = pad_x^T(g_pad) * leaky'(y),  gb += sum gy.
 // Thread t owns channel group t % C4 for the pixels t / C4, t / C4 + PPB, ... of its block's slab, so the bias
 // partial sums stay in registers; one shared-memory tree + one atomicAdd per (block, channel).
@@ -263,6 +293,17 @@ int b3d_wrap_x_inplace(float* buf, long long rows, int W, int C, int amount, int
     B3D_REQUIRE(buf, B3D_EINVAL, "b3d_wrap_x_inplace: null pointer");
     B3D_CHECK_ALIGNED(buf);
     wrap_x_kernel<<<grid_for(rows * 2 * amount * (C / 4)), NT, 0, (cudaStream_t)stream>>>((float4*)buf, rows, W, C / 4, amount, mode);
+    B3D_LAUNCH_OK();
+    return B3D_OK;
+}
+int b3d_wrap_x_bwd_inplace(float* g, long long rows, int W, int C, int amount, int mode, void* stream) {
+    B3D_REQUIRE(rows >= 0 && W >= 2 && C >= 4 && C % 4 == 0 && amount >= 0 && (mode == 0 || mode == 1), B3D_EINVAL,
+                "b3d_wrap_x_bwd_inplace: bad arguments");
+    B3D_REQUIRE(mode == 0 ? amount <= W : 2 * amount <= W, B3D_EINVAL, "b3d_wrap_x_bwd_inplace: amount=%d too large for W=%d", amount, W);
+    if (rows == 0 || amount == 0) return B3D_OK;
+    B3D_REQUIRE(g, B3D_EINVAL, "b3d_wrap_x_bwd_inplace: null pointer");
+    B3D_CHECK_ALIGNED(g);
+    wrap_x_bwd_kernel<<<grid_for(rows * (mode ? 2 * amount : 2) * (C / 4)), NT, 0, (cudaStream_t)stream>>>((float4*)g, rows, W, C / 4, amount, mode);
     B3D_LAUNCH_OK();
     return B3D_OK;
 }

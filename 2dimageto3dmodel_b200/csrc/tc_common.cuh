@@ -210,6 +210,54 @@ __device__ __forceinline__ void stats_accumulate(const float (&v)[32], bool vali
     atomicAdd(sm_stats + c + lane, s);
     atomicAdd(sm_stats + BN_ + c + lane, q);
 }
+// sums only (bias gradient of a fused activation adjoint): half the shuffles
+__device__ __forceinline__ void stats_accumulate_sum(const float (&v)[32], bool valid, float* sm_stats, int c) {
+    float a[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) a[i] = valid ? v[i] : 0.f;
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int ofs = 16; ofs >= 1; ofs >>= 1) {
+        const bool up = (lane & ofs) != 0;
+#pragma unroll
+        for (int i = 0; i < ofs; ++i) {
+            const float sa = up ? a[i] : a[i + ofs], ka = up ? a[i + ofs] : a[i];
+            a[i] = ka + __shfl_xor_sync(0xffffffffu, sa, ofs);
+        }
+    }
+    atomicAdd(sm_stats + c + lane, a[0]);
+}
+// Activation adjoint fused into an input-gradient epilogue: v[i] *= (m[i] >= 0 ? 1 : slope), m = the 32 activated forward
+// values at this lane's output pixel (LeakyReLU keeps the sign, so the activated tensor is its own mask; the same rule as
+// pad_leaky_bias_bwd_kernel in ew_kernels.cu).  The epilogue warps fetch the signs of a whole work item as bit words
+// BEFORE they wait for the accumulator (the loads overlap the item's MMA main loop instead of sitting between tcgen05.ld
+// and the stores).  `vec`: all 32 channels exist and are 16-byte aligned; channels >= nch read as "pass".
+__device__ __forceinline__ uint32_t act_mask_bits32(const float* m, bool vec, int nch) {
+    uint32_t bits = 0;
+    if (vec) {
+        float4 t[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = __ldg(reinterpret_cast<const float4*>(m) + i);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            bits |= ((t[i].x >= 0.f ? 1u : 0u) | (t[i].y >= 0.f ? 2u : 0u) | (t[i].z >= 0.f ? 4u : 0u) | (t[i].w >= 0.f ? 8u : 0u)) << (4 * i);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) bits |= ((i >= nch || __ldg(m + (i < nch ? i : 0)) >= 0.f) ? 1u : 0u) << i;
+    }
+    return bits;
+}
+template <int NW>
+__device__ __forceinline__ uint32_t pick_word(const uint32_t (&w)[NW], int idx) {      // register-resident dynamic index
+    uint32_t r = w[0];
+#pragma unroll
+    for (int k = 1; k < NW; ++k) r = (k == idx) ? w[k] : r;
+    return r;
+}
+__device__ __forceinline__ void apply_act_bits32(float (&v)[32], uint32_t bits, float slope) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = ((bits >> i) & 1u) ? v[i] : v[i] * slope;
+}
 // one epilogue warp after all four are done with the item (named barrier 1, 128 threads): flush + clear
 __device__ __forceinline__ void stats_flush(float* sm_stats, int BN_, double* gstats, int C, int c0, int ep_tid) {
     asm volatile("bar.sync 1, 128;" ::: "memory");

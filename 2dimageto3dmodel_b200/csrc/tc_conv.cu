@@ -43,6 +43,11 @@ struct ConvParams {
     double* stats;                    // nullable: [2][Cout] fp64 sum / sum of squares of the (pre-bias) output, accumulated
     int fold;                         // > 0: the A operand is folded on the fly from a raw [N,H,W,8] tensor (thin stems): K slice ks
     int fold_y0;                      //      = image rows y + fold_y0 + 4 ks .. + 3 of the 8 channels (tensor map dims c, row, x, n)
+    const float* mask;                // nullable: tensor of the output's geometry; acc *= (mask >= 0 ? 1 : mslope) before statistics / bias
+    float mslope;                     //           (LeakyReLU adjoint fused into the input-gradient epilogue)
+    int stats_sum;                    // statistics: sums only (the bias gradient of the fused adjoint)
+    int ncls;                         // >= 1 output classes in ONE launch (the stride-2 input gradient's parity classes): class c uses taps
+    int cooy[4], coox[4];             //      [c * ntaps, (c + 1) * ntaps) of dy / dx / wtap and the output offset (cooy[c], coox[c])
 };
 
 template <int BN, int STAGES>
@@ -258,7 +263,9 @@ conv_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         if (lane == 0) {
             uint32_t git = 0;
             for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
-                const int g = w % groups, c0 = (w / groups) * BN;
+                // classes are the fastest index: the CTAs that work on the same pixel tiles at the same time share them in L2
+                const int cls = w % p.ncls, wq = w / p.ncls, tb = cls * p.ntaps;
+                const int g = wq % groups, c0 = (wq / groups) * BN;
                 int x0[R], y0[R], n0[R];
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
@@ -279,15 +286,15 @@ conv_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         if (p.fold)     // box {8 ch, BW px, 4 rows}: lands as [row][pixel][8 floats] = four 32-byte-swizzled K-step tiles
-                            tc::tma_load_4d(a + r * S::A_TILE, &tmap_x, full + s, 0, x0[r] + p.dx[tap], y0[r] + p.fold_y0 + 4 * ks, n0[r]);
+                            tc::tma_load_4d(a + r * S::A_TILE, &tmap_x, full + s, 0, x0[r] + p.dx[tb + tap], y0[r] + p.fold_y0 + 4 * ks, n0[r]);
                         else
-                            tc::tma_load_4d(a + r * S::A_TILE, &tmap_x, full + s, ks * BK, p.sx * x0[r] + p.dx[tap], p.sy * y0[r] + p.dy[tap], n0[r]);
+                            tc::tma_load_4d(a + r * S::A_TILE, &tmap_x, full + s, ks * BK, p.sx * x0[r] + p.dx[tb + tap], p.sy * y0[r] + p.dy[tb + tap], n0[r]);
                     }
                     if constexpr (WMN) {
 #pragma unroll
-                        for (int nb = 0; nb < BN / 32; ++nb) tc::tma_load_3d(b + nb * 4096, &tmap_w, full + s, c0 + nb * 32, ks * BK, p.wtap[tap]);
+                        for (int nb = 0; nb < BN / 32; ++nb) tc::tma_load_3d(b + nb * 4096, &tmap_w, full + s, c0 + nb * 32, ks * BK, p.wtap[tb + tap]);
                     } else {
-                        tc::tma_load_3d(b, &tmap_w, full + s, ks * BK, c0, p.wtap[tap]);
+                        tc::tma_load_3d(b, &tmap_w, full + s, ks * BK, c0, p.wtap[tb + tap]);
                     }
                 }
             }
@@ -329,8 +336,30 @@ conv_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         const int bx = row % p.BW, by = (row / p.BW) % p.BH, bi = row / (p.BW * p.BH);
         uint32_t j = 0;
         for (int w = blockIdx.x; w < work_items; w += gridDim.x, ++j) {
-            const int g = w % groups, c0 = (w / groups) * BN;
+            const int cls = w % p.ncls, wq = w / p.ncls;
+            const int g = wq % groups, c0 = (wq / groups) * BN;
+            const int ooy = p.cooy[cls], oox = p.coox[cls];
             const uint32_t buf = j & 1;
+            constexpr int NW = R * (BN / 32);
+            uint32_t mbits[NW];
+            if (p.mask) {                                     // signs of the item's activation mask, fetched under its main loop
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    int t = g * R + r;
+                    const bool tile_ok = t < tiles;
+                    const int tx = t % p.tiles_x;
+                    t /= p.tiles_x;
+                    const int n = (t / p.tiles_y) * p.BI + bi, y = (t % p.tiles_y) * p.BH + by, x = p.xbase + tx * p.BW + bx;
+                    const bool valid = tile_ok && n < p.N && y < p.Hout && x < p.Wout;
+                    const size_t off = (((size_t)n * p.OH + (size_t)(p.osy * y + ooy)) * p.OW + (size_t)(p.osx * x + oox)) * p.OC;
+#pragma unroll
+                    for (int cc = 0; cc < BN / 32; ++cc) {
+                        const int cb = c0 + 32 * cc;
+                        mbits[r * (BN / 32) + cc] = (valid && cb < p.Cout)
+                            ? tc::act_mask_bits32(p.mask + off + cb, cb + 32 <= p.Cout && (p.OC & 3) == 0, p.Cout - cb) : 0xffffffffu;
+                    }
+                }
+            }
             tc::mbar_wait(acc_full + buf, (j >> 1) & 1);
             tc::tc_fence_after();
 #pragma unroll 1
@@ -341,7 +370,8 @@ conv_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                 t /= p.tiles_x;
                 const int n = (t / p.tiles_y) * p.BI + bi, y = (t % p.tiles_y) * p.BH + by, x = p.xbase + tx * p.BW + bx;
                 const bool valid = tile_ok && n < p.N && y < p.Hout && x < p.Wout;
-                float* dst = out + (((size_t)n * p.OH + (size_t)(p.osy * y + p.ooy)) * p.OW + (size_t)(p.osx * x + p.oox)) * p.OC;
+                const size_t off = (((size_t)n * p.OH + (size_t)(p.osy * y + ooy)) * p.OW + (size_t)(p.osx * x + oox)) * p.OC;
+                float* dst = out + off;
 #pragma unroll 1
                 for (int c = 0; c < BN; c += 32) {
                     float v[32];
@@ -351,7 +381,11 @@ conv_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                         __syncwarp();
                         if (lane == 0) tc::mbar_arrive(acc_empty + buf);
                     }
-                    if (p.stats) tc::stats_accumulate(v, valid, sm_stats, BN, c);
+                    if (p.mask) tc::apply_act_bits32(v, tc::pick_word<NW>(mbits, r * (BN / 32) + c / 32), p.mslope);
+                    if (p.stats) {
+                        if (p.stats_sum) tc::stats_accumulate_sum(v, valid, sm_stats, c);
+                        else tc::stats_accumulate(v, valid, sm_stats, BN, c);
+                    }
                     if (valid) {
                         const int cb = c0 + c;
                         if (cb + 32 <= p.Cout && (p.OC & 3) == 0) {
@@ -573,7 +607,7 @@ int launch_persistent(const CUtensorMap& mx, const CUtensorMap& mw, const ConvPa
     static_assert(S::TOTAL <= 227 * 1024, "persistent conv pipeline does not fit shared memory");
     B3D_CUDA_OK(cudaFuncSetAttribute(conv_tf32_persistent_kernel<BN, STAGES, WMN, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     const int groups = b3d::ceil_div(tiles, R);
-    const int work = groups * b3d::ceil_div(p.Cout, BN);
+    const int work = groups * b3d::ceil_div(p.Cout, BN) * p.ncls;
     const int slots = S::CTAS_PER_SM * 148;
     const int grid = work < slots ? work : slots;
     conv_tf32_persistent_kernel<BN, STAGES, WMN, R><<<grid, PTHREADS, S::TOTAL, st>>>(mx, mw, p, bias, out, tiles, groups, work);
@@ -606,7 +640,7 @@ extern "C" {
 int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* out, int N, int H, int W, int Cin,
                     int Hout, int Wout, int Cout, int ntaps, const int* dy, const int* dx, int sy, int sx, int OH,
                     int OW, int OC, int osy, int osx, int ooy, int oox, float leaky, int w_cin_major, const int* wtap,
-                    int wtaps_total, double* stats, int fold_kh, int fold_pad, void* stream) {
+                    int wtaps_total, double* stats, int fold_kh, int fold_pad, const b3d_conv_opts* opts, void* stream) {
     B3D_REQUIRE(N > 0 && H > 0 && W > 0 && Hout > 0 && Wout > 0 && Cout > 0, B3D_EINVAL, "b3d_conv2d_tf32: bad sizes");
     B3D_REQUIRE(Cin > 0 && Cin % BK == 0, B3D_EINVAL, "b3d_conv2d_tf32: Cin=%d must be a multiple of %d", Cin, BK);
     B3D_REQUIRE(ntaps >= 1 && ntaps <= MAX_TAPS && dy && dx, B3D_EINVAL, "b3d_conv2d_tf32: bad taps");
@@ -621,18 +655,31 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
     b3d::clear_variant();
 
     static const int persist_env = getenv("B3D_CONV_PERSIST") ? atoi(getenv("B3D_CONV_PERSIST")) : 1;
-    const int persist = persist_env || stats != nullptr || fold_kh > 0;   // statistics epilogue / on-the-fly fold: persistent kernels
+    const float* mask = opts ? opts->mask : nullptr;
+    const float mslope = opts ? opts->mask_slope : 1.f;
+    const int stats_sum = (opts && opts->stats_sum_only) ? 1 : 0;
+    const int xpitch = (opts && opts->x_row_pitch) ? opts->x_row_pitch : W;
+    // nclass > 1: the tap lists hold nclass groups of ntaps / nclass taps; class c writes at (class_ooy[c], class_oox[c])
+    const int ncls = (opts && opts->nclass > 1) ? opts->nclass : 1;
+    B3D_REQUIRE(ncls <= 4 && ntaps % ncls == 0 && (ncls == 1 || (sy == 1 && sx == 1 && fold_kh == 0)), B3D_EINVAL,
+                "b3d_conv2d_tf32: nclass=%d needs <= 4 equal tap groups of a stride-1 launch", ncls);
+    const int tpc = ntaps / ncls;                              // taps per class
+    int cooy[4] = {ooy, ooy, ooy, ooy}, coox[4] = {oox, oox, oox, oox};
+    for (int c = 0; c < ncls && ncls > 1; ++c) { cooy[c] = opts->class_ooy[c]; coox[c] = opts->class_oox[c]; }
+    B3D_REQUIRE(xpitch >= W && (fold_kh == 0 || xpitch == W), B3D_EINVAL, "b3d_conv2d_tf32: x_row_pitch=%d must be >= W=%d (and absent with the on-the-fly fold)", xpitch, W);
+    // statistics epilogue / on-the-fly fold / fused activation adjoint: persistent kernels
+    const int persist = persist_env || stats != nullptr || fold_kh > 0 || mask != nullptr || ncls > 1;
     if (fold_kh > 0) {
         // x is the RAW stem input [N, H, W, 8]; the convolution is kh x kw with the kh rows folded into the K dimension:
         // Cin = 32 * ceil(8 kh / 32) "channels", taps = the kw horizontal ones (dy ignored), zero rows = the y padding
         B3D_REQUIRE(fold_kh <= 8 && Cin == 32 * ((8 * fold_kh + 31) / 32) && sy == 1 && sx == 1 && !w_cin_major && !wtap && Wout % BM == 0,
                     B3D_EINVAL, "b3d_conv2d_tf32: on-the-fly fold needs 8 input channels, stride 1 and Wout %% 128 == 0 (Wout=%d)", Wout);
     }
-    B3D_REQUIRE(!stats || (osy == 1 && osx == 1), B3D_EINVAL, "b3d_conv2d_tf32: statistics need a dense output");
+    B3D_REQUIRE(!stats || mask || (osy == 1 && osx == 1), B3D_EINVAL, "b3d_conv2d_tf32: statistics need a dense output");
     static const int wide = getenv("B3D_CONV_BN256") ? atoi(getenv("B3D_CONV_BN256")) : 1;
     // 256-wide output-channel tiles halve the input-tile bytes per FLOP through the L2 -> SM fabric (the bound of the
     // per-tap formulation, profiles/r1_c_*.md) when there are >= 256 output channels and enough tiles to fill the GPU
-    const bool bn256 = persist && wide && Cout % 256 == 0 && (long long)N * Hout * Wout / BM * (Cout / 256) >= 148;
+    const bool bn256 = persist && wide && Cout % 256 == 0 && (long long)N * Hout * Wout / BM * (Cout / 256) * ncls >= 148;
     const int BN = bn256 ? 256 : Cout > 64 ? 128 : 64;
     cudaStream_t st = (cudaStream_t)stream;
     CUtensorMap mw;
@@ -657,17 +704,18 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
     int g_kw = 0, g_kh = 0, g_step = 0, g_wstep = 1;
     if (sy == 1 && sx == 1 && !w_cin_major && fold_kh == 0) {
         int kw_ = 1;
-        while (kw_ < ntaps && dy[kw_] == dy[0]) ++kw_;
+        while (kw_ < tpc && dy[kw_] == dy[0]) ++kw_;
         const int step = kw_ > 1 ? dx[1] - dx[0] : 1;
         const int wstep = (wtap && kw_ > 1) ? wtap[1] - wtap[0] : 1;
-        bool grid_ok = ntaps % kw_ == 0 && ntaps / kw_ <= 5 && (kw_ == 2 || kw_ == 3 || kw_ == 5) && (step == 1 || step == -1) &&
-                       wstep >= 1 && wstep <= 2 && (osy == osx) && (osy == 1 || osy == 2);
-        for (int t = 0; grid_ok && t < ntaps; ++t) {
-            grid_ok = dy[t] == dy[(t / kw_) * kw_] && dx[t] == dx[0] + (t % kw_) * step;
-            if (wtap) grid_ok = grid_ok && wtap[t] == wtap[(t / kw_) * kw_] + (t % kw_) * wstep;
+        bool grid_ok = tpc % kw_ == 0 && tpc / kw_ <= 5 && (kw_ == 2 || kw_ == 3 || kw_ == 5) && (step == 1 || step == -1) &&
+                       wstep >= 1 && wstep <= 2 && (osy == osx) && (osy == 1 || osy == 2) && (ncls == 1 || wtap != nullptr);
+        for (int t = 0; grid_ok && t < ntaps; ++t) {             // every class: the same column pattern, its own rows / weight taps
+            const int tc_ = t % tpc, t0 = t - tc_;
+            grid_ok = dy[t] == dy[t0 + (tc_ / kw_) * kw_] && dx[t] == dx[0] + (tc_ % kw_) * step;
+            if (wtap) grid_ok = grid_ok && wtap[t] == wtap[t0 + (tc_ / kw_) * kw_] + (tc_ % kw_) * wstep;
         }
         static const int rowwin_env = getenv("B3D_CONV_ROWWIN") ? atoi(getenv("B3D_CONV_ROWWIN")) : 1;
-        if (grid_ok && rowwin_env) { g_kw = kw_; g_kh = ntaps / kw_; g_step = step; g_wstep = wstep; }
+        if (grid_ok && rowwin_env) { g_kw = kw_; g_kh = tpc / kw_; g_step = step; g_wstep = wstep; }
     }
     auto run = [&](int xlo, int xhi) -> int {
         const int wspan = xhi - xlo;
@@ -675,13 +723,19 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
             b3d::RowWinArgs a{};
             a.x = x; a.wt = wt; a.bias = bias; a.out = out;
             a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Hout = Hout; a.Cout = Cout; a.xlo = xlo; a.xhi = xhi;
-            a.kh = g_kh; a.kw = g_kw;
-            for (int r = 0; r < g_kh; ++r) a.dy[r] = dy[r * g_kw];
+            a.kh = g_kh; a.kw = g_kw; a.ncls = ncls;
             a.dx0 = g_step > 0 ? dx[0] : dx[g_kw - 1];
             for (int t = 0; t < g_kw; ++t) a.shift[t] = dx[t] - a.dx0;
-            a.OH = OH; a.OW = OW; a.OC = OC; a.ooy = ooy; a.oox = oox; a.leaky = leaky; a.stats = stats;
+            a.OH = OH; a.OW = OW; a.OC = OC; a.leaky = leaky; a.stats = stats;
             a.osy = osy; a.osx = osx; a.wtaps_total = wtaps_total; a.wtap_step = g_wstep;
-            for (int r = 0; r < g_kh; ++r) a.wtap0[r] = wtap ? wtap[r * g_kw] : r * g_kw;
+            a.mask = mask; a.mslope = mslope; a.stats_sum = stats_sum; a.xpitch = xpitch;
+            for (int c = 0; c < ncls; ++c) {
+                a.ooy[c] = cooy[c]; a.oox[c] = coox[c];
+                for (int r = 0; r < g_kh; ++r) {
+                    a.dy[c][r] = dy[c * tpc + r * g_kw];
+                    a.wtap0[c][r] = wtap ? wtap[c * tpc + r * g_kw] : r * g_kw;
+                }
+            }
             const int rc = b3d::conv_rowwin_launch(a, st);
             if (rc <= 0) return rc;                           // launched (0) or a real error (< 0); 1 = not covered
         }
@@ -693,12 +747,14 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
         p.tiles_x = b3d::ceil_div(wspan, p.BW);
         p.tiles_y = b3d::ceil_div(Hout, p.BH);
         const int tiles = p.tiles_x * p.tiles_y * b3d::ceil_div(N, p.BI);
-        p.ntaps = ntaps; p.kslices = Cin / BK; p.sy = sy; p.sx = sx;
+        p.ntaps = tpc; p.kslices = Cin / BK; p.sy = sy; p.sx = sx; p.ncls = ncls;
         for (int t = 0; t < ntaps; ++t) { p.dy[t] = dy[t]; p.dx[t] = dx[t]; p.wtap[t] = wtap ? wtap[t] : t; }
+        for (int c = 0; c < 4; ++c) { p.cooy[c] = cooy[c]; p.coox[c] = coox[c]; }
         p.OH = OH; p.OW = OW; p.OC = OC; p.osy = osy; p.osx = osx; p.ooy = ooy; p.oox = oox;
         p.leaky = leaky;
         p.dbg_lbo = 4096; p.dbg_sbo = 512; p.dbg_lt = 1;     // 32-bit MN-major: SWIZZLE_128B_BASE32B, 4-row atoms
         p.stats = stats;
+        p.mask = mask; p.mslope = mslope; p.stats_sum = stats_sum;
         p.fold = fold_kh; p.fold_y0 = -fold_pad;
         CUtensorMap mx;
         if (fold_kh > 0) {
@@ -709,7 +765,7 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
             if (int rc = tc::make_tmap_f32(&mx, x, 4, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_32B)) return rc;
         } else {
         const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-        const uint64_t strides[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
+        const uint64_t strides[3] = {(uint64_t)Cin * 4, (uint64_t)xpitch * Cin * 4, (uint64_t)H * xpitch * Cin * 4};
         const uint32_t box[4] = {(uint32_t)BK, (uint32_t)(sx * (p.BW - 1) + 1), (uint32_t)(sy * (p.BH - 1) + 1), (uint32_t)p.BI};
         const uint32_t es[4] = {1, (uint32_t)sx, (uint32_t)sy, 1};
         if (int rc = tc::make_tmap_f32(&mx, x, 4, dims, strides, box, es)) return rc;
@@ -720,7 +776,7 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
             // stacked pixel tiles (1 CTA / SM, deeper stages) once there is work for ~2 waves of them
             static const int stack_env = getenv("B3D_CONV_STACK") ? atoi(getenv("B3D_CONV_STACK")) : 1;
             const int R = BN == 128 ? 2 : 4;
-            const bool stack = stack_env && BN < 256 && (long long)b3d::ceil_div(tiles, R) * b3d::ceil_div(Cout, BN) >= 2 * 148;
+            const bool stack = stack_env && BN < 256 && (long long)b3d::ceil_div(tiles, R) * b3d::ceil_div(Cout, BN) * ncls >= 2 * 148;
             return w_cin_major ? dispatch_persistent<true>(BN, stack, mx, mw, p, bias, out, tiles, st)
                                : dispatch_persistent<false>(BN, stack, mx, mw, p, bias, out, tiles, st);
         }
@@ -747,7 +803,8 @@ int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* o
 // dy [N,Hout,Wout,Cout], x [N,H,W,Cin] NHWC (x already padded along x; Cin, Cout multiples of 4),
 // dw [Cout,Cin,kh,kw] (accumulated into)
 int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, int N, int H, int W, int Cin, int Hout, int Wout,
-                          int Cout, int kh, int kw, int pad_y, int stride, int x_off, int tap_major, int fold_kh, void* stream) {
+                          int Cout, int kh, int kw, int pad_y, int stride, int x_off, int tap_major, int fold_kh, int dy_row_pitch,
+                          void* stream) {
     B3D_REQUIRE(N > 0 && Cin > 0 && Cout > 0 && H > 0 && W > 0 && Hout > 0 && Wout > 0, B3D_EINVAL,
                 "b3d_conv2d_wgrad_tf32: bad sizes");
     B3D_REQUIRE(kh * kw <= MAX_TAPS && (stride == 1 || stride == 2) && x_off >= 0, B3D_EINVAL, "b3d_conv2d_wgrad_tf32: bad kernel/stride");
@@ -787,7 +844,9 @@ int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, int N, int
     CUtensorMap mdy, mx;
     {   // dims: (32 channels, W, H, N, channel block) — the block dim is outermost so that a box of BM/32 blocks is contiguous
         const uint64_t dims[5] = {32, (uint64_t)Wout, (uint64_t)Hout, (uint64_t)N, (uint64_t)Cout / 32};
-        const uint64_t strides[4] = {(uint64_t)Cout * 4, (uint64_t)Wout * Cout * 4, (uint64_t)Hout * Wout * Cout * 4, 128};
+        const uint64_t dpitch = dy_row_pitch > 0 ? dy_row_pitch : Wout;            // pixels per row of dy in memory
+        B3D_REQUIRE(dpitch >= (uint64_t)Wout, B3D_EINVAL, "b3d_conv2d_wgrad_tf32: dy_row_pitch=%d must be >= Wout=%d", dy_row_pitch, Wout);
+        const uint64_t strides[4] = {(uint64_t)Cout * 4, dpitch * Cout * 4, (uint64_t)Hout * dpitch * Cout * 4, 128};
         const uint32_t box[5] = {32, (uint32_t)p.BWk, (uint32_t)p.BHk, 1, (uint32_t)(BM / 32)};
         if (int rc = tc::make_tmap_f32(&mdy, dy, 5, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
     }

@@ -22,12 +22,15 @@ constexpr int BM = 128, BK = 32, UMMA_K = 8, NTHREADS = 192;
 struct RowParams {
     int N, Hout, Cout, xlo, xhi;
     int tiles_x, tiles, groups, work;
-    int kh, kslices;
-    int dy[5], dx0, shift[5];
-    int OH, OW, OC, ooy, oox, osy, osx;
-    int wtap0[5];
+    int kh, kslices, ncls;
+    int dy[4][5], dx0, shift[5];
+    int OH, OW, OC, ooy[4], oox[4], osy, osx;
+    int wtap0[4][5];
     float leaky;
     double* stats;
+    const float* mask;     // nullable: activation adjoint fused into the epilogue (see ConvParams in tc_conv.cu)
+    float mslope;
+    int stats_sum;
 };
 
 template <int BN, int KW, int R, int STAGES>
@@ -86,7 +89,9 @@ conv_rowwin_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         if (lane == 0) {
             uint32_t git = 0;
             for (int w = blockIdx.x; w < p.work; w += gridDim.x) {
-                const int g = w % p.groups, c0 = (w / p.groups) * BN;
+                // classes are the fastest index: CTAs working on the same pixel tiles at the same time share them in L2
+                const int cls = w % p.ncls, wq = w / p.ncls;
+                const int g = wq % p.groups, c0 = (wq / p.groups) * BN;
                 int x0[R], y0[R], n0[R];
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
@@ -105,8 +110,8 @@ conv_rowwin_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
                     tc::mbar_arrive_expect_tx(full + s, S::TX_BYTES);
 #pragma unroll
                     for (int r = 0; r < R; ++r)
-                        tc::tma_load_4d(a + r * S::WIN_STRIDE, &tmap_x, full + s, ks * BK, x0[r] + p.dx0, y0[r] + p.dy[fr], n0[r]);
-                    tc::tma_load_3d(a + R * S::WIN_STRIDE, &tmap_w, full + s, ks * BK, c0, p.wtap0[fr]);
+                        tc::tma_load_4d(a + r * S::WIN_STRIDE, &tmap_x, full + s, ks * BK, x0[r] + p.dx0, y0[r] + p.dy[cls][fr], n0[r]);
+                    tc::tma_load_3d(a + R * S::WIN_STRIDE, &tmap_w, full + s, ks * BK, c0, p.wtap0[cls][fr]);
                 }
             }
         }
@@ -147,8 +152,30 @@ conv_rowwin_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         const int row = q * 32 + lane;
         uint32_t j = 0;
         for (int w = blockIdx.x; w < p.work; w += gridDim.x, ++j) {
-            const int g = w % p.groups, c0 = (w / p.groups) * BN;
+            const int cls = w % p.ncls, wq = w / p.ncls;
+            const int g = wq % p.groups, c0 = (wq / p.groups) * BN;
+            const int ooy = p.ooy[cls], oox = p.oox[cls];
             const uint32_t buf = j & 1;
+            constexpr int CW = BN < 32 ? 1 : BN / 32, NW = R * CW;
+            uint32_t mbits[NW];
+            if (p.mask) {                                         // signs of the item's activation mask, fetched under its main loop
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    int t = g * R + r;
+                    const bool tile_ok = t < p.tiles;
+                    const int x = p.xlo + (t % p.tiles_x) * BM + row;
+                    t /= p.tiles_x;
+                    const int y = t % p.Hout, n = t / p.Hout;
+                    const bool valid = tile_ok && x < p.xhi;
+                    const size_t off = (((size_t)n * p.OH + (size_t)(p.osy * y + ooy)) * p.OW + (size_t)(p.osx * x + oox)) * p.OC;
+#pragma unroll
+                    for (int cc = 0; cc < CW; ++cc) {
+                        const int cb = c0 + 32 * cc;
+                        mbits[r * CW + cc] = (valid && cb < p.Cout)
+                            ? tc::act_mask_bits32(p.mask + off + cb, cb + 32 <= p.Cout && (p.OC & 3) == 0, p.Cout - cb) : 0xffffffffu;
+                    }
+                }
+            }
             tc::mbar_wait(acc_full + buf, (j >> 1) & 1);
             tc::tc_fence_after();
 #pragma unroll 1
@@ -159,7 +186,8 @@ conv_rowwin_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
                 t /= p.tiles_x;
                 const int y = t % p.Hout, n = t / p.Hout;
                 const bool valid = tile_ok && x < p.xhi;
-                float* dst = out + (((size_t)n * p.OH + (size_t)(p.osy * y + p.ooy)) * p.OW + (size_t)(p.osx * x + p.oox)) * p.OC;
+                const size_t off = (((size_t)n * p.OH + (size_t)(p.osy * y + ooy)) * p.OW + (size_t)(p.osx * x + oox)) * p.OC;
+                float* dst = out + off;
 #pragma unroll 1
                 for (int c = 0; c < BN; c += 32) {
                     float v[32];
@@ -169,7 +197,11 @@ conv_rowwin_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
                         __syncwarp();
                         if (lane == 0) tc::mbar_arrive(acc_empty + buf);
                     }
-                    if (BN >= 32 && p.stats) tc::stats_accumulate(v, valid, sm_stats, BN, c);
+                    if (p.mask) tc::apply_act_bits32(v, tc::pick_word<NW>(mbits, r * CW + c / 32), p.mslope);
+                    if (BN >= 32 && p.stats) {
+                        if (p.stats_sum) tc::stats_accumulate_sum(v, valid, sm_stats, c);
+                        else tc::stats_accumulate(v, valid, sm_stats, BN, c);
+                    }
                     if (valid) {
                         const int cb = c0 + c;
                         if (cb + 32 <= p.Cout && (p.OC & 3) == 0) {
@@ -216,17 +248,23 @@ int launch_rowwin(const b3d::RowWinArgs& a, cudaStream_t st) {
     p.tiles_x = b3d::ceil_div(a.xhi - a.xlo, BM);
     p.tiles = p.tiles_x * a.Hout * a.N;
     p.groups = b3d::ceil_div(p.tiles, R);
-    p.work = p.groups * b3d::ceil_div(a.Cout, BN);
+    p.ncls = a.ncls < 1 ? 1 : a.ncls;
+    p.work = p.groups * b3d::ceil_div(a.Cout, BN) * p.ncls;
     p.kh = a.kh; p.kslices = a.Cin / BK;
-    for (int i = 0; i < 5; ++i) { p.dy[i] = a.dy[i]; p.shift[i] = a.shift[i]; }
+    for (int i = 0; i < 5; ++i) p.shift[i] = a.shift[i];
+    for (int c = 0; c < 4; ++c) {
+        p.ooy[c] = a.ooy[c]; p.oox[c] = a.oox[c];
+        for (int i = 0; i < 5; ++i) { p.dy[c][i] = a.dy[c][i]; p.wtap0[c][i] = a.wtap0[c][i]; }
+    }
     p.dx0 = a.dx0;
-    p.OH = a.OH; p.OW = a.OW; p.OC = a.OC; p.ooy = a.ooy; p.oox = a.oox; p.leaky = a.leaky; p.stats = a.stats;
+    p.OH = a.OH; p.OW = a.OW; p.OC = a.OC; p.leaky = a.leaky; p.stats = a.stats;
     p.osy = a.osy; p.osx = a.osx;
-    for (int i = 0; i < 5; ++i) p.wtap0[i] = a.wtap0[i];
+    p.mask = a.mask; p.mslope = a.mslope; p.stats_sum = a.stats_sum;
     CUtensorMap mx, mw;
     {
         const uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.N};
-        const uint64_t strides[3] = {(uint64_t)a.Cin * 4, (uint64_t)a.W * a.Cin * 4, (uint64_t)a.H * a.W * a.Cin * 4};
+        const uint64_t pitch = a.xpitch ? a.xpitch : a.W;                  // pixels per image row in memory
+        const uint64_t strides[3] = {(uint64_t)a.Cin * 4, pitch * a.Cin * 4, (uint64_t)a.H * pitch * a.Cin * 4};
         const uint32_t box[4] = {(uint32_t)BK, (uint32_t)S::WIN_ROWS, 1, 1};
         if (int rc = tc::make_tmap_f32(&mx, a.x, 4, dims, strides, box)) return rc;
     }
@@ -255,7 +293,7 @@ int conv_rowwin_launch(const RowWinArgs& a, cudaStream_t st) {
     // MMA work: measured slower than the per-tap kernel (0.71 vs 0.62 ms, profiles/r2_e_conv_layers.md)
     if (a.kh * (a.Cin / BK) < 4) return 1;
     // one CTA per SM: worth it only with >= ~2 waves of stacked work items
-    const long long tiles = (long long)ceil_div(a.xhi - a.xlo, BM) * a.Hout * a.N;
+    const long long tiles = (long long)ceil_div(a.xhi - a.xlo, BM) * a.Hout * a.N * (a.ncls < 1 ? 1 : a.ncls);
     if (a.Cout <= 16 && a.kw == 5 && a.stats == nullptr) {
         // 1-16 output channels (conv_final 64 -> 3): N = 16 tensor-core tiles — 13 of 16 columns are padding, still ~2.5x the
         // fp32 CUDA-core kernel (one window load feeds five taps)

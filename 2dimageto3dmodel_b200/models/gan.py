@@ -11,6 +11,7 @@ kernels read; x-padding (replicate for the symmetric generator, circular for the
 as in the reference, y-padding is the convolution's zero padding (TMA out-of-bounds fill).
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -19,7 +20,7 @@ import torch.nn.functional as F
 from b3d import B3DError
 from b3d.bank import WeightBank
 from b3d.conv import conv2d as _tc_conv2d
-from b3d.conv import conv2d_banked
+from b3d.conv import ActLink, conv2d_banked
 from b3d.ew import CIRCULAR, REPLICATE, CBNBatch, cbn_act_pad, pad_x
 from rendering.utils import adjust_poles, symmetrize_texture
 
@@ -61,15 +62,20 @@ def _norm_and_bias(args):
     raise ValueError(f"norm_d={args.norm_d!r}")
 
 
-def _conv_norm_act(conv, norm, x, pad_next=0, lw=None):
+def _conv_norm_act(conv, norm, x, pad_next=0, lw=None, link_in=None, link_out=None):
     """pad_x(LeakyReLU(0.2)(norm(conv(x))), pad_next, circular): one fused kernel when there is no norm layer.
     lw: the layer's weights from the network's WeightBank (spectral norm + kernel layouts done for all layers at once);
-    None = the module's own forward (torch's spectral-norm hook)."""
+    None = the module's own forward (torch's spectral-norm hook).
+    link_in / link_out (b3d.conv.ActLink, banked layers only): this layer's input is the sole use of the previous layer's
+    padded output / this layer's padded output has exactly one consumer, the next convolution — the backward pass then
+    applies LeakyReLU', the padding's adjoint and the bias sum in the consumer's input-gradient epilogue."""
     if lw is not None:
-        run = lambda **kw: conv2d_banked(x, lw, pad_y=conv.padding[0], stride=conv.stride[0], **kw)
+        run = lambda **kw: conv2d_banked(x, lw, pad_y=conv.padding[0], stride=conv.stride[0], link_in=link_in, **kw)
     else:
         run = lambda **kw: conv(x, **kw)
     if norm is None and conv.out_channels in (16, 32, 64, 128, 256, 512, 1024):
+        if lw is not None and pad_next:
+            return run(leaky=0.2, pad_out=pad_next, pad_mode=CIRCULAR, link_out=link_out)
         return run(leaky=0.2, pad_out=pad_next, pad_mode=CIRCULAR)
     y = run(leaky=0.2) if norm is None else F.leaky_relu(norm(run()), 0.2)
     return pad_x(y, pad_next, CIRCULAR) if pad_next else y
@@ -109,6 +115,12 @@ class _DiscriminatorBase(nn.Module):
                 dev_copy = self._pos_emb_dev = self.pos_emb.to(x.device)
             parts.append(dev_copy.expand(x.shape[0], -1, -1, -1))
         return torch.cat(parts, dim=1) if len(parts) > 1 else x
+
+    def _links(self, n, W):
+        """ActLinks for the first n conv -> conv hand-overs of the stack (the last padded activation also feeds the
+        projection, so it keeps the stand-alone backward pass)."""
+        on = bool(W) and self.circular and not getattr(self, 'disable_act_chain', False) and not os.environ.get("B3D_NO_ACT_CHAIN")
+        return [ActLink() if on else None for _ in range(n)]
 
     def _project(self, y, feat, c, caption):
         a = self.args
@@ -155,9 +167,10 @@ class MeshDiscriminator(_DiscriminatorBase):
             with torch.no_grad():
                 mask = F.avg_pool2d(x[:, 3:4], 4)
         p1, p2 = (1, 2) if self.circular else (0, 0)       # x padding of the 4x4 / 5x5 layers, applied by the producer
-        x = _conv_norm_act(self.conv1, None, self.pad(x), p1, W.get(prefix + "conv1"))
-        x = _conv_norm_act(self.conv2, self.bn2, x, p1, W.get(prefix + "conv2"))
-        x = _conv_norm_act(self.conv3, self.bn3, x, p2, W.get(prefix + "conv3"))
+        l1, l2 = self._links(2, W)
+        x = _conv_norm_act(self.conv1, None, self.pad(x), p1, W.get(prefix + "conv1"), link_out=l1)
+        x = _conv_norm_act(self.conv2, self.bn2, x, p1, W.get(prefix + "conv2"), link_in=l1, link_out=l2)
+        x = _conv_norm_act(self.conv3, self.bn3, x, p2, W.get(prefix + "conv3"), link_in=l2)
         feat = x[..., p2:x.shape[3] - p2]
         y = self._project(_head(self.conv4, x, W.get(prefix + "conv4")), feat, c, caption)
         return y, mask
@@ -207,10 +220,11 @@ class TextureDiscriminator(_DiscriminatorBase):
                 mask = F.avg_pool2d(x[:, 3:4], 16 if self.stride_first else 8)
         x = self._with_positions(x)
         p1, p2 = (1, 2) if self.circular else (0, 0)       # x padding of the 4x4 / 5x5 layers, applied by the producer
-        x = _conv_norm_act(self.conv1, None, self.padconv1(x), p1, W.get(prefix + "conv1"))
-        x = _conv_norm_act(self.conv2, self.bn2, x, p1, W.get(prefix + "conv2"))
-        x = _conv_norm_act(self.conv3, self.bn3, x, p1, W.get(prefix + "conv3"))
-        x = _conv_norm_act(self.conv4, self.bn4, x, p2, W.get(prefix + "conv4"))
+        l1, l2, l3 = self._links(3, W)
+        x = _conv_norm_act(self.conv1, None, self.padconv1(x), p1, W.get(prefix + "conv1"), link_out=l1)
+        x = _conv_norm_act(self.conv2, self.bn2, x, p1, W.get(prefix + "conv2"), link_in=l1, link_out=l2)
+        x = _conv_norm_act(self.conv3, self.bn3, x, p1, W.get(prefix + "conv3"), link_in=l2, link_out=l3)
+        x = _conv_norm_act(self.conv4, self.bn4, x, p2, W.get(prefix + "conv4"), link_in=l3)
         feat = x[..., p2:x.shape[3] - p2]
         y = self._project(_head(self.conv5, x, W.get(prefix + "conv5")), feat, c, caption)
         return y, mask

@@ -214,11 +214,35 @@ B3D_API int b3d_chamfer_bwd(const float* query, const float* cand, const int32_t
  * fprop: dy = r - pad_y, dx = s.  dgrad: dy = pad_y - r, dx = -s with wt[t] = W[:,:,r,s]^T (strided dgrad = one
  * call per output parity class with osy = osx = 2).  leaky = negative slope of the fused LeakyReLU (1 = none).
  * ------------------------------------------------------------------------------------------ */
+/* Optional extras of b3d_conv2d_tf32 (all zero = none).  They exist for the discriminators' backward pass
+ * (models/gan.py:163-177,294-302: conv -> bias -> LeakyReLU -> wrap-around x padding -> next conv), where the input
+ * gradient of layer L+1 IS the gradient of layer L's padded, activated output:
+ *   mask        tensor with the geometry of `out` (the activated forward tensor the gradient belongs to): the epilogue
+ *               stores acc * (mask >= 0 ? 1 : mask_slope) — the LeakyReLU adjoint without a pass of its own; `stats`
+ *               then receives the sums of the masked values (stats_sum_only = 1: the sum of squares is skipped), i.e. the
+ *               bias gradient once the pad columns are folded back (b3d_wrap_x_bwd_inplace).
+ *   x_row_pitch x is a W-pixel-wide window of rows that are x_row_pitch pixels apart in memory (image n at
+ *               n * H * x_row_pitch pixels): the interior of a padded gradient buffer is read in place; columns outside
+ *               [0, W) read as zero even though the memory behind them is valid.
+ *   nclass      2..4: ONE launch computes nclass outputs that share x, the strides and the logical extent (Hout, Wout) —
+ *               the output-parity classes of a stride-2 input gradient.  dy / dx / wtap hold nclass consecutive groups of
+ *               ntaps / nclass taps; class c is written at (osy*y + class_ooy[c], osx*x + class_oox[c]) (ooy / oox are
+ *               ignored).  Classes are the fastest-varying work index, so the CTAs that read the same pixel tiles of x
+ *               run at the same time and share them in L2 (four separate launches re-read x four times from HBM).           */
+typedef struct b3d_conv_opts {
+    const float* mask;
+    float mask_slope;
+    int stats_sum_only;
+    int x_row_pitch;
+    int nclass;
+    int class_ooy[4];
+    int class_oox[4];
+} b3d_conv_opts;
 B3D_API int b3d_conv2d_tf32(const float* x, const float* wt, const float* bias, float* out, int N, int H, int W,
                             int Cin, int Hout, int Wout, int Cout, int ntaps, const int* dy, const int* dx,
                             int sy, int sx, int OH, int OW, int OC, int osy, int osx, int ooy, int oox,
                             float leaky, int w_cin_major, const int* wtap, int wtaps_total, double* stats, int fold_kh,
-                            int fold_pad, void* stream);
+                            int fold_pad, const b3d_conv_opts* opts, void* stream);
 /* wtap (nullable): loop tap t reads weight tap wtap[t] of a tap-major array that holds wtaps_total taps — the stride-2
  * input-gradient parity classes address their tap subsets of the full weight array without a gathered copy.
  * stats (nullable): [2][Cout] fp64, ACCUMULATED into by the epilogue: per-channel sum and sum of squares of the output
@@ -244,7 +268,9 @@ B3D_API int b3d_conv2d_flat_tf32(const float* x, const float* wt, const float* b
  * dw [Cout,Cin,kh,kw] is ACCUMULATED into (caller zeroes it).                                          */
 B3D_API int b3d_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw, int N, int H, int W, int Cin,
                                   int Hout, int Wout, int Cout, int kh, int kw, int pad_y, int stride,
-                                  int x_off, int tap_major, int fold_kh, void* stream);
+                                  int x_off, int tap_major, int fold_kh, int dy_row_pitch, void* stream);
+/* dy_row_pitch > 0: dy is a Wout-pixel-wide window of rows dy_row_pitch pixels apart (the interior of a padded gradient
+ * buffer, read in place); 0 = dense [N,Hout,Wout,Cout].                                                                   */
 /* tap_major != 0: dw is the tap-major array [kh*kw][Cout][Cin] (the layout b3d_conv2d_tf32 reads, 16-byte vector
  * reductions) instead of [Cout][Cin][kh][kw].  fold_kh > 0: x is the raw 8-channel stem input, folded on the fly as in
  * b3d_conv2d_tf32 (kh = 1, kw = the horizontal taps, Cin = folded channel count, pad_y = the fold's y padding).              */
@@ -316,6 +342,11 @@ B3D_API int b3d_fold_rows_bwd(const float* gout, float* gx, int N, int H, int W,
  * (b3d_conv2d_tf32 with OW = W + 2*amount, oox = amount): fills the 2*amount pad columns (mode 0 replicate / 1 circular).
  * Replaces circpad (rendering/utils.py:29-33) / F.pad (models/gan.py:329) after a conv without a full-tensor copy. */
 B3D_API int b3d_wrap_x_inplace(float* buf, long long rows, int W, int C, int amount, int mode, void* stream);
+/* Adjoint of b3d_wrap_x_inplace, in place: the gradients of the 2*amount pad columns of g [rows, W + 2*amount, C] are
+ * added to the interior columns they were copied from (mode 1: column W + j += column j, column amount + j += column
+ * W + amount + j; mode 0: the edge columns collect their side's pad columns).  The pad columns keep their values: consumers
+ * read the interior through x_row_pitch / dy_row_pitch.  amount <= W, C % 4 == 0. */
+B3D_API int b3d_wrap_x_bwd_inplace(float* g, long long rows, int W, int C, int amount, int mode, void* stream);
 /* Backward of conv -> bias -> LeakyReLU(slope) -> x padding in one pass (models/gan.py discriminators :163-177,
  * :294-302): gy [rows, W, C] = pad^T(gout_pad [rows, W + 2*amount, C]) * leaky'(y_pad interior); gbias [C] (nullable)
  * accumulates sum(gy) (caller zeroes it).  C = 4 * power of two. */
