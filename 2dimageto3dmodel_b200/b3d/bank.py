@@ -69,7 +69,7 @@ class WeightBank:
         for sp in self.specs:
             sp["u_off"], sp["v_off"], sp["scal_off"] = off_out, off_out + _r64(sp["Cout"]), off_out + _r64(sp["Cout"]) + _r64(sp["K"])
             off_out = sp["scal_off"] + 64
-            sp["t_off"], sp["s_off"] = off_scr, off_scr + _r64(sp["K"])
+            sp["t_off"], sp["s_off"] = off_scr, off_scr + _r64(2 * sp["K"])       # t: K int64 fixed-point accumulators
             off_scr = sp["s_off"] + _r64(sp["Cout"])
             sp["dw_off"] = off_w
             off_w += _r64(sp["Cout"] * sp["K"])

@@ -32,7 +32,7 @@ struct alignas(16) BankLayer {
     const float* w;      // weight_orig [Cout][Cin][kh][kw]
     float* u;            // [Cout]   (spectral norm only; updated in place in training mode)
     float* v;            // [K]
-    long long t_off;     // scratch [K]:    W^T u            (scratch is zeroed before the forward)
+    long long t_off;     // scratch [2K floats = K int64]: W^T u in 2^-36 fixed point (scratch is zeroed before the forward)
     long long s_off;     // scratch [Cout]: W v (/ |t|)
     long long wf_off;    // out: F layout
     long long wd_off;    // out: D layout, or -1
@@ -47,6 +47,15 @@ struct alignas(16) BankLayer {
 };
 
 struct Item { int layer, a, b, c; };
+
+// W^T u is summed over row chunks by different CTAs.  fp32 atomics would make the sum depend on the arrival order (and with
+// the tf32 rounding of the emitted weights a last-bit difference becomes a 2^-11 one: the same step would not repeat
+// bit-for-bit), so the partial sums are accumulated as 64-bit integers in units of 2^-36: integer addition is associative,
+// the result is the same whatever the order (resolution 1.5e-11, range +-1.3e8; |t| <= sigma_max(W), a few tens at most).
+constexpr double T_SCALE = 68719476736.0;
+__device__ __forceinline__ float t_value(const float* scratch, long long t_off, int k) {
+    return (float)((double)reinterpret_cast<const long long*>(scratch + t_off)[k] * (1.0 / T_SCALE));
+}
 
 __device__ __forceinline__ float block_reduce_sum(float v, float* red) {
     v = b3d::warp_sum(v);
@@ -73,7 +82,8 @@ bank_wtu_kernel(const BankLayer* __restrict__ layers, const Item* __restrict__ i
     const float* w = L.w + (size_t)r0 * K + col;
 #pragma unroll 8
     for (int r = r0; r < r1; ++r, w += K) acc = fmaf(__ldg(w), __ldg(L.u + r), acc);
-    atomicAdd(scratch + L.t_off + col, acc);
+    atomicAdd(reinterpret_cast<unsigned long long*>(scratch + L.t_off) + col,
+              (unsigned long long)__double2ll_rn((double)acc * T_SCALE));
 }
 
 // training: s[row] = (W[row] . t) / max(|t|, eps)       eval: s[row] = W[row] . v         item: (layer, chunk of 8 rows)
@@ -83,11 +93,10 @@ bank_wv_kernel(const BankLayer* __restrict__ layers, const Item* __restrict__ it
     const Item it = items[blockIdx.x];
     const BankLayer L = layers[it.layer];
     const int K = L.Cin * L.kh * L.kw;
-    const float* vec = training ? scratch + L.t_off : L.v;
     float inv = 1.f;
     if (training) {
         float p = 0.f;
-        for (int k = threadIdx.x; k < K; k += NT) { const float x = vec[k]; p = fmaf(x, x, p); }
+        for (int k = threadIdx.x; k < K; k += NT) { const float x = t_value(scratch, L.t_off, k); p = fmaf(x, x, p); }
         inv = 1.f / fmaxf(sqrtf(block_reduce_sum(p, red)), SN_EPS);
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -95,7 +104,7 @@ bank_wv_kernel(const BankLayer* __restrict__ layers, const Item* __restrict__ it
     if (row >= L.Cout) return;
     const float* w = L.w + (size_t)row * K;
     float acc = 0.f;
-    for (int k = lane; k < K; k += 32) acc = fmaf(__ldg(w + k), vec[k], acc);
+    for (int k = lane; k < K; k += 32) acc = fmaf(__ldg(w + k), training ? t_value(scratch, L.t_off, k) : L.v[k], acc);
     acc = b3d::warp_sum(acc);
     if (lane == 0) scratch[L.s_off + row] = acc * inv;
 }
@@ -134,18 +143,17 @@ bank_emit_kernel(const BankLayer* __restrict__ layers, const Item* __restrict__ 
     float sigma = 1.f, inv_s = 1.f;
     if (L.sn) {
         const float* sv = scratch + L.s_off;
-        const float* tv = scratch + L.t_off;
         sigma = layer_sigma(L, sv, training, red, &inv_s);
         if (it.a == 0 && it.b == 0) {       // one CTA per layer publishes u, v (in place + this call's copies) and sigma
             if (threadIdx.x == 0) { outb[L.scal_off] = sigma; outb[L.scal_off + 1] = 0.f; }
             float inv_t = 1.f;
             if (training) {
                 float p = 0.f;
-                for (int k = threadIdx.x; k < K; k += NT) { const float x = tv[k]; p = fmaf(x, x, p); }
+                for (int k = threadIdx.x; k < K; k += NT) { const float x = t_value(scratch, L.t_off, k); p = fmaf(x, x, p); }
                 inv_t = 1.f / fmaxf(sqrtf(block_reduce_sum(p, red)), SN_EPS);
             }
             for (int k = threadIdx.x; k < K; k += NT) {
-                const float x = training ? tv[k] * inv_t : L.v[k];
+                const float x = training ? t_value(scratch, L.t_off, k) * inv_t : L.v[k];
                 if (training) L.v[k] = x;
                 outb[L.v_off + k] = x;
             }
