@@ -194,6 +194,25 @@ fold_rows_fwd_kernel(const float* __restrict__ x, float4* __restrict__ out, int 
         }
         float4* orow = out + (long long)row * W * Cp4 + k4;
         constexpr int U = 4;                                 // independent pixels in flight per thread
+        if ((C & 3) == 0) {
+            // C % 4 == 0: the four channels of a quad come from one image row (same r) -> one 16-byte load per output quad
+            // (streaming / evict-first stores were measured here and in cbn_act_fwd_rows: no difference on B200)
+            for (int xb = px0; xb < W; xb += U * PPB) {
+                float4 v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int xx = xb + u * PPB;
+                    v[u] = (xx < W && src[0] >= 0) ? __ldg(reinterpret_cast<const float4*>(x + src[0] + (long long)xx * C))
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int xx = xb + u * PPB;
+                    if (xx < W) orow[(long long)xx * Cp4] = v[u];
+                }
+            }
+            continue;
+        }
         for (int xb = px0; xb < W; xb += U * PPB) {
             float v[U][4];
 #pragma unroll
