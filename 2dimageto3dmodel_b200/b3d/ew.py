@@ -54,6 +54,36 @@ def fold_rows(x_nhwc, kh, pad_y, Cp):
     return _FoldRows.apply(x_nhwc, int(kh), int(pad_y), int(Cp))
 
 
+class _StemInput(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_nchw, pos, amount, mode):
+        x = dev(x_nchw.detach(), "x")
+        pos = dev(pos, "positions")
+        N, C1, H, W = x.shape
+        C2 = pos.shape[0]
+        if tuple(pos.shape[1:]) != (H, W):
+            raise B3DError(f"stem_input: positions {tuple(pos.shape)} do not match the image {tuple(x.shape)}")
+        out = torch.empty(N, H, W + 2 * amount, C1 + C2, device=x.device, dtype=torch.float32)
+        check(lib.b3d_stem_input_fwd(ptr(x), ptr(pos), ptr(out), N, C1, C2, H, W, amount, mode, stream_ptr(x)))
+        ctx.cfg = (amount, mode, x.shape, C2)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        amount, mode, shape, C2 = ctx.cfg
+        N, C1, H, W = shape
+        g = dev(g, "grad")
+        gx = torch.empty(shape, device=g.device, dtype=torch.float32)
+        check(lib.b3d_stem_input_bwd(ptr(g), ptr(gx), N, C1, C2, H, W, amount, mode, stream_ptr(g)))
+        return gx, None, None, None
+
+
+def stem_input(x_nchw, pos, amount, mode):
+    """pad_x(cat(x, pos broadcast over the batch), amount, mode) in one pass: x [N,C1,H,W] contiguous NCHW, pos [C2,H,W],
+    C1 + C2 in (4, 8) -> logically-NCHW view of the NHWC tensor [N,H,W + 2*amount,C1 + C2] (what the convolutions read)."""
+    return _StemInput.apply(x_nchw, pos, int(amount), int(mode)).permute(0, 3, 1, 2)
+
+
 def pad_x(x_nchw, amount, mode):
     """Padding along x of a logically-NCHW (channels-last) tensor; returns the same kind of tensor."""
     if amount == 0:

@@ -76,6 +76,68 @@ wrap_x_kernel(float4* __restrict__ buf, long long rows, int W, int C4, int a, in
     }
 }
 
+// Discriminator stem input in one pass (models/gan.py:102-111 `_with_positions` + the wrap-around padding in front of conv1,
+// :95-96): out[n, y, xo, :] = concat(x[n, :, y, xs], pos[:, y, xs]) with xs = the source column of padded column xo —
+// NCHW image planes + NCHW positional planes -> x-padded NHWC, instead of cat -> NCHW-to-NHWC copy -> pad (three passes).
+// One thread per output pixel: plane reads are coalesced along x, the pixel's C1 + C2 floats are written as float4s.
+template <int CT>
+__global__ void __launch_bounds__(NT)
+stem_input_fwd_kernel(const float* __restrict__ x, const float* __restrict__ pos, float4* __restrict__ out, int N, int C1, int H,
+                      int W, int a, int mode) {
+    const int Wo = W + 2 * a;
+    const long long total = (long long)N * H * Wo;
+    const size_t plane = (size_t)H * W;
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+        const int xo = (int)(i % Wo);
+        const long long r = i / Wo;
+        const int y = (int)(r % H), n = (int)(r / H);
+        const int xs = src_col(xo, a, W, mode);
+        const float* xp = x + (size_t)n * C1 * plane + (size_t)y * W + xs;
+        const float* pp = pos + (size_t)y * W + xs;
+        float v[CT];
+#pragma unroll
+        for (int c = 0; c < CT; ++c) v[c] = c < C1 ? __ldg(xp + (size_t)c * plane) : __ldg(pp + (size_t)(c - C1) * plane);
+#pragma unroll
+        for (int q = 0; q < CT / 4; ++q) out[i * (CT / 4) + q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+}
+// adjoint w.r.t. x: gx[n, c, y, xs] = sum of gout[n, y, xo, c] over the padded columns xo that read xs (c < C1)
+template <int CT>
+__global__ void __launch_bounds__(NT)
+stem_input_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gx, int N, int C1, int H, int W, int a, int mode) {
+    const int Wo = W + 2 * a;
+    const long long total = (long long)N * H * W;
+    const size_t plane = (size_t)H * W;
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+        const int xs = (int)(i % W);
+        const long long r = i / W;
+        const int y = (int)(r % H), n = (int)(r / H);
+        const float* g = gout + (size_t)r * Wo * CT;
+        float s[CT];
+#pragma unroll
+        for (int c = 0; c < CT; ++c) s[c] = c < C1 ? g[(size_t)(xs + a) * CT + c] : 0.f;
+        if (a > 0) {
+            if (mode == 0) {
+                if (xs == 0)
+                    for (int k = 0; k < a; ++k)
+                        for (int c = 0; c < C1; ++c) s[c] += g[(size_t)k * CT + c];
+                if (xs == W - 1)
+                    for (int k = 0; k < a; ++k)
+                        for (int c = 0; c < C1; ++c) s[c] += g[(size_t)(W + a + k) * CT + c];
+            } else {
+                if (xs < a)
+                    for (int c = 0; c < C1; ++c) s[c] += g[(size_t)(xs + a + W) * CT + c];
+                if (xs >= W - a)
+                    for (int c = 0; c < C1; ++c) s[c] += g[(size_t)(xs + a - W) * CT + c];
+            }
+        }
+        float* o = gx + (size_t)n * C1 * plane + (size_t)y * W + xs;
+#pragma unroll
+        for (int c = 0; c < CT; ++c)
+            if (c < C1) o[(size_t)c * plane] = s[c];
+    }
+}
+
 // Adjoint of the wrap fill, in place: pad-column gradients are added to the interior columns they were copied from.
 // mode 1 (circular): one thread per (row, pad column, channel quad); mode 0 (replicate): one thread per (row, side, quad).
 __global__ void __launch_bounds__(NT)
@@ -312,6 +374,32 @@ int b3d_wrap_x_inplace(float* buf, long long rows, int W, int C, int amount, int
     B3D_REQUIRE(buf, B3D_EINVAL, "b3d_wrap_x_inplace: null pointer");
     B3D_CHECK_ALIGNED(buf);
     wrap_x_kernel<<<grid_for(rows * 2 * amount * (C / 4)), NT, 0, (cudaStream_t)stream>>>((float4*)buf, rows, W, C / 4, amount, mode);
+    B3D_LAUNCH_OK();
+    return B3D_OK;
+}
+int b3d_stem_input_fwd(const float* x, const float* pos, float* out, int N, int C1, int C2, int H, int W, int amount, int mode,
+                       void* stream) {
+    B3D_REQUIRE(N >= 0 && C1 >= 1 && C2 >= 0 && H > 0 && W > 0 && amount >= 0 && amount <= W && (mode == 0 || mode == 1), B3D_EINVAL,
+                "b3d_stem_input_fwd: bad arguments");
+    B3D_REQUIRE(C1 + C2 == 8 || C1 + C2 == 4, B3D_EINVAL, "b3d_stem_input_fwd: C1 + C2 = %d must be 4 or 8", C1 + C2);
+    if (N == 0) return B3D_OK;
+    B3D_REQUIRE(x && out && (pos || C2 == 0), B3D_EINVAL, "b3d_stem_input_fwd: null pointer");
+    B3D_CHECK_ALIGNED(out);
+    const int g = grid_for((long long)N * H * (W + 2 * amount));
+    if (C1 + C2 == 8) stem_input_fwd_kernel<8><<<g, NT, 0, (cudaStream_t)stream>>>(x, pos, (float4*)out, N, C1, H, W, amount, mode);
+    else stem_input_fwd_kernel<4><<<g, NT, 0, (cudaStream_t)stream>>>(x, pos, (float4*)out, N, C1, H, W, amount, mode);
+    B3D_LAUNCH_OK();
+    return B3D_OK;
+}
+int b3d_stem_input_bwd(const float* gout, float* gx, int N, int C1, int C2, int H, int W, int amount, int mode, void* stream) {
+    B3D_REQUIRE(N >= 0 && C1 >= 1 && C2 >= 0 && H > 0 && W > 0 && amount >= 0 && amount <= W && (mode == 0 || mode == 1), B3D_EINVAL,
+                "b3d_stem_input_bwd: bad arguments");
+    B3D_REQUIRE(C1 + C2 == 8 || C1 + C2 == 4, B3D_EINVAL, "b3d_stem_input_bwd: C1 + C2 = %d must be 4 or 8", C1 + C2);
+    if (N == 0) return B3D_OK;
+    B3D_REQUIRE(gout && gx, B3D_EINVAL, "b3d_stem_input_bwd: null pointer");
+    const int g = grid_for((long long)N * H * W);
+    if (C1 + C2 == 8) stem_input_bwd_kernel<8><<<g, NT, 0, (cudaStream_t)stream>>>(gout, gx, N, C1, H, W, amount, mode);
+    else stem_input_bwd_kernel<4><<<g, NT, 0, (cudaStream_t)stream>>>(gout, gx, N, C1, H, W, amount, mode);
     B3D_LAUNCH_OK();
     return B3D_OK;
 }

@@ -21,7 +21,7 @@ from b3d import B3DError
 from b3d.bank import WeightBank
 from b3d.conv import conv2d as _tc_conv2d
 from b3d.conv import ActLink, conv2d_banked
-from b3d.ew import CIRCULAR, REPLICATE, CBNBatch, cbn_act_pad, pad_x
+from b3d.ew import CIRCULAR, REPLICATE, CBNBatch, cbn_act_pad, pad_x, stem_input
 from rendering.utils import adjust_poles, symmetrize_texture
 
 
@@ -105,16 +105,30 @@ class _DiscriminatorBase(nn.Module):
         if positional_embeddings:
             self.pos_emb = None
 
+    def _positions(self, x):
+        """[1,4,H,W] positional channels on x's device (computed for the first input's size, uploaded once)."""
+        if self.pos_emb is None:
+            self.pos_emb = torch.FloatTensor(positional_encoding(x.shape[2], x.shape[3])).unsqueeze(0)
+        dev_copy = getattr(self, '_pos_emb_dev', None)
+        if dev_copy is None or dev_copy.device != x.device:
+            dev_copy = self._pos_emb_dev = self.pos_emb.to(x.device)
+        return dev_copy
+
     def _with_positions(self, x, extra=()):
         parts = [x, *extra]
         if self.positional_embeddings:
-            if self.pos_emb is None:
-                self.pos_emb = torch.FloatTensor(positional_encoding(x.shape[2], x.shape[3])).unsqueeze(0)
-            dev_copy = getattr(self, '_pos_emb_dev', None)
-            if dev_copy is None or dev_copy.device != x.device:      # uploaded once, not per forward
-                dev_copy = self._pos_emb_dev = self.pos_emb.to(x.device)
-            parts.append(dev_copy.expand(x.shape[0], -1, -1, -1))
+            parts.append(self._positions(x).expand(x.shape[0], -1, -1, -1))
         return torch.cat(parts, dim=1) if len(parts) > 1 else x
+
+    def _stem_input(self, x, amount):
+        """pad_x(_with_positions(x), amount, circular) — as one kernel (b3d.ew.stem_input) for the 4 + 4 channel texture stems."""
+        if (self.circular and self.positional_embeddings and x.is_cuda and x.dtype == torch.float32 and x.shape[1] == 4
+                and not getattr(self, 'disable_stem_input', False)):
+            pos = self._positions(x)[0]
+            if tuple(pos.shape[1:]) == tuple(x.shape[2:]):
+                return stem_input(x.contiguous(), pos, amount, CIRCULAR)
+        x = self._with_positions(x)
+        return pad_x(x, amount, CIRCULAR) if self.circular else x
 
     def _links(self, n, W):
         """ActLinks for the first n conv -> conv hand-overs of the stack (the last padded activation also feeds the
@@ -218,10 +232,10 @@ class TextureDiscriminator(_DiscriminatorBase):
         if self.args.mask_output:
             with torch.no_grad():
                 mask = F.avg_pool2d(x[:, 3:4], 16 if self.stride_first else 8)
-        x = self._with_positions(x)
         p1, p2 = (1, 2) if self.circular else (0, 0)       # x padding of the 4x4 / 5x5 layers, applied by the producer
         l1, l2, l3 = self._links(3, W)
-        x = _conv_norm_act(self.conv1, None, self.padconv1(x), p1, W.get(prefix + "conv1"), link_out=l1)
+        x = self._stem_input(x, 1 if self.stride_first else 2)          # positional channels + the padding in front of conv1
+        x = _conv_norm_act(self.conv1, None, x, p1, W.get(prefix + "conv1"), link_out=l1)
         x = _conv_norm_act(self.conv2, self.bn2, x, p1, W.get(prefix + "conv2"), link_in=l1, link_out=l2)
         x = _conv_norm_act(self.conv3, self.bn3, x, p1, W.get(prefix + "conv3"), link_in=l2, link_out=l3)
         x = _conv_norm_act(self.conv4, self.bn4, x, p2, W.get(prefix + "conv4"), link_in=l3)

@@ -332,6 +332,13 @@ B3D_API int b3d_bank_backward(const void* layers, const void* items_dot, int n_d
  * ------------------------------------------------------------------------------------------ */
 B3D_API int b3d_pad_x_fwd(const float* x, float* out, long long rows, int W, int C, int amount, int mode, void* stream);
 B3D_API int b3d_pad_x_bwd(const float* gout, float* gx, long long rows, int W, int C, int amount, int mode, void* stream);
+/* Discriminator stem input (models/gan.py:102-111 `_with_positions`, :95-96 wrap-around padding, then conv1 :163-166) in one
+ * pass: out [N, H, W + 2*amount, C1 + C2] (NHWC) = x-padding (mode 0 replicate / 1 circular) of concat(x [N,C1,H,W] (NCHW
+ * planes), pos [C2,H,W] broadcast over N).  C1 + C2 = 4 or 8.  _bwd: gx [N,C1,H,W] = adjoint w.r.t. x (pos is a constant). */
+B3D_API int b3d_stem_input_fwd(const float* x, const float* pos, float* out, int N, int C1, int C2, int H, int W, int amount,
+                               int mode, void* stream);
+B3D_API int b3d_stem_input_bwd(const float* gout, float* gx, int N, int C1, int C2, int H, int W, int amount, int mode,
+                               void* stream);
 /* Thin-stem fold in front of the 5x5 discriminator stems (models/gan.py:163, :294 — 8 / 11 input channels): the kh
  * vertical taps become channels, out [N, H + 2*pad_y - kh + 1, W, Cp][.., r*C + c] = x [N,H,W,C][n, y + r - pad_y, x, c]
  * (zero rows = the y padding, zero channels up to Cp), so the tensor cores see kw taps of kh*C real channels.  _bwd is
