@@ -491,7 +491,9 @@ def conv2d_banked(x_nchw, lw, pad_y=0, stride=1, leaky=1.0, pad_out=0, pad_mode=
         if (lw.Cin == 8 and stride == 1 and not x_crop and Wout % 128 == 0 and x.shape[0] * x.shape[1] * (Wout // 128) >= 2 * 148
                 and not need_wgrad and not os.environ.get("B3D_FOLD_MATERIALIZE")):
             # 8-channel stems of wide images when no weight gradient is taken (generator step: the discriminator is frozen):
-            # the forward kernel folds the kh rows on the fly (TMA boxes of 4 rows x 8 channels), no folded tensor is written
+            # the forward kernel folds the kh rows on the fly (TMA boxes of 4 rows x 8 channels), no folded tensor is written.
+            # Same-box A/B inside the step graph: 41.21 ms with it, 41.45 ms with the materialised fold (B3D_FOLD_MATERIALIZE=1)
+            # — although a cold-cache ncu launch of the 32-byte-swizzle kernel alone looks slower than fold + conv.
             fold_raw = lw.kh
         else:
             from .ew import fold_rows

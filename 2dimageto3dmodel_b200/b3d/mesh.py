@@ -117,6 +117,34 @@ def render(verts, faces, uv, texture, ft=None, background=None, H=256, W=256):
     return _Render.apply(verts, uv, texture, faces, ft, background, int(H), int(W))
 
 
+class _FaceNormals(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, verts, faces):
+        v = dev(verts.detach(), "vertices")
+        fi = _i32(faces, "faces")
+        if v.dim() != 3 or v.shape[2] != 3 or fi.dim() != 2 or fi.shape[1] != 3:
+            raise B3DError(f"face_normals: vertices {tuple(v.shape)} / faces {tuple(fi.shape)}")
+        B, V, _ = v.shape
+        out = torch.empty(B, fi.shape[0], 3, device=v.device, dtype=torch.float32)
+        check(lib.b3d_face_normals_fwd(ptr(v), ptr(fi), B, V, fi.shape[0], ptr(out), stream_ptr(v)))
+        ctx.save_for_backward(v, fi)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        v, fi = ctx.saved_tensors
+        B, V, _ = v.shape
+        g = dev(g, "grad")
+        dv = torch.empty_like(v)
+        check(lib.b3d_face_normals_bwd(ptr(v), ptr(fi), ptr(g), B, V, fi.shape[0], ptr(dv), stream_ptr(v)))
+        return dv, None
+
+
+def face_normals(verts, faces):
+    """Unit face normals [B,F,3] of vertices [B,V,3] (MeshTemplate.compute_normals, rendering/mesh_template.py:113-123)."""
+    return _FaceNormals.apply(verts, faces)
+
+
 class _FlatLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, norms, ff):

@@ -57,6 +57,58 @@ flat_loss_bwd_kernel(const float* __restrict__ norms, const int32_t* __restrict_
     atomicAdd(db + 3 * f + 2, gz);
 }
 
+// Unit face normals of a deformed mesh (rendering/mesh_template.py:148-152 = reference :113-123):
+// n_f = normalize((v_b - v_a) x (v_c - v_a)), F.normalize semantics (n / max(|n|, 1e-12)).  One thread per (image, face):
+// replaces three gathers, two subtractions, cross, norm, clamp and a division (and ~35 launches of their autograd graph,
+// three of them sort-based index_put) by one launch each way.
+constexpr float NORMALIZE_EPS = 1e-12f;
+__global__ void __launch_bounds__(NT)
+face_normals_fwd_kernel(const float* __restrict__ verts, const int32_t* __restrict__ faces, int B, int V, int F,
+                        float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * NT + threadIdx.x;
+    if (i >= (long long)B * F) return;
+    const int f = (int)(i % F), b = (int)(i / F);
+    const float* vb = verts + (size_t)b * V * 3;
+    const int ia = faces[3 * f], ib = faces[3 * f + 1], ic = faces[3 * f + 2];
+    const float ax = vb[3 * ia], ay = vb[3 * ia + 1], az = vb[3 * ia + 2];
+    const float ux = vb[3 * ib] - ax, uy = vb[3 * ib + 1] - ay, uz = vb[3 * ib + 2] - az;
+    const float vx = vb[3 * ic] - ax, vy = vb[3 * ic + 1] - ay, vz = vb[3 * ic + 2] - az;
+    const float nx = uy * vz - uz * vy, ny = uz * vx - ux * vz, nz = ux * vy - uy * vx;
+    const float inv = 1.f / fmaxf(sqrtf(nx * nx + ny * ny + nz * nz), NORMALIZE_EPS);
+    out[3 * i] = nx * inv; out[3 * i + 1] = ny * inv; out[3 * i + 2] = nz * inv;
+}
+// dverts [B,V,3] (zeroed by the caller) += adjoint; g = d loss / d normals
+__global__ void __launch_bounds__(NT)
+face_normals_bwd_kernel(const float* __restrict__ verts, const int32_t* __restrict__ faces, const float* __restrict__ g, int B, int V,
+                        int F, float* __restrict__ dverts) {
+    const long long i = (long long)blockIdx.x * NT + threadIdx.x;
+    if (i >= (long long)B * F) return;
+    const int f = (int)(i % F), b = (int)(i / F);
+    const float* vb = verts + (size_t)b * V * 3;
+    float* db = dverts + (size_t)b * V * 3;
+    const int ia = faces[3 * f], ib = faces[3 * f + 1], ic = faces[3 * f + 2];
+    const float ax = vb[3 * ia], ay = vb[3 * ia + 1], az = vb[3 * ia + 2];
+    const float ux = vb[3 * ib] - ax, uy = vb[3 * ib + 1] - ay, uz = vb[3 * ib + 2] - az;
+    const float vx = vb[3 * ic] - ax, vy = vb[3 * ic + 1] - ay, vz = vb[3 * ic + 2] - az;
+    const float nx = uy * vz - uz * vy, ny = uz * vx - ux * vz, nz = ux * vy - uy * vx;
+    const float len = sqrtf(nx * nx + ny * ny + nz * nz);
+    float gx = g[3 * i], gy = g[3 * i + 1], gz = g[3 * i + 2];
+    if (len > NORMALIZE_EPS) {          // d(n / |n|) = (g - nh (nh . g)) / |n|
+        const float inv = 1.f / len;
+        const float hx = nx * inv, hy = ny * inv, hz = nz * inv;
+        const float d = hx * gx + hy * gy + hz * gz;
+        gx = (gx - hx * d) * inv; gy = (gy - hy * d) * inv; gz = (gz - hz * d) * inv;
+    } else {                            // clamped denominator: n / eps
+        gx /= NORMALIZE_EPS; gy /= NORMALIZE_EPS; gz /= NORMALIZE_EPS;
+    }
+    // n = u x v:  du = v x g,  dv = g x u
+    const float dux = vy * gz - vz * gy, duy = vz * gx - vx * gz, duz = vx * gy - vy * gx;
+    const float dvx = gy * uz - gz * uy, dvy = gz * ux - gx * uz, dvz = gx * uy - gy * ux;
+    atomicAdd(db + 3 * ib, dux); atomicAdd(db + 3 * ib + 1, duy); atomicAdd(db + 3 * ib + 2, duz);
+    atomicAdd(db + 3 * ic, dvx); atomicAdd(db + 3 * ic + 1, dvy); atomicAdd(db + 3 * ic + 2, dvz);
+    atomicAdd(db + 3 * ia, -(dux + dvx)); atomicAdd(db + 3 * ia + 1, -(duy + dvy)); atomicAdd(db + 3 * ia + 2, -(duz + dvz));
+}
+
 // image [B,H,W,3], alpha [B,H,W], target [B,4,H,W]; sse += sum of squared error; counts[b] = {inter, union}
 __global__ void __launch_bounds__(NT)
 rgba_mse_iou_fwd_kernel(const float* __restrict__ image, const float* __restrict__ alpha,
@@ -127,6 +179,22 @@ int b3d_flat_loss_bwd(const float* norms, const int32_t* ff, int B, int F, int K
     cudaStream_t st = (cudaStream_t)stream;
     B3D_CUDA_OK(cudaMemsetAsync(dnorms, 0, sizeof(float) * 3 * (size_t)B * F, st));
     flat_loss_bwd_kernel<<<dim3(b3d::ceil_div(F, NT), B), NT, 0, st>>>(norms, ff, B, F, K, gloss, dnorms);
+    B3D_LAUNCH_OK();
+    return B3D_OK;
+}
+
+int b3d_face_normals_fwd(const float* verts, const int32_t* faces, int B, int V, int F, float* normals, void* stream) {
+    B3D_REQUIRE(B > 0 && V > 0 && F > 0 && verts && faces && normals, B3D_EINVAL, "b3d_face_normals_fwd: bad arguments");
+    face_normals_fwd_kernel<<<b3d::ceil_div(B * F, NT), NT, 0, (cudaStream_t)stream>>>(verts, faces, B, V, F, normals);
+    B3D_LAUNCH_OK();
+    return B3D_OK;
+}
+int b3d_face_normals_bwd(const float* verts, const int32_t* faces, const float* gnormals, int B, int V, int F, float* dverts,
+                         void* stream) {
+    B3D_REQUIRE(B > 0 && V > 0 && F > 0 && verts && faces && gnormals && dverts, B3D_EINVAL, "b3d_face_normals_bwd: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    B3D_CUDA_OK(cudaMemsetAsync(dverts, 0, sizeof(float) * 3 * (size_t)B * V, st));
+    face_normals_bwd_kernel<<<b3d::ceil_div(B * F, NT), NT, 0, st>>>(verts, faces, gnormals, B, V, F, dverts);
     B3D_LAUNCH_OK();
     return B3D_OK;
 }

@@ -176,6 +176,13 @@ B3D_API int b3d_mesh_render_bwd(const float* fgeo, const float* fuv, const float
                                 const float* imwei, const float* d_imout, const float* d_improb,
                                 float* dfp2d, float* dfuv, float* dtex, void* stream);
 
+/* MeshTemplate.compute_normals                  rendering/mesh_template.py:113-123
+ * verts [B,V,3], faces [F,3] int32 -> normals [B,F,3] = normalize((v_b - v_a) x (v_c - v_a)) (F.normalize: n / max(|n|, 1e-12)).
+ * bwd: gnormals [B,F,3] -> dverts [B,V,3] (zeroed by the call, accumulated with atomics).  Vertex ids must lie in [0, V). */
+B3D_API int b3d_face_normals_fwd(const float* verts, const int32_t* faces, int B, int V, int F, float* normals, void* stream);
+B3D_API int b3d_face_normals_bwd(const float* verts, const int32_t* faces, const float* gnormals, int B, int V, int F,
+                                 float* dverts, void* stream);
+
 /* loss_flat(mesh, norms)                        utils/losses.py:5-17
  * norms [B,F,3]; ff [F,K] int32 face adjacency (negative ids index from the end, as torch does);
  * loss [1] out (zeroed by the call).  bwd: gloss [1] upstream gradient -> dnorms [B,F,3].        */
