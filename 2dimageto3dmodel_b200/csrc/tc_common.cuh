@@ -102,10 +102,60 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// ---- MMA issue from a CONVERGENT warp -------------------------------------------------------------------------------
+// ncu (profiles/r2_h_issue_loop.md): with the issue loop inside `if (lane == 0)` every loop variable lives in vector
+// registers, so ptxas wraps each tcgen05.mma in an ELECT / R2UR.BROADCAST "waterfall" loop to move the TMEM address into a
+// uniform register and rebuilds both descriptors with shift / mask / or chains: ~13 SASS instructions and a branch per MMA.
+// At N = 64 an MMA occupies the tensor pipe for ~53 cycles but the issuing thread needed ~95 — the 64-wide layers were bound
+// by instruction issue, not by tensor, L2 or shared-memory bandwidth.  Fix: all 32 lanes of the MMA warp walk the loop
+// (warp-uniform control flow: ptxas keeps the loop state, the descriptors and the TMEM addresses in UNIFORM registers), the
+// TMEM base goes through a warp reduction (REDUX writes a uniform register), descriptors are advanced with one integer add
+// on their low word, and only an elected lane executes the tcgen05 instructions: 3.4 instructions per MMA.
+__device__ __forceinline__ uint32_t elect_one() {          // 1 in exactly one lane of the (fully active) warp
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred;
+}
+__device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }   // same v in all lanes
+// Descriptor words: the high word (stride offset, version, layout type) does not depend on the address; the low word holds
+// the start address in 16-byte units in bits [0,14) (+ the leading byte offset in [16,30)), so the descriptor of
+// `addr + off` is `lo(addr) + (off >> 4)` — no carry out of the field for any shared-memory address.
+__device__ __forceinline__ uint32_t desc_lo(uint64_t d) { return (uint32_t)d; }
+__device__ __forceinline__ uint32_t desc_hi(uint64_t d) { return (uint32_t)(d >> 32); }
+__device__ __forceinline__ void umma_tf32_words_if(uint32_t on, uint32_t tmem_d, uint32_t lo_a, uint32_t hi_a, uint32_t lo_b,
+                                                   uint32_t hi_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 p, %6, 0;\n"
+        "setp.ne.b32 q, %7, 0;\n"
+        "mov.b64 da, {%1, %2};\n"
+        "mov.b64 db, {%3, %4};\n"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(lo_a), "r"(hi_a), "r"(lo_b), "r"(hi_b), "r"(idesc), "r"(accumulate), "r"(on)
+        : "memory");
+}
 // arrive on an mbarrier when all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
+}
+__device__ __forceinline__ void umma_commit_if(uint32_t on, uint64_t* bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "setp.ne.b32 q, %1, 0;\n"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(on)
+        : "memory");
 }
 // 32 lanes x 32 columns of fp32: thread t of the warp gets lane (lane_base + t), columns col .. col+31
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {

@@ -300,35 +300,36 @@ conv_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = tc::umma_idesc_tf32(BM, BN, false, WMN);
-            uint32_t git = 0, j = 0;
-            for (int w = blockIdx.x; w < work_items; w += gridDim.x, ++j) {
-                const uint32_t buf = j & 1;
-                tc::mbar_wait(acc_empty + buf, ((j >> 1) & 1) ^ 1);      // the epilogue has drained this buffer
+        // convergent issue loop (tc_common.cuh "MMA issue from a CONVERGENT warp"): all lanes walk it, one elected lane issues
+        const uint32_t leader = tc::elect_one();
+        const uint32_t tmem_u = tc::warp_uniform(tmem_acc);
+        constexpr uint32_t idesc = tc::umma_idesc_tf32(BM, BN, false, WMN);
+        uint32_t git = 0, j = 0;
+        for (int w = blockIdx.x; w < work_items; w += gridDim.x, ++j) {
+            const uint32_t buf = j & 1;
+            tc::mbar_wait(acc_empty + buf, ((j >> 1) & 1) ^ 1);      // the epilogue has drained this buffer
+            tc::tc_fence_after();
+            const uint32_t acc = tmem_u + buf * (R * BN);
+            for (int it = 0; it < KI; ++it, ++git) {
+                const int s = git % STAGES, ph = (git / STAGES) & 1;
+                tc::mbar_wait(full + s, ph);
                 tc::tc_fence_after();
-                const uint32_t acc = tmem_acc + buf * (R * BN);
-                for (int it = 0; it < KI; ++it, ++git) {
-                    const int s = git % STAGES, ph = (git / STAGES) & 1;
-                    tc::mbar_wait(full + s, ph);
-                    tc::tc_fence_after();
-                    const uint32_t a = tc::smem_u32(base + s * S::STAGE_BYTES);
-                    const uint32_t b = a + S::A_BYTES;
+                const uint32_t a = tc::smem_u32(base + s * S::STAGE_BYTES);
+                const uint32_t b = a + S::A_BYTES;
+                // on-the-fly fold: K step k = image row k of the 4-row box, a [128 px][32 B] tile of its own (32-byte swizzle)
+                const uint64_t da0 = p.fold ? tc::umma_desc_k32(a) : tc::umma_desc_k128(a);
+                const uint64_t db0 = WMN ? tc::umma_desc_mn128(b, p.dbg_lbo, p.dbg_sbo, p.dbg_lt) : tc::umma_desc_k128(b);
+                const uint32_t astep = p.fold ? (BM * 32) >> 4 : (UMMA_K * 4) >> 4, bstep = WMN ? 1024 >> 4 : (UMMA_K * 4) >> 4;
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t db = WMN ? tc::umma_desc_mn128(b + k * 1024, p.dbg_lbo, p.dbg_sbo, p.dbg_lt) : tc::umma_desc_k128(b + k * UMMA_K * 4);
+                for (int k = 0; k < BK / UMMA_K; ++k) {
 #pragma unroll
-                        for (int r = 0; r < R; ++r) {
-                            // on-the-fly fold: K step k = image row k of the 4-row box, a [128 px][32 B] tile of its own
-                            const uint64_t da = p.fold ? tc::umma_desc_k32(a + r * S::A_TILE + k * (BM * 32))
-                                                       : tc::umma_desc_k128(a + r * S::A_TILE + k * UMMA_K * 4);
-                            tc::umma_tf32(acc + r * BN, da, db, idesc, (it | k) ? 1u : 0u);
-                        }
-                    }
-                    tc::umma_commit(empty + s);
+                    for (int r = 0; r < R; ++r)
+                        tc::umma_tf32_words_if(leader, acc + r * BN, tc::desc_lo(da0) + r * (S::A_TILE >> 4) + k * astep, tc::desc_hi(da0),
+                                               tc::desc_lo(db0) + k * bstep, tc::desc_hi(db0), idesc, (it | k) ? 1u : 0u);
                 }
-                tc::umma_commit(acc_full + buf);
+                tc::umma_commit_if(leader, empty + s);
             }
+            tc::umma_commit_if(leader, acc_full + buf);
         }
     } else {
         const int q = warp & 3;

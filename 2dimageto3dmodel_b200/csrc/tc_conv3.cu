@@ -116,36 +116,38 @@ conv_rowwin_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = tc::umma_idesc_tf32(BM, BN, false, false);
-            uint32_t git = 0, j = 0;
-            for (int w = blockIdx.x; w < p.work; w += gridDim.x, ++j) {
-                const uint32_t buf = j & 1;
-                tc::mbar_wait(acc_empty + buf, ((j >> 1) & 1) ^ 1);
+        // convergent issue loop (tc_common.cuh "MMA issue from a CONVERGENT warp"): all lanes walk it, one elected lane issues
+        const uint32_t leader = tc::elect_one();
+        const uint32_t tmem_u = tc::warp_uniform(tmem_acc);
+        constexpr uint32_t idesc = tc::umma_idesc_tf32(BM, BN, false, false);
+        uint32_t git = 0, j = 0;
+        for (int w = blockIdx.x; w < p.work; w += gridDim.x, ++j) {
+            const uint32_t buf = j & 1;
+            tc::mbar_wait(acc_empty + buf, ((j >> 1) & 1) ^ 1);
+            tc::tc_fence_after();
+            const uint32_t acc = tmem_u + buf * (R * BN);
+            for (int it = 0; it < KI; ++it, ++git) {
+                const int s = git % STAGES, ph = (git / STAGES) & 1;
+                tc::mbar_wait(full + s, ph);
                 tc::tc_fence_after();
-                const uint32_t acc = tmem_acc + buf * (R * BN);
-                for (int it = 0; it < KI; ++it, ++git) {
-                    const int s = git % STAGES, ph = (git / STAGES) & 1;
-                    tc::mbar_wait(full + s, ph);
-                    tc::tc_fence_after();
-                    const uint32_t a = tc::smem_u32(base + s * S::STAGE_BYTES);
-                    const uint32_t b = a + R * S::WIN_STRIDE;
+                const uint32_t a = tc::smem_u32(base + s * S::STAGE_BYTES);
+                const uint64_t da0 = tc::umma_desc_k128(a), db0 = tc::umma_desc_k128(a + R * S::WIN_STRIDE);
+                const uint32_t hi = tc::desc_hi(da0);
 #pragma unroll
-                    for (int t = 0; t < KW; ++t) {
-                        const uint32_t arow = (uint32_t)p.shift[t] * 128u;
+                for (int t = 0; t < KW; ++t) {
+                    const uint32_t lat = tc::desc_lo(da0) + (uint32_t)p.shift[t] * (128u >> 4);     // window row shift of tap t
 #pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k) {
-                            const uint64_t db = tc::umma_desc_k128(b + t * (BN * 128) + k * UMMA_K * 4);
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint32_t lb = tc::desc_lo(db0) + ((t * (BN * 128) + k * UMMA_K * 4) >> 4);
 #pragma unroll
-                            for (int r = 0; r < R; ++r)
-                                tc::umma_tf32(acc + r * BN, tc::umma_desc_k128(a + r * S::WIN_STRIDE + arow + k * UMMA_K * 4), db, idesc,
-                                              (it | t | k) ? 1u : 0u);
-                        }
+                        for (int r = 0; r < R; ++r)
+                            tc::umma_tf32_words_if(leader, acc + r * BN, lat + ((r * S::WIN_STRIDE + k * UMMA_K * 4) >> 4), hi, lb, hi, idesc,
+                                                   (it | t | k) ? 1u : 0u);
                     }
-                    tc::umma_commit(empty + s);
                 }
-                tc::umma_commit(acc_full + buf);
+                tc::umma_commit_if(leader, empty + s);
             }
+            tc::umma_commit_if(leader, acc_full + buf);
         }
     } else {
         const int q = warp & 3;
