@@ -525,24 +525,25 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = tc::umma_idesc_tf32(BM, BN, true, true);
-            for (int it = 0; it < KI; ++it) {
-                const int st = it % STAGES, ph = (it / STAGES) & 1;
-                tc::mbar_wait(full + st, ph);
-                tc::tc_fence_after();
-                const uint32_t a = tc::smem_u32(base + st * S::STAGE_BYTES);
-                const uint32_t b = a + S::A_BYTES;
+        // convergent issue loop (tc_common.cuh "MMA issue from a CONVERGENT warp"): all lanes walk it, one elected lane issues
+        const uint32_t leader = tc::elect_one();
+        const uint32_t tmem_u = tc::warp_uniform(tmem_acc);
+        constexpr uint32_t idesc = tc::umma_idesc_tf32(BM, BN, true, true);
+        for (int it = 0; it < KI; ++it) {
+            const int st = it % STAGES, ph = (it / STAGES) & 1;
+            tc::mbar_wait(full + st, ph);
+            tc::tc_fence_after();
+            const uint32_t a = tc::smem_u32(base + st * S::STAGE_BYTES);
+            const uint64_t da0 = tc::umma_desc_mn128(a, BLK, 512), db0 = tc::umma_desc_mn128(a + S::A_BYTES, XBLK, 512);
 #pragma unroll
-                for (int t = 0; t < T; ++t)
+            for (int t = 0; t < T; ++t)
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k)      // 8 pixel rows (two 4-row swizzle atoms, 1024 B) per MMA
-                        tc::umma_tf32(tmem_acc + t * BN, tc::umma_desc_mn128(a + k * 1024, BLK, 512),
-                                      tc::umma_desc_mn128(b + (t + 8 * k) * 128, XBLK, 512), idesc, (it | k) ? 1u : 0u);
-                tc::umma_commit(empty + st);
-            }
-            tc::umma_commit(acc_full);
+                for (int k = 0; k < BK / UMMA_K; ++k)      // 8 pixel rows (two 4-row swizzle atoms, 1024 B) per MMA
+                    tc::umma_tf32_words_if(leader, tmem_u + t * BN, tc::desc_lo(da0) + k * (1024 >> 4), tc::desc_hi(da0),
+                                           tc::desc_lo(db0) + (((t + 8 * k) * 128) >> 4), tc::desc_hi(db0), idesc, (it | k) ? 1u : 0u);
+            tc::umma_commit_if(leader, empty + st);
         }
+        tc::umma_commit_if(leader, acc_full);
     } else if (KI > 0) {
         const int q = warp & 3;
         const int co = co0 + q * 32 + lane;

@@ -116,31 +116,34 @@ conv_flat_tf32_kernel(const __grid_constant__ CUtensorMap tmap_main, const __gri
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = tc::umma_idesc_tf32(BM, BN);
-            int it = 0;
-            for (int ks = 0; ks < p.kslices; ++ks) {
-                const int sa = ks & 1;
-                tc::mbar_wait(a_full + sa, (ks >> 1) & 1);
-                const uint32_t a0 = tc::smem_u32(a_buf + sa * a_stage_bytes);
-                for (int t = 0; t < p.ntaps; ++t, ++it) {
-                    const int s = it % NB, ph = (it / NB) & 1;
-                    tc::mbar_wait(b_full + s, ph);
-                    tc::tc_fence_after();
-                    const uint32_t b0 = tc::smem_u32(b_buf + s * B_BYTES);
-                    for (int j = 0; j < p.R; ++j) {
-                        const uint32_t arow = a0 + (uint32_t)(p.off[t] + j * BM) * 128u;
+        // convergent issue loop (tc_common.cuh "MMA issue from a CONVERGENT warp"): all lanes walk it, one elected lane issues
+        const uint32_t leader = tc::elect_one();
+        const uint32_t tmem_u = tc::warp_uniform(tmem_acc);
+        constexpr uint32_t idesc = tc::umma_idesc_tf32(BM, BN);
+        int it = 0;
+        for (int ks = 0; ks < p.kslices; ++ks) {
+            const int sa = ks & 1;
+            tc::mbar_wait(a_full + sa, (ks >> 1) & 1);
+            const uint32_t a0 = tc::smem_u32(a_buf + sa * a_stage_bytes);
+            for (int t = 0; t < p.ntaps; ++t, ++it) {
+                const int s = it % NB, ph = (it / NB) & 1;
+                tc::mbar_wait(b_full + s, ph);
+                tc::tc_fence_after();
+                const uint64_t db0 = tc::umma_desc_k128(tc::smem_u32(b_buf + s * B_BYTES));
+                for (int j = 0; j < p.R; ++j) {
+                    const uint32_t arow = a0 + (uint32_t)(p.off[t] + j * BM) * 128u;
 #pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k)
-                            tc::umma_tf32(tmem_acc + j * BN, desc_k128_at(arow + k * UMMA_K * 4, p.use_base_offset),
-                                          tc::umma_desc_k128(b0 + k * UMMA_K * 4), idesc, (ks | t | k) ? 1u : 0u);
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t da = desc_k128_at(arow + k * UMMA_K * 4, p.use_base_offset);
+                        tc::umma_tf32_words_if(leader, tmem_u + j * BN, tc::desc_lo(da), tc::desc_hi(da),
+                                               tc::desc_lo(db0) + ((k * UMMA_K * 4) >> 4), tc::desc_hi(db0), idesc, (ks | t | k) ? 1u : 0u);
                     }
-                    tc::umma_commit(b_empty + s);
                 }
-                tc::umma_commit(a_empty + sa);
+                tc::umma_commit_if(leader, b_empty + s);
             }
-            tc::umma_commit(acc_full);
+            tc::umma_commit_if(leader, a_empty + sa);
         }
+        tc::umma_commit_if(leader, acc_full);
     } else {
         const int q = warp & 3;
         tc::mbar_wait(acc_full, 0);
