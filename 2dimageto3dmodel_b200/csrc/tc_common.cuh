@@ -76,6 +76,51 @@ __device__ __forceinline__ void tma_load_5d(void* smem, const CUtensorMap* m, ui
         : "memory");
 }
 
+// The same, issued only where `on` is non-zero: the producer warps run their loops convergently too (see "MMA issue from a
+// CONVERGENT warp" below: coordinates, shared-memory addresses and barrier addresses stay in uniform registers, no per-load
+// ELECT / R2UR waterfall) and one elected lane performs the arrive and the bulk-tensor copies.
+__device__ __forceinline__ void mbar_arrive_expect_tx_if(uint32_t on, uint64_t* bar, uint32_t bytes) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "setp.ne.b32 q, %2, 0;\n"
+        "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(bytes), "r"(on)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_if(uint32_t on, void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "setp.ne.b32 q, %6, 0;\n"
+        "@q cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+        "}\n" ::"r"(smem_u32(smem)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(on)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_if(uint32_t on, void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                               int c3) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "setp.ne.b32 q, %7, 0;\n"
+        "@q cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n"
+        "}\n" ::"r"(smem_u32(smem)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(on)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_if(uint32_t on, void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                               int c3, int c4) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "setp.ne.b32 q, %8, 0;\n"
+        "@q cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n"
+        "}\n" ::"r"(smem_u32(smem)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(on)
+        : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------- tcgen05
 template <uint32_t COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {     // one full warp

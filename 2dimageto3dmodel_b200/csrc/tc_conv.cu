@@ -260,7 +260,8 @@ conv_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
     const int KI = p.ntaps * p.kslices;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {
+            const uint32_t leader = tc::elect_one();          // convergent producer loop: one elected lane arrives / issues the copies
             uint32_t git = 0;
             for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
                 // classes are the fastest index: the CTAs that work on the same pixel tiles at the same time share them in L2
@@ -282,19 +283,19 @@ conv_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
                     const int tap = it / p.kslices, ks = it % p.kslices;
                     unsigned char* a = base + s * S::STAGE_BYTES;
                     unsigned char* b = a + S::A_BYTES;
-                    tc::mbar_arrive_expect_tx(full + s, S::STAGE_BYTES);
+                    tc::mbar_arrive_expect_tx_if(leader, full + s, S::STAGE_BYTES);
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         if (p.fold)     // box {8 ch, BW px, 4 rows}: lands as [row][pixel][8 floats] = four 32-byte-swizzled K-step tiles
-                            tc::tma_load_4d(a + r * S::A_TILE, &tmap_x, full + s, 0, x0[r] + p.dx[tb + tap], y0[r] + p.fold_y0 + 4 * ks, n0[r]);
+                            tc::tma_load_4d_if(leader, a + r * S::A_TILE, &tmap_x, full + s, 0, x0[r] + p.dx[tb + tap], y0[r] + p.fold_y0 + 4 * ks, n0[r]);
                         else
-                            tc::tma_load_4d(a + r * S::A_TILE, &tmap_x, full + s, ks * BK, p.sx * x0[r] + p.dx[tb + tap], p.sy * y0[r] + p.dy[tb + tap], n0[r]);
+                            tc::tma_load_4d_if(leader, a + r * S::A_TILE, &tmap_x, full + s, ks * BK, p.sx * x0[r] + p.dx[tb + tap], p.sy * y0[r] + p.dy[tb + tap], n0[r]);
                     }
                     if constexpr (WMN) {
 #pragma unroll
-                        for (int nb = 0; nb < BN / 32; ++nb) tc::tma_load_3d(b + nb * 4096, &tmap_w, full + s, c0 + nb * 32, ks * BK, p.wtap[tb + tap]);
+                        for (int nb = 0; nb < BN / 32; ++nb) tc::tma_load_3d_if(leader, b + nb * 4096, &tmap_w, full + s, c0 + nb * 32, ks * BK, p.wtap[tb + tap]);
                     } else {
-                        tc::tma_load_3d(b, &tmap_w, full + s, ks * BK, c0, p.wtap[tb + tap]);
+                        tc::tma_load_3d_if(leader, b, &tmap_w, full + s, ks * BK, c0, p.wtap[tb + tap]);
                     }
                 }
             }
@@ -503,7 +504,8 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
     const uint32_t tmem_acc = *tmem_slot;
 
     if (warp == 0 || warp == 6) {           // warp 0 streams dY, warp 6 streams X (two TMA issue lanes, one barrier)
-        if (lane == 0) {
+        {
+            const uint32_t leader = tc::elect_one();          // convergent producer loops: one elected lane arrives / issues the copies
             for (int it = 0; it < KI; ++it) {
                 const int st = it % STAGES, ph = (it / STAGES) & 1;
                 tc::mbar_wait(empty + st, ph ^ 1);
@@ -513,14 +515,14 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
                 unsigned char* a = base + st * S::STAGE_BYTES;
                 // channels are split as (32, C/32) in the tensor maps: ONE 5-D box lands all 32-channel blocks back to back
                 if (warp == 0) {
-                    tc::mbar_arrive_expect_tx(full + st, S::STAGE_BYTES);
-                    tc::tma_load_5d(a, &tmap_dy, full + st, 0, x0, y0, n, co0 / 32);
+                    tc::mbar_arrive_expect_tx_if(leader, full + st, S::STAGE_BYTES);
+                    tc::tma_load_5d_if(leader, a, &tmap_dy, full + st, 0, x0, y0, n, co0 / 32);
                 } else if (p.fold) {      // (c, row, x, n) boxes of 4 rows x 8 channels per pixel: one per 32-"channel" block
 #pragma unroll
                     for (int blk = 0; blk < BN / 32; ++blk)
-                        tc::tma_load_4d(a + S::A_BYTES + blk * XBLK, &tmap_x, full + st, 0, y0 - p.pad_y + 4 * (ci0 / 32 + blk), x0 + s + p.xoff, n);
+                        tc::tma_load_4d_if(leader, a + S::A_BYTES + blk * XBLK, &tmap_x, full + st, 0, y0 - p.pad_y + 4 * (ci0 / 32 + blk), x0 + s + p.xoff, n);
                 } else {
-                    tc::tma_load_5d(a + S::A_BYTES, &tmap_x, full + st, 0, p.st * x0 + s + p.xoff, p.st * y0 + r - p.pad_y, n, ci0 / 32);
+                    tc::tma_load_5d_if(leader, a + S::A_BYTES, &tmap_x, full + st, 0, p.st * x0 + s + p.xoff, p.st * y0 + r - p.pad_y, n, ci0 / 32);
                 }
             }
         }

@@ -86,7 +86,8 @@ conv_rowwin_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     const int KI = p.kh * p.kslices;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {
+            const uint32_t leader = tc::elect_one();          // convergent producer loop: one elected lane arrives / issues the copies
             uint32_t git = 0;
             for (int w = blockIdx.x; w < p.work; w += gridDim.x) {
                 // classes are the fastest index: CTAs working on the same pixel tiles at the same time share them in L2
@@ -107,11 +108,11 @@ conv_rowwin_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
                     tc::mbar_wait(empty + s, ph ^ 1);
                     const int fr = it / p.kslices, ks = it % p.kslices;
                     unsigned char* a = base + s * S::STAGE_BYTES;
-                    tc::mbar_arrive_expect_tx(full + s, S::TX_BYTES);
+                    tc::mbar_arrive_expect_tx_if(leader, full + s, S::TX_BYTES);
 #pragma unroll
                     for (int r = 0; r < R; ++r)
-                        tc::tma_load_4d(a + r * S::WIN_STRIDE, &tmap_x, full + s, ks * BK, x0[r] + p.dx0, y0[r] + p.dy[cls][fr], n0[r]);
-                    tc::tma_load_3d(a + R * S::WIN_STRIDE, &tmap_w, full + s, ks * BK, c0, p.wtap0[cls][fr]);
+                        tc::tma_load_4d_if(leader, a + r * S::WIN_STRIDE, &tmap_x, full + s, ks * BK, x0[r] + p.dx0, y0[r] + p.dy[cls][fr], n0[r]);
+                    tc::tma_load_3d_if(leader, a + R * S::WIN_STRIDE, &tmap_w, full + s, ks * BK, c0, p.wtap0[cls][fr]);
                 }
             }
         }
