@@ -237,6 +237,35 @@ __device__ __forceinline__ float scaled(float S, bool has_scale, float sc) {
 
 constexpr int TILE_THREADS = 512;
 
+// One sorted record (gz, gy, gx, bits(index)) splatted into a shared patch covering cells [cy0, cy1] x [cx0, cx1]
+// (row pitch `pitch`), depth-major.  zlo / zhi [ncol]: occupied depth range of every column (see splat_bins).
+__device__ __forceinline__ void splat_record(const float4 g, int cy0, int cy1, int cx0, int cx1, int pitch, int ncol,
+                                             int mode, float* A, int* zlo, int* zhi) {
+    const float fzf = floorf(g.x), fyf = floorf(g.y), fxf = floorf(g.z);
+    const int ly = (int)fyf - cy0, lx = (int)fxf - cx0;
+    if (ly < -1 || ly > cy1 - cy0 || lx < -1 || lx > cx1 - cx0) return;
+    const int fz = (int)fzf;
+    float wz[2], wy[2], wx[2];
+    axis_weights(g.x, fzf, mode, wz[0], wz[1]);
+    axis_weights(g.y, fyf, mode, wy[0], wy[1]);
+    axis_weights(g.z, fxf, mode, wx[0], wx[1]);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int cy = ly + j;
+        if (cy < 0 || cy > cy1 - cy0) continue;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int cx = lx + k;
+            if (cx < 0 || cx > cx1 - cx0) continue;
+            atomicMin(&zlo[cy * pitch + cx], fz);
+            atomicMax(&zhi[cy * pitch + cx], fz + 1);
+#pragma unroll
+            for (int i = 0; i < 2; ++i)     // trilinear_interpolation.py:40-41: (gz_i*gy_j)*gx_k
+                atomicAdd(&A[(fz + i) * ncol + cy * pitch + cx], mul(mul(wz[i], wy[j]), wx[k]));
+        }
+    }
+}
+
 // Splat the points of the bins overlapping base cells [cy0-1, cy1] x [cx0-1, cx1] into a shared patch
 // covering cells [cy0, cy1] x [cx0, cx1] (row pitch `pitch`), depth-major.
 // zlo / zhi [ncol] (initialised to V / -1 by the caller): occupied depth range of every column — cells outside it are
@@ -248,32 +277,96 @@ __device__ __forceinline__ void splat_bins(const float4* __restrict__ sorted, co
     const int bx_lo = max(cx0 - 1, 0) / BIN_X, bx_hi = min(cx1 / BIN_X, nbx - 1);
     for (int by = by_lo; by <= by_hi; ++by) {
         const int lo = bs[by * nbx + bx_lo], hi = bs[by * nbx + bx_hi + 1];
-        for (int n = lo + threadIdx.x; n < hi; n += TILE_THREADS) {
-            const float4 g = __ldg(sorted + n);
-            const float fzf = floorf(g.x), fyf = floorf(g.y), fxf = floorf(g.z);
-            const int ly = (int)fyf - cy0, lx = (int)fxf - cx0;
-            if (ly < -1 || ly > cy1 - cy0 || lx < -1 || lx > cx1 - cx0) continue;
-            const int fz = (int)fzf;
-            float wz[2], wy[2], wx[2];
-            axis_weights(g.x, fzf, mode, wz[0], wz[1]);
-            axis_weights(g.y, fyf, mode, wy[0], wy[1]);
-            axis_weights(g.z, fxf, mode, wx[0], wx[1]);
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int cy = ly + j;
-                if (cy < 0 || cy > cy1 - cy0) continue;
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const int cx = lx + k;
-                    if (cx < 0 || cx > cx1 - cx0) continue;
-                    atomicMin(&zlo[cy * pitch + cx], fz);
-                    atomicMax(&zhi[cy * pitch + cx], fz + 1);
-#pragma unroll
-                    for (int i = 0; i < 2; ++i)     // trilinear_interpolation.py:40-41: (gz_i*gy_j)*gx_k
-                        atomicAdd(&A[(fz + i) * ncol + cy * pitch + cx], mul(mul(wz[i], wy[j]), wx[k]));
-                }
-            }
+        for (int n = lo + threadIdx.x; n < hi; n += TILE_THREADS)
+            splat_record(__ldg(sorted + n), cy0, cy1, cx0, cx1, pitch, ncol, mode, A, zlo, zhi);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// TMA staging of the bin records (B3D_PC_TMA).  After the counting sort the records of the bins [bx_lo, bx_hi] of one bin
+// row are contiguous, so the records a patch needs are a handful of contiguous runs: one elected thread streams them into
+// a two-stage shared-memory ring with cp.async.bulk (the TMA's 1-D bulk copy, completion counted in bytes on an mbarrier)
+// and the CTA consumes them from shared memory.  The first two stages are issued BEFORE the patch is zero-filled, so the
+// global-memory latency of the records hides behind the 64-190 KB of shared-memory stores instead of following them.
+// ----------------------------------------------------------------------------------------------
+constexpr int STG_REC = 512;       // records per stage (8 KB): one per thread
+constexpr int STG_N = 2;
+constexpr size_t STG_BYTES = (size_t)STG_N * STG_REC * sizeof(float4);
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "PC_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra PC_WAIT_DONE;\n"
+        "bra PC_WAIT_LOOP;\n"
+        "PC_WAIT_DONE:\n"
+        "}\n" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+
+// The records of bins [bx_lo, bx_hi] of bin rows [by_lo, by_hi], as one sequence cut into chunks of STG_REC.
+struct BinStream {
+    const float4* sp;
+    const int32_t* bs;
+    float4* stg;          // [STG_N][STG_REC]
+    uint64_t* bars;       // [STG_N]
+    int nbx, by_lo, by_hi, bx_lo, bx_hi, total, nchunks;
+
+    __device__ __forceinline__ void open(const float4* sp_, const int32_t* bs_, float4* stg_, uint64_t* bars_, int nbx_, int by_lo_,
+                                         int by_hi_, int bx_lo_, int bx_hi_) {
+        sp = sp_; bs = bs_; stg = stg_; bars = bars_; nbx = nbx_;
+        by_lo = by_lo_; by_hi = by_hi_; bx_lo = bx_lo_; bx_hi = bx_hi_;
+        total = 0;
+        for (int by = by_lo; by <= by_hi; ++by) total += bs[by * nbx + bx_hi + 1] - bs[by * nbx + bx_lo];
+        nchunks = (total + STG_REC - 1) / STG_REC;
+    }
+    __device__ __forceinline__ int count(int c) const { return min(STG_REC, total - c * STG_REC); }
+    // one thread: bulk copies of chunk c into stage c % STG_N (one copy per bin row the chunk intersects)
+    __device__ __forceinline__ void issue(int c) const {
+        const int c0 = c * STG_REC, c1 = min(c0 + STG_REC, total);
+        uint64_t* bar = bars + (c % STG_N);
+        float4* dst = stg + (c % STG_N) * STG_REC;
+        mbar_expect_tx(bar, (uint32_t)(c1 - c0) * (uint32_t)sizeof(float4));
+        int pos = 0;
+        for (int by = by_lo; by <= by_hi && pos < c1; ++by) {
+            const int lo = bs[by * nbx + bx_lo], n = bs[by * nbx + bx_hi + 1] - lo;
+            const int a = max(c0, pos), e = min(c1, pos + n);
+            if (a < e) bulk_g2s(dst + (a - c0), sp + lo + (a - pos), (uint32_t)(e - a) * (uint32_t)sizeof(float4), bar);
+            pos += n;
         }
+    }
+    __device__ __forceinline__ void prefetch() const {       // one thread: fill the ring
+        for (int c = 0; c < nchunks && c < STG_N; ++c) issue(c);
+    }
+};
+
+// Consume a prefetched BinStream: fn(record) for every record, all threads of the CTA taking part.  `parity` carries the
+// mbarrier phase bits of the stages from one stream to the next (bit s = the phase the next wait on stage s expects).
+template <typename F>
+__device__ __forceinline__ void stream_consume(const BinStream& st, uint32_t& parity, F fn) {
+    for (int c = 0; c < st.nchunks; ++c) {
+        const int s = c % STG_N;
+        mbar_wait(st.bars + s, (parity >> s) & 1u);
+        parity ^= 1u << s;
+        const int cnt = st.count(c);
+        for (int i = threadIdx.x; i < cnt; i += TILE_THREADS) fn(st.stg[s * STG_REC + i]);
+        __syncthreads();                                     // every thread is done with stage s before it is refilled
+        if (threadIdx.x == 0 && c + STG_N < st.nchunks) st.issue(c + STG_N);
     }
 }
 
@@ -291,25 +384,43 @@ __device__ __forceinline__ void clamp_patch(float* A, int n) {
 // occupancies and reduces it to (transmittance of the block, silhouette gathered inside the block);
 // a second, short pass chains the blocks of each column.
 // ----------------------------------------------------------------------------------------------
-template <int KT>
+template <int KT, bool TMA>
 __global__ void __launch_bounds__(TILE_THREADS)
 pc_sil_fwd_kernel(const float4* __restrict__ sorted, const int32_t* __restrict__ bin_start, const Taps taps,
                   const float* __restrict__ scale, int N, int V, int TY, int mode, int nbx, int nby,
                   float* __restrict__ sil) {
-    extern __shared__ float sm[];
+    extern __shared__ __align__(128) float sm[];
+    __shared__ __align__(8) uint64_t bars[STG_N];
     const int b = blockIdx.z, ty0 = blockIdx.y * TY, tx0 = blockIdx.x * TX;
     const int ncol = TY * TX, nzb = (V + ZB - 1) / ZB;
-    float* A = sm;                       // [V][ncol]
-    float* blkP = sm + V * ncol;         // [nzb][ncol] transmittance of the block
+    float* A = sm + (TMA ? STG_BYTES / sizeof(float) : 0);   // [V][ncol] (behind the record ring when staging with TMA)
+    float* blkP = A + V * ncol;          // [nzb][ncol] transmittance of the block
     float* blkS = blkP + nzb * ncol;     // [nzb][ncol] silhouette collected inside the block
     int* zlo = reinterpret_cast<int*>(blkS + nzb * ncol);    // [ncol] first / last occupied depth of the column
     int* zhi = zlo + ncol;
     const int tid = threadIdx.x;
+    const int cy1 = min(ty0 + TY, V) - 1, cx1 = min(tx0 + TX, V) - 1;
+    const float4* sp = sorted + (size_t)b * N;
+    const int32_t* bs = bin_start + (size_t)b * (nbx * nby + 1);
+    BinStream st;
+    uint32_t parity = 0;
+    if (TMA) {
+        st.open(sp, bs, reinterpret_cast<float4*>(sm), bars, nbx, max(ty0 - 1, 0) / BIN_Y, min(cy1 / BIN_Y, nby - 1),
+                max(tx0 - 1, 0) / BIN_X, min(cx1 / BIN_X, nbx - 1));
+        if (tid == 0) {                  // the records are on their way while the CTA zero-fills the patch
+            for (int s = 0; s < STG_N; ++s) mbar_init(bars + s, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the barriers as the bulk copies' async proxy sees them
+            st.prefetch();
+        }
+    }
     for (int i = tid; i < V * ncol; i += TILE_THREADS) A[i] = 0.f;
     for (int i = tid; i < ncol; i += TILE_THREADS) { zlo[i] = V; zhi[i] = -1; }
     __syncthreads();
-    splat_bins(sorted + (size_t)b * N, bin_start + (size_t)b * (nbx * nby + 1), nbx, nby, ty0,
-               min(ty0 + TY, V) - 1, tx0, min(tx0 + TX, V) - 1, TX, ncol, mode, A, zlo, zhi);
+    if (TMA)
+        stream_consume(st, parity, [&](const float4 g) { splat_record(g, ty0, cy1, tx0, cx1, TX, ncol, mode, A, zlo, zhi); });
+    else
+        splat_bins(sp, bs, nbx, nby, ty0, cy1, tx0, cx1, TX, ncol, mode, A, zlo, zhi);
     __syncthreads();
     clamp_patch(A, V * ncol);
     __syncthreads();
@@ -359,17 +470,18 @@ pc_sil_fwd_kernel(const float4* __restrict__ sorted, const int32_t* __restrict__
 // ----------------------------------------------------------------------------------------------
 // backward (patch with a +1 halo so that every point is owned by exactly one CTA)
 // ----------------------------------------------------------------------------------------------
-template <int KT>
+template <int KT, bool TMA>
 __global__ void __launch_bounds__(TILE_THREADS)
 pc_sil_bwd_kernel(const float4* __restrict__ sorted, const int32_t* __restrict__ bin_start, const Taps taps,
                   const float* __restrict__ scale, const float* __restrict__ dsil, int N, int V, int TY, int mode,
                   int nbx, int nby, float4* __restrict__ dpg, float* __restrict__ dscale) {
-    extern __shared__ float sm[];
+    extern __shared__ __align__(128) float sm[];
     __shared__ float red[32];
+    __shared__ __align__(8) uint64_t bars[STG_N];
     const int b = blockIdx.z, ty0 = blockIdx.y * TY, tx0 = blockIdx.x * TX;
     const int cy1 = min(ty0 + TY, V - 1), cx1 = min(tx0 + TX, V - 1);     // extended patch, clipped to the grid
     const int EX = TX + 1, ncol = (TY + 1) * EX, nzb = (V + ZB - 1) / ZB;
-    float* A1 = sm;                      // clamped occupancy (sign = clamp mask) -> dG
+    float* A1 = sm + (TMA ? STG_BYTES / sizeof(float) : 0);   // clamped occupancy (sign = clamp mask) -> dG
     float* A2 = A1 + V * ncol;           // blurred S -> dS
     float* blkA = A2 + V * ncol;         // [nzb][ncol] transmittance of the block
     float* blkB = blkA + nzb * ncol;     // [nzb][ncol] offset of the block's Q recurrence -> Q just after the block
@@ -377,13 +489,36 @@ pc_sil_bwd_kernel(const float4* __restrict__ sorted, const int32_t* __restrict__
     int* zlo = reinterpret_cast<int*>(blkT + nzb * ncol);    // [ncol] first / last occupied depth of the column
     int* zhi = zlo + ncol;
     const int tid = threadIdx.x;
+    const float4* sp = sorted + (size_t)b * N;
+    const int32_t* bs = bin_start + (size_t)b * (nbx * nby + 1);
+    BinStream st;
+    uint32_t parity = 0;
+    if (TMA) {
+        st.open(sp, bs, reinterpret_cast<float4*>(sm), bars, nbx, max(ty0 - 1, 0) / BIN_Y, min(cy1 / BIN_Y, nby - 1),
+                max(tx0 - 1, 0) / BIN_X, min(cx1 / BIN_X, nbx - 1));
+        if (tid == 0) {                  // the records are on their way while the CTA zero-fills the patch
+            for (int s = 0; s < STG_N; ++s) mbar_init(bars + s, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the barriers as the bulk copies' async proxy sees them
+            st.prefetch();
+        }
+    }
     for (int i = tid; i < V * ncol; i += TILE_THREADS) A1[i] = 0.f;
     for (int i = tid; i < ncol; i += TILE_THREADS) { zlo[i] = V; zhi[i] = -1; }
     __syncthreads();
-    const float4* sp = sorted + (size_t)b * N;
-    const int32_t* bs = bin_start + (size_t)b * (nbx * nby + 1);
-    splat_bins(sp, bs, nbx, nby, ty0, cy1, tx0, cx1, EX, ncol, mode, A1, zlo, zhi);
+    if (TMA)
+        stream_consume(st, parity, [&](const float4 g) { splat_record(g, ty0, cy1, tx0, cx1, EX, ncol, mode, A1, zlo, zhi); });
+    else
+        splat_bins(sp, bs, nbx, nby, ty0, cy1, tx0, cx1, EX, ncol, mode, A1, zlo, zhi);
     __syncthreads();
+    // the records of the OWNED bins (the gather at the end of the kernel) stream in under the four passes below
+    const int oy1 = min(ty0 + TY, V) - 1, ox1 = min(tx0 + TX, V) - 1;   // owned base cells
+    const int gby_lo = ty0 / BIN_Y, gby_hi = min(oy1 / BIN_Y, nby - 1);
+    const int gbx_lo = tx0 / BIN_X, gbx_hi = min(ox1 / BIN_X, nbx - 1);
+    if (TMA) {
+        st.open(sp, bs, reinterpret_cast<float4*>(sm), bars, nbx, gby_lo, gby_hi, gbx_lo, gbx_hi);
+        if (tid == 0) st.prefetch();
+    }
     clamp_patch(A1, V * ncol);
     __syncthreads();
 
@@ -494,35 +629,36 @@ pc_sil_bwd_kernel(const float4* __restrict__ sorted, const int32_t* __restrict__
 
     // gather: every in-bounds point is owned by the patch holding its base cell
     float4* dp = dpg + (size_t)b * N;
-    const int oy1 = min(ty0 + TY, V) - 1, ox1 = min(tx0 + TX, V) - 1;   // owned base cells
-    const int by_lo = ty0 / BIN_Y, by_hi = min(oy1 / BIN_Y, nby - 1);
-    const int bx_lo = tx0 / BIN_X, bx_hi = min(ox1 / BIN_X, nbx - 1);
-    for (int by = by_lo; by <= by_hi; ++by) {
-        const int lo = bs[by * nbx + bx_lo], hi = bs[by * nbx + bx_hi + 1];
-        for (int n = lo + tid; n < hi; n += TILE_THREADS) {
-            const float4 g = __ldg(sp + n);
-            const float fzf = floorf(g.x), fyf = floorf(g.y), fxf = floorf(g.z);
-            const int ly = (int)fyf - ty0, lx = (int)fxf - tx0;
-            if (ly < 0 || ly >= TY || lx < 0 || lx >= TX) continue;
-            const int fz = (int)fzf;
-            float wz[2], wy[2], wx[2];
-            axis_weights(g.x, fzf, mode, wz[0], wz[1]);
-            axis_weights(g.y, fyf, mode, wy[0], wy[1]);
-            axis_weights(g.z, fxf, mode, wx[0], wx[1]);
-            float dz = 0.f, dy = 0.f, dx = 0.f;
+    auto gather = [&](const float4 g) {
+        const float fzf = floorf(g.x), fyf = floorf(g.y), fxf = floorf(g.z);
+        const int ly = (int)fyf - ty0, lx = (int)fxf - tx0;
+        if (ly < 0 || ly >= TY || lx < 0 || lx >= TX) return;
+        const int fz = (int)fzf;
+        float wz[2], wy[2], wx[2];
+        axis_weights(g.x, fzf, mode, wz[0], wz[1]);
+        axis_weights(g.y, fyf, mode, wy[0], wy[1]);
+        axis_weights(g.z, fxf, mode, wx[0], wx[1]);
+        float dz = 0.f, dy = 0.f, dx = 0.f;
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
+        for (int i = 0; i < 2; ++i)
 #pragma unroll
-                for (int j = 0; j < 2; ++j)
+            for (int j = 0; j < 2; ++j)
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const float d = A1[(fz + i) * ncol + (ly + j) * EX + lx + k];
-                        // d w0/dg = -1, d w1/dg = +1 in both modes (floor has zero gradient)
-                        dz += d * (i ? 1.f : -1.f) * wy[j] * wx[k];
-                        dy += d * wz[i] * (j ? 1.f : -1.f) * wx[k];
-                        dx += d * wz[i] * wy[j] * (k ? 1.f : -1.f);
-                    }
-            dp[__float_as_int(g.w)] = make_float4(dz, dy, dx, 0.f);
+                for (int k = 0; k < 2; ++k) {
+                    const float d = A1[(fz + i) * ncol + (ly + j) * EX + lx + k];
+                    // d w0/dg = -1, d w1/dg = +1 in both modes (floor has zero gradient)
+                    dz += d * (i ? 1.f : -1.f) * wy[j] * wx[k];
+                    dy += d * wz[i] * (j ? 1.f : -1.f) * wx[k];
+                    dx += d * wz[i] * wy[j] * (k ? 1.f : -1.f);
+                }
+        dp[__float_as_int(g.w)] = make_float4(dz, dy, dx, 0.f);
+    };
+    if (TMA) {
+        stream_consume(st, parity, gather);
+    } else {
+        for (int by = gby_lo; by <= gby_hi; ++by) {
+            const int lo = bs[by * nbx + gbx_lo], hi = bs[by * nbx + gbx_hi + 1];
+            for (int n = lo + tid; n < hi; n += TILE_THREADS) gather(__ldg(sp + n));
         }
     }
 }
@@ -614,7 +750,7 @@ __global__ void __launch_bounds__(NTHREADS) clamp01_kernel(float* __restrict__ x
 // ----------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------
-constexpr size_t SMEM_BUDGET = 220 * 1024;
+constexpr size_t SMEM_BUDGET = 210 * 1024;      // the patch; + 16 KB record ring (B3D_PC_TMA) + static barriers <= 227 KB
 
 size_t patch_bytes(int V, int ty, bool bwd) {
     const size_t nzb = (V + ZB - 1) / ZB;
@@ -656,21 +792,44 @@ int set_smem(K kernel, size_t bytes) {
     return B3D_OK;
 }
 
+// B3D_PC_TMA=0/1: stage the bin records through shared memory with cp.async.bulk (default: see pc_tma_default)
+constexpr int pc_tma_default = 0;
+bool pc_tma() {
+    static const int v = getenv("B3D_PC_TMA") ? atoi(getenv("B3D_PC_TMA")) : pc_tma_default;
+    return v != 0;
+}
+
+template <int KT, bool TMA>
+int launch_sil_fwd(dim3 grid, size_t smem, cudaStream_t st, const float* sorted, const int32_t* bin_start, const Taps& t,
+                   const float* scale, int N, int V, int TY, int mode, float* sil) {
+    if (int rc = set_smem(pc_sil_fwd_kernel<KT, TMA>, smem)) return rc;
+    pc_sil_fwd_kernel<KT, TMA><<<grid, TILE_THREADS, smem, st>>>((const float4*)sorted, bin_start, t, scale, N, V, TY, mode,
+                                                                 bins_x(V), bins_y(V), sil);
+    B3D_LAUNCH_OK();
+    return B3D_OK;
+}
+
 int sil_fwd_impl(const float* sorted, const int32_t* bin_start, const Taps& t, const float* scale, int B, int N,
                  int V, int mode, float* sil, cudaStream_t st) {
     const int TY = pick_ty(V, false);
     B3D_REQUIRE(TY > 0, B3D_EINVAL, "b3d_pc_silhouette_fwd: V=%d does not fit the shared-memory patch", V);
-    const size_t smem = patch_bytes(V, TY, false);
+    const bool tma = pc_tma();
+    const size_t smem = patch_bytes(V, TY, false) + (tma ? STG_BYTES : 0);
+    if (tma) B3D_CHECK_ALIGNED(sorted);
     dim3 grid(b3d::ceil_div(V, TX), b3d::ceil_div(V, TY), B);
-    if (t.n == 21) {
-        if (int rc = set_smem(pc_sil_fwd_kernel<21>, smem)) return rc;
-        pc_sil_fwd_kernel<21><<<grid, TILE_THREADS, smem, st>>>((const float4*)sorted, bin_start, t, scale, N, V, TY,
-                                                               mode, bins_x(V), bins_y(V), sil);
-    } else {
-        if (int rc = set_smem(pc_sil_fwd_kernel<0>, smem)) return rc;
-        pc_sil_fwd_kernel<0><<<grid, TILE_THREADS, smem, st>>>((const float4*)sorted, bin_start, t, scale, N, V, TY,
-                                                              mode, bins_x(V), bins_y(V), sil);
-    }
+    if (t.n == 21)
+        return tma ? launch_sil_fwd<21, true>(grid, smem, st, sorted, bin_start, t, scale, N, V, TY, mode, sil)
+                   : launch_sil_fwd<21, false>(grid, smem, st, sorted, bin_start, t, scale, N, V, TY, mode, sil);
+    return tma ? launch_sil_fwd<0, true>(grid, smem, st, sorted, bin_start, t, scale, N, V, TY, mode, sil)
+               : launch_sil_fwd<0, false>(grid, smem, st, sorted, bin_start, t, scale, N, V, TY, mode, sil);
+}
+
+template <int KT, bool TMA>
+int launch_sil_bwd(dim3 grid, size_t smem, cudaStream_t st, const float* sorted, const int32_t* bin_start, const Taps& t,
+                   const float* scale, const float* dsil, int N, int V, int TY, int mode, float* dpg, float* dscale) {
+    if (int rc = set_smem(pc_sil_bwd_kernel<KT, TMA>, smem)) return rc;
+    pc_sil_bwd_kernel<KT, TMA><<<grid, TILE_THREADS, smem, st>>>((const float4*)sorted, bin_start, t, scale, dsil, N, V, TY, mode,
+                                                                 bins_x(V), bins_y(V), (float4*)dpg, dscale);
     B3D_LAUNCH_OK();
     return B3D_OK;
 }
@@ -679,20 +838,16 @@ int sil_bwd_impl(const float* sorted, const int32_t* bin_start, const Taps& t, c
                  const float* dsil, int B, int N, int V, int mode, float* dpg, float* dscale, cudaStream_t st) {
     const int TY = pick_ty(V, true);
     B3D_REQUIRE(TY > 0, B3D_EINVAL, "b3d_pc_silhouette_bwd: V=%d does not fit the shared-memory patch", V);
-    const size_t smem = patch_bytes(V, TY, true);
+    const bool tma = pc_tma();
+    const size_t smem = patch_bytes(V, TY, true) + (tma ? STG_BYTES : 0);
+    if (tma) B3D_CHECK_ALIGNED(sorted);
     if (dscale) B3D_CUDA_OK(cudaMemsetAsync(dscale, 0, sizeof(float) * B, st));
     dim3 grid(b3d::ceil_div(V, TX), b3d::ceil_div(V, TY), B);
-    if (t.n == 21) {
-        if (int rc = set_smem(pc_sil_bwd_kernel<21>, smem)) return rc;
-        pc_sil_bwd_kernel<21><<<grid, TILE_THREADS, smem, st>>>((const float4*)sorted, bin_start, t, scale, dsil, N, V,
-                                                               TY, mode, bins_x(V), bins_y(V), (float4*)dpg, dscale);
-    } else {
-        if (int rc = set_smem(pc_sil_bwd_kernel<0>, smem)) return rc;
-        pc_sil_bwd_kernel<0><<<grid, TILE_THREADS, smem, st>>>((const float4*)sorted, bin_start, t, scale, dsil, N, V,
-                                                              TY, mode, bins_x(V), bins_y(V), (float4*)dpg, dscale);
-    }
-    B3D_LAUNCH_OK();
-    return B3D_OK;
+    if (t.n == 21)
+        return tma ? launch_sil_bwd<21, true>(grid, smem, st, sorted, bin_start, t, scale, dsil, N, V, TY, mode, dpg, dscale)
+                   : launch_sil_bwd<21, false>(grid, smem, st, sorted, bin_start, t, scale, dsil, N, V, TY, mode, dpg, dscale);
+    return tma ? launch_sil_bwd<0, true>(grid, smem, st, sorted, bin_start, t, scale, dsil, N, V, TY, mode, dpg, dscale)
+               : launch_sil_bwd<0, false>(grid, smem, st, sorted, bin_start, t, scale, dsil, N, V, TY, mode, dpg, dscale);
 }
 
 int check_sil_args(const char* who, const void* sorted, const void* bin_start, const void* taps, int ktaps, int B,
@@ -720,6 +875,8 @@ void fill_taps(Taps& t, const float* host, int n) {
 extern "C" {
 
 int b3d_pc_bin_count(int V) { return V >= 2 ? bins_x(V) * bins_y(V) : 0; }
+
+int b3d_pc_tma_staging(void) { return pc_tma() ? 1 : 0; }
 
 int b3d_pc_project(const float* points, const float* quat, int B, int N, int V, float fov, float cam_dist,
                    float* pg, float* coords, int32_t* base, uint8_t* inb, float* sorted, int32_t* bin_start,

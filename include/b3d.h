@@ -72,6 +72,10 @@ B3D_API uint64_t b3d_launch_count(void);
  * sorted    [B,N,4]  out, nullable: (gz,gy,gx, bits(point index)) of the in-bounds points, bin-sorted
  * bin_start [B, b3d_pc_bin_count(V)+1] out, int32 (with sorted): start of every bin in `sorted`      */
 B3D_API int b3d_pc_bin_count(int V);
+/* 1 when the silhouette kernels stage the bin records through shared memory with cp.async.bulk (the TMA's 1-D bulk copy,
+ * mbarrier byte-count completion; the first stages are in flight while the patch is zero-filled), 0 when they read them with
+ * plain loads.  Process-wide, read once: environment B3D_PC_TMA=0/1 overrides the built-in default. */
+B3D_API int b3d_pc_tma_staging(void);
 B3D_API int b3d_pc_project(const float* points, const float* quat, int B, int N, int V, float fov,
                            float cam_dist, float* pg, float* coords, int32_t* base, uint8_t* inb,
                            float* sorted, int32_t* bin_start, void* stream);
