@@ -51,6 +51,10 @@ def _sig(name, *argtypes):
 
 _sig("b3d_pc_bin_count", _i)
 _sig("b3d_pc_tma_staging")
+_sig("b3d_inception_input", _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp)
+_sig("b3d_maxpool3x3s2_nhwc", _vp, _i, _i, _i, _i, _vp, _i, _vp)
+_sig("b3d_mean_hw_nhwc", _vp, _i, _i, _i, _vp, _vp)
+_sig("b3d_fid_accumulate", _vp, _i, _i, _vp, _vp, _vp)
 _sig("b3d_pc_project", _vp, _vp, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp)
 _sig("b3d_pc_silhouette_fwd_hosttaps", _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp)
 _sig("b3d_pc_silhouette_bwd_hosttaps", _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp)

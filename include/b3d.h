@@ -421,6 +421,25 @@ B3D_API int b3d_cbn_bwd_reduce_sync(const void* const* peer_data, const void* co
                                     unsigned* epoch, int* err, const float* S1, const float* S2, int s_pitch, const float* gt,
                                     float* red, int N, int C, void* stream);
 
+/* ---- FID evaluation (reference: main.py:188-412 evaluate_fid, utils/fid.py, utils/inception.py) ----------
+ * The Inception-v3 convolutions run on b3d_conv2d_tf32 (BatchNorm folded into weights and bias, ReLU = leaky slope 0 in the
+ * epilogue, every branch written into its channel slice of the concatenated tensor through OC / the output pointer); 3x3
+ * average pools are folded into the 1x1 convolution that follows them (nine taps of w / 9).  The rest:
+ * b3d_inception_input   utils/inception.py:123-131: img [B,3,H,W] planes in (0,1) -> bilinear resize to OH x OW
+ *                       (align_corners=False; identity when the size already matches), 2x - 1 when normalize != 0, written
+ *                       as NHWC [B,OH,OW,OC] with channels 3..OC-1 zero (OC % 4 == 0: one 32-channel K slice for the stem)
+ * b3d_maxpool3x3s2_nhwc nn.MaxPool2d(3, stride=2) on x [N,H,W,C]; `out` points at the first channel of the destination slice
+ *                       of a tensor with OC channels per pixel ([N,(H-3)/2+1,(W-3)/2+1,OC]); C, OC multiples of 4
+ * b3d_mean_hw_nhwc      AdaptiveAvgPool2d((1,1)): x [N,HW,C] -> out [N,C]
+ * b3d_fid_accumulate    utils/fid.py:27-30 calculate_stats as running sums: sum [D] += sum_k feat[k,:],
+ *                       outer [D,D] += feat^T feat, both fp64 (feat [n,D] fp32); mu = sum / n,
+ *                       sigma = (outer - n mu mu^T) / (n - 1) afterwards (np.cov's unbiased estimate).                        */
+B3D_API int b3d_inception_input(const float* img, int B, int H, int W, int OH, int OW, int OC, int normalize, float* out,
+                                void* stream);
+B3D_API int b3d_maxpool3x3s2_nhwc(const float* x, int N, int H, int W, int C, float* out, int OC, void* stream);
+B3D_API int b3d_mean_hw_nhwc(const float* x, int N, int HW, int C, float* out, void* stream);
+B3D_API int b3d_fid_accumulate(const float* feat, int n, int D, double* sum, double* outer, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
