@@ -51,6 +51,8 @@ def _sig(name, *argtypes):
 
 _sig("b3d_pc_bin_count", _i)
 _sig("b3d_pc_tma_staging")
+_sig("b3d_pc_stage_records")
+_sig("b3d_pc_stream_plan", _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i)
 _sig("b3d_inception_input", _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp)
 _sig("b3d_maxpool3x3s2_nhwc", _vp, _i, _i, _i, _i, _vp, _i, _vp)
 _sig("b3d_mean_hw_nhwc", _vp, _i, _i, _i, _vp, _vp)

@@ -301,22 +301,41 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "PC_WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra PC_WAIT_DONE;\n"
-        "bra PC_WAIT_LOOP;\n"
-        "PC_WAIT_DONE:\n"
-        "}\n" ::"r"(smem_addr(bar)),
-        "r"(parity)
-        : "memory");
+    // bounded: a byte count that never completes (a bug, or a fault of the copy) traps instead of hanging the GPU
+    for (uint32_t tries = 0; tries < (1u << 22); ++tries) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_addr(bar)), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
                  "l"(src), "r"(bytes), "r"(smem_addr(bar))
                  : "memory");
+}
+
+// Records [c0, c1) of the sequence "bins [bx_lo, bx_hi] of bin row by_lo, then of by_lo + 1, ... by_hi" as contiguous runs of
+// the sorted array: f(offset inside the chunk, first record, count) per run.  Host + device: b3d_pc_stream_plan exposes it
+// to the CPU tests.
+template <typename F>
+__host__ __device__ __forceinline__ void chunk_runs(const int32_t* bs, int nbx, int by_lo, int by_hi, int bx_lo, int bx_hi, int c0,
+                                                    int c1, F f) {
+    int pos = 0;
+    for (int by = by_lo; by <= by_hi && pos < c1; ++by) {
+        const int lo = bs[by * nbx + bx_lo], n = bs[by * nbx + bx_hi + 1] - lo;
+        const int a = c0 > pos ? c0 : pos, e = c1 < pos + n ? c1 : pos + n;
+        if (a < e) f(a - c0, lo + (a - pos), e - a);
+        pos += n;
+    }
 }
 
 // The records of bins [bx_lo, bx_hi] of bin rows [by_lo, by_hi], as one sequence cut into chunks of STG_REC.
@@ -342,13 +361,10 @@ struct BinStream {
         uint64_t* bar = bars + (c % STG_N);
         float4* dst = stg + (c % STG_N) * STG_REC;
         mbar_expect_tx(bar, (uint32_t)(c1 - c0) * (uint32_t)sizeof(float4));
-        int pos = 0;
-        for (int by = by_lo; by <= by_hi && pos < c1; ++by) {
-            const int lo = bs[by * nbx + bx_lo], n = bs[by * nbx + bx_hi + 1] - lo;
-            const int a = max(c0, pos), e = min(c1, pos + n);
-            if (a < e) bulk_g2s(dst + (a - c0), sp + lo + (a - pos), (uint32_t)(e - a) * (uint32_t)sizeof(float4), bar);
-            pos += n;
-        }
+        const float4* src = sp;
+        chunk_runs(bs, nbx, by_lo, by_hi, bx_lo, bx_hi, c0, c1, [=](int off, int first, int cnt) {
+            bulk_g2s(dst + off, src + first, (uint32_t)cnt * (uint32_t)sizeof(float4), bar);
+        });
     }
     __device__ __forceinline__ void prefetch() const {       // one thread: fill the ring
         for (int c = 0; c < nchunks && c < STG_N; ++c) issue(c);
@@ -877,6 +893,23 @@ extern "C" {
 int b3d_pc_bin_count(int V) { return V >= 2 ? bins_x(V) * bins_y(V) : 0; }
 
 int b3d_pc_tma_staging(void) { return pc_tma() ? 1 : 0; }
+
+int b3d_pc_stage_records(void) { return STG_REC; }
+
+int b3d_pc_stream_plan(const int32_t* bin_start_host, int nbx, int by_lo, int by_hi, int bx_lo, int bx_hi, int chunk, int* dst_off,
+                       int* src_first, int* count, int cap) {
+    B3D_REQUIRE(bin_start_host && nbx > 0 && by_lo >= 0 && by_hi >= by_lo && bx_lo >= 0 && bx_hi >= bx_lo && bx_hi < nbx && chunk >= 0 &&
+                    (cap == 0 || (dst_off && src_first && count)), B3D_EINVAL, "b3d_pc_stream_plan: bad arguments");
+    int total = 0;
+    for (int by = by_lo; by <= by_hi; ++by) total += bin_start_host[by * nbx + bx_hi + 1] - bin_start_host[by * nbx + bx_lo];
+    const int c0 = chunk * STG_REC, c1 = c0 + STG_REC < total ? c0 + STG_REC : total;
+    int runs = 0;
+    chunk_runs(bin_start_host, nbx, by_lo, by_hi, bx_lo, bx_hi, c0, c1, [&](int off, int first, int cnt) {
+        if (runs < cap) { dst_off[runs] = off; src_first[runs] = first; count[runs] = cnt; }
+        ++runs;
+    });
+    return runs;
+}
 
 int b3d_pc_project(const float* points, const float* quat, int B, int N, int V, float fov, float cam_dist,
                    float* pg, float* coords, int32_t* base, uint8_t* inb, float* sorted, int32_t* bin_start,

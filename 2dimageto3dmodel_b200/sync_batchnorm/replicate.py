@@ -10,7 +10,7 @@ class DataParallelWithCallback(nn.Module):
         super().__init__()
         if device_ids is not None and len(device_ids) > 1:
             raise RuntimeError("single-process multi-GPU DataParallel is not part of the B200 design: launch one "
-                               "process per GPU with torchrun (see parallel.py / INTEGRATION.md)")
+                               "process per GPU with torchrun (see gan_training.py / INTEGRATION.md)")
         self.module = module
 
     def forward(self, *args, **kwargs):

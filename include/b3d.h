@@ -76,6 +76,13 @@ B3D_API int b3d_pc_bin_count(int V);
  * mbarrier byte-count completion; the first stages are in flight while the patch is zero-filled), 0 when they read them with
  * plain loads.  Process-wide, read once: environment B3D_PC_TMA=0/1 overrides the built-in default. */
 B3D_API int b3d_pc_tma_staging(void);
+/* Host-only view of that staging (CPU tests): records per ring stage, and the contiguous runs of `sorted` that bulk copies
+ * bring in for chunk `chunk` of the record sequence "bins [bx_lo, bx_hi] of bin rows by_lo .. by_hi" given one sample's
+ * bin_start (HOST memory): run r copies count[r] records starting at record src_first[r] to offset dst_off[r] of the stage.
+ * Returns the number of runs (the arrays hold the first `cap`), negative on bad arguments. */
+B3D_API int b3d_pc_stage_records(void);
+B3D_API int b3d_pc_stream_plan(const int32_t* bin_start_host, int nbx, int by_lo, int by_hi, int bx_lo, int bx_hi, int chunk,
+                               int* dst_off, int* src_first, int* count, int cap);
 B3D_API int b3d_pc_project(const float* points, const float* quat, int B, int N, int V, float fov,
                            float cam_dist, float* pg, float* coords, int32_t* base, uint8_t* inb,
                            float* sorted, int32_t* bin_start, void* stream);

@@ -18,7 +18,7 @@ def test_pointcloud_suite_on_the_other_record_path():
     other = "0" if b3d.lib.b3d_pc_tma_staging() else "1"
     env = dict(os.environ, B3D_PC_TMA=other)
     files = [os.path.join(ROOT, "tests", f) for f in ("test_pointcloud_gpu.py", "test_silhouette_losses.py")]
-    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider", "--timeout", "300"] + files,
-                       env=env, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider", "--timeout", "100"] + files,
+                       env=env, cwd=ROOT, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, f"B3D_PC_TMA={other}:\n{r.stdout[-3000:]}\n{r.stderr[-2000:]}"
     assert " passed" in r.stdout
