@@ -24,7 +24,8 @@ s = (0.5 + 0.5 * torch.rand(B, 1, generator=g)).to(dev).requires_grad_(True)
 w = torch.rand(B, V, V, generator=g).to(dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 rec = {}
-for it in range(25):
+ITERS = int(os.environ.get("ITERS", 25))
+for it in range(ITERS):
     flush.zero_()
     for t in (p, q, s):
         t.grad = None
