@@ -91,12 +91,14 @@ class FIDEvaluator:
 
     # ------------------------------------------------------------------------------------------------ the loop
     @torch.no_grad()
-    def evaluate(self, eval_batches, fast=False, seed=None, keep_features=False):
+    def evaluate(self, eval_batches, fast=False, seed=None, keep_features=False, distributed=False):
         """eval_batches: iterable of dicts like the reference's eval_loader yields — 'idx' [B], 'rotation' [B,4], 'scale' [B]
         or [B,1], 'translation' [B,3]; optional 'class' [B] or [B,1], 'image' [B,3,R,R] in (0,1) (needed while the real
         statistics are not set), 'texture' + 'mesh' (pseudo-ground-truth: enables the texture-only / mesh-only scores unless
-        fast).  seed: main.py:223-227 (args.evaluate): reseeds the noise stream.  Returns a dict of scores (+ the feature
-        matrices with keep_features)."""
+        fast).  seed: main.py:223-227 (args.evaluate): reseeds the noise stream.  distributed: every rank passes ITS shard of
+        the evaluation set; the feature sums are all-reduced (torch.distributed) before the distances, so all ranks return the
+        scores of the whole set (the validation-subset scores need the individual features and stay per rank).  Returns a dict
+        of scores (+ the feature matrices with keep_features)."""
         self.generator.eval()
         gen = torch.Generator().manual_seed(seed) if seed is not None else None
         st = {k: FIDStatistics(self.dim, self.device) for k in ("combined", "texture_only", "mesh_only", "real")}
@@ -119,6 +121,9 @@ class FIDEvaluator:
             if has_pseudogt:
                 self.render_and_score(data['mesh'], pred_tex, data, st["texture_only"], feats["texture_only"] if feats else None)
                 self.render_and_score(pred_mesh_map, data['texture'], data, st["mesh_only"], feats["mesh_only"] if feats else None)
+        if distributed:
+            for k in st:
+                st[k].all_reduce()
         if self.m_real is None:
             self.m_real, self.s_real = st["real"].finalize()
         out = {}

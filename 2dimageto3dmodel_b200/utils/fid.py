@@ -65,6 +65,19 @@ class FIDStatistics:
         check(lib.b3d_fid_accumulate(ptr(f), f.shape[0], self.dim, ptr(self.sum), ptr(self.outer), stream_ptr(f)))
         self.n += int(f.shape[0])
 
+    def all_reduce(self, group=None):
+        """One process per GPU, every rank scores its shard of the evaluation set: sum the running sums over the ranks
+        (the reference instead scatters every batch over `gpu_ids` inside one process, main.py:163, :254-279).  The sums are
+        additive, so the reduced statistics equal the single-process ones up to fp64 summation order."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return self
+        n = torch.tensor([float(self.n)], dtype=torch.float64, device=self.sum.device)
+        for t in (self.sum, self.outer, n):
+            dist.all_reduce(t, group=group)
+        self.n = int(round(float(n)))
+        return self
+
     def finalize(self):
         """-> (mu [D], sigma [D,D]) as float64 numpy arrays, the values np.mean / np.cov(rowvar=False) give."""
         if self.n < 2:
