@@ -7,9 +7,12 @@ Parity status
   * PINNED (against the reference's own Python, imported in the authoring container by
     tests/golden/make_golden_mesh.py): qrot / circpad / fragment shader / loss_flat / face adjacency
     `ff` / mean_iou / transform_vertices.
-  * MeshTemplate (mesh_template.py) cannot be imported without kaolin; it is restated here line by
-    line and pinned only through the pieces above plus structural facts of the shipped templates
-    (SURVEY.md §8c (2)).
+  * PINNED: MeshTemplate (mesh_template.py:14-170: index sets, topology / tangent maps, get_vertex_positions,
+    deform, adjust_uv_and_texture, compute_normals).  The reference's class imports kaolin for ONE call
+    (TriangleMesh.from_obj) and hard-codes .cuda(); tests/golden/make_golden_template.py supplies a stand-in for
+    exactly those two things and runs the class UNMODIFIED on the CPU (-> tests/golden/template_reference.npz;
+    tests/test_template_reference.py: this restatement and the drop-in equal it on 16 / 31-ring spheres, symmetric
+    and not, and on the shipped OBJ templates).  kaolin's OBJ parser itself is the one piece not exercised.
   * PARITY UNPINNED: `rasterize` restates kaolin @ e7e5131 `linear_rasterizer` from SURVEY.md App. B
     (kaolin is not in the container and not installable); it is validated for self-consistency
     only (coverage = point-in-triangle, z order, barycentrics sum to 1, autograd = finite differences).
