@@ -13,6 +13,9 @@ Parity status
     exactly those two things and runs the class UNMODIFIED on the CPU (-> tests/golden/template_reference.npz;
     tests/test_template_reference.py: this restatement and the drop-in equal it on 16 / 31-ring spheres, symmetric
     and not, and on the shipped OBJ templates).  kaolin's OBJ parser itself is the one piece not exercised.
+  * PINNED: `render` / `ortho_projection` / `forward_renderer` — everything AROUND the rasteriser: the reference's
+    Renderer.forward (renderer.py:39-77) is run unmodified with this file's `rasterize` standing in for kaolin's
+    (tests/golden/make_golden_renderer.py -> renderer_reference.npz) and `render` must reproduce it exactly.
   * PARITY UNPINNED: `rasterize` restates kaolin @ e7e5131 `linear_rasterizer` from SURVEY.md App. B
     (kaolin is not in the container and not installable); it is validated for self-consistency
     only (coverage = point-in-triangle, z order, barycentrics sum to 1, autograd = finite differences).

@@ -90,3 +90,31 @@ def test_shipped_templates_through_probes(rings):
     _close(t.compute_normals(t.get_vertex_positions(dmap))[:, ::53], G[tag + "_normals_probe"])
     assert (len(t.pos_indices), len(t.neg_indices), t.mesh.vertices.shape[0], t.mesh.faces.shape[0]) == \
         tuple(G[tag + "_counts"][[0, 1, 3, 4]])
+
+
+def test_oracle_render_wiring_equals_the_reference_renderer():
+    """tests/golden/renderer_reference.npz: the reference's Renderer.forward run unmodified with the oracle's rasteriser
+    standing in for kaolin's (make_golden_renderer.py) — pins everything around the rasteriser in oracle/mesh.py:render."""
+    d = np.load(os.path.join(GOLDEN, "renderer_reference.npz"))
+    path = _path(16)
+    T = M.TemplateData(M.load_obj(path), path)
+    H = int(d["H"][0])
+    mesh_map, q, s, t, tex, bg = (torch.tensor(d[k]) for k in ("mesh_map", "q", "s", "t", "tex", "bg"))
+    vtx = M.transform_vertices(M.get_vertex_positions(T, mesh_map), s, t, q)
+    p3d, p2d, nrm = M.ortho_projection(vtx, T.faces)
+    for a, k in ((p3d, "p3d"), (p2d, "p2d"), (nrm, "normal")):
+        _close(a, d[k], 0.0)
+    uvs, padded = M.adjust_uv_and_texture(T, tex)
+    img, alpha, n1, _ = M.render(vtx, T.faces, uvs, padded, T.face_textures, H, H)
+    _close(img, d["img"], 0.0)
+    _close(alpha, d["alpha"], 0.0)
+    _close(n1, d["normal1"], 0.0)
+    img_bg, hard, _, _ = M.render(vtx, T.faces, uvs, padded, T.face_textures, H, H, background_image=bg, return_hardmask=True)
+    _close(img_bg, d["img_bg"], 0.0)
+    _close(hard, d["hard"], 0.0)
+    img_noft, _, _, _ = M.render(vtx, T.faces, uvs[:, :T.vertices.shape[0]], padded, None, H, H)
+    _close(img_noft, d["img_noft"], 0.0)
+    # the convenience wrapper the GPU tests call
+    img2, alpha2, _ = M.forward_renderer(T, vtx, tex, H, H)
+    _close(img2, d["img"], 0.0)
+    _close(alpha2, d["alpha"], 0.0)
