@@ -19,7 +19,7 @@ from fid_evaluation import FIDEvaluator  # noqa: E402
 from models import gan  # noqa: E402
 from rendering.mesh_template import MeshTemplate  # noqa: E402
 from tools.uvsphere import write_uvsphere_obj  # noqa: E402
-from utils.inception import BasicConv2d, InceptionV3  # noqa: E402
+from utils.inception import InceptionV3  # noqa: E402
 
 dev = torch.device("cuda:0")
 B = int(os.environ.get("B", 32))
