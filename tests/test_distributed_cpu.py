@@ -77,3 +77,64 @@ def test_syncbn_single_process_is_plain_batchnorm():
     assert list(a.state_dict()) == list(b.state_dict())
     m = convert_model(torch.nn.Sequential(torch.nn.Conv2d(3, 3, 1), torch.nn.BatchNorm2d(3)))
     assert isinstance(m[1], SynchronizedBatchNorm2d)
+
+
+def _worker_golden(rank, world, port, q):
+    for p in (PKG, ROOT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import numpy as np
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sync_batchnorm import SynchronizedBatchNorm2d
+    d = np.load(os.path.join(ROOT, "tests", "golden", "syncbn_reference.npz"))
+    bn = SynchronizedBatchNorm2d(6).train()
+    with torch.no_grad():
+        bn.weight.copy_(torch.tensor(d["weight"]))
+        bn.bias.copy_(torch.tensor(d["bias"]))
+    out = []
+    for step in range(2):
+        lo, hi = rank * 4, rank * 4 + 4
+        x = torch.tensor(d[f"x{step}"][lo:hi]).requires_grad_(True)
+        bn.zero_grad()
+        y = bn(x)
+        (y * torch.tensor(d[f"w{step}"][lo:hi])).sum().backward()
+        gw, gb = bn.weight.grad.clone(), bn.bias.grad.clone()
+        dist.all_reduce(gw)                        # parameter gradients: summed over the replicas (DataParallel semantics)
+        dist.all_reduce(gb)
+        out.append((y.detach().numpy(), x.grad.numpy(), gw.numpy(), gb.numpy(), bn.running_mean.numpy().copy(),
+                    bn.running_var.numpy().copy()))
+    xs = torch.tensor(d["x_small"][rank * 2:rank * 2 + 2])
+    out.append(bn(xs).detach().numpy())
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_syncbn_world2_equals_the_reference_parallel_branch():
+    """tests/golden/syncbn_reference.npz: the reference's own parallel-branch code executed on the whole batch
+    (make_golden_syncbn.py); two ranks with half a batch each must reproduce outputs, input / parameter gradients and the
+    running statistics after two training steps, and the clamp-the-variance behaviour on a near-constant channel."""
+    import numpy as np
+    d = np.load(os.path.join(ROOT, "tests", "golden", "syncbn_reference.npz"))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker_golden, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for step in range(2):
+        y = np.concatenate([res[r][step][0] for r in range(2)])
+        dx = np.concatenate([res[r][step][1] for r in range(2)])
+        assert np.abs(y - d[f"y{step}"]).max() < 2e-5 and np.abs(dx - d[f"dx{step}"]).max() < 2e-5
+        for r in range(2):
+            _, _, gw, gb, rm, rv = res[r][step]
+            assert np.abs(gw - d[f"dweight{step}"]).max() < 1e-3 * np.abs(d[f"dweight{step}"]).max()
+            assert np.abs(gb - d[f"dbias{step}"]).max() < 1e-3 * np.abs(d[f"dbias{step}"]).max() + 1e-5
+            assert np.abs(rm - d[f"running_mean{step}"]).max() < 1e-6 and np.abs(rv - d[f"running_var{step}"]).max() < 1e-5
+    ys = np.concatenate([res[r][2] for r in range(2)])
+    assert np.abs(ys - d["y_small"]).max() < 1e-3 * np.abs(d["y_small"]).max()
