@@ -75,3 +75,42 @@ def test_equal_to_reference_modules():
     ck = os.path.join(REF, "gan_weights/pretrained_weights_cub/checkpoint_latest.pth")
     G5 = gan.Generator(GC.make_args(512, 3), 64)
     G5.load_state_dict(torch.load(ck, map_location="cpu")["generator_running_avg"], strict=True)
+
+
+def test_model_wrapper_and_running_average_match_the_reference_step_logic():
+    """tests/golden/wrapper_reference.npz: main.py's ModelWrapper / divide_pred / update_generator_running_avg EXECUTED from the
+    script's syntax tree on tiny stand-in networks (make_golden_wrapper.py).  The drop-in wrapper (gan_training.ModelWrapper)
+    and the trainer's running-average update must reproduce losses, outputs and the averaged state dict."""
+    import sys
+    import types
+    sys.path.insert(0, GOLDEN)
+    import wrapper_common as WC
+    from gan_training import GANTrainer, ModelWrapper
+    d = np.load(os.path.join(GOLDEN, "wrapper_reference.npz"))
+    for tag, nd, res in (("w21", 2, 512), ("unw", 2, 256), ("nd3", 3, 512)):
+        args = WC.make_args(nd, res)
+        gi, D = WC.build()
+        mw = ModelWrapper(args, gi, D).train()
+        x = WC.inputs()
+        loss, tex, mesh = mw('g', None, x["X_alpha"], None, x["C"], None, x["noise"])
+        lf, lr, _, _ = mw('d', x["X_tex"], x["X_alpha"], x["X_mesh"], x["C"], None, x["noise"])
+        for got, key in ((loss, "_g_loss"), (tex, "_g_tex"), (mesh, "_g_mesh"), (lf, "_d_fake"), (lr, "_d_real")):
+            ref = d[tag + key]
+            assert np.abs(got.detach().numpy().reshape(ref.shape) - ref).max() < 1e-6, (tag, key)
+        if tag != "w21":
+            continue
+        mw.eval()
+        itex, imesh, attn = mw('inference', None, None, None, x["C"], None, x["noise"])
+        assert attn is None and np.abs(itex.numpy() - d["inf_tex"]).max() < 1e-6 and np.abs(imesh.numpy() - d["inf_mesh"]).max() < 1e-6
+        mw.train()
+        with torch.no_grad():
+            for p in mw.generator.parameters():
+                p.add_(0.05 * torch.randn(p.shape, generator=torch.Generator().manual_seed(p.numel())))
+            mw.generator.bn.num_batches_tracked.fill_(7)
+        holder = types.SimpleNamespace(args=args, trainer=mw)
+        for epoch in (5, 50, 500):
+            GANTrainer.update_generator_running_avg(holder, epoch)
+            for k, v in mw.generator_running_avg.state_dict().items():
+                ref = d[f"avg{epoch}_{k}"]
+                assert np.abs(v.numpy().astype(np.float64) - ref).max() < 1e-6, (epoch, k)
+    assert float(d["w21_g_loss"][0]) != float(d["unw_g_loss"][0])    # the [2, 1] discriminator weights act at 512^2 / nd = 2 only
