@@ -102,3 +102,50 @@ def test_forward_wiring_matches_reference_golden_on_cpu(monkeypatch):
         got = float(params[str(name)].grad.norm())
         assert abs(got - ref) <= 2e-3 * ref + 1e-6, (str(name), got, ref)
     assert np.abs(net.bn4e.running_mean.numpy() - d["bn4e_mean"]).max() < 1e-5
+
+
+@pytest.mark.parametrize("tag,deltas,z0", [("deltas", True, False), ("full", True, True), ("z0", False, True)])
+def test_training_iteration_matches_the_reference_loop(tag, deltas, z0, monkeypatch):
+    """tests/golden/recon_step_reference.npz: the training-loop body of run_reconstruction.py (:409-465) EXECUTED from the
+    script's syntax tree for four iterations on stand-in network / template / renderer (make_golden_recon_step.py).
+    ReconTrainer.step — on the same stand-ins, with its fused CUDA pieces (RGBA-MSE + IoU kernel, flat-loss kernel, fused
+    vertex pipeline) replaced by their torch definitions — must reproduce every iteration's loss, the warm-up factor and the
+    updated network / DatasetParams parameters (two Adams)."""
+    import recon_step_common as RS
+    import reconstruction_training as RT
+    from models.reconstruction import DatasetParams
+    from oracle import mesh as OM
+    d = np.load(os.path.join(GOLDEN, "recon_step_reference.npz"))
+    args = RS.make_args(deltas, z0)
+
+    def rgba_mse_iou(image, alpha, X_real):                  # b3d.mesh.rgba_mse_iou = run_reconstruction.py:429-436
+        X_fake = torch.cat((image, alpha), dim=3).permute(0, 3, 1, 2)
+        return torch.nn.functional.mse_loss(X_fake, X_real), OM.mean_iou(X_fake[:, 3], X_real[:, 3])
+    monkeypatch.setattr(RT, "rgba_mse_iou", rgba_mse_iou)
+    monkeypatch.setattr(RT, "loss_flat", lambda mesh, norms: OM.loss_flat(mesh.ff, mesh.faces.shape[0], norms))
+
+    tpl = RS.Template()
+    tpl.vertices_and_pose = lambda m, s, t, r, z=None: (lambda raw: (raw, OM.transform_vertices(raw, s, t, r, z)))(tpl.get_vertex_positions(m))
+    tr = object.__new__(RT.ReconTrainer)                      # the constructor builds the CUDA network; wire the stand-ins instead
+    tr.args, tr.tpl, tr.world, tr.renderer = args, tpl, 1, None
+    tr.generator = RS.build_net()
+    tr.optimizer = torch.optim.Adam(tr.generator.parameters(), lr=args.lr)
+    tr.dataset_params = DatasetParams(args, 10)
+    tr.optimizer_dataset = torch.optim.Adam(tr.dataset_params.parameters(), lr=args.lr_dataset)
+    tr.flat_warmup = torch.full((), 10.0)
+    losses = []
+    for i, (X, s, t, r, idx) in enumerate(RS.batches()):
+        loss, recon, flat, miou = tr.step(X, s, t, r, idx.squeeze(-1))
+        losses.append(float(loss))
+        if i == 0:
+            ref = str(d[tag + ".log0"])
+            assert f"recon_loss {float(recon):.5f} flat_loss {float(flat):.5f} total {float(loss):.5f} iou {float(miou):.5f}" in ref
+    assert np.abs(np.array(losses) - d[tag + ".g_curve"]).max() < 2e-6
+    assert abs(float(tr.flat_warmup) - float(d[tag + ".flat_warmup"])) < 1e-5     # 10 -> 9.6 (an fp32 device scalar here, a Python float there)
+    for k, v in tr.generator.state_dict().items():
+        # four Adam steps of 1e-2: a wrong learning rate / optimiser / loss weight moves parameters by >= 1e-3; Adam's
+        # g / sqrt(v) normalisation amplifies rounding differences of small-gradient elements to ~1e-5
+        assert np.abs(v.numpy().astype(np.float64) - d[f"{tag}.net.{k}"]).max() < 1e-4, k
+    for k, v in tr.dataset_params.state_dict().items():
+        assert np.abs(v.numpy() - d[f"{tag}.dp.{k}"]).max() < 1e-4, k
+    assert any(np.abs(d[f"{tag}.dp.{k}"] - (1.0 if k == "ds_z0" else 0.0)).max() > 1e-2 for k in tr.dataset_params.state_dict())
