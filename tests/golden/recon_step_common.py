@@ -26,10 +26,10 @@ class TinyNet(nn.Module):
 class Template:
     """get_vertex_positions / compute_normals / forward_renderer of rendering/mesh_template.py, on a fixed toy topology."""
 
-    def __init__(self):
+    def __init__(self, map_size=4):
         g = torch.Generator().manual_seed(2)
         self.base = torch.randn(V, 3, generator=g) * 0.3
-        self.mix = torch.randn(3 * 4 * 4, V * 3, generator=g) * 0.2
+        self.mix = torch.randn(3 * map_size * map_size, V * 3, generator=g) * 0.2
         faces = torch.stack([torch.randperm(V, generator=g)[:3] for _ in range(F_)])
         ff = torch.stack([torch.tensor([(i + 1) % F_, (i + 3) % F_, (i + 5) % F_]) for i in range(F_)])
         self.mesh = types.SimpleNamespace(faces=faces, ff=ff)

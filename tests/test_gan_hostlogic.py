@@ -114,3 +114,39 @@ def test_model_wrapper_and_running_average_match_the_reference_step_logic():
                 ref = d[f"avg{epoch}_{k}"]
                 assert np.abs(v.numpy().astype(np.float64) - ref).max() < 1e-6, (epoch, k)
     assert float(d["w21_g_loss"][0]) != float(d["unw_g_loss"][0])    # the [2, 1] discriminator weights act at 512^2 / nd = 2 only
+
+
+def test_training_iteration_matches_the_reference_loop(monkeypatch):
+    """tests/golden/gan_loop_reference.npz: the training-loop body of main.py (:672-727) EXECUTED from the script's syntax tree for
+    six iterations (G D D G D D) on stand-in networks / template (make_golden_gan_loop.py).  GANTrainer.step — same stand-ins,
+    its flat-loss kernel replaced by the torch definition — must reproduce the loss curves, the generator, the discriminator and
+    the running-average generator after both Adams."""
+    sys.path.insert(0, GOLDEN)
+    import recon_step_common as RS
+    import wrapper_common as WC
+    import gan_training as GT
+    from oracle import mesh as OM
+    d = np.load(os.path.join(GOLDEN, "gan_loop_reference.npz"))
+    args = WC.make_args(2, 512)
+    args.d_steps_per_g, args.mesh_regularization, args.lr_g, args.lr_d = 2, 0.0001, 0.01, 0.04
+    monkeypatch.setattr(GT, "loss_flat", lambda mesh, norms: OM.loss_flat(mesh.ff, mesh.faces.shape[0], norms))
+    gi, D = WC.build()
+    tr = object.__new__(GT.GANTrainer)                         # the constructor builds the CUDA networks; wire the stand-ins instead
+    tr.args, tr.mesh_template, tr.world, tr.total_it = args, RS.Template(map_size=8), 1, 0
+    tr.trainer = GT.ModelWrapper(args, gi, D).train()
+    tr.optimizer_g = torch.optim.Adam(tr.trainer.generator.parameters(), lr=args.lr_g, betas=(0.0, 0.9))
+    tr.optimizer_d = torch.optim.Adam(tr.trainer.discriminator.parameters(), lr=args.lr_d, betas=(0.0, 0.9))
+    torch.manual_seed(77)
+    g_curve, d_curve = [], []
+    for i in range(6):
+        x = WC.inputs(seed=50 + i, B=4)
+        out = tr.step(x["X_tex"], x["X_alpha"], x["X_mesh"], x["C"], epoch=0)
+        (g_curve if i % 3 == 0 else d_curve).append(float(out))
+    assert np.abs(np.array(g_curve) - d["g_curve"][1:]).max() < 2e-6
+    assert np.abs(np.array(d_curve) - (d["d_fake_curve"][1:] + d["d_real_curve"][1:])).max() < 5e-6
+    for name, mod in (("g", tr.trainer.generator), ("avg", tr.trainer.generator_running_avg), ("d", tr.trainer.discriminator)):
+        for k, v in mod.state_dict().items():
+            ref = d[f"{name}.{k}"]
+            assert np.abs(v.numpy().astype(np.float64) - ref).max() < 1e-4, (name, k)      # Adam amplifies rounding to ~1e-5
+    moved = max(np.abs(d[f"g.{k}"] - d[f"avg.{k}"]).max() for k in tr.trainer.generator.state_dict() if "num_batches" not in k)
+    assert moved > 1e-3                                        # epoch 0: alpha^100, the average trails the live generator
