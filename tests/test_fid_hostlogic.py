@@ -239,3 +239,50 @@ def test_evaluation_loop_host_logic(monkeypatch):
     ev2.set_real_statistics(ev.m_real, ev.s_real, validation=True, num_images=7)
     with pytest.raises(ValueError):
         ev2.evaluate(batches(2, image=False), seed=1234)           # 'Not supported': more validation images than generated
+
+
+def test_evaluator_matches_the_reference_evaluate_fid(monkeypatch):
+    """tests/golden/fid_loop_reference.npz: main.py's `evaluate_fid` (:188-412) EXECUTED from the script's syntax tree on stand-in
+    generator / template / renderer / extractor, with the reference's own utils/fid.py (make_golden_fid_loop.py).  FIDEvaluator on
+    the same stand-ins (feature sums in torch instead of the CUDA kernel) must give the same scores: the seeded truncated-noise
+    stream, the three renders per batch, real statistics from the images, the seeded validation subset, the fast mode.
+    Tolerance 1e-5 relative (observed 2e-8): 18 samples in 64 dimensions make every covariance singular, where the reference's
+    scipy.linalg.sqrtm itself warns about its accuracy."""
+    import sys
+    sys.path.insert(0, GOLDEN)
+    import fid_loop_common as FL
+    import recon_step_common as RS
+    import wrapper_common as WC
+    import fid_evaluation as FE
+    from oracle import mesh as OM
+    from utils import fid as UF
+
+    def update(self, feat):
+        f = feat.detach().double()
+        self.sum += f.sum(0)
+        self.outer += f.t() @ f
+        self.n += f.shape[0]
+    monkeypatch.setattr(UF.FIDStatistics, "update", update)
+    d = np.load(os.path.join(GOLDEN, "fid_loop_reference.npz"))
+    gi, _ = WC.build()
+    G = gi()
+    G2 = gi()
+    G2.load_state_dict(G.state_dict())          # ModelWrapper's running-average copy: the SECOND instance, same weights
+    tpl = RS.Template(map_size=8)
+    tpl.vertices_and_pose = lambda m, s, t, r: (lambda raw: (raw, OM.transform_vertices(raw, s, t, r)))(tpl.get_vertex_positions(m))
+    ev = FE.FIDEvaluator(G2, tpl, inception=FL.Extractor(), evaluation_res=FL.RES, latent_dim=8, truncation_sigma=1.0, device="cpu")
+
+    def close(a, b):
+        assert abs(a - b) <= 1e-5 * abs(b), (a, b)
+    out = ev.evaluate(FL.eval_set(), seed=1234)
+    for k, ref in zip(("fid", "fid_texture_only", "fid_mesh_only"), d["run1"]):
+        close(out[k], ref)
+    np.testing.assert_allclose(ev.m_real, d["m_real"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(ev.s_real, d["s_real"], rtol=0, atol=1e-6)
+    ev.set_real_statistics(d["m_val"], d["s_val"], validation=True, num_images=11)
+    out = ev.evaluate(FL.eval_set(), seed=1234)
+    for k, ref in zip(("fid", "fid_texture_only", "fid_mesh_only", "fid_val", "fid_texture_only_val", "fid_mesh_only_val"), d["run2"]):
+        close(out[k], ref)
+    out = ev.evaluate(FL.eval_set(), seed=1234, fast=True)
+    close(out["fid"], d["run3"][0])
+    assert set(out) == {"fid", "num_generated"}
