@@ -78,3 +78,59 @@ def test_reference_dataset_reads_our_records(tmp_path, monkeypatch):
     for k in ours:
         assert torch.equal(theirs[k], ours[k]), k
     assert torch.equal(ref.AbstractDataset.mirror_tex(ours['texture']), mirror_tex(ours['texture']))
+
+
+def test_export_pipeline_matches_the_reference_export_loop(tmp_path):
+    """tests/golden/pseudogt_reference.npz: the export loop of run_reconstruction.py (:542-604) with its nested InverseRenderer
+    (:506-527) EXECUTED from the script's syntax tree through the reference's own MeshTemplate / Renderer classes
+    (make_golden_pseudogt.py).  The construction the GPU tests compare the CUDA renderer with (tests/test_inverse_renderer_gpu.py:
+    oracle render with a differentiable texture -> autograd visibility; UV-space render of the photograph) plus the drop-in's
+    host pieces (DatasetParams, visibility_to_mask, make_record, save / load) must reproduce the records it wrote."""
+    from conftest import GOLDEN
+    sys.path.insert(0, GOLDEN)
+    import pseudogt_common as PC
+    from data.pseudo_gt import load_pseudo_ground_truth, make_record, pseudo_gt_dir, save_pseudo_gt, visibility_to_mask
+    from models.reconstruction import DatasetParams
+    from oracle import mesh as M
+    d = np.load(os.path.join(GOLDEN, "pseudogt_reference.npz"))
+    path = M.write_uvsphere_obj(str(tmp_path / "uvsphere_16rings.obj"), rings=16)
+    T = M.TemplateData(M.load_obj(path), path)
+    net = PC.build_net().eval()
+    dp = DatasetParams(types.SimpleNamespace(optimize_deltas=True, optimize_z0=False), 10)
+    with torch.no_grad():
+        dp.ds_translation.copy_(torch.tensor(d["ds_translation"]))
+        dp.ds_scale.copy_(torch.tensor(d["ds_scale"]))
+    seen = []
+    for net_image, inception_image, hd_image, s, t, q, indices in PC.batches():
+        with torch.no_grad():
+            pred_tex, mesh_map = net(net_image)
+            td, sd = dp(indices.squeeze(-1), 'deltas')
+            vtx = M.transform_vertices(M.get_vertex_positions(T, mesh_map), s, t, q, scale_delta=sd, translation_delta=td)
+        tex = pred_tex.clone().requires_grad_(True)
+        img, _, _ = M.forward_renderer(T, vtx, tex, PC.RENDER, PC.RENDER)
+        vis, = torch.autograd.grad(img, tex, torch.ones_like(img))
+        with torch.no_grad():
+            B = hd_image.shape[0]
+            uvs = (vtx[..., :2] + 1) / 2
+            verts = torch.cat((T.uvs.unsqueeze(0) * 2 - 1, torch.zeros(1, T.uvs.shape[0], 1)), dim=-1).expand(B, -1, -1)
+            outs = []
+            for idx in ([0, 1, 2], [3, 3, 3]):             # three channels per pass, as the CUDA InverseRenderer does
+                o, hard, _, _ = M.render(verts, T.face_textures, uvs, hd_image[:, idx], ft=T.faces, H=PC.PSEUDO, W=PC.PSEUDO, return_hardmask=True)
+                outs.append(o)
+            inverse_tex = torch.cat((outs[0], outs[1][..., :1]), dim=3)
+            mask = visibility_to_mask(vis, PC.PSEUDO)
+            inverse_tex, inverse_alpha = (inverse_tex * mask).permute(0, 3, 1, 2), (hard * mask).permute(0, 3, 1, 2)
+        for i, idx in enumerate(indices.view(-1).tolist()):
+            rec = make_record(mesh_map[i], inverse_tex[i], inverse_alpha[i], inception_image[i])
+            assert np.abs(rec['mesh'].numpy() - d[f"{idx}.mesh"]).max() < 1e-7
+            assert np.array_equal(rec['image'].numpy(), d[f"{idx}.image"])
+            # fp16 records: at most one unit in the last place apart (fp32 render differences of 1e-6 can flip a rounding)
+            assert np.array_equal(rec['texture_alpha'].numpy(), d[f"{idx}.texture_alpha"])
+            assert np.abs(rec['texture'].float().numpy() - d[f"{idx}.texture"].astype(np.float32)).max() <= 1e-3
+            assert rec['texture'].shape == (4, PC.PSEUDO, PC.PSEUDO) and rec['texture_alpha'].shape == (1, PC.PSEUDO, PC.PSEUDO)
+            save_pseudo_gt(pseudo_gt_dir(str(tmp_path), PC.PSEUDO), idx, rec)
+            back = load_pseudo_ground_truth(str(tmp_path), PC.PSEUDO, idx)
+            assert torch.equal(back['texture_alpha'], torch.tensor(d[f"{idx}.texture_alpha"]).float())
+            seen.append(idx)
+    assert sorted(seen) == [0, 1, 2, 13]
+    assert 0.3 < float(np.mean([float((d[f"{i}.texture_alpha"] != 0).mean()) for i in seen])) < 0.95
