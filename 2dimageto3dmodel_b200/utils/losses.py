@@ -70,5 +70,6 @@ class GANLoss(nn.Module):
                 pred = pred[-1]
             term = self.loss(pred, target_is_real, for_discriminator,
                              None if mask is None else mask[i], None if weight is None else weight[i])
-            total = total + (term if term.dim() == 0 else term.view(term.size(0), -1).mean(dim=1))
+            # a scalar term becomes shape [1] (losses.py:112-114: bs = 1, mean over view(1, -1)), so list inputs return [1] or [B]
+            total = total + (term.view(1) if term.dim() == 0 else term.view(term.size(0), -1).mean(dim=1))
         return total / (len(input) if weight is None else sum(weight))

@@ -96,7 +96,8 @@ def test_model_wrapper_and_running_average_match_the_reference_step_logic():
         lf, lr, _, _ = mw('d', x["X_tex"], x["X_alpha"], x["X_mesh"], x["C"], None, x["noise"])
         for got, key in ((loss, "_g_loss"), (tex, "_g_tex"), (mesh, "_g_mesh"), (lf, "_d_fake"), (lr, "_d_real")):
             ref = d[tag + key]
-            assert np.abs(got.detach().numpy().reshape(ref.shape) - ref).max() < 1e-6, (tag, key)
+            assert got.shape == ref.shape, (tag, key, got.shape, ref.shape)       # incl. the [1]-shaped losses of list inputs
+            assert np.abs(got.detach().numpy() - ref).max() < 1e-6, (tag, key)
         if tag != "w21":
             continue
         mw.eval()
